@@ -1,0 +1,204 @@
+"""Host side of the operator pack: per-graph sparse operators and their block-diagonal batch.
+
+The reference materialises dense per-graph tensors ``W (N,N,J+2)``, ``WL (M,M,J+2)``,
+``Pm, Pd (N,M)`` (functions/operators.py:11-83) and zero-pads them per batch
+(functions/batching.py:77-185).  Here the same operators are held as CSR index/value arrays -
+exactly the non-zeros the reference would produce, quirks included:
+
+* ``W[:,:,1]`` is the weighted degree, A keeps its weights (operators.py:22-25);
+* the line-graph enumeration bumps ``e`` once per undirected edge (operators.py:59), so of the
+  M = nnz(A) line-graph nodes only columns 0..E hold an edge (column E = reverse of the last
+  edge) and columns E+1..M-1 are phantom ``(0,0,0)`` rows that still link to every stored edge
+  leaving node 0 (operators.py:68-71);
+* ``AL[m1,m2] = w(m2)``; ``Pm``/``Pd`` columns are the union of edges c and c-1 with the
+  later write winning (operators.py:52-66).
+
+Powers ``A^(2^j)`` / ``AL^(2^j)`` are NOT built here: they are squared on the GPU by the SpGEMM
+kernel at batch-pack time (``pack.py``).  This module is pure index bookkeeping (numpy, O(nnz));
+all arithmetic on features happens in the CUDA kernels.
+"""
+import numpy as np
+
+I32 = np.int32
+F32 = np.float32
+
+
+def _csr_from_sorted_coo(n_rows, rows, cols, *vals):
+    """COO sorted by (row, col) -> (rowptr, col, *vals)."""
+    rowptr = np.zeros(n_rows + 1, dtype=np.int64)
+    np.add.at(rowptr, rows + 1, 1)
+    return (np.cumsum(rowptr).astype(I32), cols.astype(I32)) + tuple(v.astype(F32) for v in vals)
+
+
+def _sort_coo(rows, cols, *vals):
+    order = np.lexsort((cols, rows))
+    return (rows[order], cols[order]) + tuple(v[order] for v in vals)
+
+
+class GraphOps(object):
+    """Sparse twin of ``graph_operators([V, A], J, dual=True)`` for ONE graph (local indices).
+
+    Attributes (numpy): ``N, M, E``; A as CSR ``a_*`` and its transpose ``at_*``; weighted degree
+    ``deg``; the line-graph operator ``b_*`` / ``bt_*`` with ``dl`` = its row sums (this is also
+    the initial edge feature XL, batching.py:171); incidence ``p_*`` (rows = nodes) and ``pt_*``
+    (rows = line-graph nodes), each with the two value arrays ``pm`` and ``pd`` on one pattern.
+    """
+
+    __slots__ = ("N", "M", "E", "a_rowptr", "a_col", "a_val", "at_rowptr", "at_col", "at_val",
+                 "deg", "b_rowptr", "b_col", "b_val", "bt_rowptr", "bt_col", "bt_val", "dl",
+                 "p_rowptr", "p_col", "p_pm", "p_pd", "pt_rowptr", "pt_col", "pt_pm", "pt_pd",
+                 "dual")
+
+    @classmethod
+    def from_dense(cls, A, dual=True):
+        A = np.asarray(A, dtype=F32)
+        r, c = np.nonzero(A)                       # row-major order
+        return cls.from_coo(A.shape[0], r, c, A[r, c], dual=dual, presorted=True)
+
+    @classmethod
+    def from_coo(cls, N, rows, cols, vals, dual=True, presorted=False):
+        """(rows, cols, vals): every stored entry of A, both directions of each edge."""
+        rows = np.asarray(rows, dtype=np.int64)
+        cols = np.asarray(cols, dtype=np.int64)
+        vals = np.asarray(vals, dtype=F32)
+        keep = vals != 0
+        if not keep.all():
+            rows, cols, vals = rows[keep], cols[keep], vals[keep]
+        if not presorted:
+            rows, cols, vals = _sort_coo(rows, cols, vals)
+        self = cls()
+        self.N, self.dual = int(N), bool(dual)
+        self.a_rowptr, self.a_col, self.a_val = _csr_from_sorted_coo(N, rows, cols, vals)
+        tr, tc, tv = _sort_coo(cols, rows, vals)
+        self.at_rowptr, self.at_col, self.at_val = _csr_from_sorted_coo(N, tr, tc, tv)
+        deg = np.zeros(N, dtype=F32)
+        np.add.at(deg, rows, vals)       # small exact values: order-independent
+        self.deg = deg
+        self.M = int(vals.shape[0])
+        if not dual:
+            self.E = int(np.count_nonzero(cols > rows))
+            return self
+        self._build_line_graph(rows, cols, vals)
+        return self
+
+    # ------------------------------------------------------------------------------------
+    def _build_line_graph(self, rows, cols, vals):
+        N, M = self.N, self.M
+        fwd = cols > rows                                   # operators.py:49-51, i<j row-major
+        iu, ju, wu = rows[fwd], cols[fwd], vals[fwd]
+        E = self.E = int(iu.shape[0])
+        if E and M <= E:
+            raise ValueError("adjacency must be symmetric: the reference writes line-graph "
+                             "column E, which needs M=nnz(A) > E (operators.py:60-66)")
+        src = np.zeros(M, dtype=np.int64)
+        dst = np.zeros(M, dtype=np.int64)
+        w = np.zeros(M, dtype=F32)
+        if E:
+            src[:E], dst[:E], w[:E] = iu, ju, wu
+            src[E], dst[E], w[E] = ju[-1], iu[-1], wu[-1]
+        # ---- AL[m1, m2] = w(m2) iff dst(m1) == src(m2) and src(m1) != dst(m2)  (:68-71)
+        fstart = np.zeros(N + 1, dtype=np.int64)            # forward edges are grouped by source
+        np.add.at(fstart, iu + 1, 1)
+        fstart = np.cumsum(fstart)
+        cnt = fstart[dst + 1] - fstart[dst]                 # candidates per line-graph node m1
+        m1 = np.repeat(np.arange(M, dtype=np.int64), cnt)
+        within = np.arange(m1.shape[0], dtype=np.int64) - np.repeat(np.cumsum(cnt) - cnt, cnt)
+        m2 = fstart[dst[m1]] + within
+        if E:                                               # the one stored reverse edge
+            extra = np.nonzero(dst == src[E])[0]
+            m1 = np.concatenate([m1, extra])
+            m2 = np.concatenate([m2, np.full(extra.shape[0], E, dtype=np.int64)])
+        ok = src[m1] != dst[m2]
+        m1, m2 = m1[ok], m2[ok]
+        bv = w[m2]
+        m1, m2, bv = _sort_coo(m1, m2, bv)
+        self.b_rowptr, self.b_col, self.b_val = _csr_from_sorted_coo(M, m1, m2, bv)
+        t1, t2, tv = _sort_coo(m2, m1, bv)
+        self.bt_rowptr, self.bt_col, self.bt_val = _csr_from_sorted_coo(M, t1, t2, tv)
+        dl = np.zeros(M, dtype=F32)
+        np.add.at(dl, m1, bv)
+        self.dl = dl
+        # ---- Pm / Pd  (:52-66): column c gets edge c (+1 at i, -1 at j) written AFTER edge c-1
+        #      (-1 at i, +1 at j); Pm is 1 on the union.
+        c = np.arange(E, dtype=np.int64)
+        node = np.concatenate([iu, ju, iu, ju])
+        colm = np.concatenate([c + 1, c + 1, c, c])
+        pdv = np.concatenate([-np.ones(E), np.ones(E), np.ones(E), -np.ones(E)]).astype(F32)
+        prio = np.concatenate([np.zeros(2 * E), np.ones(2 * E)])      # later write wins
+        order = np.lexsort((prio, colm, node))
+        node, colm, pdv = node[order], colm[order], pdv[order]
+        last = np.ones(node.shape[0], dtype=bool)
+        if node.shape[0] > 1:
+            last[:-1] = (node[1:] != node[:-1]) | (colm[1:] != colm[:-1])
+        node, colm, pdv = node[last], colm[last], pdv[last]
+        pmv = np.ones(node.shape[0], dtype=F32)
+        self.p_rowptr, self.p_col, self.p_pm, self.p_pd = _csr_from_sorted_coo(N, node, colm, pmv, pdv)
+        tc, tn, tpm, tpd = _sort_coo(colm, node, pmv, pdv)
+        self.pt_rowptr, self.pt_col, self.pt_pm, self.pt_pd = _csr_from_sorted_coo(M, tc, tn, tpm, tpd)
+
+    # ------------------------------------------------------------------------------------
+    def nbytes(self):
+        return sum(getattr(self, s).nbytes for s in self.__slots__
+                   if isinstance(getattr(self, s, None), np.ndarray))
+
+    def dense(self):
+        """(W, WL, Pm, Pd) for J=1 as dense numpy arrays - host bookkeeping check only."""
+        def densify(n_r, n_c, rowptr, col, val):
+            D = np.zeros((n_r, n_c), dtype=F32)
+            r = np.repeat(np.arange(n_r), np.diff(rowptr))
+            D[r, col] = val
+            return D
+        N, M = self.N, self.M
+        W = np.zeros((N, N, 3), dtype=F32)
+        W[:, :, 0] = np.eye(N, dtype=F32)
+        W[:, :, 1] = np.diag(self.deg)
+        W[:, :, 2] = densify(N, N, self.a_rowptr, self.a_col, self.a_val)
+        if not self.dual:
+            return W
+        WL = np.zeros((M, M, 3), dtype=F32)
+        WL[:, :, 0] = np.eye(M, dtype=F32)
+        WL[:, :, 1] = np.diag(self.dl)
+        WL[:, :, 2] = densify(M, M, self.b_rowptr, self.b_col, self.b_val)
+        Pm = densify(N, M, self.p_rowptr, self.p_col, self.p_pm)
+        Pd = densify(N, M, self.p_rowptr, self.p_col, self.p_pd)
+        return W, WL, Pm, Pd
+
+
+_FIELDS = {
+    # name -> (rowptr, row space, col space, value arrays)
+    "a": ("a_rowptr", "n", "n", ("a_col", "a_val")),
+    "at": ("at_rowptr", "n", "n", ("at_col", "at_val")),
+    "b": ("b_rowptr", "m", "m", ("b_col", "b_val")),
+    "bt": ("bt_rowptr", "m", "m", ("bt_col", "bt_val")),
+    "p": ("p_rowptr", "n", "m", ("p_col", "p_pm", "p_pd")),
+    "pt": ("pt_rowptr", "m", "n", ("pt_col", "pt_pm", "pt_pd")),
+}
+
+
+def concat_block_diagonal(graphs, dual=True):
+    """Block-diagonal batch of ``GraphOps``: global row/col indices, per-graph offsets.
+
+    Returns a dict of numpy arrays: ``node_off``/``edge_off`` (bs+1), ``deg``, ``dl`` and, for each
+    operator in ``a, at[, b, bt, p, pt]``, ``<op>_rowptr`` and its index/value arrays."""
+    bs = len(graphs)
+    n = np.array([g.N for g in graphs], dtype=np.int64)
+    m = np.array([g.M for g in graphs], dtype=np.int64)
+    out = {"node_off": np.concatenate([[0], np.cumsum(n)]).astype(I32),
+           "edge_off": np.concatenate([[0], np.cumsum(m)]).astype(I32),
+           "deg": np.concatenate([g.deg for g in graphs]) if bs else np.zeros(0, F32)}
+    off = {"n": out["node_off"].astype(np.int64), "m": out["edge_off"].astype(np.int64)}
+    names = list(_FIELDS) if dual else ["a", "at"]
+    if dual:
+        out["dl"] = np.concatenate([g.dl for g in graphs])
+    for name in names:
+        rp_name, rspace, cspace, arrs = _FIELDS[name]
+        nnz = np.array([getattr(g, arrs[0]).shape[0] for g in graphs], dtype=np.int64)
+        nnz_off = np.concatenate([[0], np.cumsum(nnz)])
+        rp = [getattr(g, rp_name)[:-1].astype(np.int64) + nnz_off[i] for i, g in enumerate(graphs)]
+        out[rp_name] = np.concatenate(rp + [nnz_off[-1:]]).astype(I32)
+        out[arrs[0]] = np.concatenate(
+            [getattr(g, arrs[0]).astype(np.int64) + off[cspace][i] for i, g in enumerate(graphs)]
+        ).astype(I32)
+        for a in arrs[1:]:
+            out[a] = np.concatenate([getattr(g, a) for g in graphs]).astype(F32)
+    return out
