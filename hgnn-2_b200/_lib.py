@@ -1,0 +1,158 @@
+"""ctypes binding of libhgnn_b200.so (the C ABI of include/hgnn_b200.h).
+
+There is NO fallback: if the shared library is missing the import fails, and every call checks the
+status code and raises ``RuntimeError`` with ``hgnn_last_error()``.  Tensors must be CUDA,
+contiguous and of the expected dtype - the host layer never silently computes on the CPU.
+"""
+import ctypes
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libhgnn_b200.so")
+
+if not os.path.exists(LIB_PATH):
+    raise ImportError(
+        "hgnn_b200: %s is missing - build it with `python -c 'import __graft_entry__ as g; "
+        "g.build()'` (nvcc, sm_100a).  There is no CPU fallback." % LIB_PATH)
+
+lib = ctypes.CDLL(LIB_PATH)
+
+c_int, c_ll, c_float, c_void = ctypes.c_int, ctypes.c_longlong, ctypes.c_float, ctypes.c_void_p
+
+OP_IDENT, OP_DIAG, OP_CSR = 0, 1, 2
+MAX_OPS = 8
+
+
+class OpT(ctypes.Structure):
+    _fields_ = [("kind", c_int), ("diag", c_void), ("rowptr", c_void), ("col", c_void),
+                ("val", c_void)]
+
+
+class SideT(ctypes.Structure):
+    _fields_ = [("R", c_int), ("ops", ctypes.POINTER(OpT)), ("n_ops", c_int), ("Xs", c_void),
+                ("Fs", c_int), ("p_rowptr", c_void), ("p_col", c_void), ("p_pm", c_void),
+                ("p_pd", c_void), ("Xc", c_void), ("Fc", c_int)]
+
+
+_P = c_void
+_SIGS = {
+    "hgnn_pack_rows": [_P, c_int, c_int, c_int, _P, _P, _P],
+    "hgnn_unpack_rows": [_P, c_int, c_int, c_int, _P, _P, _P, _P],
+    "hgnn_dense_count_nnz": [_P, _P, c_ll, c_ll, c_ll, c_int, _P, _P, _P, _P],
+    "hgnn_dense_fill_csr": [_P, _P, c_ll, c_ll, c_ll, c_int, _P, _P, _P, _P, _P, _P, _P],
+    "hgnn_exclusive_scan_i32": [_P, _P, c_int, _P],
+    "hgnn_csr_to_dense": [_P, _P, _P, c_int, _P, _P, _P, c_ll, c_ll, c_ll, _P],
+    "hgnn_csr_row_sums": [_P, _P, c_int, _P, _P],
+    "hgnn_spgemm_count_products": [c_int, _P, _P, _P, _P, _P],
+    "hgnn_spgemm_expand": [c_int, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P],
+    "hgnn_spgemm_fill": [c_int, _P, _P, _P, _P, _P, _P, _P, c_int, _P],
+    "hgnn_gmul_fwd": [ctypes.POINTER(OpT), c_int, c_int, c_int, _P, _P, _P],
+    "hgnn_gmul_bwd": [ctypes.POINTER(OpT), c_int, c_int, c_int, _P, _P, _P],
+    "hgnn_bn_stats": [_P, c_int, c_int, _P, _P, _P, _P, c_float, _P, _P, c_ll, _P],
+    "hgnn_bn_stats_eval": [c_int, _P, _P, _P, _P, _P, _P],
+    "hgnn_bn_apply": [_P, c_int, c_int, _P, _P, _P],
+    "hgnn_bn_bwd_reduce": [_P, _P, c_int, c_int, _P, _P, c_int, _P, _P, _P, c_ll, _P],
+    "hgnn_side_bwd_pre": [_P, _P, c_int, c_int, _P, c_int, _P, _P, _P, c_ll, _P],
+    "hgnn_side_fwd": [ctypes.POINTER(SideT), _P, _P, c_int, _P, _P, c_int, c_int, _P, _P, _P, _P,
+                      _P, c_float, _P, _P, c_ll, _P],
+    "hgnn_side_bwd_gather": [ctypes.POINTER(OpT), c_int, c_int, _P, c_int, _P, c_int, _P, c_int, _P,
+                             c_int, c_int, c_int, _P, c_int, _P, _P, _P, c_ll, _P],
+    "hgnn_segment_sum": [_P, c_int, c_int, _P, _P, _P, _P, _P],
+    "hgnn_segment_bcast": [_P, c_int, c_int, _P, _P, _P],
+    "hgnn_ccn2_collapse6to3": [_P, c_int, c_int, _P, _P],
+    "hgnn_ccn2_collapse6to3_bwd": [_P, c_int, c_int, _P, _P],
+    "hgnn_ccn2_update_fwd": [c_int, c_int, _P, _P, _P, _P, c_int, _P, _P, c_int, _P, _P],
+    "hgnn_ccn2_update_bwd": [c_int, c_int, _P, _P, _P, _P, c_int, _P, c_int, _P, _P, _P, _P, _P, _P, c_ll, _P],
+    "hgnn_ccn1_update_fwd": [c_int, c_int, _P, _P, _P, c_int, _P, _P, c_int, _P, _P],
+    "hgnn_ccn1_update_bwd": [c_int, c_int, _P, _P, _P, c_int, _P, c_int, _P, _P, _P, _P, _P, _P, c_ll, _P],
+    "hgnn_adamax_step": [_P, _P, _P, _P, c_ll, c_float, c_float, c_float, c_float, c_float, _P, _P],
+}
+EXPORTS = sorted(list(_SIGS) + ["hgnn_last_error", "hgnn_version", "hgnn_workspace_bytes"])
+
+for _name, _args in _SIGS.items():
+    _fn = getattr(lib, _name)
+    _fn.argtypes = _args
+    _fn.restype = c_int
+lib.hgnn_last_error.restype = ctypes.c_char_p
+lib.hgnn_last_error.argtypes = []
+lib.hgnn_version.restype = c_int
+lib.hgnn_workspace_bytes.restype = c_ll
+lib.hgnn_workspace_bytes.argtypes = [c_int]
+
+# number of kernel launches issued through the C ABI (bench.py reports it as gpu_launches)
+launch_count = 0
+
+
+def call(name, *args):
+    """Invoke one C-ABI entry point; raise on a non-zero status."""
+    global launch_count
+    rc = getattr(lib, name)(*args)
+    if rc != 0:
+        raise RuntimeError("%s failed (%d): %s" % (name, rc, lib.hgnn_last_error().decode()))
+    launch_count += 1
+
+
+def require_cuda():
+    if not torch.cuda.is_available():
+        raise RuntimeError("hgnn_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+
+
+def ptr(t, dtype=None):
+    """Device pointer of a contiguous CUDA tensor (None -> NULL)."""
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise RuntimeError("hgnn_b200: expected a CUDA tensor (no CPU fallback)")
+    if not t.is_contiguous():
+        raise RuntimeError("hgnn_b200: expected a contiguous tensor")
+    if dtype is not None and t.dtype != dtype:
+        raise RuntimeError("hgnn_b200: expected dtype %s, got %s" % (dtype, t.dtype))
+    return t.data_ptr()
+
+
+def fptr(t):
+    return ptr(t, torch.float32)
+
+
+def iptr(t):
+    return ptr(t, torch.int32)
+
+
+def stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+_ws_cache = {}
+
+
+def workspace(width, device):
+    """Zero-initialised scratch for cross-CTA reductions (kernels reset their ticket counter, so
+    one buffer per (device, stream) is reused by every call on that stream)."""
+    need = int(lib.hgnn_workspace_bytes(int(width)))
+    key = (device.index if device.index is not None else torch.cuda.current_device(), stream())
+    buf = _ws_cache.get(key)
+    if buf is None or buf.numel() < need:
+        buf = torch.zeros(max(need, 1 << 20), dtype=torch.uint8, device=device)
+        _ws_cache[key] = buf
+    return buf.data_ptr(), buf.numel()
+
+
+def make_ops(descs):
+    """descs: list of ('ident',) | ('diag', vec) | ('csr', rowptr, col, val) -> (OpT array, n)."""
+    n = len(descs)
+    if n < 1 or n > MAX_OPS:
+        raise RuntimeError("hgnn_b200: between 1 and %d operators are supported, got %d (J too large)"
+                           % (MAX_OPS, n))
+    arr = (OpT * n)()
+    for i, d in enumerate(descs):
+        if d[0] == "ident":
+            arr[i].kind = OP_IDENT
+        elif d[0] == "diag":
+            arr[i].kind = OP_DIAG
+            arr[i].diag = fptr(d[1])
+        else:
+            arr[i].kind = OP_CSR
+            arr[i].rowptr, arr[i].col, arr[i].val = iptr(d[1]), iptr(d[2]), fptr(d[3])
+    return arr, n

@@ -1,0 +1,74 @@
+"""``GNN_simple`` / ``GNN_lg`` - mirror of the reference's models/gnns/model_mnb.py (:19-66, :69-129).
+
+Same constructor signatures, module names (``layer0``, ``layer{i}``, ``layerlast``), attributes
+(``.dual``, ``.J`` read by scripts/train_mnb.py:29-30) and forward signatures.  The forward converts
+the padded ``(bs, F, Nmax)`` inputs to packed rows once, runs the layer stack on the fused kernels
+and returns ``(bs, dim_output)`` like the reference.
+"""
+import torch.nn as nn
+
+from ..._lib import require_cuda
+from ...pack import resolve_pack
+from ..layers import layers_mnb
+
+
+class GNN_simple(nn.Module):
+    """Power GNN.  ``task`` and ``gru`` are accepted and unused, as in the reference (:42)."""
+
+    def __init__(self, task, n_features, n_layers, dim_input, dim_output=1, J=1, gru=False):
+        super(GNN_simple, self).__init__()
+        self.dual = False
+        self.J = J
+        self.gru = False
+        self.n_features = n_features
+        self.n_layers = n_layers
+        self.n_outputs = dim_output
+        self.featuremap_in = [dim_input, n_features]
+        self.featuremap_mi = [2 * n_features, n_features]
+        self.featuremap_end = [2 * n_features, dim_output]
+        self.layer0 = layers_mnb.layer_simple(self.featuremap_in, J + 2, gru)
+        for i in range(n_layers - 2):
+            self.add_module('layer{}'.format(i + 1), layers_mnb.layer_simple(self.featuremap_mi, J + 2, gru))
+        self.layerlast = layers_mnb.layer_last(self.featuremap_end, J + 2)
+
+    def forward(self, state, N_batch, mask):
+        require_cuda()
+        X, W = state
+        pack = resolve_pack(W, N_batch=N_batch)
+        cur, _ = self.layer0.forward_packed(layers_mnb._pack_nodes(pack, X), pack)
+        for i in range(self.n_layers - 2):
+            cur, _ = self._modules['layer{}'.format(i + 1)].forward_packed(cur, pack)
+        return self.layerlast.forward_packed(cur, pack)
+
+
+class GNN_lg(nn.Module):
+    """GNN on the line graph with the non-backtracking operator; ``order`` in {1, 2, 3} selects
+    layer_with_lg_{1,2,3} (reference :102-120; any other value falls through to 3 there too)."""
+
+    def __init__(self, task, n_features, n_layers, dim_input, dim_output=1, J=1, order=1):
+        super(GNN_lg, self).__init__()
+        self.dual = True
+        self.J = J
+        self.n_features = n_features
+        self.n_layers = n_layers
+        self.n_outputs = dim_output
+        self.order = order
+        self.featuremap_in = [dim_input, 1, n_features]
+        self.featuremap_mi = [2 * n_features, 2 * n_features, n_features]
+        self.featuremap_end = [2 * n_features, dim_output]
+        cls = {1: layers_mnb.layer_with_lg_1, 2: layers_mnb.layer_with_lg_2}.get(order, layers_mnb.layer_with_lg_3)
+        self.layer0 = cls(self.featuremap_in, J + 2)
+        for i in range(n_layers - 2):
+            self.add_module('layer{}'.format(i + 1), cls(self.featuremap_mi, J + 2))
+        self.layerlast = layers_mnb.layer_last_lg(self.featuremap_end, J + 2)
+
+    def forward(self, state, N_batch, mask, E_batch, mask_lg):
+        require_cuda()
+        X, XL, W, WL, Pm, Pd = state
+        pack = resolve_pack(W, WL, Pm, Pd, N_batch, E_batch)
+        Xp = layers_mnb._pack_nodes(pack, X)
+        XLp = layers_mnb._pack_edges(pack, XL)
+        Xp, XLp, _, _ = self.layer0.forward_packed(Xp, XLp, pack)
+        for i in range(self.n_layers - 2):
+            Xp, XLp, _, _ = self._modules['layer{}'.format(i + 1)].forward_packed(Xp, XLp, pack)
+        return self.layerlast.forward_packed(Xp, XLp, pack)

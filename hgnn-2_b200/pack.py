@@ -1,0 +1,447 @@
+"""Device-resident block-diagonal operator pack and the handles that stand in for the reference's
+dense ``W / WL / Pm / Pd / mask`` tensors.
+
+Reference boundary: functions/batching.py:77-185 returns dense ``W (bs,N,N,K)``, ``WL (bs,M,M,K)``,
+``Pm, Pd (bs,N,M)`` and masks; scripts/train_mnb.py:56-70 only sets ``.requires_grad``, calls
+``.cuda()`` and hands them back to the model.  ``OperatorHandle`` / ``MaskHandle`` support exactly
+that, while the data stays CSR (SURVEY.md section 8b "Tensors crossing it").
+
+HBM layout: all index/value arrays of a batch live in ONE contiguous device buffer (a single
+host->device copy from pinned memory), 16-byte aligned sub-arrays: int32 rowptr/col, fp32 values,
+block-diagonal with global row numbers.  At C2 (32 graphs, N=1000) that is ~10 MB instead of the
+reference's 9.6 GB of dense WL.
+"""
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import call, fptr, iptr, stream
+from .sparse_ops import GraphOps, concat_block_diagonal
+
+
+class Csr(object):
+    """CSR triple (or quad, for the Pm/Pd pair) of device tensors."""
+    __slots__ = ("rowptr", "col", "val", "val2", "n_rows")
+
+    def __init__(self, rowptr, col, val, val2=None):
+        self.rowptr, self.col, self.val, self.val2 = rowptr, col, val, val2
+        self.n_rows = rowptr.numel() - 1
+
+    @property
+    def nnz(self):
+        return self.col.numel()
+
+    def desc(self, second=False):
+        return ("csr", self.rowptr, self.col, self.val2 if second else self.val)
+
+
+def _upload(arrays, device):
+    """One pinned staging buffer + one H2D copy for a dict of int32/float32 numpy arrays."""
+    offs, total = {}, 0
+    for k, a in arrays.items():
+        offs[k] = total
+        total += (a.nbytes + 15) & ~15
+    host = torch.empty(max(total, 16), dtype=torch.uint8, pin_memory=True)
+    hv = host.numpy()
+    for k, a in arrays.items():
+        hv[offs[k]:offs[k] + a.nbytes] = a.view(np.uint8).reshape(-1)
+    dev = host.to(device, non_blocking=True)
+    out = {}
+    for k, a in arrays.items():
+        dt = torch.int32 if a.dtype == np.int32 else torch.float32
+        out[k] = dev[offs[k]:offs[k] + a.nbytes].view(dt)
+    return out, dev, total
+
+
+def exclusive_scan(counts):
+    """counts (n,) int32 device -> (n+1,) int32 exclusive prefix sums (hgnn_exclusive_scan_i32)."""
+    n = counts.numel()
+    out = torch.empty(n + 1, dtype=torch.int32, device=counts.device)
+    call("hgnn_exclusive_scan_i32", iptr(counts), iptr(out), n, stream())
+    return out
+
+
+def spgemm(A, B, clip=False):
+    """C = A @ B for block-diagonal CSR operands (functions/operators.py:26-29, 78-81)."""
+    R = A.n_rows
+    dev = A.rowptr.device
+    if R == 0 or A.nnz == 0 or B.nnz == 0:
+        return Csr(torch.zeros(R + 1, dtype=torch.int32, device=dev),
+                   torch.empty(0, dtype=torch.int32, device=dev),
+                   torch.empty(0, dtype=torch.float32, device=dev))
+    cnt = torch.empty(R, dtype=torch.int32, device=dev)
+    call("hgnn_spgemm_count_products", R, iptr(A.rowptr), iptr(A.col), iptr(B.rowptr), iptr(cnt), stream())
+    prodptr = exclusive_scan(cnt)
+    total = int(prodptr[-1].item())
+    pcol = torch.empty(max(total, 1), dtype=torch.int32, device=dev)
+    pval = torch.empty(max(total, 1), dtype=torch.float32, device=dev)
+    pflag = torch.empty(max(total, 1), dtype=torch.int32, device=dev)
+    rowcnt = torch.empty(R, dtype=torch.int32, device=dev)
+    call("hgnn_spgemm_expand", R, iptr(A.rowptr), iptr(A.col), fptr(A.val), iptr(B.rowptr), iptr(B.col),
+         fptr(B.val), iptr(prodptr), iptr(pcol), fptr(pval), iptr(pflag), iptr(rowcnt), stream())
+    c_rowptr = exclusive_scan(rowcnt)
+    nnz = int(c_rowptr[-1].item())
+    c_col = torch.empty(max(nnz, 1), dtype=torch.int32, device=dev)[:nnz]
+    c_val = torch.empty(max(nnz, 1), dtype=torch.float32, device=dev)[:nnz]
+    call("hgnn_spgemm_fill", R, iptr(prodptr), iptr(pcol), fptr(pval), iptr(pflag), iptr(c_rowptr),
+         iptr(c_col), fptr(c_val), 1 if clip else 0, stream())
+    return Csr(c_rowptr, c_col, c_val)
+
+
+def dense_to_csr(D1, D2, bs, row_off, col_off, n_rows):
+    """Strided dense (bs, rows, cols) view(s) -> CSR on the device.  Pattern = nz(D1) | nz(D2)."""
+    dev = D1.device
+    sb, sr, sc = D1.stride()
+    if D2 is not None and D2.stride() != D1.stride():
+        raise RuntimeError("hgnn_b200: Pm and Pd must share one memory layout")
+    if n_rows == 0 or D1.numel() == 0:
+        z = torch.zeros(n_rows + 1, dtype=torch.int32, device=dev)
+        e = torch.empty(0, dtype=torch.float32, device=dev)
+        return Csr(z, torch.empty(0, dtype=torch.int32, device=dev), e, e if D2 is not None else None)
+    cnt = torch.empty(n_rows, dtype=torch.int32, device=dev)
+    p1 = D1.data_ptr()
+    p2 = D2.data_ptr() if D2 is not None else None
+    call("hgnn_dense_count_nnz", p1, p2, sb, sr, sc, bs, iptr(row_off), iptr(col_off), iptr(cnt), stream())
+    rowptr = exclusive_scan(cnt)
+    nnz = int(rowptr[-1].item())
+    col = torch.empty(max(nnz, 1), dtype=torch.int32, device=dev)[:nnz]
+    v1 = torch.empty(max(nnz, 1), dtype=torch.float32, device=dev)[:nnz]
+    v2 = torch.empty(max(nnz, 1), dtype=torch.float32, device=dev)[:nnz] if D2 is not None else None
+    call("hgnn_dense_fill_csr", p1, p2, sb, sr, sc, bs, iptr(row_off), iptr(col_off), iptr(rowptr),
+         iptr(col), fptr(v1), fptr(v2), stream())
+    return Csr(rowptr, col, v1, v2)
+
+
+class BatchPack(object):
+    """Block-diagonal CSR operators of one batch, resident in HBM.
+
+    ``node_ops()`` / ``edge_ops()`` give the K = J+2 operator descriptors in the reference's channel
+    order [I, D, A, A^2, ...] (layers_mnb.py:409); ``*_T`` the transposed operators the backward
+    kernels gather with.  ``p`` (rows = nodes) and ``pt`` (rows = line-graph nodes) hold Pm and Pd
+    on one sparsity pattern.
+    """
+
+    def __init__(self):
+        self.J = 1
+        self.dual = True
+        self.generic = False     # True: built from dense tensors, all K operators are plain CSR
+        self.requires_grad = False
+
+    # ---- construction from host GraphOps (the fast path) ----------------------------------
+    @classmethod
+    def from_graphs(cls, graphs, J=1, dual=True, device="cuda", clip_powers=False):
+        _lib.require_cuda()
+        self = cls()
+        device = torch.device(device)
+        self.J, self.dual, self.device = int(J), bool(dual), device
+        host = concat_block_diagonal(graphs, dual=dual)
+        self.bs = len(graphs)
+        self.n_nodes = np.array([g.N for g in graphs], dtype=np.int64)
+        self.n_edges = np.array([g.M for g in graphs], dtype=np.int64)
+        self.Nmax = int(self.n_nodes.max())
+        self.Emax = int(self.n_edges.max()) if dual else 0
+        self.Rn, self.Rm = int(self.n_nodes.sum()), int(self.n_edges.sum())
+        host["pad_n"] = (self.Nmax - self.n_nodes).astype(np.float32)
+        dev, self._buffer, self.nbytes = _upload(host, device)
+        self.node_off, self.edge_off = dev["node_off"], dev["edge_off"]
+        self.pad_n = dev["pad_n"]
+        self.deg = dev["deg"]
+        self.a = [Csr(dev["a_rowptr"], dev["a_col"], dev["a_val"])]
+        self.at = [Csr(dev["at_rowptr"], dev["at_col"], dev["at_val"])]
+        if dual:
+            self.dl = dev["dl"]
+            self.b = [Csr(dev["b_rowptr"], dev["b_col"], dev["b_val"])]
+            self.bt = [Csr(dev["bt_rowptr"], dev["bt_col"], dev["bt_val"])]
+            self.p = Csr(dev["p_rowptr"], dev["p_col"], dev["p_pm"], dev["p_pd"])
+            self.pt = Csr(dev["pt_rowptr"], dev["pt_col"], dev["pt_pm"], dev["pt_pd"])
+        for _ in range(1, self.J):   # A^(2^j): repeated squaring on the GPU, unclipped by default
+            self.a.append(spgemm(self.a[-1], self.a[-1], clip_powers))
+            self.at.append(spgemm(self.at[-1], self.at[-1], clip_powers))
+            if dual:
+                self.b.append(spgemm(self.b[-1], self.b[-1], clip_powers))
+                self.bt.append(spgemm(self.bt[-1], self.bt[-1], clip_powers))
+        return self
+
+    # ---- construction from the reference's dense tensors (compatibility path) --------------
+    @classmethod
+    def from_dense(cls, W, WL=None, Pm=None, Pd=None, N_batch=None, E_batch=None):
+        """W (bs,N,N,K) [, WL (bs,M,M,K), Pm, Pd (bs,N,M)] CUDA tensors -> generic CSR operators.
+        Every one of the K slices is extracted as it is (no assumption that slice 0 is I)."""
+        _lib.require_cuda()
+        self = cls()
+        self.generic = True
+        self.device = W.device
+        self.dual = WL is not None
+        self.bs, self.Nmax, _, K = W.shape
+        self.J = K - 2
+        n = N_batch.detach().to("cpu", torch.int64).numpy()
+        self.n_nodes = n
+        self.Rn = int(n.sum())
+        off = np.concatenate([[0], np.cumsum(n)]).astype(np.int32)
+        self.node_off = torch.from_numpy(off).to(self.device)
+        self.pad_n = torch.from_numpy((self.Nmax - n).astype(np.float32)).to(self.device)
+        self.gen_node = [dense_to_csr(W[:, :, :, k], None, self.bs, self.node_off, self.node_off, self.Rn)
+                         for k in range(K)]
+        self.gen_node_T = [dense_to_csr(W[:, :, :, k].transpose(1, 2), None, self.bs, self.node_off,
+                                        self.node_off, self.Rn) for k in range(K)]
+        if self.dual:
+            e = E_batch.detach().to("cpu", torch.int64).numpy()
+            self.n_edges = e
+            self.Emax = WL.shape[1]
+            self.Rm = int(e.sum())
+            eoff = np.concatenate([[0], np.cumsum(e)]).astype(np.int32)
+            self.edge_off = torch.from_numpy(eoff).to(self.device)
+            self.gen_edge = [dense_to_csr(WL[:, :, :, k], None, self.bs, self.edge_off, self.edge_off,
+                                          self.Rm) for k in range(K)]
+            self.gen_edge_T = [dense_to_csr(WL[:, :, :, k].transpose(1, 2), None, self.bs, self.edge_off,
+                                            self.edge_off, self.Rm) for k in range(K)]
+            self.p = dense_to_csr(Pm, Pd, self.bs, self.node_off, self.edge_off, self.Rn)
+            self.pt = dense_to_csr(Pm.transpose(1, 2), Pd.transpose(1, 2), self.bs, self.edge_off,
+                                   self.node_off, self.Rm)
+        else:
+            self.n_edges, self.Emax, self.Rm = np.zeros(self.bs, np.int64), 0, 0
+        return self
+
+    # ---- operator descriptor lists ------------------------------------------------------------
+    def node_ops(self):
+        if self.generic:
+            return [c.desc() for c in self.gen_node]
+        return [("ident",), ("diag", self.deg)] + [c.desc() for c in self.a]
+
+    def node_ops_T(self):
+        if self.generic:
+            return [c.desc() for c in self.gen_node_T]
+        return [("ident",), ("diag", self.deg)] + [c.desc() for c in self.at]
+
+    def edge_ops(self):
+        if self.generic:
+            return [c.desc() for c in self.gen_edge]
+        return [("ident",), ("diag", self.dl)] + [c.desc() for c in self.b]
+
+    def edge_ops_T(self):
+        if self.generic:
+            return [c.desc() for c in self.gen_edge_T]
+        return [("ident",), ("diag", self.dl)] + [c.desc() for c in self.bt]
+
+    @property
+    def K(self):
+        return self.J + 2
+
+    # ---- densify (bit-exact operator checks, sparse=False batches) ------------------------------
+    def _scatter(self, csr, second, D, row_off, col_off):
+        if csr.n_rows == 0 or csr.nnz == 0 or D.numel() == 0:
+            return
+        sb, sr, sc = D.stride()
+        call("hgnn_csr_to_dense", iptr(csr.rowptr), iptr(csr.col), fptr(csr.val2 if second else csr.val),
+             self.bs, iptr(row_off), iptr(col_off), D.data_ptr(), sb, sr, sc, stream())
+
+    def dense_W(self):
+        W = torch.zeros(self.bs, self.Nmax, self.Nmax, self.K, device=self.device)
+        if self.generic:
+            for k, c in enumerate(self.gen_node):
+                self._scatter(c, False, W[:, :, :, k], self.node_off, self.node_off)
+            return W
+        eye = _diag_csr(self.Rn, None, self.device)
+        self._scatter(eye, False, W[:, :, :, 0], self.node_off, self.node_off)
+        self._scatter(_diag_csr(self.Rn, self.deg, self.device), False, W[:, :, :, 1], self.node_off, self.node_off)
+        for j, c in enumerate(self.a):
+            self._scatter(c, False, W[:, :, :, 2 + j], self.node_off, self.node_off)
+        return W
+
+    def dense_WL(self):
+        WL = torch.zeros(self.bs, self.Emax, self.Emax, self.K, device=self.device)
+        if self.generic:
+            for k, c in enumerate(self.gen_edge):
+                self._scatter(c, False, WL[:, :, :, k], self.edge_off, self.edge_off)
+            return WL
+        self._scatter(_diag_csr(self.Rm, None, self.device), False, WL[:, :, :, 0], self.edge_off, self.edge_off)
+        self._scatter(_diag_csr(self.Rm, self.dl, self.device), False, WL[:, :, :, 1], self.edge_off, self.edge_off)
+        for j, c in enumerate(self.b):
+            self._scatter(c, False, WL[:, :, :, 2 + j], self.edge_off, self.edge_off)
+        return WL
+
+    def dense_P(self, second):
+        P = torch.zeros(self.bs, self.Nmax, self.Emax, device=self.device)
+        self._scatter(self.p, second, P, self.node_off, self.edge_off)
+        return P
+
+    def dense_mask(self, lg=False):
+        n = torch.as_tensor(self.n_edges if lg else self.n_nodes, device=self.device)
+        size = self.Emax if lg else self.Nmax
+        keep = (torch.arange(size, device=self.device).view(1, -1) < n.view(-1, 1)).float()
+        return keep.unsqueeze(2) * keep.unsqueeze(1)
+
+
+def _diag_csr(R, vec, device):
+    idx = torch.arange(R + 1, dtype=torch.int32, device=device)
+    val = torch.ones(R, device=device) if vec is None else vec
+    return Csr(idx, idx[:R].contiguous(), val.contiguous())
+
+
+# --------------------------------------------------------------------------------------------
+# handles that quack like the reference's dense tensors
+# --------------------------------------------------------------------------------------------
+
+
+class OperatorHandle(object):
+    """Stands in for one of W / WL / Pm / Pd.  ``name`` in {"W","WL","Pm","Pd"}; ``transposed``
+    mirrors ``Pm.transpose(2, 1)`` (layers_mnb.py:214-215)."""
+
+    def __init__(self, pack, name, transposed=False):
+        self.pack, self.name, self.transposed = pack, name, transposed
+        self.requires_grad = False
+
+    def cuda(self, *a, **k):
+        return self
+
+    def to(self, *a, **k):
+        return self
+
+    @property
+    def is_cuda(self):
+        return True
+
+    @property
+    def device(self):
+        return self.pack.device
+
+    @property
+    def shape(self):
+        p = self.pack
+        if self.name == "W":
+            return torch.Size([p.bs, p.Nmax, p.Nmax, p.K])
+        if self.name == "WL":
+            return torch.Size([p.bs, p.Emax, p.Emax, p.K])
+        return torch.Size([p.bs, p.Emax, p.Nmax] if self.transposed else [p.bs, p.Nmax, p.Emax])
+
+    def size(self, dim=None):
+        return self.shape if dim is None else self.shape[dim]
+
+    def transpose(self, d0, d1):
+        if self.name not in ("Pm", "Pd") or {d0 % 3, d1 % 3} != {1, 2}:
+            raise RuntimeError("hgnn_b200: only Pm/Pd.transpose(2, 1) is defined on operator handles")
+        return OperatorHandle(self.pack, self.name, not self.transposed)
+
+    def to_dense(self):
+        """The reference's dense tensor, produced on the GPU from the CSR pack (bit-exact)."""
+        if self.name == "W":
+            return self.pack.dense_W()
+        if self.name == "WL":
+            return self.pack.dense_WL()
+        P = self.pack.dense_P(self.name == "Pd")
+        return P.transpose(2, 1) if self.transposed else P
+
+    def __repr__(self):
+        return "OperatorHandle(%s%s, shape=%s)" % (self.name, ".T" if self.transposed else "", tuple(self.shape))
+
+
+class MaskHandle(object):
+    """Stands in for ``mask`` / ``mask_lg`` (batching.py:182-183) without the (bs, M, M) tensor."""
+
+    def __init__(self, pack, lg):
+        self.pack, self.lg = pack, lg
+        self.requires_grad = False
+
+    def cuda(self, *a, **k):
+        return self
+
+    def to(self, *a, **k):
+        return self
+
+    @property
+    def shape(self):
+        s = self.pack.Emax if self.lg else self.pack.Nmax
+        return torch.Size([self.pack.bs, s, s])
+
+    def to_dense(self):
+        return self.pack.dense_mask(self.lg)
+
+    def __getitem__(self, idx):
+        return self.to_dense()[idx]
+
+
+def is_handle(x):
+    return isinstance(x, (OperatorHandle, MaskHandle))
+
+
+_DENSE_CACHE = {}
+
+
+def resolve_pack(W, WL=None, Pm=None, Pd=None, N_batch=None, E_batch=None):
+    """The BatchPack behind a model input: handles carry it; dense tensors are converted on the
+    device (cached on the identity/version of the tensors, so a loop over one batch converts once)."""
+    if isinstance(W, OperatorHandle):
+        return W.pack
+    if not torch.is_tensor(W):
+        raise TypeError("hgnn_b200: W must be a tensor or an OperatorHandle, got %r" % type(W))
+    if not W.is_cuda:
+        raise RuntimeError("hgnn_b200: operators must be CUDA tensors or OperatorHandles - there is "
+                           "no CPU fallback (call .cuda() as scripts/train_mnb.py:60 does)")
+    if N_batch is None:
+        raise RuntimeError("hgnn_b200: N_batch is required to convert dense operators")
+    ts = [t for t in (W, WL, Pm, Pd, N_batch, E_batch) if t is not None]
+    key = tuple((t.data_ptr(), t._version, tuple(t.shape)) for t in ts)
+    hit = _DENSE_CACHE.get("last")
+    if hit is not None and hit[0] == key:
+        return hit[1]
+    with torch.no_grad():
+        pack = BatchPack.from_dense(W.detach(), None if WL is None else WL.detach(),
+                                    None if Pm is None else Pm.detach(),
+                                    None if Pd is None else Pd.detach(), N_batch, E_batch)
+    _DENSE_CACHE["last"] = (key, pack, ts)   # keep the tensors alive so data_ptr stays unique
+    return pack
+
+
+# --------------------------------------------------------------------------------------------
+# per-graph handles: the sparse form of one instance's [W, WL, Pm, Pd]  
+# --------------------------------------------------------------------------------------------
+
+
+class SparseAdj(object):
+    """Edge-list adjacency standing in for the dense ``A (N,N)`` of an instance
+    (functions/data_generator.py:85 format ``[X, A, y, W, WL, Pm, Pd]``) when N is too large for a
+    dense matrix.  ``rows, cols, vals`` list every stored entry (both directions of each edge)."""
+
+    def __init__(self, N, rows, cols, vals):
+        self.N = int(N)
+        self.rows = np.asarray(rows, dtype=np.int64)
+        self.cols = np.asarray(cols, dtype=np.int64)
+        self.vals = np.asarray(vals, dtype=np.float32)
+
+    @property
+    def shape(self):
+        return torch.Size([self.N, self.N])
+
+    def nnz(self):
+        return int(np.count_nonzero(self.vals))
+
+    def to_dense(self):
+        A = torch.zeros(self.N, self.N)
+        A[torch.from_numpy(self.rows), torch.from_numpy(self.cols)] = torch.from_numpy(self.vals)
+        return A
+
+    def __add__(self, other):     # scripts/train_ccn.py:36 does ``A + torch.eye(N)``
+        return self.to_dense() + other
+
+
+class GraphHandle(object):
+    """One of W / WL / Pm / Pd of a single graph, backed by host ``GraphOps`` (sparse instance)."""
+
+    def __init__(self, graph_ops, name, J=1):
+        self.graph_ops, self.name, self.J = graph_ops, name, J
+        self.requires_grad = False
+
+    @property
+    def shape(self):
+        g = self.graph_ops
+        return {"W": torch.Size([g.N, g.N, self.J + 2]), "WL": torch.Size([g.M, g.M, self.J + 2]),
+                "Pm": torch.Size([g.N, g.M]), "Pd": torch.Size([g.N, g.M])}[self.name]
+
+    def to_dense(self):
+        """Dense tensor (CPU) identical to the reference's graph_operators output."""
+        pack = BatchPack.from_graphs([self.graph_ops], self.J, dual=self.graph_ops.dual)
+        h = OperatorHandle(pack, self.name)
+        return h.to_dense()[0].cpu()
+
+    def __repr__(self):
+        return "GraphHandle(%s, shape=%s)" % (self.name, tuple(self.shape))

@@ -1,0 +1,218 @@
+/* hgnn_b200.h -- C ABI of the B200-native (sm_100a) HGNN-2 aggregation hot path.
+ *
+ * The reference (AmmieQi/HGNN-2) has no FFI: its boundary is Python.  Each
+ * entry point below names the reference code it replaces (paths relative to the reference
+ * checkout).  The Python host layer (hgnn-2_b200/) binds these with ctypes; INTEGRATION.md shows
+ * the stub a maintainer of the reference would add.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the comment says "host";
+ *   - every call is asynchronous on `stream` (a cudaStream_t passed as void*), never allocates,
+ *     never frees, never synchronises; the caller (PyTorch caching allocator) owns all buffers;
+ *   - return value 0 = ok, <0 = error; hgnn_last_error() gives the thread-local message;
+ *   - feature matrices are row-major "packed rows": (R, F) fp32, one row per real node / line-graph
+ *     node of the block-diagonal batch (no padding).  The reference's (bs, F, Nmax) channel-major
+ *     padded layout is converted at the boundary by hgnn_pack_rows / hgnn_unpack_rows;
+ *   - indices are int32; CSR column indices are global row numbers of the batch.
+ */
+#ifndef HGNN_B200_H
+#define HGNN_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HGNN_B200_VERSION 100
+
+#define HGNN_OP_IDENT 0 /* y = x                         (W[:,:,0] = I,  functions/operators.py:20) */
+#define HGNN_OP_DIAG 1  /* y = diag[r] * x               (W[:,:,1] = D,  functions/operators.py:22-23) */
+#define HGNN_OP_CSR 2   /* y = sum_k val[k] x[col[k]]    (A^(2^j), AL^(2^j), Pm, Pd and transposes) */
+#define HGNN_MAX_OPS 8
+
+#define HGNN_OK 0
+#define HGNN_ERR_ARG (-1)
+#define HGNN_ERR_CUDA (-2)
+#define HGNN_ERR_WORKSPACE (-3)
+
+typedef void* hgnn_stream_t;
+
+/* One graph operator applied to packed rows. */
+typedef struct hgnn_op_t {
+    int kind;            /* HGNN_OP_* */
+    const float* diag;   /* DIAG: (R,) */
+    const int* rowptr;   /* CSR: (R+1,) */
+    const int* col;      /* CSR: (nnz,) */
+    const float* val;    /* CSR: (nnz,) */
+} hgnn_op_t;
+
+const char* hgnn_last_error(void);
+int hgnn_version(void);
+/* Workspace (bytes) the fused kernels need for per-CTA partials; `width` = number of fp32/fp64
+ * values reduced across CTAs (see each call). */
+long long hgnn_workspace_bytes(int width);
+
+/* ---- layout conversion (boundary of functions/batching.py:77-185) ------------------------- */
+/* dense (bs, F, Nmax) channel-major padded  ->  packed (R, F); off = (bs+1) row offsets. */
+int hgnn_pack_rows(const float* dense, int bs, int F, int Nmax, const int* off, float* packed,
+                   hgnn_stream_t stream);
+/* packed (R, F) -> dense (bs, F, Nmax); padded slots get pad_fill[f] (NULL = 0). */
+int hgnn_unpack_rows(const float* packed, int bs, int F, int Nmax, const int* off,
+                     const float* pad_fill, float* dense, hgnn_stream_t stream);
+
+/* ---- dense -> CSR (accepting the reference's dense W / WL / Pm / Pd tensors) --------------- */
+/* D[b][r][c] = base[b*sb + r*sr + c*sc] (element strides); rows r < row_off[b+1]-row_off[b],
+ * cols c < col_off[b+1]-col_off[b].  Pattern = (D1 != 0) | (D2 != 0); D2 may be NULL. */
+int hgnn_dense_count_nnz(const float* D1, const float* D2, long long sb, long long sr, long long sc,
+                         int bs, const int* row_off, const int* col_off, int* rowcnt,
+                         hgnn_stream_t stream);
+int hgnn_dense_fill_csr(const float* D1, const float* D2, long long sb, long long sr, long long sc,
+                        int bs, const int* row_off, const int* col_off, const int* rowptr,
+                        int* col, float* val1, float* val2, hgnn_stream_t stream);
+/* out[i] = sum_{k<i} in[k], i = 0..n (n+1 outputs). */
+int hgnn_exclusive_scan_i32(const int* in, int* out, int n, hgnn_stream_t stream);
+/* CSR -> dense scatter into a pre-zeroed strided dense tensor (bit-exact operator checks). */
+int hgnn_csr_to_dense(const int* rowptr, const int* col, const float* val, int bs,
+                      const int* row_off, const int* col_off, float* D, long long sb, long long sr,
+                      long long sc, hgnn_stream_t stream);
+/* out[r] = sum of row r's values (weighted degree, functions/operators.py:22,74). */
+int hgnn_csr_row_sums(const int* rowptr, const float* val, int R, float* out, hgnn_stream_t stream);
+
+/* ---- SpGEMM for the power operators C = A*A (functions/operators.py:26-29, 78-81) ---------- */
+/* step 1: prodcnt[r] = number of partial products of row r (then scan -> prodptr). */
+int hgnn_spgemm_count_products(int R, const int* a_rowptr, const int* a_col, const int* b_rowptr,
+                               int* prodcnt, hgnn_stream_t stream);
+/* step 2: expand products into scratch (pcol, pval), flag first occurrences (pflag), rowcnt[r] = #unique. */
+int hgnn_spgemm_expand(int R, const int* a_rowptr, const int* a_col, const float* a_val,
+                       const int* b_rowptr, const int* b_col, const float* b_val,
+                       const int* prodptr, int* pcol, float* pval, int* pflag, int* rowcnt,
+                       hgnn_stream_t stream);
+/* step 3: merge equal columns, emit CSR sorted by column; clip!=0 binarises (min(v,1)); the
+ * reference does NOT clip, so the host layer passes clip=0 by default. */
+int hgnn_spgemm_fill(int R, const int* prodptr, const int* pcol, const float* pval,
+                     const int* pflag, const int* c_rowptr, int* c_col, float* c_val, int clip,
+                     hgnn_stream_t stream);
+
+/* ---- gmul primitives (models/layers/layers_mnb.py:391-434, functions/utils.py:24-81) ------- */
+/* Y[r, t*F + f] = (ops[t] X)[r, f], t < n_ops.   `ops` is a HOST array. X: (R_in, F); Y: (R, n_ops*F).
+ * graph_oper.forward: ops = [IDENT, DIAG(deg), CSR(A), CSR(A^2) ...]; P_multi.forward: one CSR. */
+int hgnn_gmul_fwd(const hgnn_op_t* ops, int n_ops, int R, int F, const float* X, float* Y,
+                  hgnn_stream_t stream);
+/* gX[r, f] = sum_t (opsT[t] G_t)[r, f] with G_t = G[:, t*F:(t+1)*F]; opsT = transposed operators. */
+int hgnn_gmul_bwd(const hgnn_op_t* opsT, int n_ops, int R, int F, const float* G, float* gX,
+                  hgnn_stream_t stream);
+
+/* ---- masked batch-norm (models/layers/batch_normalization.py:23-108) ---------------------- */
+/* Per-feature batch statistics of packed rows (all R rows are real slots): stats = [mean(F),
+ * std(F) = sqrt(var_biased + 1e-5), scale(F) = weight/std, shift(F) = bias - weight*mean/std];
+ * running_* updated in place as 0.9*batch + 0.1*running (NULL = skip).  ws: hgnn_workspace_bytes(2F). */
+int hgnn_bn_stats(const float* Z, int R, int F, const float* weight, const float* bias,
+                  float* running_mean, float* running_std, float momentum, float* stats,
+                  void* ws, long long ws_bytes, hgnn_stream_t stream);
+/* eval mode: stats from running_mean / running_std (batch_normalization.py:39-41). */
+int hgnn_bn_stats_eval(int F, const float* weight, const float* bias, const float* running_mean,
+                       const float* running_std, float* stats, hgnn_stream_t stream);
+/* Y = scale*Z + shift. */
+int hgnn_bn_apply(const float* Z, int R, int F, const float* stats, float* Y, hgnn_stream_t stream);
+/* backward, step 1: coef(3F+2): gZ = c0[f]*g + c1[f] + c2[f]*Z ; coef[3F] = d weight, coef[3F+1] =
+ * d bias (scalars).  train!=0 uses batch statistics; eval mode gives c0 = scale, c1 = c2 = 0.
+ * gshift (F, or NULL): gradient that reached stats.shift, i.e. the value the reference's BN leaves
+ * in padded slots (batch_normalization.py:75); it is folded into the same coefficients. */
+int hgnn_bn_bwd_reduce(const float* gY, const float* Z, int R, int F, const float* stats,
+                       const float* weight, int train, const float* gshift, float* coef, void* ws,
+                       long long ws_bytes, hgnn_stream_t stream);
+/* backward, step 2 (+ ReLU mask of the conv branch): gPre[r,o] = (c0*g + c1 + c2*Z) * (o < relu_from
+ * || Z > 0); coef == NULL means "no batch-norm" (gPre = g * mask).  dbias[o] = sum_r gPre[r,o].
+ * ws: hgnn_workspace_bytes(2F). */
+int hgnn_side_bwd_pre(const float* gY, const float* Z, int R, int F, const float* coef,
+                      int relu_from, float* gPre, float* dbias, void* ws, long long ws_bytes,
+                      hgnn_stream_t stream);
+
+/* ---- fused layer side: gather -> concat -> two 1x1 convs -> ReLU -> BN statistics ----------- */
+/* One "side" of a GNN / LGNN layer (models/layers/layers_mnb.py:52-69, 189-225, 256-290, 322-358,
+ * readouts :88-95, :379-388):
+ *   x1[r] = [ ops[0] Xs, ..., ops[n_ops-1] Xs,  Pm Xc,  Pd Xc ][r]       (Cin = n_ops*Fs + 2*Fc)
+ *   Z[r]  = [ Wa x1 + ba  (Ha outputs) ,  Wb x1 + bb  (Hb outputs) ],  ReLU on outputs >= relu_from
+ * The cross part is skipped when p_rowptr == NULL (then Fc must be 0).  Wa: (Ha, Cin), Wb: (Hb, Cin)
+ * row-major = Conv1d(k=1).weight.  If stats != NULL the per-feature batch statistics of Z are
+ * reduced in the same launch (as hgnn_bn_stats).  ws: hgnn_workspace_bytes(2*(Ha+Hb)). */
+typedef struct hgnn_side_t {
+    int R;                  /* output rows */
+    const hgnn_op_t* ops;   /* host array of n_ops self operators */
+    int n_ops;
+    const float* Xs;        /* (R, Fs) */
+    int Fs;
+    const int* p_rowptr;    /* (R+1,) incidence rows of this side, or NULL */
+    const int* p_col;
+    const float* p_pm;
+    const float* p_pd;
+    const float* Xc;        /* (Rc, Fc) */
+    int Fc;
+} hgnn_side_t;
+
+int hgnn_side_fwd(const hgnn_side_t* side, const float* Wa, const float* ba, int Ha,
+                  const float* Wb, const float* bb, int Hb, int relu_from, float* Z,
+                  const float* bn_weight, const float* bn_bias, float* running_mean,
+                  float* running_std, float momentum, float* stats, void* ws, long long ws_bytes,
+                  hgnn_stream_t stream);
+
+/* Backward gather of one side.  With G = gPre (R_g, Fg) from hgnn_side_bwd_pre and the TRANSPOSED
+ * operators (rows = the rows of X being differentiated):
+ *   T[u]  = [ opsT[0] G, ..., opsT[n-1] G ][u]                              (n*Fg values)
+ *   gX[u, f] (+)= sum_{t,o} W[o, col0 + t*Fx + f] * T[u, t*Fg + o]          (W = [Wa; Wb])
+ *   dW[o, col0 + t*Fx + f] = sum_u T[u, t*Fg + o] * X[u, f]
+ * Self part: opsT = transposed self operators, col0 = 0, X = Xs.  Cross part: two CSR ops (Pm^T,
+ * Pd^T pattern of the other side), col0 = n_ops*Fs, X = Xc.  accumulate != 0 adds into gX.
+ * gX may be NULL (input needs no gradient).  dWa/dWb: (Ha, Cin)/(Hb, Cin); only the columns
+ * [col0, col0 + n*Fx) are written.  ws: hgnn_workspace_bytes(n*Fg*Fx). */
+int hgnn_side_bwd_gather(const hgnn_op_t* opsT, int n_ops, int R, const float* G, int Fg,
+                         const float* X, int Fx, const float* Wa, int Ha, const float* Wb, int Hb,
+                         int Cin, int col0, float* gX, int accumulate, float* dWa, float* dWb,
+                         void* ws, long long ws_bytes, hgnn_stream_t stream);
+
+/* ---- readout (layers_mnb.py:92, :386): y[b,o] = sum_{rows of graph b} Y[r,o] + pad[b]*bias[o] */
+int hgnn_segment_sum(const float* Y, int bs, int F, const int* off, const float* pad_count,
+                     const float* bias, float* out, hgnn_stream_t stream);
+/* G[r, o] = g[graph(r), o]  (backward of the sum). */
+int hgnn_segment_bcast(const float* g, int bs, int F, const int* off, float* G,
+                       hgnn_stream_t stream);
+
+/* ---- CCN second-order covariant contraction (functions/contraction.py, utils_ccn.py) ------ */
+/* Stand-alone collapse6to3 (contraction.py:106-121) on a general rank-6 tensor:
+ * F6 (C, n, n, n, n, n) -> out (n, n, 18*C); and its backward gout (n, n, 18C) -> gF6. */
+int hgnn_ccn2_collapse6to3(const float* F6, int C, int n, float* out, hgnn_stream_t stream);
+int hgnn_ccn2_collapse6to3_bwd(const float* gout, int C, int n, float* gF6, hgnn_stream_t stream);
+/* Batched per-vertex level update (utils_ccn.py:281-300 with python_contract :37-45):
+ *   vertices v = 0..V-1 of all graphs; nbr_ptr (V+1), nbr (sorted receptive field, global vertex
+ *   ids, includes v); nmax = largest receptive field; f_off (V+1) = prefix sums of d_v^2:
+ *   F[v] is (d_v, d_v, C) at Fprev + f_off[v]*C.
+ *   Fnext[v] = relu( Linear_{18C->H}( contract18( promote_{j in nbr(v)} Fprev[j],  adj = I ) ) ). */
+int hgnn_ccn2_update_fwd(int V, int nmax, const int* nbr_ptr, const int* nbr, const long long* f_off,
+                         const float* Fprev, int C, const float* W, const float* b, int H,
+                         float* Fnext, hgnn_stream_t stream);
+/* Backward: gPre = gFnext * (Fnext > 0) is formed on the fly.  gFprev (same layout as Fprev; NULL =
+ * skip) is written, not accumulated; dW (H,18C) and db (H) are written.
+ * ws: hgnn_workspace_bytes(H*18*C+H). */
+int hgnn_ccn2_update_bwd(int V, int nmax, const int* nbr_ptr, const int* nbr, const long long* f_off,
+                         const float* Fprev, int C, const float* W, int H, const float* Fnext,
+                         const float* gFnext, float* gFprev, float* dW, float* db, void* ws,
+                         long long ws_bytes, hgnn_stream_t stream);
+/* 1-D variant (utils_ccn.py:303-324): F[v] is (d_v, C) at row nbr_ptr[v]; 2 contractions (row /
+ * column sums of the promoted stack).  ws: hgnn_workspace_bytes(H*2*C+H). */
+int hgnn_ccn1_update_fwd(int V, int nmax, const int* nbr_ptr, const int* nbr, const float* Fprev,
+                         int C, const float* W, const float* b, int H, float* Fnext,
+                         hgnn_stream_t stream);
+int hgnn_ccn1_update_bwd(int V, int nmax, const int* nbr_ptr, const int* nbr, const float* Fprev,
+                         int C, const float* W, int H, const float* Fnext, const float* gFnext,
+                         float* gFprev, float* dW, float* db, void* ws, long long ws_bytes,
+                         hgnn_stream_t stream);
+
+/* ---- optimizer: fused Adamax step over one flat parameter buffer (scripts/main_gnn.py:160-167
+ * uses torch.optim.Adamax(lr); same update rule, one launch for all parameters) -------------- */
+int hgnn_adamax_step(float* param, const float* grad, float* exp_avg, float* exp_inf, long long n,
+                     float lr, float beta1, float beta2, float eps, float grad_scale,
+                     int* step /* device counter, incremented by the call */, hgnn_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HGNN_B200_H */

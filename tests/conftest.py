@@ -43,6 +43,8 @@ def rel_err(a, b, floor=0.0):
     return (a - b).abs().max().item() / denom
 
 
-def grad_floor(g, prefix="grad/"):
-    """1e-3 x the largest reference gradient entry: the floor used for near-zero gradients."""
-    return 1e-3 * max(float(np.abs(v).max()) for k, v in g.items() if k.startswith(prefix) and v.size)
+def grad_floor(g, prefix="grad/", frac=1e-3):
+    """frac x the largest reference gradient entry: the floor used for near-zero gradients.  The
+    GPU tests use frac=0.1 (absolute tolerance 1e-5 of the largest gradient): a mathematically zero
+    gradient is a cancelling sum whose rounding noise scales with its terms, not with its value."""
+    return frac * max(float(np.abs(v).max()) for k, v in g.items() if k.startswith(prefix) and v.size)
