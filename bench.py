@@ -1,0 +1,419 @@
+#!/usr/bin/env python
+"""bench.py -- LGNN training throughput on synthetic binary-SBM graphs (BASELINE.json configs[1]).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+One "step" = one LGNN training step (forward + cross-entropy + backward + gradient all-reduce +
+Adamax) over one batch of 32 SBM graphs with N=1000 nodes per GPU (weak scaling: every rank owns its
+own 32 graphs; the only collective is the flat-gradient all-reduce).  Model =
+``GNN_lg(task=0, h=2, L=20, dim_input=5, dim_output=2, J=1, order=1)`` - the reference's script
+defaults (scripts/main_gnn.py:59,75-77), fp32.
+
+Printed JSON (one line, rank 0):
+  value   graphs/s with the batch already packed in HBM (CUDA-graph replay of the whole step, CUDA
+          events per step, L2 flushed between steps, max over ranks);
+  e2e     graphs/s through the public API from HOST instances: prepare_batch (block-diagonal CSR
+          concat + one pinned H2D copy) -> model -> loss -> backward -> optimizer -> loss.item();
+  roofline  the dominant aggregation kernel (fused edge-side update) timed alone with CUDA events,
+          algorithmic bytes per SURVEY.md 8(d) / DESIGN.md, against MEASURED_PEAKS.json;
+  cpu_baseline  the CPU oracle port (oracle/hgnn_oracle.py = the reference's dense torch.mm loops)
+          timed on the host cores on a bounded sample of the same workload.
+``--impl reference`` times that CPU port alone (the reference is pure Python and cannot travel to
+the GPU box).
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+METRIC = "lgnn_sbm_train_graphs_per_s"
+UNIT = "graphs/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--bs", type=int, default=32, help="graphs per GPU")
+    ap.add_argument("--nodes", type=int, default=1000)
+    ap.add_argument("--h", type=int, default=2)
+    ap.add_argument("--layers", type=int, default=20)
+    ap.add_argument("--order", type=int, default=1)
+    ap.add_argument("--J", type=int, default=1)
+    ap.add_argument("--no-graph", action="store_true", help="time eager launches instead of a CUDA graph")
+    ap.add_argument("--skip-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--skip-e2e", action="store_true")
+    ap.add_argument("--cpu-sample", type=int, default=1, help="graphs per CPU-baseline step")
+    return ap.parse_args()
+
+
+def workload_config(a):
+    return {"workload": "LGNN (GNN_lg order %d, L=%d, h=%d, J=%d) on 2-class binary SBM N=%d (a=7,b=3), "
+                        "batch %d graphs per GPU, fp32 fwd+bwd+Adamax" % (a.order, a.layers, a.h, a.J, a.nodes, a.bs),
+            "graphs_per_gpu": a.bs, "nodes_per_graph": a.nodes, "layers": a.layers, "h": a.h, "J": a.J,
+            "order": a.order, "parallelism": "dp%d (graphs sharded, flat-gradient all-reduce)" % a.gpus,
+            "l2": "256 MiB buffer written between timed steps (L2 flush)"}
+
+
+# --------------------------------------------------------------------------------------------
+# CPU baseline: the oracle port of the reference's dense path, on the host cores
+# --------------------------------------------------------------------------------------------
+def cpu_reference_setup(a, n_graphs, first_id=0):
+    from oracle import hgnn_oracle as O
+    from hgnn_b200 import synth
+    inst = []
+    for i in range(n_graphs):
+        s = synth.sbm_instance(first_id + i, N=a.nodes, J=a.J, sparse=True)
+        A = s[1].to_dense()
+        inst.append([s[0], A, s[2]] + list(O.graph_operators([s[0], A], a.J, True)))
+    batch = O.prepare_batch(inst, 0, a.J)
+    p = O.init_gnn_params("lg", a.h, a.layers, 5, 2, a.J, a.order, seed=0)
+    for v in p.values():
+        v.requires_grad_()
+    labels = torch.tensor([int(i[2][0]) for i in inst])
+    opt = torch.optim.Adamax(list(p.values()), lr=1e-3)
+    return O, batch, p, labels, opt
+
+
+def cpu_reference_step(a, O, batch, p, labels, opt):
+    X, W, _, XL, WL, Pm, Pd, mask, mask_lg, N_batch, E_batch = batch
+    opt.zero_grad()
+    out = O.gnn_lg_forward(p, a.layers, a.order, [X, XL, W, WL, Pm, Pd], N_batch, mask, E_batch, mask_lg)
+    loss = torch.nn.functional.cross_entropy(out, labels)
+    loss.backward()
+    opt.step()
+    return float(loss)
+
+
+def cpu_baseline(a, steps=1, warmup=0):
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    state = cpu_reference_setup(a, a.cpu_sample)
+    for _ in range(warmup):
+        cpu_reference_step(a, *state)
+    times = []
+    for _ in range(steps):
+        t0 = time.perf_counter()
+        cpu_reference_step(a, *state)
+        times.append(time.perf_counter() - t0)
+    dt = sum(times) / len(times)
+    return {"value": a.cpu_sample / dt, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": "%d graph(s) of the same SBM N=%d workload per step (dense operators: WL is "
+                      "%d MB per graph), %d timed step(s) of fwd+loss+bwd+Adamax, operators prebuilt"
+                      % (a.cpu_sample, a.nodes, int(state[1][4][0].numel() * 4 / 1e6), steps),
+            "ms_per_step": dt * 1e3}
+
+
+def run_reference(a):
+    """--impl reference: the CPU port alone, K timed steps after W warm-ups, rank 0 only."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cb = cpu_baseline(a, steps=a.steps, warmup=a.warmup)
+    line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": a.gpus,
+            "steps": a.steps, "warmup": a.warmup, "ms_per_step": cb["ms_per_step"],
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "config": workload_config(a),
+            "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0,
+            "note": "reference = pure-Python CPU code; timed through the oracle port of its dense "
+                    "torch.mm path on the host cores (the checkout cannot travel to the GPU box)"}
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------------------------
+# clocks sampling during the timed region
+# --------------------------------------------------------------------------------------------
+class ClockSampler(object):
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.samples, self.stop = index, [], False
+        self.t = threading.Thread(target=self._run, daemon=True)
+
+    def _run(self):
+        while not self.stop:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True,
+                                     timeout=5).stdout.strip()
+                if out:
+                    self.samples.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.1)
+
+    def __enter__(self):
+        self.t.start()
+        return self
+
+    def __exit__(self, *exc):
+        self.stop = True
+        self.t.join(timeout=6)
+
+    def summary(self):
+        sm = [float(s[0]) for s in self.samples if s and s[0].replace(".", "").isdigit()]
+        mx = [float(s[1]) for s in self.samples if len(s) > 1 and s[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for s in self.samples for n, v in zip(names, s[2:6]) if v.lower().startswith("active")})
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(self.samples)}
+
+
+# --------------------------------------------------------------------------------------------
+# our arm
+# --------------------------------------------------------------------------------------------
+def lgnn_layer_algorithmic_bytes(pack, F):
+    """one sparse operator application Y = S X moves 4(R_out+1) [rowptr] + 8 nnz
+    [col+val] + 4 R_in F [features once] + 4 R_out K_out F [write]; diagonal operators add 4 R_out;
+    the Pm/Pd pair costs 12 B per non-zero.  Returns (edge side, node side) bytes of ONE forward
+    application with feature width F on both node and edge states."""
+    Rn, Rm, K = pack.Rn, pack.Rm, pack.K
+    nnzA, nnzB, nnzP = pack.a[0].nnz, pack.b[0].nnz, pack.p.nnz
+    gmul_a = 4 * (Rn + 1) + 8 * nnzA + 4 * Rn + 4 * Rn * F + 4 * Rn * K * F
+    gmul_b = 4 * (Rm + 1) + 8 * nnzB + 4 * Rm + 4 * Rm * F + 4 * Rm * K * F
+    pmul_n = 4 * (Rn + 1) + 12 * nnzP + 4 * Rm * F + 4 * Rn * 2 * F       # Pm/Pd . XL  -> nodes
+    pmul_e = 4 * (Rm + 1) + 12 * nnzP + 4 * Rn * F + 4 * Rm * 2 * F       # Pm^T/Pd^T . X -> edges
+    return gmul_b + pmul_e, gmul_a + pmul_n
+
+
+def time_dominant_kernel(a, model, pack, reps=30):
+    """The fused edge-side update of a middle layer (csrc/side.cu side_fwd_kernel), timed alone on the
+    current stream with CUDA events, L2 flushed before every launch."""
+    import ctypes
+    from hgnn_b200 import _lib
+    from hgnn_b200.models.layers import layers_mnb
+    from hgnn_b200.ops import _side_struct
+    layer = model._modules["layer1"]
+    _, edge = layers_mnb._side_cfgs(pack)
+    F = 2 * a.h
+    dev = pack.device
+    g = torch.Generator(device="cuda").manual_seed(1)
+    XL = torch.randn(pack.Rm, F, device=dev, generator=g)
+    Xn = torch.randn(pack.Rn, F, device=dev, generator=g)
+    Z = torch.empty(pack.Rm, F, device=dev)
+    stats = torch.empty(4 * F, device=dev)
+    side, keep = _side_struct(edge, XL, Xn)
+    Wa, Wb = layer.cv4.weight.detach().view(a.h, -1), layer.cv3.weight.detach().view(a.h, -1)
+    ws, wsb = _lib.workspace(2 * F, dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    rm, rs = torch.zeros(F, device=dev), torch.zeros(F, device=dev)
+
+    def launch():
+        _lib.call("hgnn_side_fwd", ctypes.byref(side), _lib.fptr(Wa), _lib.fptr(layer.cv4.bias.detach()),
+                  a.h, _lib.fptr(Wb), _lib.fptr(layer.cv3.bias.detach()), a.h, a.h, _lib.fptr(Z),
+                  _lib.fptr(layer.bn2.weight.detach()), _lib.fptr(layer.bn2.bias.detach()),
+                  _lib.fptr(rm), _lib.fptr(rs), 0.1, _lib.fptr(stats), ws, wsb, _lib.stream())
+    for _ in range(3):
+        launch()
+    times = []
+    for _ in range(reps):
+        flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        launch()
+        e1.record()
+        e1.synchronize()
+        times.append(e0.elapsed_time(e1) * 1e-3)
+    return statistics.mean(times), min(times)
+
+
+def run_ours(a):
+    import torch.distributed as dist
+    import hgnn_b200
+    from hgnn_b200 import _lib, synth
+    from hgnn_b200.dist import FlatParams, FusedAdamax
+    from hgnn_b200.functions.batching import prepare_batch
+    from hgnn_b200.models.gnns.model_mnb import GNN_lg
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    if world != a.gpus and rank == 0:
+        print("warning: --gpus %d but WORLD_SIZE=%d" % (a.gpus, world), file=sys.stderr)
+
+    # ---- data: every rank owns its own a.bs graphs (weak scaling), two distinct host batches
+    n_host_batches = 2
+    host_batches = [synth.sbm_dataset(a.bs, N=a.nodes, J=a.J, sparse=True,
+                                      first_id=(rank * n_host_batches + k) * a.bs) for k in range(n_host_batches)]
+    torch.manual_seed(0)
+    model = GNN_lg(0, a.h, a.layers, 5, 2, a.J, a.order).to(dev).train()
+    fp = FlatParams(model)
+    fp.broadcast(0)
+    opt = FusedAdamax(fp, lr=1e-3)
+
+    def to_device(batch):
+        X, W, T, XL, WL, Pm, Pd, mask, mask_lg, N_batch, E_batch = batch
+        labels = T.squeeze(1).long()
+        staged = [X.pin_memory(), XL.pin_memory(), labels.pin_memory()]
+        Xd, XLd, yd = [t.to(dev, non_blocking=True) for t in staged]
+        h2d = W.pack.nbytes + sum(t.numel() * t.element_size() for t in staged)
+        return (Xd, XLd, W, WL, Pm, Pd, mask, mask_lg, N_batch, E_batch, yd), h2d
+
+    def train_step(dbatch):
+        Xd, XLd, W, WL, Pm, Pd, mask, mask_lg, N_batch, E_batch, yd = dbatch
+        fp.zero_grad()
+        out = model([Xd, XLd, W, WL, Pm, Pd], N_batch, mask, E_batch, mask_lg)
+        loss = torch.nn.functional.cross_entropy(out, yd)
+        loss.backward()
+        fp.all_reduce_grad()
+        opt.step(grad_scale=1.0 / world)
+        return loss
+
+    resident, h2d_bytes = to_device(prepare_batch(host_batches[0], 0, a.J))
+    pack = resident[2].pack
+    torch.cuda.synchronize()
+
+    # ---- warm-up (eager), then capture the whole step in a CUDA graph
+    launches0 = hgnn_b200.launch_count()
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        for _ in range(max(3, a.warmup)):
+            loss = train_step(resident)
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
+    launches_per_step = (hgnn_b200.launch_count() - launches0) // max(3, a.warmup)
+    graph = None
+    if not a.no_graph:
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            static_loss = train_step(resident)
+
+    def step():
+        if graph is not None:
+            graph.replay()
+            return static_loss
+        return train_step(resident)
+
+    for _ in range(a.warmup):
+        step()
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    events = []
+    with ClockSampler(local) as clocks:
+        for _ in range(a.steps):
+            flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            loss = step()
+            e1.record()
+            events.append((e0, e1))
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        # keep the sampler alive for at least a few samples under load
+        t_end = time.time() + 0.5
+        while time.time() < t_end:
+            step()
+        torch.cuda.synchronize()
+    elapsed = sum(e0.elapsed_time(e1) for e0, e1 in events) * 1e-3
+    t = torch.tensor([elapsed], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    elapsed = float(t.item())
+    value = a.bs * world * a.steps / elapsed
+    final_loss = float(loss.item())
+
+    # ---- end to end through the public API: host instances -> prepare_batch -> step -> loss.item()
+    e2e = None
+    if not a.skip_e2e:
+        e2e_steps = max(3, min(a.steps, 10))
+        for k in range(2):
+            db, _ = to_device(prepare_batch(host_batches[k % n_host_batches], 0, a.J))
+            train_step(db).item()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        t0 = time.perf_counter()
+        h2d_tot = 0
+        for k in range(e2e_steps):
+            db, nb = to_device(prepare_batch(host_batches[k % n_host_batches], 0, a.J))
+            h2d_tot += nb
+            train_step(db).item()
+        torch.cuda.synchronize()
+        dt = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        e2e = {"value": a.bs * world * e2e_steps / float(dt.item()), "unit": UNIT,
+               "h2d_bytes_per_step": h2d_tot // e2e_steps, "d2h_bytes_per_step": 4,
+               "steps": e2e_steps, "ms_per_step": float(dt.item()) * 1e3 / e2e_steps,
+               "path": "prepare_batch(host instances) -> pinned H2D -> GNN_lg fwd -> CE loss -> bwd -> "
+                       "all-reduce -> fused Adamax -> loss.item()"}
+
+    if rank != 0:
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant aggregation kernel
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_kind = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6.65 TB/s"
+    t_mean, t_min = time_dominant_kernel(a, model, pack)
+    edge_bytes, node_bytes = lgnn_layer_algorithmic_bytes(pack, 2 * a.h)
+    achieved = edge_bytes / t_mean / 1e9
+    roofline = {"bound": "hbm", "kernel": "side_fwd_kernel<4> (fused edge-side update: gmul(B) + Pm^T/Pd^T "
+                                          "+ cv3/cv4 + ReLU + BN stats)",
+                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": None, "peak_kind": peak_kind, "algorithmic_bytes_per_launch": edge_bytes,
+                "launch_us_mean": t_mean * 1e6, "launch_us_min": t_min * 1e6,
+                "note": "L2 flushed before each launch; at h=2 the per-launch working set (~%d MB) is "
+                        "L2-sized and the kernel is latency-bound (SURVEY.md 8d)" % (edge_bytes // 1000000)}
+
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps,
+            "warmup": a.warmup, "ms_per_step": elapsed * 1e3 / a.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(a), "clocks": clocks.summary(), "e2e": e2e,
+            "gpu_launches": launches_per_step * a.steps, "launches_per_step": launches_per_step,
+            "cuda_graph": graph is not None, "final_loss": final_loss, "roofline": roofline,
+            "pack": {"rows_nodes": pack.Rn, "rows_line_graph": pack.Rm, "nnz_A": pack.a[0].nnz,
+                     "nnz_B": pack.b[0].nnz, "nnz_P": pack.p.nnz, "bytes": pack.nbytes}}
+    if not a.skip_cpu:
+        line["cpu_baseline"] = {k: v for k, v in cpu_baseline(a).items() if k != "ms_per_step"}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm")
+        run_ours(a)
+
+
+if __name__ == "__main__":
+    main()

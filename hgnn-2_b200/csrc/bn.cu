@@ -1,18 +1,19 @@
 // bn.cu -- masked batch-norm on packed rows: statistics, apply, backward.
 // Reference: models/layers/batch_normalization.py:23-108.  HBM-bound elementwise / column
-// reductions; cross-CTA sums are reduced in CTA order by the last CTA (bit-reproducible).
+// reductions; cross-CTA sums go through fp64 atomics into the workspace accumulators and the last
+// CTA (ticket) finalises them in the same launch.
 #include "bn_common.cuh"
 
 int hgnn_grid_cap(int width);
 
-#define BN_MAX_F 256
+#define BN_MAX_F 128
 
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 bn_stats_kernel(const float* __restrict__ Z, int R, int F, const float* weight, const float* bias,
                 float* running_mean, float* running_std, float momentum, float* stats,
                 unsigned int* counter, double* partial) {
-    __shared__ double red[512];
+    __shared__ double red[768];
     ColOwner co(F, blockDim.x);
     double s1 = 0.0, s2 = 0.0;
     if (co.active) {
@@ -23,9 +24,9 @@ bn_stats_kernel(const float* __restrict__ Z, int R, int F, const float* weight, 
             s2 += x * x;
         }
     }
-    cta_column_partials(s1, s2, F, co, red, partial);
+    cta_column_accumulate(s1, s2, F, co, red, partial);
     if (last_block_ticket(counter)) {
-        bn_finalize(partial, gridDim.x, F, R, weight, bias, running_mean, running_std, momentum, stats);
+        bn_finalize_accum(partial, F, R, weight, bias, running_mean, running_std, momentum, stats);
         if (threadIdx.x == 0) *counter = 0;
     }
 }
@@ -34,13 +35,13 @@ extern "C" int hgnn_bn_stats(const float* Z, int R, int F, const float* weight, 
                              float* running_mean, float* running_std, float momentum, float* stats,
                              void* ws, long long ws_bytes, hgnn_stream_t stream) {
     HGNN_REQUIRE(Z && stats && ws && R > 0, "bad argument");
-    HGNN_REQUIRE(F >= 1 && F <= BN_MAX_F, "feature width must be in [1, 256]");
+    HGNN_REQUIRE(F >= 1 && F <= BN_MAX_F, "feature width must be in [1, 128]");
     if (ws_bytes < hgnn_workspace_bytes(2 * F)) {
         hgnn_set_error("hgnn_bn_stats: workspace too small");
         return HGNN_ERR_WORKSPACE;
     }
     int rows_per_cta = 256 / F;
-    int grid = min(ceil_div(R, rows_per_cta * 4), hgnn_grid_cap(2 * F));
+    int grid = min(ceil_div(R, rows_per_cta * 4), HGNN_SM_COUNT * 8);
     bn_stats_kernel<<<grid, 256, 0, to_stream(stream)>>>(
         Z, R, F, weight, bias, running_mean, running_std, momentum, stats, (unsigned int*)ws,
         (double*)((char*)ws + HGNN_WS_HEADER));
@@ -116,7 +117,7 @@ bn_bwd_reduce_kernel(const float* __restrict__ gY, const float* __restrict__ Z, 
                      const float* __restrict__ stats, const float* weight, int train,
                      const float* __restrict__ gshift, float* coef, unsigned int* counter,
                      double* partial) {
-    __shared__ double red[512];
+    __shared__ double red[768];
     ColOwner co(F, blockDim.x);
     double s1 = 0.0, s2 = 0.0;
     if (co.active) {
@@ -129,15 +130,13 @@ bn_bwd_reduce_kernel(const float* __restrict__ gY, const float* __restrict__ Z, 
             s2 += (double)g * (double)xh;
         }
     }
-    cta_column_partials(s1, s2, F, co, red, partial);
+    cta_column_accumulate(s1, s2, F, co, red, partial);
     if (last_block_ticket(counter)) {
-        // fixed order: thread 0 walks the features after every thread has produced its sums
+        double* tot = red + 512;
+        double a_keep = 0.0, b_keep = 0.0;
         for (int f = threadIdx.x; f < F; f += blockDim.x) {
-            double a = 0.0, b = 0.0;
-            for (int p = 0; p < (int)gridDim.x; ++p) {
-                a += partial[(size_t)p * 2 * F + f];
-                b += partial[(size_t)p * 2 * F + F + f];
-            }
+            const int nb = hgnn_ws_bins(2 * F);
+            double a = accum_take(partial, 2 * F, nb, f), b = accum_take(partial, 2 * F, nb, F + f);
             double mean = stats[f], sd = stats[F + f];
             double c0 = (double)weight[0] / sd;
             double c1 = 0.0, c2 = 0.0;
@@ -157,18 +156,23 @@ bn_bwd_reduce_kernel(const float* __restrict__ gY, const float* __restrict__ Z, 
                     c1 += -sft * w / ((double)R * sd) - k * mean;
                 }
             }
-            red[f] = a;
-            red[256 + f] = b;
+            a_keep = a;
+            b_keep = b;
             coef[f] = (float)c0;
             coef[F + f] = (float)c1;
             coef[2 * F + f] = (float)c2;
         }
         __syncthreads();
+        if ((int)threadIdx.x < F) {      // F <= 256 = blockDim: one feature per thread
+            tot[threadIdx.x] = a_keep;
+            tot[F + threadIdx.x] = b_keep;
+        }
+        __syncthreads();
         if (threadIdx.x == 0) {
             double gw = 0.0, gb = 0.0;
             for (int f = 0; f < F; ++f) {
-                gb += red[f];
-                gw += red[256 + f];
+                gb += tot[f];
+                gw += tot[F + f];
             }
             coef[3 * F] = (float)gw;
             coef[3 * F + 1] = (float)gb;
@@ -181,13 +185,13 @@ extern "C" int hgnn_bn_bwd_reduce(const float* gY, const float* Z, int R, int F,
                                   const float* weight, int train, const float* gshift, float* coef,
                                   void* ws, long long ws_bytes, hgnn_stream_t stream) {
     HGNN_REQUIRE(gY && Z && stats && weight && coef && ws && R > 0, "bad argument");
-    HGNN_REQUIRE(F >= 1 && F <= BN_MAX_F, "feature width must be in [1, 256]");
+    HGNN_REQUIRE(F >= 1 && F <= BN_MAX_F, "feature width must be in [1, 128]");
     if (ws_bytes < hgnn_workspace_bytes(2 * F)) {
         hgnn_set_error("hgnn_bn_bwd_reduce: workspace too small");
         return HGNN_ERR_WORKSPACE;
     }
     int rows_per_cta = 256 / F;
-    int grid = min(ceil_div(R, rows_per_cta * 4), hgnn_grid_cap(2 * F));
+    int grid = min(ceil_div(R, rows_per_cta * 4), HGNN_SM_COUNT * 8);
     bn_bwd_reduce_kernel<<<grid, 256, 0, to_stream(stream)>>>(
         gY, Z, R, F, stats, weight, train, gshift, coef, (unsigned int*)ws,
         (double*)((char*)ws + HGNN_WS_HEADER));
@@ -201,7 +205,7 @@ __global__ void __launch_bounds__(256)
 side_bwd_pre_kernel(const float* __restrict__ gY, const float* __restrict__ Z, int R, int F,
                     const float* __restrict__ coef, int relu_from, float* __restrict__ gPre,
                     float* dbias, unsigned int* counter, double* partial) {
-    __shared__ double red[512];
+    __shared__ double red[768];
     ColOwner co(F, blockDim.x);
     double s1 = 0.0;
     if (co.active) {
@@ -221,11 +225,12 @@ side_bwd_pre_kernel(const float* __restrict__ gY, const float* __restrict__ Z, i
             s1 += (double)g;
         }
     }
-    cta_column_partials(s1, 0.0, F, co, red, partial);
+    cta_column_accumulate(s1, 0.0, F, co, red, partial);
     if (last_block_ticket(counter)) {
         for (int f = threadIdx.x; f < F; f += blockDim.x) {
-            double a = 0.0;
-            for (int p = 0; p < (int)gridDim.x; ++p) a += partial[(size_t)p * 2 * F + f];
+            const int nb = hgnn_ws_bins(2 * F);
+            const double a = accum_take(partial, 2 * F, nb, f);
+            accum_take(partial, 2 * F, nb, F + f);
             if (dbias) dbias[f] = (float)a;
         }
         if (threadIdx.x == 0) *counter = 0;
@@ -236,13 +241,13 @@ extern "C" int hgnn_side_bwd_pre(const float* gY, const float* Z, int R, int F, 
                                  int relu_from, float* gPre, float* dbias, void* ws,
                                  long long ws_bytes, hgnn_stream_t stream) {
     HGNN_REQUIRE(gY && Z && gPre && ws && R > 0, "bad argument");
-    HGNN_REQUIRE(F >= 1 && F <= BN_MAX_F, "feature width must be in [1, 256]");
+    HGNN_REQUIRE(F >= 1 && F <= BN_MAX_F, "feature width must be in [1, 128]");
     if (ws_bytes < hgnn_workspace_bytes(2 * F)) {
         hgnn_set_error("hgnn_side_bwd_pre: workspace too small");
         return HGNN_ERR_WORKSPACE;
     }
     int rows_per_cta = 256 / F;
-    int grid = min(ceil_div(R, rows_per_cta * 4), hgnn_grid_cap(2 * F));
+    int grid = min(ceil_div(R, rows_per_cta * 4), HGNN_SM_COUNT * 8);
     side_bwd_pre_kernel<<<grid, 256, 0, to_stream(stream)>>>(
         gY, Z, R, F, coef, relu_from, gPre, dbias, (unsigned int*)ws,
         (double*)((char*)ws + HGNN_WS_HEADER));

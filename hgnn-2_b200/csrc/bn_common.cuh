@@ -20,35 +20,40 @@ struct ColOwner {
     }
 };
 
-// Reduce per-thread (s1, s2) of column owners across the CTA (fixed order) and store the CTA's
-// partial: partial[cta][0..F) = s1, [F..2F) = s2.  `red` is shared memory for 2*blockDim doubles.
-__device__ __forceinline__ void cta_column_partials(double s1, double s2, int F, const ColOwner& co,
-                                                    double* red, double* partial) {
-    red[threadIdx.x] = co.active ? s1 : 0.0;
-    red[blockDim.x + threadIdx.x] = co.active ? s2 : 0.0;
-    __syncthreads();
-    if ((int)threadIdx.x < F) {
-        double a = 0.0, b = 0.0;
-        for (int k = 0; k < co.rows_per_pass; ++k) {
-            a += red[k * F + threadIdx.x];
-            b += red[blockDim.x + k * F + threadIdx.x];
+// Reduce per-thread (s1, s2) of column owners across the CTA (fixed order), then add the CTA's sums
+// into the fp64 accumulators accum[0..F) (s1) and accum[F..2F) (s2).  `red` = 2*blockDim doubles.
+__device__ __forceinline__ void cta_column_accumulate(double s1, double s2, int F, const ColOwner& co,
+                                                      double* red, double* accum) {
+    double a = 0.0, b = 0.0;
+    if ((32 % F) == 0 && (blockDim.x % F) == 0) {      // every thread is an owner: shuffle tree
+        a = cta_reduce_mod(s1, F, red);
+        b = cta_reduce_mod(s2, F, red);
+    } else {
+        red[threadIdx.x] = co.active ? s1 : 0.0;
+        red[blockDim.x + threadIdx.x] = co.active ? s2 : 0.0;
+        __syncthreads();
+        if ((int)threadIdx.x < F) {
+            for (int k = 0; k < co.rows_per_pass; ++k) {
+                a += red[k * F + threadIdx.x];
+                b += red[blockDim.x + k * F + threadIdx.x];
+            }
         }
-        partial[(size_t)blockIdx.x * 2 * F + threadIdx.x] = a;
-        partial[(size_t)blockIdx.x * 2 * F + F + threadIdx.x] = b;
+    }
+    if ((int)threadIdx.x < F) {
+        const int nb = hgnn_ws_bins(2 * F);
+        accum_add(accum, 2 * F, nb, threadIdx.x, a);
+        accum_add(accum, 2 * F, nb, F + threadIdx.x, b);
     }
 }
 
-// Last CTA: sum the partials in CTA order and emit stats = [mean, std, scale, shift] (4F floats).
-__device__ __forceinline__ void bn_finalize(const double* partial, int nparts, int F, long long n,
-                                            const float* weight, const float* bias,
-                                            float* running_mean, float* running_std, float momentum,
-                                            float* stats) {
+// Last CTA: read (and re-zero) the accumulated sums, emit stats = [mean, std, scale, shift] (4F).
+__device__ __forceinline__ void bn_finalize_accum(double* accum, int F, long long n,
+                                                  const float* weight, const float* bias,
+                                                  float* running_mean, float* running_std,
+                                                  float momentum, float* stats) {
     for (int f = threadIdx.x; f < F; f += blockDim.x) {
-        double a = 0.0, b = 0.0;
-        for (int p = 0; p < nparts; ++p) {
-            a += partial[(size_t)p * 2 * F + f];
-            b += partial[(size_t)p * 2 * F + F + f];
-        }
+        const int nb = hgnn_ws_bins(2 * F);
+        const double a = accum_take(accum, 2 * F, nb, f), b = accum_take(accum, 2 * F, nb, F + f);
         double mean = a / (double)n;
         double var = b / (double)n - mean * mean;
         if (var < 0.0) var = 0.0;

@@ -220,7 +220,7 @@ ccn2_bwd_kernel(int V, const int* __restrict__ nbr_ptr, const int* __restrict__ 
                 const long long* __restrict__ f_off, const float* __restrict__ Fprev, int C,
                 const float* __restrict__ W, int H, const float* __restrict__ Fnext,
                 const float* __restrict__ gFnext, float* __restrict__ gFprev,
-                float* dW, float* db, unsigned int* counter, float* partial, int nmax) {
+                float* dW, float* db, unsigned int* counter, double* accum, int nmax) {
     extern __shared__ __align__(16) float smem[];
     CcnSmem s = carve(smem, nmax, C);
     const int Cin = 18 * C;
@@ -359,11 +359,10 @@ ccn2_bwd_kernel(int V, const int* __restrict__ nbr_ptr, const int* __restrict__ 
         }
     }
     __syncthreads();
-    for (int k = tid; k < P; k += CCN_THREADS) partial[(size_t)blockIdx.x * P + k] = dacc[k];
+    for (int k = tid; k < P; k += CCN_THREADS) accum_add(accum, P, hgnn_ws_bins(P), k, (double)dacc[k]);
     if (last_block_ticket(counter)) {
         for (int k = tid; k < P; k += CCN_THREADS) {
-            float a = 0.f;
-            for (int bkt = 0; bkt < (int)gridDim.x; ++bkt) a += partial[(size_t)bkt * P + k];
+            const float a = (float)accum_take(accum, P, hgnn_ws_bins(P), k);
             if (k < H * Cin) dW[k] = a; else db[k - H * Cin] = a;
         }
         if (tid == 0) *counter = 0;
@@ -393,10 +392,10 @@ extern "C" int hgnn_ccn2_update_bwd(int V, int nmax, const int* nbr_ptr, const i
         cudaFuncSetAttribute(ccn2_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CCN_MAX_SMEM);
         attr_set = true;
     }
-    int grid = min(V, hgnn_grid_cap(P));
+    int grid = min(V, HGNN_SM_COUNT * 8);
     ccn2_bwd_kernel<<<grid, CCN_THREADS, floats * sizeof(float), to_stream(stream)>>>(
         V, nbr_ptr, nbr, f_off, Fprev, C, W, H, Fnext, gFnext, gFprev, dW, db, (unsigned int*)ws,
-        (float*)((char*)ws + HGNN_WS_HEADER), nmax);
+        (double*)((char*)ws + HGNN_WS_HEADER), nmax);
     return hgnn_check_launch("hgnn_ccn2_update_bwd");
 }
 
@@ -472,7 +471,7 @@ ccn1_bwd_kernel(int V, const int* __restrict__ nbr_ptr, const int* __restrict__ 
                 const float* __restrict__ Fprev, int C, const float* __restrict__ W, int H,
                 const float* __restrict__ Fnext, const float* __restrict__ gFnext,
                 float* __restrict__ gFprev, float* dW, float* db, unsigned int* counter,
-                float* partial, int nmax) {
+                double* accum, int nmax) {
     extern __shared__ __align__(16) float smem[];
     int* r = reinterpret_cast<int*>(smem);
     int* m = r + nmax;
@@ -547,11 +546,10 @@ ccn1_bwd_kernel(int V, const int* __restrict__ nbr_ptr, const int* __restrict__ 
         }
     }
     __syncthreads();
-    for (int k = tid; k < P; k += CCN_THREADS) partial[(size_t)blockIdx.x * P + k] = dacc[k];
+    for (int k = tid; k < P; k += CCN_THREADS) accum_add(accum, P, hgnn_ws_bins(P), k, (double)dacc[k]);
     if (last_block_ticket(counter)) {
         for (int k = tid; k < P; k += CCN_THREADS) {
-            float a = 0.f;
-            for (int bkt = 0; bkt < (int)gridDim.x; ++bkt) a += partial[(size_t)bkt * P + k];
+            const float a = (float)accum_take(accum, P, hgnn_ws_bins(P), k);
             if (k < H * 2 * C) dW[k] = a; else db[k - H * 2 * C] = a;
         }
         if (tid == 0) *counter = 0;
@@ -580,10 +578,10 @@ extern "C" int hgnn_ccn1_update_bwd(int V, int nmax, const int* nbr_ptr, const i
         cudaFuncSetAttribute(ccn1_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CCN_MAX_SMEM);
         attr_set = true;
     }
-    int grid = min(V, hgnn_grid_cap(P));
+    int grid = min(V, HGNN_SM_COUNT * 8);
     ccn1_bwd_kernel<<<grid, CCN_THREADS, floats * sizeof(float), to_stream(stream)>>>(
         V, nbr_ptr, nbr, Fprev, C, W, H, Fnext, gFnext, gFprev, dW, db, (unsigned int*)ws,
-        (float*)((char*)ws + HGNN_WS_HEADER), nmax);
+        (double*)((char*)ws + HGNN_WS_HEADER), nmax);
     return hgnn_check_launch("hgnn_ccn1_update_bwd");
 }
 

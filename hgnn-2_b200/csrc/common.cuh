@@ -65,11 +65,40 @@ static inline int make_oplist(const hgnn_op_t* ops, int n_ops, OpList* out) {
     return 0;
 }
 
-// ---- cross-CTA deterministic reduction ("last block done") ---------------------------------
-// Each CTA writes its partial vector to ws[cta][width]; the CTA that takes the last ticket
-// reduces all partials in CTA order (fixed order => bit-reproducible) and runs the finalizer.
-// Workspace layout: [0, 256) bytes = ticket counter (self-resetting), then partials.
+// ---- cross-CTA reduction ("last block done") -------------------------------------------------
+// Workspace layout: [0, 256) bytes = ticket counter (self-resetting), then NB x width fp64
+// accumulators (all zero on entry and on exit).  Every CTA adds its partial sums into bin
+// blockIdx % NB with fire-and-forget fp64 atomics (binning keeps same-address contention at
+// grid/NB); the CTA that takes the last ticket sums the bins in a fixed order, re-zeroes them and
+// runs the finalizer in the same launch.
 #define HGNN_WS_HEADER 256
+
+// number of accumulator bins for a reduction of `width` values (host and device agree on this)
+__host__ __device__ inline int hgnn_ws_bins(int width) {
+    int nb = 32;
+    while (nb > 1 && (long long)nb * width > 4096) nb >>= 1;
+    return nb;
+}
+
+__device__ __forceinline__ void accum_add(double* accum, int width, int nb, int idx, double v) {
+    atomicAdd(accum + (size_t)(blockIdx.x & (nb - 1)) * width + idx, v);
+}
+
+// last CTA only: total of column idx over the bins (fixed order), re-zeroing as it goes
+__device__ __forceinline__ double accum_take(double* accum, int width, int nb, int idx) {
+    double t0 = 0.0, t1 = 0.0;
+    for (int b = 0; b < nb; b += 2) {
+        double* p0 = accum + (size_t)b * width + idx;
+        t0 += __ldcg(p0);
+        *p0 = 0.0;
+        if (b + 1 < nb) {
+            double* p1 = p0 + width;
+            t1 += __ldcg(p1);
+            *p1 = 0.0;
+        }
+    }
+    return t0 + t1;
+}
 
 __device__ __forceinline__ bool last_block_ticket(unsigned int* counter) {
     __shared__ bool is_last;
@@ -93,4 +122,62 @@ __device__ __forceinline__ double warp_sum_d(double v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     return v;
+}
+
+// Last-CTA reduction of per-CTA partial vectors: out[c] = sum_p partial[p*width + c], p in CTA
+// order.  All threads take part (column c is split into blockDim/width row chunks that are then
+// combined in a fixed order), so the tail costs ~nparts/chunks dependent L2 loads per thread
+// instead of nparts.  `scratch` = blockDim.x elements of shared memory; `out` may be shared or
+// global.  Ends with a __syncthreads().
+template <typename T>
+__device__ __forceinline__ void lastblock_reduce(const T* __restrict__ partial, int nparts, int width,
+                                                 T* out, T* scratch) {
+    const int nthr = blockDim.x;
+    for (int c0 = 0; c0 < width; c0 += nthr) {
+        const int w = min(nthr, width - c0);
+        const int nch = nthr / w;
+        const int c = threadIdx.x % w, ch = threadIdx.x / w;
+        T acc = (T)0;
+        if (ch < nch) {
+            int p = ch;
+            T a0 = (T)0, a1 = (T)0, a2 = (T)0, a3 = (T)0;   // four loads in flight
+            for (; p + 3 * nch < nparts; p += 4 * nch) {
+                a0 += __ldcg(partial + (size_t)p * width + c0 + c);
+                a1 += __ldcg(partial + (size_t)(p + nch) * width + c0 + c);
+                a2 += __ldcg(partial + (size_t)(p + 2 * nch) * width + c0 + c);
+                a3 += __ldcg(partial + (size_t)(p + 3 * nch) * width + c0 + c);
+            }
+            for (; p < nparts; p += nch) a0 += __ldcg(partial + (size_t)p * width + c0 + c);
+            acc = (a0 + a1) + (a2 + a3);
+        }
+        scratch[threadIdx.x] = acc;
+        __syncthreads();
+        if ((int)threadIdx.x < w) {
+            T t = (T)0;
+            for (int k = 0; k < nch; ++k) t += scratch[k * w + threadIdx.x];
+            out[c0 + threadIdx.x] = t;
+        }
+        __syncthreads();
+    }
+}
+
+// Sum `v` over all threads of the CTA that share (threadIdx.x % M); M must divide 32.  Threads
+// tid < M return the total of column tid; `sm` = (blockDim/32)*32 doubles.  Two __syncthreads().
+__device__ __forceinline__ double cta_reduce_mod(double v, int M, double* sm) {
+    for (int off = 16; off >= M; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    __syncthreads();
+    if (lane < M) sm[warp * 32 + lane] = v;
+    __syncthreads();
+    double t = 0.0;
+    if ((int)threadIdx.x < M)
+        for (int w = 0; w < nw; ++w) t += sm[w * 32 + threadIdx.x];
+    return t;
+}
+
+// grid that gives every CTA the same number of tiles (no ragged second wave)
+static inline int balanced_grid(int ntiles, int max_ctas) {
+    if (ntiles <= max_ctas) return ntiles < 1 ? 1 : ntiles;
+    int per = (ntiles + max_ctas - 1) / max_ctas;
+    return (ntiles + per - 1) / per;
 }

@@ -32,8 +32,11 @@ int hgnn_grid_cap(int width) {
     return (int)(g < HGNN_SM_COUNT ? HGNN_SM_COUNT : g);
 }
 
+// Workspace = 256-byte header (ticket counter) + hgnn_ws_bins(width) x `width` fp64 accumulators; it must be all zero on
+// entry and every kernel leaves it all zero again.
 extern "C" long long hgnn_workspace_bytes(int width) {
-    return HGNN_WS_HEADER + (long long)hgnn_grid_cap(width) * (width < 1 ? 1 : width) * 8;
+    const int w = width < 1 ? 1 : width;
+    return HGNN_WS_HEADER + (long long)hgnn_ws_bins(w) * w * 8;
 }
 
 // ---------------------------------------------------------------------------------------------

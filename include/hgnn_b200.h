@@ -47,8 +47,9 @@ typedef struct hgnn_op_t {
 
 const char* hgnn_last_error(void);
 int hgnn_version(void);
-/* Workspace (bytes) the fused kernels need for per-CTA partials; `width` = number of fp32/fp64
- * values reduced across CTAs (see each call). */
+/* Workspace (bytes) for cross-CTA reductions: a ticket counter + binned fp64 accumulators for `width` values (see each
+ * call for its width).  The buffer must be ALL ZERO before the first use; every kernel leaves it all
+ * zero again, so one buffer per stream can serve every call. */
 long long hgnn_workspace_bytes(int width);
 
 /* ---- layout conversion (boundary of functions/batching.py:77-185) ------------------------- */
