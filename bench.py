@@ -55,7 +55,7 @@ def parse():
     ap.add_argument("--no-graph", action="store_true", help="time eager launches instead of a CUDA graph")
     ap.add_argument("--skip-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--skip-e2e", action="store_true")
-    ap.add_argument("--cpu-sample", type=int, default=1, help="graphs per CPU-baseline step")
+    ap.add_argument("--cpu-sample", type=int, default=2, help="graphs per CPU-baseline step")
     return ap.parse_args()
 
 
@@ -94,7 +94,7 @@ def cpu_reference_step(a, O, batch, p, labels, opt):
     loss = torch.nn.functional.cross_entropy(out, labels)
     loss.backward()
     opt.step()
-    return float(loss)
+    return float(loss.detach())
 
 
 def cpu_baseline(a, steps=1, warmup=0):

@@ -395,9 +395,13 @@ static int resident_ctas(K kernel, size_t smem) {
     static size_t seen_smem[16];
     static int seen_occ[16];
     static int n_seen = 0;
+    static size_t attr_smem = 48 * 1024;     // the opt-in limit only ever grows
+    if (smem > attr_smem) {
+        cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        attr_smem = smem;
+    }
     for (int i = 0; i < n_seen; ++i)
         if (seen_smem[i] == smem) return HGNN_SM_COUNT * seen_occ[i];
-    if (smem > 48 * 1024) cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     int occ = 0;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, SIDE_THREADS, smem) != cudaSuccess || occ < 1)
         occ = 1;
