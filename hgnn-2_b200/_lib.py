@@ -36,8 +36,31 @@ class SideT(ctypes.Structure):
                 ("p_pd", c_void), ("Xc", c_void), ("Fc", c_int)]
 
 
+class BnRefT(ctypes.Structure):
+    _fields_ = [("acc", c_void), ("affine", c_void), ("weight", c_void), ("bias", c_void), ("n_rows", c_int)]
+
+
+class SideBwdT(ctypes.Structure):
+    _fields_ = [("gY", c_void), ("Z", c_void), ("Fg", c_int), ("relu_from", c_int), ("Rg", c_int),
+                ("acc_f", c_void), ("acc_b", c_void), ("bn_weight", c_void),
+                ("Wa", c_void), ("Ha", c_int), ("Wb", c_void), ("Hb", c_int), ("Cin", c_int),
+                ("dW_bins", c_void), ("db_bins", c_void),
+                ("R_self", c_int), ("ops_T", ctypes.POINTER(OpT)), ("n_ops", c_int), ("Xs", c_void),
+                ("Fs", c_int), ("bn_self", BnRefT), ("gXs", c_void), ("accumulate_self", c_int),
+                ("acc_b_self", c_void),
+                ("R_cross", c_int), ("pt_rowptr", c_void), ("pt_col", c_void), ("pt_pm", c_void),
+                ("pt_pd", c_void), ("Xc", c_void), ("Fc", c_int), ("bn_cross", BnRefT), ("gXc", c_void),
+                ("accumulate_cross", c_int), ("acc_b_cross", c_void)]
+
+
 _P = c_void
 _SIGS = {
+    "hgnn_lg_side_fwd": [ctypes.POINTER(SideT), ctypes.POINTER(BnRefT), ctypes.POINTER(BnRefT), _P, _P, c_int,
+                         _P, _P, c_int, c_int, _P, _P, _P],
+    "hgnn_lg_side_bwd": [ctypes.POINTER(SideBwdT), _P],
+    "hgnn_bins_reduce": [_P, _P, _P, _P, _P, c_int, _P, _P],
+    "hgnn_bn_running_update": [_P, _P, _P, _P, _P, c_int, c_float, _P, _P],
+    "hgnn_readout_bwd_prep": [_P, c_int, c_int, _P, _P, _P, _P, _P],
     "hgnn_pack_rows": [_P, c_int, c_int, c_int, _P, _P, _P],
     "hgnn_unpack_rows": [_P, c_int, c_int, c_int, _P, _P, _P, _P],
     "hgnn_dense_count_nnz": [_P, _P, c_ll, c_ll, c_ll, c_int, _P, _P, _P, _P],
@@ -69,7 +92,7 @@ _SIGS = {
     "hgnn_ccn1_update_bwd": [c_int, c_int, _P, _P, _P, c_int, _P, c_int, _P, _P, _P, _P, _P, _P, c_ll, _P],
     "hgnn_adamax_step": [_P, _P, _P, _P, c_ll, c_float, c_float, c_float, c_float, c_float, _P, _P],
 }
-EXPORTS = sorted(list(_SIGS) + ["hgnn_last_error", "hgnn_version", "hgnn_workspace_bytes"])
+EXPORTS = sorted(list(_SIGS) + ["hgnn_last_error", "hgnn_version", "hgnn_workspace_bytes", "hgnn_bins_for"])
 
 for _name, _args in _SIGS.items():
     _fn = getattr(lib, _name)
@@ -80,6 +103,8 @@ lib.hgnn_last_error.argtypes = []
 lib.hgnn_version.restype = c_int
 lib.hgnn_workspace_bytes.restype = c_ll
 lib.hgnn_workspace_bytes.argtypes = [c_int]
+lib.hgnn_bins_for.restype = c_int
+lib.hgnn_bins_for.argtypes = [c_int]
 
 # number of kernel launches issued through the C ABI (bench.py reports it as gpu_launches)
 launch_count = 0

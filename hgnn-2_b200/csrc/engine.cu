@@ -1,0 +1,1032 @@
+// engine.cu -- the model-level LGNN / GNN training engine kernels ("v2" data flow).
+//
+// The layer-level kernels of side.cu mirror the reference's module boundaries: one launch for the
+// fused side update, then separate launches for BN apply, BN backward reduce, ReLU/BN backward and
+// the two transposed gathers - 12 launches per LGNN layer, each with its own ticket/finalise tail.
+// At the script default h=2 a launch moves <= 25 MB, so the step is bound by launch count and by
+// dependent memory hops, not by bandwidth (profiles/README.md).  The engine therefore keeps
+// activations RAW (pre-batch-norm) in HBM and moves everything that used to be a launch into the
+// prologue / gather of the neighbouring kernels:
+//
+//   forward  (1 launch per side):  consumers normalise their inputs on load (scale/shift derived in
+//            the prologue from the producer's fp64 (sum z, sum z^2) accumulators), gather, concat,
+//            conv, ReLU, write raw Z and add Z's own statistics to ITS accumulators.  No ticket.
+//   backward (1 launch per side):  the BN + ReLU backward  gPre = (c0 g + c1 + c2 z) * mask  is
+//            evaluated on the fly while gathering through the transposed operators; the launch
+//            covers both the self rows and the cross rows, writes / accumulates the input
+//            gradients, adds (sum g, sum g*xhat) of what it produced to the accumulators of the
+//            tensors it differentiates, and adds dW / dbias partials to binned fp64 accumulators.
+//   step end (1 launch):           hgnn_bins_reduce turns every accumulator into the flat fp32
+//            gradient buffer; hgnn_bn_running_update applies the running-statistics rule.
+//
+// Reference semantics are unchanged (models/layers/layers_mnb.py:52-69,189-225,256-290,322-358,
+// batch_normalization.py:34-43,65-93); parity is tested against the same golden vectors.
+#include "common.cuh"
+
+#define ENG_THREADS 256
+#define ENG_MAX_SMEM (200 * 1024)
+#define ENG_LONG_ROW 32
+#define ENG_CTA_ROW 1024
+#define ENG_MAX_DEFER 192
+#define ENG_BN_EPS 1e-5
+
+namespace eng {
+
+template <int VEC> struct V;
+template <> struct V<1> {
+    float v;
+    __device__ __forceinline__ static V load(const float* p) { V r; r.v = __ldg(p); return r; }
+    __device__ __forceinline__ static V loads(const float* p) { V r; r.v = *p; return r; }
+    __device__ __forceinline__ static V zero() { V r; r.v = 0.f; return r; }
+    __device__ __forceinline__ static V splat(float a) { V r; r.v = a; return r; }
+    __device__ __forceinline__ void fma(float a, const V& x) { v = fmaf(a, x.v, v); }
+    __device__ __forceinline__ void affine(const V& s, const V& t) { v = fmaf(v, s.v, t.v); }
+    __device__ __forceinline__ void scale(float a) { v *= a; }
+    __device__ __forceinline__ void add(const V& o) { v += o.v; }
+    __device__ __forceinline__ void warp_reduce() { v = warp_sum(v); }
+    __device__ __forceinline__ void store(float* p) const { *p = v; }
+    __device__ __forceinline__ void store_scalar(float* p) const { p[0] = v; }
+    __device__ __forceinline__ float get(int) const { return v; }
+    __device__ __forceinline__ void set(int, float a) { v = a; }
+};
+template <> struct V<4> {
+    float4 v;
+    __device__ __forceinline__ static V load(const float* p) { V r; r.v = __ldg(reinterpret_cast<const float4*>(p)); return r; }
+    __device__ __forceinline__ static V loads(const float* p) { V r; r.v = *reinterpret_cast<const float4*>(p); return r; }
+    __device__ __forceinline__ static V zero() { V r; r.v = make_float4(0.f, 0.f, 0.f, 0.f); return r; }
+    __device__ __forceinline__ static V splat(float a) { V r; r.v = make_float4(a, a, a, a); return r; }
+    __device__ __forceinline__ void fma(float a, const V& x) {
+        v.x = fmaf(a, x.v.x, v.x); v.y = fmaf(a, x.v.y, v.y); v.z = fmaf(a, x.v.z, v.z); v.w = fmaf(a, x.v.w, v.w);
+    }
+    __device__ __forceinline__ void affine(const V& s, const V& t) {
+        v.x = fmaf(v.x, s.v.x, t.v.x); v.y = fmaf(v.y, s.v.y, t.v.y);
+        v.z = fmaf(v.z, s.v.z, t.v.z); v.w = fmaf(v.w, s.v.w, t.v.w);
+    }
+    __device__ __forceinline__ void scale(float a) { v.x *= a; v.y *= a; v.z *= a; v.w *= a; }
+    __device__ __forceinline__ void add(const V& o) { v.x += o.v.x; v.y += o.v.y; v.z += o.v.z; v.w += o.v.w; }
+    __device__ __forceinline__ void warp_reduce() {
+        v.x = warp_sum(v.x); v.y = warp_sum(v.y); v.z = warp_sum(v.z); v.w = warp_sum(v.w);
+    }
+    __device__ __forceinline__ void store(float* p) const { *reinterpret_cast<float4*>(p) = v; }
+    __device__ __forceinline__ void store_scalar(float* p) const { p[0] = v.x; p[1] = v.y; p[2] = v.z; p[3] = v.w; }
+    __device__ __forceinline__ float get(int j) const { return j == 0 ? v.x : j == 1 ? v.y : j == 2 ? v.z : v.w; }
+    __device__ __forceinline__ void set(int j, float a) { if (j == 0) v.x = a; else if (j == 1) v.y = a; else if (j == 2) v.z = a; else v.w = a; }
+};
+
+// ---- row loaders -----------------------------------------------------------------------------
+// forward: y = z * scale + shift  (the producer's batch-norm applied on load)
+template <int VEC>
+struct AffineLoader {
+    const float* X;
+    int ld;
+    const float* sc;   // shared memory: scale[F]
+    const float* sh;   // shared memory: shift[F]
+    bool on;
+    __device__ __forceinline__ V<VEC> operator()(int row, int xo) const {
+        V<VEC> x = V<VEC>::load(X + (size_t)row * ld + xo);
+        if (on) x.affine(V<VEC>::loads(sc + xo), V<VEC>::loads(sh + xo));
+        return x;
+    }
+};
+
+// backward: gPre = (c0*g + c1 + c2*z) masked by the ReLU of the conv branch (z > 0 where f >= relu_from)
+template <int VEC>
+struct GpreLoader {
+    const float* G;
+    const float* Z;
+    int ld;
+    const float* c0;   // shared memory coefficient vectors [F]
+    const float* c1;
+    const float* c2;
+    int relu_from;
+    bool bn;
+    __device__ __forceinline__ V<VEC> operator()(int row, int xo) const {
+        V<VEC> g = V<VEC>::load(G + (size_t)row * ld + xo);
+        if (!bn && relu_from >= ld) return g;
+        V<VEC> z = V<VEC>::load(Z + (size_t)row * ld + xo);
+        if (bn) {
+            g.affine(V<VEC>::loads(c0 + xo), V<VEC>::loads(c1 + xo));
+#pragma unroll
+            for (int j = 0; j < VEC; ++j) g.set(j, fmaf(c2[xo + j], z.get(j), g.get(j)));
+        }
+#pragma unroll
+        for (int j = 0; j < VEC; ++j)
+            if (xo + j >= relu_from && !(z.get(j) > 0.f)) g.set(j, 0.f);
+        return g;
+    }
+};
+
+// ---- gathers -----------------------------------------------------------------------------------
+template <int VEC, typename L>
+__device__ __forceinline__ V<VEC> gather_op(const OpList& ops, int t, int row, const L& ld_, int xo) {
+    const int kind = ops.kind[t];
+    if (kind == HGNN_OP_IDENT) return ld_(row, xo);
+    if (kind == HGNN_OP_DIAG) {
+        V<VEC> x = ld_(row, xo);
+        x.scale(__ldg(ops.diag[t] + row));
+        return x;
+    }
+    const int* __restrict__ col = ops.col[t];
+    const float* __restrict__ val = ops.val[t];
+    const int k0 = __ldg(ops.rowptr[t] + row), k1 = __ldg(ops.rowptr[t] + row + 1);
+    V<VEC> acc = V<VEC>::zero();
+    for (int k = k0; k < k1; k += 4) {           // batches of 4 independent gathers
+        int c[4];
+        float v[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const bool on = k + j < k1;
+            c[j] = __ldg(col + (on ? k + j : k));
+            v[j] = on ? __ldg(val + k + j) : 0.f;
+        }
+        V<VEC> x[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) x[j] = ld_(c[j], xo);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc.fma(v[j], x[j]);
+    }
+    return acc;
+}
+
+struct DeferList {
+    int cnt;
+    int items[ENG_MAX_DEFER];
+};
+__device__ __forceinline__ int defer_code(int t, int q, int r) { return (t << 24) | (q << 12) | r; }
+
+template <int VEC, typename L>
+__device__ __forceinline__ void gather_or_defer(const OpList& ops, int t, int row, const L& ld_, int xo,
+                                                float* dst, DeferList* dl, int code) {
+    if (ops.kind[t] == HGNN_OP_CSR) {
+        const int len = __ldg(ops.rowptr[t] + row + 1) - __ldg(ops.rowptr[t] + row);
+        if (len > ENG_LONG_ROW) {
+            const int slot = atomicAdd(&dl->cnt, 1);
+            if (slot < ENG_MAX_DEFER) {
+                dl->items[slot] = code;
+                return;
+            }
+        }
+    }
+    gather_op<VEC>(ops, t, row, ld_, xo).store(dst);
+}
+
+template <int VEC, typename L>
+__device__ __forceinline__ V<VEC> strided_gather(const OpList& ops, int t, int row, const L& ld_, int xo,
+                                                 int first, int stride) {
+    const int* __restrict__ col = ops.col[t];
+    const float* __restrict__ val = ops.val[t];
+    const int k0 = __ldg(ops.rowptr[t] + row), k1 = __ldg(ops.rowptr[t] + row + 1);
+    V<VEC> a0 = V<VEC>::zero(), a1 = V<VEC>::zero();
+    int k = k0 + first;
+    for (; k + stride < k1; k += 2 * stride) {
+        V<VEC> x0 = ld_(__ldg(col + k), xo);
+        V<VEC> x1 = ld_(__ldg(col + k + stride), xo);
+        a0.fma(__ldg(val + k), x0);
+        a1.fma(__ldg(val + k + stride), x1);
+    }
+    if (k < k1) a0.fma(__ldg(val + k), ld_(__ldg(col + k), xo));
+    a0.add(a1);
+    return a0;
+}
+
+// all threads of the CTA; call between two __syncthreads()
+template <int VEC, typename L>
+__device__ __forceinline__ void gather_deferred(const OpList& ops, DeferList* dl, int row0, const L& ld_,
+                                                int Fblk, float* tile, int Tp, float* wpart) {
+    const int nd = min(dl->cnt, ENG_MAX_DEFER);
+    if (nd == 0) return;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    for (int it = warp; it < nd; it += nwarps) {
+        const int code = dl->items[it];
+        const int t = code >> 24, q = (code >> 12) & 0xfff, r = code & 0xfff;
+        const int row = row0 + r, xo = q * VEC;
+        const int len = __ldg(ops.rowptr[t] + row + 1) - __ldg(ops.rowptr[t] + row);
+        if (len > ENG_CTA_ROW) continue;
+        V<VEC> acc = strided_gather<VEC>(ops, t, row, ld_, xo, lane, 32);
+        acc.warp_reduce();
+        if (lane == 0) acc.store(tile + r * Tp + t * Fblk + xo);
+    }
+    for (int it = 0; it < nd; ++it) {
+        const int code = dl->items[it];
+        const int t = code >> 24, q = (code >> 12) & 0xfff, r = code & 0xfff;
+        const int row = row0 + r, xo = q * VEC;
+        const int len = __ldg(ops.rowptr[t] + row + 1) - __ldg(ops.rowptr[t] + row);
+        if (len <= ENG_CTA_ROW) continue;
+        V<VEC> acc = strided_gather<VEC>(ops, t, row, ld_, xo, threadIdx.x, blockDim.x);
+        acc.warp_reduce();
+        __syncthreads();
+        if (lane == 0) acc.store_scalar(wpart + warp * 4);
+        __syncthreads();
+        if ((int)threadIdx.x < VEC) {
+            float v = 0.f;
+            for (int w = 0; w < nwarps; ++w) v += wpart[w * 4 + threadIdx.x];
+            tile[r * Tp + t * Fblk + xo + threadIdx.x] = v;
+        }
+    }
+}
+
+// ---- accumulator bins ---------------------------------------------------------------------------
+// out[c] = sum over bins of acc[b*width + c]; all threads; `scratch` = blockDim doubles.  Ends synced.
+__device__ __forceinline__ void bins_total(const double* __restrict__ acc, int width, int nb,
+                                           double* out, double* scratch) {
+    if (nb * width <= (int)blockDim.x) {
+        const int e = threadIdx.x;
+        scratch[e] = (e < nb * width) ? __ldcg(acc + e) : 0.0;
+        __syncthreads();
+        if (e < width) {
+            double t0 = 0.0, t1 = 0.0;
+            for (int b = 0; b + 1 < nb; b += 2) {
+                t0 += scratch[b * width + e];
+                t1 += scratch[(b + 1) * width + e];
+            }
+            if (nb & 1) t0 += scratch[(nb - 1) * width + e];
+            out[e] = t0 + t1;
+        }
+    } else {
+        for (int c = threadIdx.x; c < width; c += blockDim.x) {
+            double t = 0.0;
+            for (int b = 0; b < nb; ++b) t += __ldcg(acc + (size_t)b * width + c);
+            out[c] = t;
+        }
+    }
+    __syncthreads();
+}
+
+// How to normalise a stored raw tensor on load.
+struct BnRef {
+    const double* acc;     // binned (sum z, sum z^2) of the producer, or NULL
+    const float* affine;   // precomputed [scale(F), shift(F)] (eval mode), or NULL
+    const float* w;        // scalar BN weight / bias (device)
+    const float* b;
+    int n;                 // rows behind the statistics
+};
+
+// Fill scale/shift (and mean/rstd when asked) for a tensor of width F.  All threads; ends synced.
+__device__ __forceinline__ bool bn_vectors(const BnRef& r, int F, float* sc, float* sh, float* mean,
+                                           float* rstd, double* tot, double* scratch) {
+    if (r.affine) {
+        for (int f = threadIdx.x; f < F; f += blockDim.x) {
+            sc[f] = r.affine[f];
+            sh[f] = r.affine[F + f];
+            if (mean) { mean[f] = 0.f; rstd[f] = 1.f; }
+        }
+        __syncthreads();
+        return true;
+    }
+    if (!r.acc) {
+        for (int f = threadIdx.x; f < F; f += blockDim.x) {
+            sc[f] = 1.f;
+            sh[f] = 0.f;
+            if (mean) { mean[f] = 0.f; rstd[f] = 1.f; }
+        }
+        __syncthreads();
+        return false;
+    }
+    bins_total(r.acc, 2 * F, hgnn_ws_bins(2 * F), tot, scratch);
+    const double w = r.w[0], b = r.b[0];
+    for (int f = threadIdx.x; f < F; f += blockDim.x) {
+        const double m = tot[f] / (double)r.n;
+        double var = tot[F + f] / (double)r.n - m * m;
+        if (var < 0.0) var = 0.0;
+        const double sd = sqrt(var + ENG_BN_EPS);
+        sc[f] = (float)(w / sd);
+        sh[f] = (float)(b - w * m / sd);
+        if (mean) { mean[f] = (float)m; rstd[f] = (float)(1.0 / sd); }
+    }
+    __syncthreads();
+    return true;
+}
+
+// ---------------------------------------------------------------------------------------------
+// forward
+// ---------------------------------------------------------------------------------------------
+struct FwdArgs {
+    int R;
+    OpList ops;
+    const float* Xs; int Fs; BnRef bn_s;
+    const int* p_rowptr; const int* p_col; const float* p_pm; const float* p_pd;
+    const float* Xc; int Fc; BnRef bn_c;
+    const float* Wa; const float* ba; int Ha;
+    const float* Wb; const float* bb; int Hb;
+    int relu_from;
+    float* Z;
+    double* acc_out;     // binned (sum z, sum z^2) of Z, or NULL
+    int TR, Cin, Cin_pad, Fout;
+};
+
+template <int VEC, int VOUT>
+__global__ void __launch_bounds__(ENG_THREADS, 4)
+fwd_kernel(const FwdArgs a) {
+    extern __shared__ __align__(16) float smem[];
+    __shared__ double dscratch[ENG_THREADS];
+    __shared__ double dtot[256];
+    __shared__ DeferList dl;
+    __shared__ float wpart[32];
+    const int Cin = a.Cin, Cp = a.Cin_pad, Fout = a.Fout, TR = a.TR;
+    const int K = a.ops.n, Fs = a.Fs, Fc = a.Fc;
+    float* Wt = smem;                              // [Cin][Fout]
+    float* bias = Wt + Cin * Fout;                 // [Fout]
+    float* sc_s = bias + ((Fout + 3) & ~3);        // [Fs] scale / shift of the self input
+    float* sh_s = sc_s + ((Fs + 3) & ~3);
+    float* sc_c = sh_s + ((Fs + 3) & ~3);          // [Fc]
+    float* sh_c = sc_c + ((Fc + 3) & ~3);
+    float* tile = sh_c + ((Fc + 3) & ~3);          // [TR][Cp]
+    const int tid = threadIdx.x;
+
+    for (int i = tid; i < Cin * Fout; i += ENG_THREADS) {
+        const int o = i / Cin, c = i - o * Cin;
+        Wt[c * Fout + o] = (o < a.Ha) ? a.Wa[(size_t)o * Cin + c] : a.Wb[(size_t)(o - a.Ha) * Cin + c];
+    }
+    for (int o = tid; o < Fout; o += ENG_THREADS)
+        bias[o] = (o < a.Ha) ? (a.ba ? a.ba[o] : 0.f) : (a.bb ? a.bb[o - a.Ha] : 0.f);
+    const bool cross = a.p_rowptr != nullptr;
+    const bool aff_s = bn_vectors(a.bn_s, Fs, sc_s, sh_s, nullptr, nullptr, dtot, dscratch);
+    const bool aff_c = cross ? bn_vectors(a.bn_c, Fc, sc_c, sh_c, nullptr, nullptr, dtot, dscratch) : false;
+    const AffineLoader<VEC> ls{a.Xs, Fs, sc_s, sh_s, aff_s};
+    const AffineLoader<VEC> lc{a.Xc, Fc, sc_c, sh_c, aff_c};
+
+    const int Qs = Fs / VEC, Qc = Fc / VEC;
+    const int Q = Qs + (cross ? Qc : 0);
+    const int xc0 = K * Fs;
+    const int NQ = Fout / VOUT;
+    const int rows_per_pass = ENG_THREADS / NQ;
+    const bool owner = tid < rows_per_pass * NQ;
+    const int oq = tid % NQ, rg = tid / NQ;
+    float s1[VOUT], s2[VOUT];
+#pragma unroll
+    for (int j = 0; j < VOUT; ++j) s1[j] = s2[j] = 0.f;
+    const int ntiles = (a.R + TR - 1) / TR;
+
+    for (int tile_id = blockIdx.x; tile_id < ntiles; tile_id += gridDim.x) {
+        const int row0 = tile_id * TR;
+        const int trc = min(TR, a.R - row0);
+        if (tid == 0) dl.cnt = 0;
+        __syncthreads();
+        for (int i = tid; i < Q * TR; i += ENG_THREADS) {
+            const int q = i / TR, r = i - q * TR;
+            if (r >= trc) continue;
+            const int row = row0 + r;
+            float* trow = tile + r * Cp;
+            if (q < Qs) {
+                const int xo = q * VEC;
+                for (int t = 0; t < K; ++t)
+                    gather_or_defer<VEC>(a.ops, t, row, ls, xo, trow + t * Fs + xo, &dl, defer_code(t, q, r));
+            } else {
+                const int xo = (q - Qs) * VEC;
+                V<VEC> am = V<VEC>::zero(), ad = V<VEC>::zero();
+                const int k0 = __ldg(a.p_rowptr + row), k1 = __ldg(a.p_rowptr + row + 1);
+                for (int k = k0; k < k1; k += 4) {
+                    int c[4];
+                    float vm[4], vd[4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const bool on = k + j < k1;
+                        c[j] = __ldg(a.p_col + (on ? k + j : k));
+                        vm[j] = on ? __ldg(a.p_pm + k + j) : 0.f;
+                        vd[j] = on ? __ldg(a.p_pd + k + j) : 0.f;
+                    }
+                    V<VEC> x[4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) x[j] = lc(c[j], xo);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        am.fma(vm[j], x[j]);
+                        ad.fma(vd[j], x[j]);
+                    }
+                }
+                am.store(trow + xc0 + xo);
+                ad.store(trow + xc0 + Fc + xo);
+            }
+        }
+        __syncthreads();
+        gather_deferred<VEC>(a.ops, &dl, row0, ls, Fs, tile, Cp, wpart);
+        __syncthreads();
+        if (owner) {
+            for (int r = rg; r < trc; r += rows_per_pass) {
+                float acc[VOUT];
+#pragma unroll
+                for (int j = 0; j < VOUT; ++j) acc[j] = bias[oq * VOUT + j];
+                const float* trow = tile + r * Cp;
+                const float* w = Wt + oq * VOUT;
+                if (VOUT == 4 && VEC == 4) {
+                    for (int c = 0; c < Cin; c += 4) {
+                        const float4 x = *reinterpret_cast<const float4*>(trow + c);
+                        const float xs[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            const float4 wv = *reinterpret_cast<const float4*>(w + (c + u) * Fout);
+                            acc[0] = fmaf(xs[u], wv.x, acc[0]);
+                            acc[1 % VOUT] = fmaf(xs[u], wv.y, acc[1 % VOUT]);
+                            acc[2 % VOUT] = fmaf(xs[u], wv.z, acc[2 % VOUT]);
+                            acc[3 % VOUT] = fmaf(xs[u], wv.w, acc[3 % VOUT]);
+                        }
+                    }
+                } else {
+#pragma unroll 4
+                    for (int c = 0; c < Cin; ++c) {
+                        const float x = trow[c];
+#pragma unroll
+                        for (int j = 0; j < VOUT; ++j) acc[j] = fmaf(x, w[c * Fout + j], acc[j]);
+                    }
+                }
+                float* zrow = a.Z + (size_t)(row0 + r) * Fout + oq * VOUT;
+#pragma unroll
+                for (int j = 0; j < VOUT; ++j) {
+                    float v = acc[j];
+                    if (oq * VOUT + j >= a.relu_from) v = fmaxf(v, 0.f);
+                    acc[j] = v;
+                    s1[j] += v;
+                    s2[j] = fmaf(v, v, s2[j]);
+                }
+                if (VOUT == 4) *reinterpret_cast<float4*>(zrow) = make_float4(acc[0], acc[1 % VOUT], acc[2 % VOUT], acc[3 % VOUT]);
+                else zrow[0] = acc[0];
+            }
+        }
+    }
+    if (a.acc_out) {
+        const int nb = hgnn_ws_bins(2 * Fout);
+        const bool tree = (32 % NQ) == 0 && (ENG_THREADS % NQ) == 0;
+#pragma unroll
+        for (int j = 0; j < VOUT; ++j) {
+            double x = 0.0, y = 0.0;
+            if (tree) {
+                x = cta_reduce_mod(owner ? (double)s1[j] : 0.0, NQ, dscratch);
+                y = cta_reduce_mod(owner ? (double)s2[j] : 0.0, NQ, dscratch);
+            } else {
+                __syncthreads();
+                dscratch[tid] = owner ? (double)s1[j] : 0.0;
+                __syncthreads();
+                if (tid < NQ) for (int k = 0; k < rows_per_pass; ++k) x += dscratch[k * NQ + tid];
+                __syncthreads();
+                dscratch[tid] = owner ? (double)s2[j] : 0.0;
+                __syncthreads();
+                if (tid < NQ) for (int k = 0; k < rows_per_pass; ++k) y += dscratch[k * NQ + tid];
+            }
+            if (tid < NQ) {
+                accum_add(a.acc_out, 2 * Fout, nb, tid * VOUT + j, x);
+                accum_add(a.acc_out, 2 * Fout, nb, Fout + tid * VOUT + j, y);
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// backward: one launch covers the self rows (tiles [0, tiles_self)) and the cross rows
+// ---------------------------------------------------------------------------------------------
+struct BwdPart {
+    int R;                 // rows of the differentiated input (0 = part absent)
+    OpList ops;            // transposed operators (cross: 2 CSR ops = Pm^T, Pd^T on one pattern)
+    const float* X; int Fx; BnRef bn;      // the raw input and how it was normalised
+    float* gX; int accumulate;             // gradient w.r.t. the NORMALISED input (NULL = not needed)
+    double* acc_b;                         // binned (sum g, sum g*xhat) of that input's producer, or NULL
+    int col0;                              // first weight column of this part
+    int TR, nT, Tp, Xp, NG, P, tiles;
+    size_t smem;
+};
+
+struct BwdArgs {
+    // the side being differentiated
+    const float* gY; const float* Z; int Fg; int relu_from; int Rg;
+    const double* acc_f; const double* acc_b; const float* bn_w;   // acc_b == NULL: no batch-norm
+    const float* Wa; int Ha; const float* Wb; int Hb; int Cin;
+    double* dW_bins;       // [nb][Fg*Cin] (row o, column c) or NULL
+    double* db_bins;       // [nb][Fg] or NULL
+    BwdPart self, cross;
+};
+
+template <int VEC, int VOUT>
+__device__ __forceinline__ void bwd_part(const BwdArgs& a, const BwdPart& p, bool is_self, int first_tile,
+                                         int tile_stride, float* smem, double* dscratch, double* dtot, DeferList* dl,
+                                         float* wpart, const float* c0, const float* c1, const float* c2,
+                                         bool has_bn) {
+    const int nT = p.nT, Tp = p.Tp, Fx = p.Fx, Xp = p.Xp, Fg = a.Fg, TR = p.TR, P = p.P, NG = p.NG;
+    // self tiles carry an extra own-row block (columns nT .. nT+Fg) whose column sums are dbias
+    float* Wsm = smem;                                // [nT][Fx]
+    float* sc = Wsm + ((nT * Fx + 3) & ~3);           // scale, shift, mean, rstd of the input [Fx] each
+    float* sh = sc + ((Fx + 3) & ~3);
+    float* mu = sh + ((Fx + 3) & ~3);
+    float* rs = mu + ((Fx + 3) & ~3);
+    float* tile = rs + ((Fx + 3) & ~3);               // [TR][Tp]
+    float* xt = tile + TR * Tp;                       // [TR][Xp]   raw rows of the input
+    float* dacc = xt + ((TR * Xp + 3) & ~3);          // [NG][P (+Fg)]
+    const int PD = is_self ? P + Fg : P;
+    const int tid = threadIdx.x;
+    const int K = p.ops.n;
+    const bool want_dw = a.dW_bins != nullptr;
+
+    for (int i = tid; i < nT * Fx; i += ENG_THREADS) {
+        const int c = i / Fx, f = i - c * Fx;
+        const int t = c / Fg, o = c - t * Fg;
+        const float* wrow = (o < a.Ha) ? a.Wa + (size_t)o * a.Cin : a.Wb + (size_t)(o - a.Ha) * a.Cin;
+        Wsm[i] = wrow[p.col0 + t * Fx + f];
+    }
+    for (int i = tid; i < NG * PD; i += ENG_THREADS) dacc[i] = 0.f;
+    const bool x_aff = bn_vectors(p.bn, Fx, sc, sh, mu, rs, dtot, dscratch);
+    const GpreLoader<VEC> lg{a.gY, a.Z, Fg, c0, c1, c2, a.relu_from, has_bn};
+
+    const int Q = Fg / VEC;
+    const int NQ = Fx / VOUT;
+    const int rows_per_pass = ENG_THREADS / NQ;
+    const bool owner = tid < rows_per_pass * NQ;
+    const int fq = tid % NQ, rg = tid / NQ;
+    const int PS = nT * NQ;
+    float sg[VOUT], sgx[VOUT];
+#pragma unroll
+    for (int j = 0; j < VOUT; ++j) sg[j] = sgx[j] = 0.f;
+
+    for (int tile_id = first_tile; tile_id < p.tiles; tile_id += tile_stride) {
+        const int row0 = tile_id * TR;
+        const int trc = min(TR, p.R - row0);
+        if (tid == 0) dl->cnt = 0;
+        __syncthreads();
+        for (int i = tid; i < Q * TR; i += ENG_THREADS) {
+            const int q = i / TR, r = i - q * TR;
+            if (r >= trc) continue;
+            const int xo = q * VEC;
+            float* trow = tile + r * Tp;
+            for (int t = 0; t < K; ++t)
+                gather_or_defer<VEC>(p.ops, t, row0 + r, lg, xo, trow + t * Fg + xo, dl, defer_code(t, q, r));
+            if (is_self) lg(row0 + r, xo).store(trow + nT + xo);     // own gPre row: dbias = column sums
+        }
+        if (VOUT == 4) {
+            for (int i = tid; i < trc * NQ; i += ENG_THREADS) {
+                const int r = i / NQ, g4 = i - r * NQ;
+                *reinterpret_cast<float4*>(xt + r * Xp + g4 * 4) =
+                    __ldg(reinterpret_cast<const float4*>(p.X + (size_t)row0 * Fx) + i);
+            }
+        } else {
+            for (int i = tid; i < trc * Fx; i += ENG_THREADS) {
+                const int r = i / Fx, f = i - r * Fx;
+                xt[r * Xp + f] = p.X[(size_t)row0 * Fx + i];
+            }
+        }
+        __syncthreads();
+        gather_deferred<VEC>(p.ops, dl, row0, lg, Fg, tile, Tp, wpart);
+        __syncthreads();
+        // ---- gX = W^T T  (+ statistics of what was produced, for the input's own BN backward)
+        if (p.gX && owner) {
+            for (int r = rg; r < trc; r += rows_per_pass) {
+                float acc[VOUT];
+#pragma unroll
+                for (int j = 0; j < VOUT; ++j) acc[j] = 0.f;
+                const float* trow = tile + r * Tp;
+                const float* w = Wsm + fq * VOUT;
+                if (VOUT == 4 && VEC == 4) {
+                    for (int c = 0; c < nT; c += 4) {
+                        const float4 x = *reinterpret_cast<const float4*>(trow + c);
+                        const float xs[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            const float4 wv = *reinterpret_cast<const float4*>(w + (c + u) * Fx);
+                            acc[0] = fmaf(xs[u], wv.x, acc[0]);
+                            acc[1 % VOUT] = fmaf(xs[u], wv.y, acc[1 % VOUT]);
+                            acc[2 % VOUT] = fmaf(xs[u], wv.z, acc[2 % VOUT]);
+                            acc[3 % VOUT] = fmaf(xs[u], wv.w, acc[3 % VOUT]);
+                        }
+                    }
+                } else {
+#pragma unroll 4
+                    for (int c = 0; c < nT; ++c) {
+                        const float x = trow[c];
+#pragma unroll
+                        for (int j = 0; j < VOUT; ++j) acc[j] = fmaf(x, w[c * Fx + j], acc[j]);
+                    }
+                }
+                if (p.acc_b) {
+#pragma unroll
+                    for (int j = 0; j < VOUT; ++j) {
+                        const int f = fq * VOUT + j;
+                        const float xh = (xt[r * Xp + f] - mu[f]) * rs[f];
+                        sg[j] += acc[j];
+                        sgx[j] = fmaf(acc[j], xh, sgx[j]);
+                    }
+                }
+                float* dst = p.gX + (size_t)(row0 + r) * Fx + fq * VOUT;
+                if (VOUT == 4) {
+                    float4 o = make_float4(acc[0], acc[1 % VOUT], acc[2 % VOUT], acc[3 % VOUT]);
+                    if (p.accumulate) {
+                        const float4 old = *reinterpret_cast<const float4*>(dst);
+                        o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
+                    }
+                    *reinterpret_cast<float4*>(dst) = o;
+                } else {
+                    dst[0] = p.accumulate ? dst[0] + acc[0] : acc[0];
+                }
+            }
+        }
+        // ---- dW[c][f] += sum_r T[r][c] * xnorm[r][f]  and (self) dbias[o] += sum_r gPre[r][o]
+        if (want_dw) {
+            for (int sidx = tid; sidx < NG * PS; sidx += ENG_THREADS) {
+                const int g = sidx / PS, q = sidx - g * PS;
+                const int c = q / NQ, g4 = q - c * NQ;
+                float acc[VOUT];
+#pragma unroll
+                for (int j = 0; j < VOUT; ++j) acc[j] = 0.f;
+                float scv[VOUT], shv[VOUT];
+#pragma unroll
+                for (int j = 0; j < VOUT; ++j) {
+                    scv[j] = x_aff ? sc[g4 * VOUT + j] : 1.f;
+                    shv[j] = x_aff ? sh[g4 * VOUT + j] : 0.f;
+                }
+                for (int r = g; r < trc; r += NG) {
+                    const float tv = tile[r * Tp + c];
+#pragma unroll
+                    for (int j = 0; j < VOUT; ++j)
+                        acc[j] = fmaf(tv, fmaf(xt[r * Xp + g4 * VOUT + j], scv[j], shv[j]), acc[j]);
+                }
+                float* d = dacc + (size_t)g * PD + c * Fx + g4 * VOUT;
+#pragma unroll
+                for (int j = 0; j < VOUT; ++j) d[j] += acc[j];
+            }
+            if (is_self) {
+                for (int sidx = tid; sidx < NG * Fg; sidx += ENG_THREADS) {
+                    const int g = sidx / Fg, o = sidx - g * Fg;
+                    float acc = 0.f;
+                    for (int r = g; r < trc; r += NG) acc += tile[r * Tp + nT + o];
+                    dacc[(size_t)g * PD + P + o] += acc;
+                }
+            }
+        }
+    }
+    // ---- flush the CTA's partial sums to the binned fp64 accumulators
+    __syncthreads();
+    if (want_dw) {
+        const int nbw = hgnn_ws_bins(Fg * a.Cin), nbb = hgnn_ws_bins(Fg);
+        for (int q = tid; q < PD; q += ENG_THREADS) {
+            float acc = 0.f;
+            for (int g = 0; g < NG; ++g) acc += dacc[(size_t)g * PD + q];
+            if (q < P) {
+                const int c = q / Fx, f = q - c * Fx;
+                const int t = c / Fg, o = c - t * Fg;
+                accum_add(a.dW_bins, Fg * a.Cin, nbw, o * a.Cin + p.col0 + t * Fx + f, (double)acc);
+            } else if (a.db_bins) {
+                accum_add(a.db_bins, Fg, nbb, q - P, (double)acc);
+            }
+        }
+    }
+    if (p.acc_b && p.gX) {
+        const int nb = hgnn_ws_bins(2 * Fx);
+        const bool tree = (32 % NQ) == 0 && (ENG_THREADS % NQ) == 0;
+#pragma unroll
+        for (int j = 0; j < VOUT; ++j) {
+            double x = 0.0, y = 0.0;
+            if (tree) {
+                x = cta_reduce_mod(owner ? (double)sg[j] : 0.0, NQ, dscratch);
+                y = cta_reduce_mod(owner ? (double)sgx[j] : 0.0, NQ, dscratch);
+            } else {
+                __syncthreads();
+                dscratch[tid] = owner ? (double)sg[j] : 0.0;
+                __syncthreads();
+                if (tid < NQ) for (int k = 0; k < rows_per_pass; ++k) x += dscratch[k * NQ + tid];
+                __syncthreads();
+                dscratch[tid] = owner ? (double)sgx[j] : 0.0;
+                __syncthreads();
+                if (tid < NQ) for (int k = 0; k < rows_per_pass; ++k) y += dscratch[k * NQ + tid];
+            }
+            if (tid < NQ) {
+                accum_add(p.acc_b, 2 * Fx, nb, tid * VOUT + j, x);
+                accum_add(p.acc_b, 2 * Fx, nb, Fx + tid * VOUT + j, y);
+            }
+        }
+    }
+}
+
+template <int VEC, int VS, int VC>
+__global__ void __launch_bounds__(ENG_THREADS, 4)
+bwd_kernel(const BwdArgs a) {
+    extern __shared__ __align__(16) float smem[];
+    __shared__ double dscratch[ENG_THREADS];
+    __shared__ double dtot[512];
+    __shared__ DeferList dl;
+    __shared__ float wpart[32];
+    __shared__ __align__(16) float coef[3 * 128];
+    const int Fg = a.Fg;
+    float* c0 = coef;
+    float* c1 = coef + 128;
+    float* c2 = coef + 256;
+    const bool has_bn = a.acc_b != nullptr;
+    if (has_bn) {
+        // coefficients of the BN backward of THIS side: gZ = c0 g + c1 + c2 z  (batch_normalization.py:65-77)
+        double* tf = dtot;            // (sum z, sum z^2)
+        double* tb = dtot + 2 * Fg;   // (sum g, sum g*xhat)
+        bins_total(a.acc_f, 2 * Fg, hgnn_ws_bins(2 * Fg), tf, dscratch);
+        bins_total(a.acc_b, 2 * Fg, hgnn_ws_bins(2 * Fg), tb, dscratch);
+        const double w = a.bn_w[0], n = (double)a.Rg;
+        for (int f = threadIdx.x; f < Fg; f += ENG_THREADS) {
+            const double m = tf[f] / n;
+            double var = tf[Fg + f] / n - m * m;
+            if (var < 0.0) var = 0.0;
+            const double sd = sqrt(var + ENG_BN_EPS);
+            const double k0 = w / sd;
+            const double k2 = -k0 * tb[Fg + f] / (n * sd);
+            c0[f] = (float)k0;
+            c2[f] = (float)k2;
+            c1[f] = (float)(-k0 * tb[f] / n - k2 * m);
+        }
+        __syncthreads();
+    }
+    const int ts = a.self.R > 0 ? a.self.tiles : 0;
+    // CTAs [0, ns) work on the self rows, the rest on the cross rows (both persistent over tiles)
+    const int ns = a.self.R > 0 ? (a.cross.R > 0 ? max(1, (int)(((long long)gridDim.x * ts) / (ts + a.cross.tiles))) : gridDim.x) : 0;
+    if ((int)blockIdx.x < ns) {
+        bwd_part<VEC, VS>(a, a.self, true, blockIdx.x, ns, smem, dscratch, dtot, &dl, wpart, c0, c1, c2, has_bn);
+    } else {
+        bwd_part<VEC, VC>(a, a.cross, false, blockIdx.x - ns, gridDim.x - ns, smem, dscratch, dtot, &dl, wpart,
+                          c0, c1, c2, has_bn);
+    }
+}
+
+}  // namespace eng
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+static inline bool eng_aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+static int eng_pad(int width, int vec) {
+    if (vec == 4) {
+        int p = (width + 3) & ~3;
+        if (((p >> 2) & 1) == 0) p += 4;
+        return p;
+    }
+    return width | 1;
+}
+
+// CTAs of `kernel` resident on the whole GPU with `smem` bytes of dynamic shared memory.  Cached per
+// (kernel address, smem); also raises the kernel's opt-in shared-memory limit when needed.  (All
+// instantiations of a kernel template share one function-pointer TYPE, so the cache must be keyed by
+// the pointer VALUE.)
+struct OccEntry { const void* fn; size_t smem; int occ; };
+static int eng_resident_impl(const void* fn, size_t smem, int threads) {
+    static OccEntry cache[64];
+    static int n_cache = 0;
+    static const void* attr_fn[32];
+    static size_t attr_smem[32];
+    static int n_attr = 0;
+    if (smem > 24 * 1024) {      // static + dynamic above 48 KB needs the opt-in; static is < 10 KB here
+        int i = 0;
+        for (; i < n_attr; ++i) if (attr_fn[i] == fn) break;
+        if (i == n_attr && n_attr < 32) { attr_fn[n_attr] = fn; attr_smem[n_attr] = 0; ++n_attr; }
+        if (i < 32 && smem > attr_smem[i]) {
+            cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            attr_smem[i] = smem;
+        }
+    }
+    for (int i = 0; i < n_cache; ++i)
+        if (cache[i].fn == fn && cache[i].smem == smem) return HGNN_SM_COUNT * cache[i].occ;
+    int occ = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, threads, smem) != cudaSuccess || occ < 1) {
+        cudaGetLastError();
+        occ = 1;
+    }
+    if (n_cache < 64) { cache[n_cache].fn = fn; cache[n_cache].smem = smem; cache[n_cache].occ = occ; ++n_cache; }
+    return HGNN_SM_COUNT * occ;
+}
+template <typename K>
+static int eng_resident(K kernel, size_t smem) {
+    return eng_resident_impl(reinterpret_cast<const void*>(kernel), smem, ENG_THREADS);
+}
+
+static eng::BnRef to_bnref(const hgnn_bn_ref_t* r) {
+    eng::BnRef o;
+    o.acc = r ? r->acc : nullptr;
+    o.affine = r ? r->affine : nullptr;
+    o.w = r ? r->weight : nullptr;
+    o.b = r ? r->bias : nullptr;
+    o.n = r ? r->n_rows : 0;
+    return o;
+}
+
+extern "C" int hgnn_lg_side_fwd(const hgnn_side_t* side, const hgnn_bn_ref_t* bn_self,
+                                const hgnn_bn_ref_t* bn_cross, const float* Wa, const float* ba, int Ha,
+                                const float* Wb, const float* bb, int Hb, int relu_from, float* Z,
+                                double* acc_out, hgnn_stream_t stream) {
+    HGNN_REQUIRE(side && Z, "null argument");
+    eng::FwdArgs a;
+    HGNN_REQUIRE(make_oplist(side->ops, side->n_ops, &a.ops) == 0 && side->n_ops >= 1, "bad operator list");
+    a.R = side->R;
+    a.Xs = side->Xs; a.Fs = side->Fs; a.bn_s = to_bnref(bn_self);
+    a.p_rowptr = side->p_rowptr; a.p_col = side->p_col; a.p_pm = side->p_pm; a.p_pd = side->p_pd;
+    a.Xc = side->Xc; a.Fc = side->p_rowptr ? side->Fc : 0; a.bn_c = to_bnref(bn_cross);
+    a.Wa = Wa; a.ba = ba; a.Ha = Ha; a.Wb = Wb; a.bb = bb; a.Hb = Hb;
+    a.relu_from = relu_from; a.Z = Z; a.acc_out = acc_out;
+    HGNN_REQUIRE(a.R >= 0 && a.Fs >= 1 && a.Xs, "bad self features");
+    HGNN_REQUIRE(!side->p_rowptr || (side->Fc >= 1 && side->Xc && side->p_col && side->p_pm && side->p_pd), "bad cross part");
+    HGNN_REQUIRE(Ha >= 0 && Hb >= 0 && Ha + Hb >= 1 && Ha + Hb <= 128, "output width must be in [1, 128]");
+    HGNN_REQUIRE(a.Fs <= 128 && a.Fc <= 128, "input widths must be <= 128");
+    HGNN_REQUIRE((Ha == 0 || Wa) && (Hb == 0 || Wb), "null weights");
+    HGNN_REQUIRE(!(a.bn_s.acc) || (a.bn_s.w && a.bn_s.b && a.bn_s.n > 0), "bad self bn reference");
+    HGNN_REQUIRE(!(a.bn_c.acc) || (a.bn_c.w && a.bn_c.b && a.bn_c.n > 0), "bad cross bn reference");
+    if (a.R == 0) return HGNN_OK;
+    a.Fout = Ha + Hb;
+    a.Cin = side->n_ops * a.Fs + 2 * a.Fc;
+    const bool vec4 = (a.Fs % 4 == 0) && (a.Fc % 4 == 0) && eng_aligned16(a.Xs) && (a.Fc == 0 || eng_aligned16(a.Xc));
+    const bool vout4 = vec4 && (a.Fout % 4 == 0) && eng_aligned16(Z);
+    a.Cin_pad = eng_pad(a.Cin, vec4 ? 4 : 1);
+    const int rows_per_pass = ENG_THREADS / (vout4 ? a.Fout / 4 : a.Fout);
+    const int items_per_row = (a.Fs + a.Fc) / (vec4 ? 4 : 1);
+    int TR = min(rows_per_pass, max(32, ENG_THREADS / max(1, items_per_row)));
+    size_t fixed = ((size_t)a.Cin * a.Fout + ((a.Fout + 3) & ~3) + 2 * ((a.Fs + 3) & ~3) + 2 * ((a.Fc + 3) & ~3)) * sizeof(float);
+    while (TR > 1 && fixed + (size_t)TR * a.Cin_pad * sizeof(float) > ENG_MAX_SMEM) TR >>= 1;
+    size_t smem = fixed + (size_t)TR * a.Cin_pad * sizeof(float);
+    if (smem > ENG_MAX_SMEM) {
+        hgnn_set_error("hgnn_lg_side_fwd: Cin=%d x Fout=%d does not fit shared memory", a.Cin, a.Fout);
+        return HGNN_ERR_ARG;
+    }
+    a.TR = TR;
+    const int ntiles = ceil_div(a.R, TR);
+    cudaStream_t s = to_stream(stream);
+    if (vec4 && vout4) {
+        int grid = balanced_grid(ntiles, eng_resident(eng::fwd_kernel<4, 4>, smem));
+        eng::fwd_kernel<4, 4><<<grid, ENG_THREADS, smem, s>>>(a);
+    } else if (vec4) {
+        int grid = balanced_grid(ntiles, eng_resident(eng::fwd_kernel<4, 1>, smem));
+        eng::fwd_kernel<4, 1><<<grid, ENG_THREADS, smem, s>>>(a);
+    } else {
+        int grid = balanced_grid(ntiles, eng_resident(eng::fwd_kernel<1, 1>, smem));
+        eng::fwd_kernel<1, 1><<<grid, ENG_THREADS, smem, s>>>(a);
+    }
+    return hgnn_check_launch("hgnn_lg_side_fwd");
+}
+
+// fill the derived fields of one backward part; returns false if it does not fit shared memory
+static bool eng_plan_part(eng::BwdPart& p, int Fg, bool vec4, bool& vout4, bool is_self) {
+    p.nT = p.ops.n * Fg;
+    p.P = p.nT * p.Fx;
+    vout4 = vec4 && (p.Fx % 4 == 0) && eng_aligned16(p.X) && (!p.gX || eng_aligned16(p.gX));
+    const int slots = p.nT * (vout4 ? p.Fx / 4 : p.Fx);
+    p.NG = slots >= ENG_THREADS ? 1 : ENG_THREADS / slots;
+    const int tw = is_self ? p.nT + Fg : p.nT;
+    p.Tp = eng_pad(tw, vec4 ? 4 : 1);
+    p.Xp = vout4 ? eng_pad(p.Fx, 4) : (p.Fx | 1);
+    const int rows_per_pass = ENG_THREADS / (vout4 ? p.Fx / 4 : p.Fx);
+    int TR = min(rows_per_pass, max(32, ENG_THREADS / max(1, Fg / (vec4 ? 4 : 1))));
+    const int PD = is_self ? p.P + Fg : p.P;
+    auto smem_for = [&](int tr) {
+        return ((size_t)((p.nT * p.Fx + 3) & ~3) + 4 * (size_t)((p.Fx + 3) & ~3) + (size_t)tr * p.Tp +
+                (size_t)((tr * p.Xp + 3) & ~3) + (size_t)p.NG * PD) * sizeof(float);
+    };
+    while (TR > 1 && smem_for(TR) > ENG_MAX_SMEM) TR >>= 1;
+    p.TR = TR;
+    p.smem = smem_for(TR);
+    p.tiles = ceil_div(p.R, TR);
+    return p.smem <= ENG_MAX_SMEM;
+}
+
+extern "C" int hgnn_lg_side_bwd(const hgnn_side_bwd_t* d, hgnn_stream_t stream) {
+    HGNN_REQUIRE(d && d->gY && d->Fg >= 1 && d->Fg <= 128, "bad argument");
+    HGNN_REQUIRE(d->Ha >= 0 && d->Hb >= 0 && d->Ha + d->Hb == d->Fg, "Ha + Hb must equal the width of gY");
+    HGNN_REQUIRE((d->Ha == 0 || d->Wa) && (d->Hb == 0 || d->Wb), "null weights");
+    HGNN_REQUIRE(!d->acc_b || (d->acc_f && d->bn_weight && d->Z), "batch-norm backward needs acc_f, bn_weight and Z");
+    HGNN_REQUIRE(d->relu_from >= d->Fg || d->Z, "ReLU backward needs Z");
+    eng::BwdArgs a;
+    a.gY = d->gY; a.Z = d->Z; a.Fg = d->Fg; a.relu_from = d->relu_from; a.Rg = d->Rg;
+    a.acc_f = d->acc_f; a.acc_b = d->acc_b; a.bn_w = d->bn_weight;
+    a.Wa = d->Wa; a.Ha = d->Ha; a.Wb = d->Wb; a.Hb = d->Hb; a.Cin = d->Cin;
+    a.dW_bins = d->dW_bins; a.db_bins = d->db_bins;
+    const bool vec4 = (d->Fg % 4 == 0) && eng_aligned16(d->gY) && (!d->Z || eng_aligned16(d->Z));
+    // self part
+    a.self.R = d->R_self;
+    bool vs4 = false, vc4 = false;
+    if (d->R_self > 0) {
+        HGNN_REQUIRE(d->ops_T && make_oplist(d->ops_T, d->n_ops, &a.self.ops) == 0 && d->n_ops >= 1, "bad operator list");
+        HGNN_REQUIRE(d->Xs && d->Fs >= 1 && d->Fs <= 128, "bad self input");
+        a.self.X = d->Xs; a.self.Fx = d->Fs; a.self.bn = to_bnref(&d->bn_self);
+        a.self.gX = d->gXs; a.self.accumulate = d->accumulate_self; a.self.acc_b = d->acc_b_self;
+        a.self.col0 = 0;
+        if (!eng_plan_part(a.self, d->Fg, vec4, vs4, true)) {
+            hgnn_set_error("hgnn_lg_side_bwd: self block %d x %d does not fit shared memory", a.self.nT, d->Fs);
+            return HGNN_ERR_ARG;
+        }
+    } else {
+        a.self.tiles = 0; a.self.smem = 0; a.self.ops.n = 0;
+    }
+    a.cross.R = d->R_cross;
+    if (d->R_cross > 0) {
+        HGNN_REQUIRE(d->pt_rowptr && d->pt_col && d->pt_pm && d->pt_pd && d->Xc && d->Fc >= 1 && d->Fc <= 128, "bad cross input");
+        hgnn_op_t cops[2];
+        for (int i = 0; i < 2; ++i) {
+            cops[i].kind = HGNN_OP_CSR; cops[i].diag = nullptr;
+            cops[i].rowptr = d->pt_rowptr; cops[i].col = d->pt_col;
+            cops[i].val = i == 0 ? d->pt_pm : d->pt_pd;
+        }
+        make_oplist(cops, 2, &a.cross.ops);
+        a.cross.X = d->Xc; a.cross.Fx = d->Fc; a.cross.bn = to_bnref(&d->bn_cross);
+        a.cross.gX = d->gXc; a.cross.accumulate = d->accumulate_cross; a.cross.acc_b = d->acc_b_cross;
+        a.cross.col0 = d->n_ops * d->Fs;
+        if (!eng_plan_part(a.cross, d->Fg, vec4, vc4, false)) {
+            hgnn_set_error("hgnn_lg_side_bwd: cross block %d x %d does not fit shared memory", a.cross.nT, d->Fc);
+            return HGNN_ERR_ARG;
+        }
+    } else {
+        a.cross.tiles = 0; a.cross.smem = 0; a.cross.ops.n = 0;
+    }
+    const int total_tiles = a.self.tiles + a.cross.tiles;
+    if (total_tiles == 0) return HGNN_OK;
+    const size_t smem = a.self.smem > a.cross.smem ? a.self.smem : a.cross.smem;
+    cudaStream_t s = to_stream(stream);
+#define ENG_LAUNCH(VEC, VS, VC)                                                                   \
+    {                                                                                             \
+        int grid = balanced_grid(total_tiles, eng_resident(eng::bwd_kernel<VEC, VS, VC>, smem));  \
+        if (a.self.tiles > 0 && a.cross.tiles > 0 && grid < 2) grid = 2;                          \
+        eng::bwd_kernel<VEC, VS, VC><<<grid, ENG_THREADS, smem, s>>>(a);                          \
+    }
+    if (vec4) {
+        if (vs4 && vc4) ENG_LAUNCH(4, 4, 4)
+        else if (vs4) ENG_LAUNCH(4, 4, 1)
+        else if (vc4) ENG_LAUNCH(4, 1, 4)
+        else ENG_LAUNCH(4, 1, 1)
+    } else {
+        ENG_LAUNCH(1, 1, 1)
+    }
+#undef ENG_LAUNCH
+    return hgnn_check_launch("hgnn_lg_side_bwd");
+}
+
+// ---------------------------------------------------------------------------------------------
+// step-end reductions
+// ---------------------------------------------------------------------------------------------
+// out[i] = sum_{b < nb[i]} sum_{c < cnt[i]} arena[off[i] + b*stride[i] + c]
+__global__ void bins_reduce_kernel(const double* __restrict__ arena, const long long* __restrict__ off,
+                                   const int* __restrict__ nb, const int* __restrict__ stride,
+                                   const int* __restrict__ cnt, int n, float* __restrict__ out) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const double* p = arena + off[i];
+        const int s = stride[i], k = cnt[i], B = nb[i];
+        double t = 0.0;
+        for (int b = 0; b < B; ++b)
+            for (int c = 0; c < k; ++c) t += p[(size_t)b * s + c];
+        out[i] = (float)t;
+    }
+}
+
+extern "C" int hgnn_bins_reduce(const double* arena, const long long* off, const int* nb, const int* stride,
+                                const int* cnt, int n, float* out, hgnn_stream_t stream) {
+    HGNN_REQUIRE(arena && off && nb && stride && cnt && out && n >= 0, "bad argument");
+    if (n == 0) return HGNN_OK;
+    bins_reduce_kernel<<<min(ceil_div(n, 128), HGNN_MAX_GRID), 128, 0, to_stream(stream)>>>(arena, off, nb, stride, cnt, n, out);
+    return hgnn_check_launch("hgnn_bins_reduce");
+}
+
+// running statistics of every BN of the model in one launch: BN k has width F[k], accumulators at
+// arena + acc_off[k] (binned (sum z, sum z^2)), n_rows[k] rows, and running [mean(F) | std(F)] at
+// running + run_off[k]:  r = (1-momentum)*batch + momentum*r   (batch_normalization.py:37-38)
+__global__ void bn_running_kernel(const double* __restrict__ arena, const long long* __restrict__ acc_off,
+                                  const int* __restrict__ F, const int* __restrict__ n_rows,
+                                  const long long* __restrict__ run_off, int n_bn, float momentum,
+                                  float* __restrict__ running) {
+    const int k = blockIdx.x;
+    if (k >= n_bn) return;
+    const int Fk = F[k], nb = hgnn_ws_bins(2 * Fk);
+    const double* acc = arena + acc_off[k];
+    float* rm = running + run_off[k];
+    float* rs = rm + Fk;
+    for (int f = threadIdx.x; f < Fk; f += blockDim.x) {
+        double a = 0.0, b = 0.0;
+        for (int bin = 0; bin < nb; ++bin) {
+            a += acc[(size_t)bin * 2 * Fk + f];
+            b += acc[(size_t)bin * 2 * Fk + Fk + f];
+        }
+        const double n = (double)n_rows[k];
+        const double m = a / n;
+        double var = b / n - m * m;
+        if (var < 0.0) var = 0.0;
+        const double sd = sqrt(var + ENG_BN_EPS);
+        rm[f] = (1.f - momentum) * (float)m + momentum * rm[f];
+        rs[f] = (1.f - momentum) * (float)sd + momentum * rs[f];
+    }
+}
+
+extern "C" int hgnn_bn_running_update(const double* arena, const long long* acc_off, const int* F,
+                                      const int* n_rows, const long long* run_off, int n_bn,
+                                      float momentum, float* running, hgnn_stream_t stream) {
+    HGNN_REQUIRE(arena && acc_off && F && n_rows && run_off && running && n_bn >= 0, "bad argument");
+    if (n_bn == 0) return HGNN_OK;
+    bn_running_kernel<<<n_bn, 64, 0, to_stream(stream)>>>(arena, acc_off, F, n_rows, run_off, n_bn, momentum, running);
+    return hgnn_check_launch("hgnn_bn_running_update");
+}
+
+// readout backward prologue (layers_mnb.py:92,:386): G[r, o] = g[graph(r), o], and the bias gradient
+// of the padded slots, sum_b pad_count[b] * g[b, o], goes straight into the dbias accumulators.
+__global__ void readout_bwd_prep_kernel(const float* __restrict__ g, int bs, int F, const int* __restrict__ off,
+                                        const float* __restrict__ pad_count, float* __restrict__ G,
+                                        double* db_bins) {
+    const int b = blockIdx.y;
+    const int r0 = off[b];
+    const long long n = (long long)(off[b + 1] - r0) * F;
+    float* dst = G + (size_t)r0 * F;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+        dst[i] = g[(size_t)b * F + (int)(i % F)];
+    if (db_bins && pad_count && blockIdx.x == 0 && (int)threadIdx.x < F)
+        atomicAdd(db_bins + threadIdx.x, (double)pad_count[b] * (double)g[(size_t)b * F + threadIdx.x]);
+}
+
+extern "C" int hgnn_readout_bwd_prep(const float* g, int bs, int F, const int* off, const float* pad_count,
+                                     float* G, double* db_bins, hgnn_stream_t stream) {
+    HGNN_REQUIRE(g && off && G && bs >= 0 && F >= 1 && F <= 256, "bad argument");
+    if (bs == 0) return HGNN_OK;
+    HGNN_REQUIRE(bs <= 65535, "bs > 65535");
+    dim3 grid(16, bs);
+    readout_bwd_prep_kernel<<<grid, 256, 0, to_stream(stream)>>>(g, bs, F, off, pad_count, G, db_bins);
+    return hgnn_check_launch("hgnn_readout_bwd_prep");
+}

@@ -388,29 +388,39 @@ static int pad_stride(int width, int vec) {
     return width | 1;
 }
 
-// CTAs of `kernel` that fit on the whole GPU at once with `smem` bytes of dynamic shared memory
-// (occupancy cached per kernel instantiation and smem size; opts in to > 48 KB when needed).
+// CTAs of `kernel` resident on the whole GPU with `smem` bytes of dynamic shared memory.  Cached per
+// (kernel address, smem); also raises the kernel's opt-in shared-memory limit when needed.  (All
+// instantiations of a kernel template share one function-pointer TYPE, so the cache must be keyed by
+// the pointer VALUE.)
+struct SideOccEntry { const void* fn; size_t smem; int occ; };
+static int side_resident_impl(const void* fn, size_t smem, int threads) {
+    static SideOccEntry cache[64];
+    static int n_cache = 0;
+    static const void* attr_fn[32];
+    static size_t attr_smem[32];
+    static int n_attr = 0;
+    if (smem > 24 * 1024) {      // static + dynamic above 48 KB needs the opt-in; static is < 10 KB here
+        int i = 0;
+        for (; i < n_attr; ++i) if (attr_fn[i] == fn) break;
+        if (i == n_attr && n_attr < 32) { attr_fn[n_attr] = fn; attr_smem[n_attr] = 0; ++n_attr; }
+        if (i < 32 && smem > attr_smem[i]) {
+            cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            attr_smem[i] = smem;
+        }
+    }
+    for (int i = 0; i < n_cache; ++i)
+        if (cache[i].fn == fn && cache[i].smem == smem) return HGNN_SM_COUNT * cache[i].occ;
+    int occ = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, threads, smem) != cudaSuccess || occ < 1) {
+        cudaGetLastError();
+        occ = 1;
+    }
+    if (n_cache < 64) { cache[n_cache].fn = fn; cache[n_cache].smem = smem; cache[n_cache].occ = occ; ++n_cache; }
+    return HGNN_SM_COUNT * occ;
+}
 template <typename K>
 static int resident_ctas(K kernel, size_t smem) {
-    static size_t seen_smem[16];
-    static int seen_occ[16];
-    static int n_seen = 0;
-    static size_t attr_smem = 48 * 1024;     // the opt-in limit only ever grows
-    if (smem > attr_smem) {
-        cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        attr_smem = smem;
-    }
-    for (int i = 0; i < n_seen; ++i)
-        if (seen_smem[i] == smem) return HGNN_SM_COUNT * seen_occ[i];
-    int occ = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, SIDE_THREADS, smem) != cudaSuccess || occ < 1)
-        occ = 1;
-    if (n_seen < 16) {
-        seen_smem[n_seen] = smem;
-        seen_occ[n_seen] = occ;
-        ++n_seen;
-    }
-    return HGNN_SM_COUNT * occ;
+    return side_resident_impl(reinterpret_cast<const void*>(kernel), smem, SIDE_THREADS);
 }
 
 extern "C" int hgnn_side_fwd(const hgnn_side_t* side, const float* Wa, const float* ba, int Ha,

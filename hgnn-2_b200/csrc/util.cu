@@ -39,6 +39,8 @@ extern "C" long long hgnn_workspace_bytes(int width) {
     return HGNN_WS_HEADER + (long long)hgnn_ws_bins(w) * w * 8;
 }
 
+extern "C" int hgnn_bins_for(int width) { return hgnn_ws_bins(width < 1 ? 1 : width); }
+
 // ---------------------------------------------------------------------------------------------
 // layout: (bs, F, Nmax) channel-major padded <-> packed (R, F)
 // One CTA per (graph, 32-node tile); transposes through shared memory so both sides coalesce.

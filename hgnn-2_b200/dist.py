@@ -44,8 +44,31 @@ class FlatParams(object):
         for p in self.params:
             p.grad = None
 
+    def _adopt_flat_grad(self):
+        """The model-level engine returns every .grad as a view of ONE flat buffer laid out in
+        parameter order: use it as is (no copy).  Returns False for any other layout."""
+        g0 = self.params[0].grad
+        if g0 is None or g0.dtype != torch.float32 or g0.storage_offset() != 0:
+            return False
+        store = g0.untyped_storage()
+        if store.nbytes() < 4 * self.n:
+            return False
+        root = store.data_ptr()
+        off = 0
+        for p in self.params:
+            g = p.grad
+            if (g is None or g.untyped_storage().data_ptr() != root or g.storage_offset() != off
+                    or not g.is_contiguous()):
+                return False
+            off += p.numel()
+        base = torch.as_strided(g0, (self.n,), (1,), 0)
+        self.grad = base
+        return True
+
     def gather_grad(self):
         """Concatenate the per-parameter gradients into the flat buffer (one or two launches)."""
+        if self._adopt_flat_grad():
+            return
         parts = [p.grad.reshape(-1) if p.grad is not None else torch.zeros(p.numel(), device=self.flat.device)
                  for p in self.params]
         torch.cat(parts, out=self.grad)

@@ -1,0 +1,388 @@
+"""Model-level training engine for ``GNN_simple`` / ``GNN_lg`` (csrc/engine.cu).
+
+``models.gnns.model_mnb`` keeps the reference's classes and signatures; their ``forward`` hands the
+whole layer stack to ``run_model`` below, which executes it as ONE ``torch.autograd.Function``:
+
+* forward: one fused launch per layer side (``hgnn_lg_side_fwd``).  Activations stay RAW
+  (pre-batch-norm) in HBM; each consumer normalises its inputs on load from the producer's fp64
+  (sum z, sum z^2) accumulators, so there is no BN-apply pass and no finalisation tail;
+* backward: one launch per layer side (``hgnn_lg_side_bwd``) - BN + ReLU backward on the fly while
+  gathering through the transposed operators, both input gradients, dW / dbias and the BN sums of
+  the produced gradients.  Input gradients accumulate in place (no torch ``add`` kernels);
+* step end: ``hgnn_bins_reduce`` converts every binned fp64 accumulator of the step into one flat
+  fp32 gradient buffer in ``model.parameters()`` order (the per-parameter ``.grad`` tensors are views
+  of it, which ``dist.FlatParams`` recognises), ``hgnn_bn_running_update`` applies the
+  running-statistics rule for all BN instances at once.
+
+Semantics = the reference's layer stack (models/gnns/model_mnb.py:58-66,124-129 over
+models/layers/layers_mnb.py); the layer-level modules keep their own (per-module) kernels for the
+reference's layer API.
+"""
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import BnRefT, SideBwdT, SideT, call, fptr, iptr, make_ops, stream
+
+
+def _bins(width):
+    return int(_lib.lib.hgnn_bins_for(int(width)))
+
+
+class _Side(object):
+    """One fused side update: out = BN(cat(cv_a(x1), relu(cv_b(x1)))), x1 = [ops(self) | Pm/Pd(cross)]."""
+    __slots__ = ("name", "kind", "src_self", "src_cross", "out", "conv_a", "conv_b", "bn", "relu_from",
+                 "Fs", "Fc", "Fout", "Cin", "dW_off", "db_off")
+
+
+class _Plan(object):
+    """Static execution plan of a model: sides in forward order, tensor table, arena layout and the
+    accumulator -> flat-gradient table."""
+
+    def __init__(self, model):
+        lg = bool(getattr(model, "dual", False))
+        order = getattr(model, "order", 0) if lg else 0
+        K = model.J + 2
+        h = model.n_features
+        self.lg, self.order, self.K = lg, order, K
+        layers = [model.layer0] + [model._modules["layer{}".format(i + 1)] for i in range(model.n_layers - 2)]
+        self.sides = []
+        self.tensors = {"X": dict(F=model.featuremap_in[0], rows="n", bn=None)}
+        if lg:
+            self.tensors["XL"] = dict(F=1, rows="m", bn=None)
+        cur_n, cur_e = "X", "XL"
+
+        def add(name, kind, src_self, src_cross, out, conv_a, conv_b, bn, relu_from, rows):
+            s = _Side()
+            s.name, s.kind, s.src_self, s.src_cross, s.out = name, kind, src_self, src_cross, out
+            s.conv_a, s.conv_b, s.bn, s.relu_from = conv_a, conv_b, bn, relu_from
+            s.Fs = self.tensors[src_self]["F"]
+            s.Fc = self.tensors[src_cross]["F"] if src_cross else 0
+            s.Fout = conv_a.weight.shape[0] + (conv_b.weight.shape[0] if conv_b is not None else 0)
+            s.Cin = K * s.Fs + 2 * s.Fc
+            assert conv_a.weight.shape[1] == s.Cin, (name, conv_a.weight.shape, s.Cin)
+            if out is not None:
+                self.tensors[out] = dict(F=s.Fout, rows=rows, bn=bn)
+            self.sides.append(s)
+
+        for li, layer in enumerate(layers):
+            n_out, e_out = "N%d" % li, "E%d" % li
+            if not lg:
+                add("L%d.node" % li, "node", cur_n, None, n_out, layer.cv2, layer.cv1, layer.bn1, 0, "n")
+                cur_n = n_out
+                continue
+            node = lambda cross: add("L%d.node" % li, "node", cur_n, cross, n_out, layer.cv2, layer.cv1,  # noqa: E731
+                                     layer.bn1, h, "n")
+            edge = lambda cross: add("L%d.edge" % li, "edge", cur_e, cross, e_out, layer.cv4, layer.cv3,  # noqa: E731
+                                     layer.bn2, h, "m")
+            if order == 1:
+                node(cur_e)
+                edge(n_out)
+            elif order == 2:
+                edge(cur_n)
+                node(e_out)
+            else:
+                node(cur_e)
+                edge(cur_n)
+            cur_n, cur_e = n_out, e_out
+        fc = model.layerlast.fc
+        add("readout", "node", cur_n, cur_e if lg else None, None, fc, None, None, fc.weight.shape[0], "n")
+
+        # ---- arena layout (fp64): per BN'd tensor acc_f | acc_b ; per side dW | db
+        off = 0
+        for name, t in self.tensors.items():
+            if t["bn"] is not None:
+                w = 2 * t["F"]
+                t["acc_f"], t["acc_b"] = off, off + _bins(w) * w
+                off += 2 * _bins(w) * w
+        for s in self.sides:
+            s.dW_off = off
+            off += _bins(s.Fout * s.Cin) * s.Fout * s.Cin
+            s.db_off = off
+            off += _bins(s.Fout) * s.Fout
+        self.arena_size = off
+
+        # ---- accumulator -> flat gradient table, in model.parameters() order
+        loc = {}
+        for s in self.sides:
+            Ha = s.conv_a.weight.shape[0]
+            wn, bnn = s.Fout * s.Cin, s.Fout
+            for conv, o0 in ((s.conv_a, 0), (s.conv_b, Ha)):
+                if conv is None:
+                    continue
+                n = conv.weight.numel()
+                loc[id(conv.weight)] = (s.dW_off + o0 * s.Cin + np.arange(n), _bins(wn), wn, 1)
+                loc[id(conv.bias)] = (s.db_off + o0 + np.arange(conv.bias.numel()), _bins(bnn), bnn, 1)
+        for name, t in self.tensors.items():
+            if t["bn"] is not None:
+                F = t["F"]
+                loc[id(t["bn"].weight)] = (np.array([t["acc_b"] + F]), _bins(2 * F), 2 * F, F)
+                loc[id(t["bn"].bias)] = (np.array([t["acc_b"]]), _bins(2 * F), 2 * F, F)
+        offs, nbs, strides, cnts = [], [], [], []
+        self.params = list(model.parameters())
+        self.param_slices = []
+        pos = 0
+        for p in self.params:
+            n = p.numel()
+            self.param_slices.append((pos, n, tuple(p.shape)))
+            pos += n
+            if id(p) in loc:
+                o, nb, st, cnt = loc[id(p)]
+                offs.append(o.astype(np.int64))
+                nbs.append(np.full(n, nb, np.int32))
+                strides.append(np.full(n, st, np.int32))
+                cnts.append(np.full(n, cnt, np.int32))
+            else:     # parameter off the hot path (GRUUpdate): zero gradient
+                offs.append(np.zeros(n, np.int64))
+                nbs.append(np.zeros(n, np.int32))
+                strides.append(np.zeros(n, np.int32))
+                cnts.append(np.zeros(n, np.int32))
+        self.n_flat = pos
+        self.table_host = (np.concatenate(offs), np.concatenate(nbs), np.concatenate(strides), np.concatenate(cnts))
+        self.bn_list = [t for t in self.tensors.values() if t["bn"] is not None]
+        self._device_tables = {}
+        self._running = None
+
+    # ---- per-device tables ---------------------------------------------------------------------
+    def tables(self, device):
+        key = str(device)
+        if key not in self._device_tables:
+            o, nb, st, cnt = self.table_host
+            self._device_tables[key] = (torch.from_numpy(o).to(device), torch.from_numpy(nb).to(device),
+                                        torch.from_numpy(st).to(device), torch.from_numpy(cnt).to(device))
+        return self._device_tables[key]
+
+    def running_flat(self, device):
+        """All running_mean / running_std buffers as views of one flat buffer (re-homed lazily, and
+        again whenever the module was moved and its buffers were replaced)."""
+        first = self.bn_list[0]["bn"] if self.bn_list else None
+        if first is None:
+            return None, None
+        r = self._running
+        if r is not None and r[0].device == device and first.running_mean.data_ptr() == r[0].data_ptr():
+            return r
+        total = sum(2 * t["F"] for t in self.bn_list)
+        flat = torch.zeros(total, device=device)
+        run_off, acc_off, Fs = [], [], []
+        pos = 0
+        for t in self.bn_list:
+            bn, F = t["bn"], t["F"]
+            flat[pos:pos + F].copy_(bn.running_mean.to(device))
+            flat[pos + F:pos + 2 * F].copy_(bn.running_std.to(device))
+            bn.running_mean = flat[pos:pos + F]
+            bn.running_std = flat[pos + F:pos + 2 * F]
+            run_off.append(pos)
+            acc_off.append(t["acc_f"])
+            Fs.append(F)
+            pos += 2 * F
+        tabs = (torch.tensor(acc_off, dtype=torch.int64, device=device),
+                torch.tensor(Fs, dtype=torch.int32, device=device),
+                torch.tensor(run_off, dtype=torch.int64, device=device))
+        self._running = (flat, tabs)
+        return self._running
+
+
+def get_plan(model):
+    plan = model.__dict__.get("_engine_plan")
+    if plan is None or [id(p) for p in plan.params] != [id(p) for p in model.parameters()]:
+        plan = _Plan(model)
+        model.__dict__["_engine_plan"] = plan
+    return plan
+
+
+def _rows_table(pack, plan, device):
+    cache = pack.__dict__.setdefault("_engine_rows", {})
+    key = id(plan)
+    if key not in cache:
+        rows = [pack.Rn if t["rows"] == "n" else pack.Rm for t in plan.bn_list]
+        cache[key] = torch.tensor(rows, dtype=torch.int32, device=device)
+    return cache[key]
+
+
+def _side_struct(pack, side, Xs, Xc):
+    node = side.kind == "node"
+    descs = pack.node_ops() if node else pack.edge_ops()
+    ops, n = make_ops(descs)
+    s = SideT()
+    s.R, s.ops, s.n_ops = (pack.Rn if node else pack.Rm), ops, n
+    s.Xs, s.Fs = fptr(Xs), Xs.shape[1]
+    if Xc is not None:
+        p = pack.p if node else pack.pt
+        s.p_rowptr, s.p_col, s.p_pm, s.p_pd = iptr(p.rowptr), iptr(p.col), fptr(p.val), fptr(p.val2)
+        s.Xc, s.Fc = fptr(Xc), Xc.shape[1]
+    else:
+        s.p_rowptr = s.p_col = s.p_pm = s.p_pd = s.Xc = None
+        s.Fc = 0
+    return s, ops
+
+
+def _bn_ref(plan, tname, arena, rows, affine=None):
+    t = plan.tensors[tname]
+    r = BnRefT()
+    if t["bn"] is None:
+        r.acc = r.affine = r.weight = r.bias = None
+        r.n_rows = 0
+        return r
+    r.weight, r.bias, r.n_rows = fptr(t["bn"].weight), fptr(t["bn"].bias), rows
+    if affine is not None:
+        r.acc, r.affine = None, affine[tname].data_ptr()
+    else:
+        r.acc, r.affine = arena.data_ptr() + 8 * t["acc_f"], None
+    return r
+
+
+def _rows_of(pack, plan, tname):
+    return pack.Rn if plan.tensors[tname]["rows"] == "n" else pack.Rm
+
+
+def _forward(plan, pack, Xp, XLp, training, arena):
+    """Runs every side; returns (dict of raw tensors, model output)."""
+    dev = Xp.device
+    vals = {"X": Xp, "XL": XLp}
+    affine = None
+    if not training:      # eval: normalise with the running statistics (batch_normalization.py:39-41)
+        affine = {}
+        for name, t in plan.tensors.items():
+            if t["bn"] is not None:
+                bn, F = t["bn"], t["F"]
+                st = torch.empty(4 * F, device=dev)
+                call("hgnn_bn_stats_eval", F, fptr(bn.weight), fptr(bn.bias), fptr(bn.running_mean),
+                     fptr(bn.running_std), fptr(st), stream())
+                affine[name] = st[2 * F:]
+    out = None
+    for s in plan.sides:
+        Xs = vals[s.src_self]
+        Xc = vals[s.src_cross] if s.src_cross else None
+        st, keep = _side_struct(pack, s, Xs, Xc)
+        bs_ = _bn_ref(plan, s.src_self, arena, _rows_of(pack, plan, s.src_self), affine)
+        bc_ = _bn_ref(plan, s.src_cross, arena, _rows_of(pack, plan, s.src_cross), affine) if s.src_cross else None
+        Ha = s.conv_a.weight.shape[0]
+        Hb = s.conv_b.weight.shape[0] if s.conv_b is not None else 0
+        Z = torch.empty(st.R, s.Fout, device=dev)
+        acc_out = None
+        if s.out is not None and training:
+            acc_out = arena.data_ptr() + 8 * plan.tensors[s.out]["acc_f"]
+        call("hgnn_lg_side_fwd", ctypes.byref(st), ctypes.byref(bs_), ctypes.byref(bc_) if bc_ is not None else None,
+             fptr(s.conv_a.weight), fptr(s.conv_a.bias), Ha,
+             fptr(s.conv_b.weight) if Hb else None, fptr(s.conv_b.bias) if Hb else None, Hb,
+             s.relu_from, fptr(Z), acc_out, stream())
+        if s.out is not None:
+            vals[s.out] = Z
+        else:     # readout: sum over all Nmax slots, padded slots add fc.bias (layers_mnb.py:92,:386)
+            out = torch.empty(pack.bs, s.Fout, device=dev)
+            call("hgnn_segment_sum", fptr(Z), pack.bs, s.Fout, iptr(pack.node_off), fptr(pack.pad_n),
+                 fptr(s.conv_a.bias), fptr(out), stream())
+    return vals, out
+
+
+class _ModelFunction(torch.autograd.Function):
+
+    @staticmethod
+    def forward(ctx, model, pack, Xp, XLp, *params):
+        plan = get_plan(model)
+        dev = Xp.device
+        arena = torch.zeros(max(plan.arena_size, 1), dtype=torch.float64, device=dev)
+        vals, out = _forward(plan, pack, Xp, XLp, True, arena)
+        run = plan.running_flat(dev)
+        if run[0] is not None:
+            flat, (acc_off, Fs, run_off) = run
+            mom = float(plan.bn_list[0]["bn"].momentum)
+            call("hgnn_bn_running_update", arena.data_ptr(), acc_off.data_ptr(), iptr(Fs),
+                 iptr(_rows_table(pack, plan, dev)), run_off.data_ptr(), len(plan.bn_list), mom, fptr(flat), stream())
+        ctx.plan, ctx.pack, ctx.vals, ctx.arena = plan, pack, vals, arena
+        ctx.need_x = Xp.requires_grad
+        return out
+
+    @staticmethod
+    def backward(ctx, g_out):
+        plan, pack, vals, arena = ctx.plan, ctx.pack, ctx.vals, ctx.arena
+        dev = g_out.device
+        g_out = g_out.contiguous().float()
+        grads, started = {}, set()
+        base = arena.data_ptr()
+
+        def grad_buf(name):
+            if name not in grads:
+                grads[name] = torch.empty_like(vals[name])
+            return grads[name]
+
+        for s in reversed(plan.sides):
+            node = s.kind == "node"
+            d = SideBwdT()
+            Ha = s.conv_a.weight.shape[0]
+            Hb = s.conv_b.weight.shape[0] if s.conv_b is not None else 0
+            if s.out is None:       # readout: gPre = g_out broadcast over the rows of each graph
+                G = torch.empty(pack.Rn, s.Fout, device=dev)
+                call("hgnn_readout_bwd_prep", fptr(g_out), pack.bs, s.Fout, iptr(pack.node_off), fptr(pack.pad_n),
+                     fptr(G), base + 8 * s.db_off, stream())
+                d.gY, d.Z, d.acc_f, d.acc_b, d.bn_weight = fptr(G), None, None, None, None
+                d.Rg = pack.Rn
+                keep_g = G
+            else:
+                t = plan.tensors[s.out]
+                if s.out not in grads:          # output never used downstream: zero gradient
+                    grads[s.out] = torch.zeros_like(vals[s.out])
+                d.gY, d.Z = fptr(grads[s.out]), fptr(vals[s.out])
+                d.acc_f, d.acc_b = base + 8 * t["acc_f"], base + 8 * t["acc_b"]
+                d.bn_weight = fptr(t["bn"].weight)
+                d.Rg = _rows_of(pack, plan, s.out)
+            d.Fg, d.relu_from = s.Fout, s.relu_from
+            d.Wa, d.Ha = fptr(s.conv_a.weight), Ha
+            d.Wb, d.Hb = (fptr(s.conv_b.weight) if Hb else None), Hb
+            d.Cin = s.Cin
+            d.dW_bins, d.db_bins = base + 8 * s.dW_off, base + 8 * s.db_off
+            # self part
+            opsT, n = make_ops(pack.node_ops_T() if node else pack.edge_ops_T())
+            d.R_self, d.ops_T, d.n_ops = (pack.Rn if node else pack.Rm), opsT, n
+            d.Xs, d.Fs = fptr(vals[s.src_self]), s.Fs
+            d.bn_self = _bn_ref(plan, s.src_self, arena, _rows_of(pack, plan, s.src_self))
+            ts = plan.tensors[s.src_self]
+            need_self = ts["bn"] is not None or (s.src_self == "X" and ctx.need_x)
+            d.gXs = fptr(grad_buf(s.src_self)) if need_self else None
+            d.accumulate_self = 1 if s.src_self in started else 0
+            d.acc_b_self = (base + 8 * ts["acc_b"]) if ts["bn"] is not None else None
+            if need_self:
+                started.add(s.src_self)
+            # cross part
+            if s.src_cross:
+                pt = pack.pt if node else pack.p      # rows = the cross tensor's rows
+                tc = plan.tensors[s.src_cross]
+                d.R_cross = _rows_of(pack, plan, s.src_cross)
+                d.pt_rowptr, d.pt_col, d.pt_pm, d.pt_pd = iptr(pt.rowptr), iptr(pt.col), fptr(pt.val), fptr(pt.val2)
+                d.Xc, d.Fc = fptr(vals[s.src_cross]), s.Fc
+                d.bn_cross = _bn_ref(plan, s.src_cross, arena, d.R_cross)
+                need_cross = tc["bn"] is not None or (s.src_cross == "X" and ctx.need_x)
+                d.gXc = fptr(grad_buf(s.src_cross)) if need_cross else None
+                d.accumulate_cross = 1 if s.src_cross in started else 0
+                d.acc_b_cross = (base + 8 * tc["acc_b"]) if tc["bn"] is not None else None
+                if need_cross:
+                    started.add(s.src_cross)
+            else:
+                d.R_cross = 0
+            call("hgnn_lg_side_bwd", ctypes.byref(d), stream())
+        offs, nbs, strides, cnts = plan.tables(dev)
+        gflat = torch.empty(plan.n_flat, device=dev)
+        call("hgnn_bins_reduce", arena.data_ptr(), offs.data_ptr(), iptr(nbs), iptr(strides), iptr(cnts),
+             plan.n_flat, fptr(gflat), stream())
+        pgrads = tuple(gflat[o:o + n].view(shape) for o, n, shape in plan.param_slices)
+        gX = grads.get("X") if ctx.need_x else None
+        return (None, None, gX, None) + pgrads
+
+
+def supported(model):
+    h2 = 2 * model.n_features
+    return h2 <= 128 and model.featuremap_in[0] <= 128 and model.J + 2 <= _lib.MAX_OPS
+
+
+def run_model(model, pack, Xp, XLp):
+    """Forward of the whole layer stack on packed rows; returns (bs, dim_output)."""
+    plan = get_plan(model)
+    if model.training and torch.is_grad_enabled():
+        return _ModelFunction.apply(model, pack, Xp, XLp, *plan.params)
+    if model.training:      # train mode without autograd: batch statistics, running stats updated
+        with torch.no_grad():
+            return _ModelFunction.apply(model, pack, Xp, XLp, *plan.params)
+    arena = torch.zeros(1, dtype=torch.float64, device=Xp.device)
+    return _forward(plan, pack, Xp, XLp, False, arena)[1]

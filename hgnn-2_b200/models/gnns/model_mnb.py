@@ -7,6 +7,7 @@ and returns ``(bs, dim_output)`` like the reference.
 """
 import torch.nn as nn
 
+from ... import engine
 from ..._lib import require_cuda
 from ...pack import resolve_pack
 from ..layers import layers_mnb
@@ -35,6 +36,8 @@ class GNN_simple(nn.Module):
         require_cuda()
         X, W = state
         pack = resolve_pack(W, N_batch=N_batch)
+        if engine.supported(self):       # whole stack on the model-level engine (csrc/engine.cu)
+            return engine.run_model(self, pack, layers_mnb._pack_nodes(pack, X), None)
         cur, _ = self.layer0.forward_packed(layers_mnb._pack_nodes(pack, X), pack)
         for i in range(self.n_layers - 2):
             cur, _ = self._modules['layer{}'.format(i + 1)].forward_packed(cur, pack)
@@ -68,6 +71,8 @@ class GNN_lg(nn.Module):
         pack = resolve_pack(W, WL, Pm, Pd, N_batch, E_batch)
         Xp = layers_mnb._pack_nodes(pack, X)
         XLp = layers_mnb._pack_edges(pack, XL)
+        if engine.supported(self):       # whole stack on the model-level engine (csrc/engine.cu)
+            return engine.run_model(self, pack, Xp, XLp)
         Xp, XLp, _, _ = self.layer0.forward_packed(Xp, XLp, pack)
         for i in range(self.n_layers - 2):
             Xp, XLp, _, _ = self._modules['layer{}'.format(i + 1)].forward_packed(Xp, XLp, pack)

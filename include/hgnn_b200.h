@@ -170,6 +170,61 @@ int hgnn_side_bwd_gather(const hgnn_op_t* opsT, int n_ops, int R, const float* G
                          int Cin, int col0, float* gX, int accumulate, float* dWa, float* dWb,
                          void* ws, long long ws_bytes, hgnn_stream_t stream);
 
+/* ---- model-level training engine (csrc/engine.cu): raw activations + on-load normalisation ---- */
+/* How a consumer normalises a stored RAW (pre-batch-norm) tensor on load: either from the binned
+ * fp64 (sum z, sum z^2) accumulators of its producer (training), from a precomputed
+ * [scale(F), shift(F)] vector (eval), or not at all (all NULL: layer-0 inputs). */
+typedef struct hgnn_bn_ref_t {
+    const double* acc;
+    const float* affine;
+    const float* weight; /* scalar BN affine (batch_normalization.py:26-27) */
+    const float* bias;
+    int n_rows;
+} hgnn_bn_ref_t;
+
+/* Forward of one layer side like hgnn_side_fwd, but inputs are normalised on load (bn_self /
+ * bn_cross, NULL = identity), Z is written RAW and its (sum z, sum z^2) are added to the binned
+ * accumulators acc_out (hgnn_ws_bins(2*Fout) x 2*Fout doubles, zeroed by the caller; NULL = no BN).
+ * No ticket, no finalisation: the consumers derive mean/std themselves. */
+int hgnn_lg_side_fwd(const hgnn_side_t* side, const hgnn_bn_ref_t* bn_self, const hgnn_bn_ref_t* bn_cross,
+                     const float* Wa, const float* ba, int Ha, const float* Wb, const float* bb, int Hb,
+                     int relu_from, float* Z, double* acc_out, hgnn_stream_t stream);
+
+/* Backward of one layer side in ONE launch.  gY = gradient w.r.t. the NORMALISED output of the side
+ * (R_g x Fg, complete), Z its raw output.  gPre = (c0 gY + c1 + c2 Z) * relu_mask is evaluated on the
+ * fly from acc_f / acc_b (acc_b == NULL: no batch-norm, gPre = gY * relu_mask).  Self part (R_self
+ * rows, transposed operators ops_T, raw input Xs normalised by bn_self) and cross part (R_cross rows,
+ * Pm^T/Pd^T pattern pt_*, raw input Xc): gX (+)= W^T T, dW/dbias partials to binned fp64
+ * accumulators, and (sum g, sum g*xhat) of the produced gradients to acc_b_self / acc_b_cross. */
+typedef struct hgnn_side_bwd_t {
+    const float* gY; const float* Z; int Fg; int relu_from; int Rg;
+    const double* acc_f; const double* acc_b; const float* bn_weight;
+    const float* Wa; int Ha; const float* Wb; int Hb; int Cin;
+    double* dW_bins; double* db_bins;
+    /* self part */
+    int R_self; const hgnn_op_t* ops_T; int n_ops; const float* Xs; int Fs; hgnn_bn_ref_t bn_self;
+    float* gXs; int accumulate_self; double* acc_b_self;
+    /* cross part (R_cross = 0: absent) */
+    int R_cross; const int* pt_rowptr; const int* pt_col; const float* pt_pm; const float* pt_pd;
+    const float* Xc; int Fc; hgnn_bn_ref_t bn_cross; float* gXc; int accumulate_cross; double* acc_b_cross;
+} hgnn_side_bwd_t;
+int hgnn_lg_side_bwd(const hgnn_side_bwd_t* desc, hgnn_stream_t stream);
+
+/* out[i] = sum_{b<nb[i]} sum_{c<cnt[i]} arena[off[i] + b*stride[i] + c]: every binned accumulator of
+ * a step -> the flat fp32 gradient buffer, one launch. */
+int hgnn_bins_reduce(const double* arena, const long long* off, const int* nb, const int* stride,
+                     const int* cnt, int n, float* out, hgnn_stream_t stream);
+/* Running statistics of all BN instances of a model in one launch (batch_normalization.py:37-38). */
+int hgnn_bn_running_update(const double* arena, const long long* acc_off, const int* F, const int* n_rows,
+                           const long long* run_off, int n_bn, float momentum, float* running,
+                           hgnn_stream_t stream);
+/* Readout backward prologue: G[r,o] = g[graph(r),o]; adds sum_b pad_count[b]*g[b,o] (the padded slots'
+ * share of d fc.bias, layers_mnb.py:92) to bin 0 of db_bins. */
+int hgnn_readout_bwd_prep(const float* g, int bs, int F, const int* off, const float* pad_count, float* G,
+                          double* db_bins, hgnn_stream_t stream);
+/* Number of accumulator bins used for a reduction of `width` values. */
+int hgnn_bins_for(int width);
+
 /* ---- readout (layers_mnb.py:92, :386): y[b,o] = sum_{rows of graph b} Y[r,o] + pad[b]*bias[o] */
 int hgnn_segment_sum(const float* Y, int bs, int F, const int* off, const float* pad_count,
                      const float* bias, float* out, hgnn_stream_t stream);

@@ -1,0 +1,86 @@
+"""GPU: the model-level engine (csrc/engine.cu) against the per-module kernels (csrc/side.cu) - the
+two code paths must agree to fp32 rounding on a C2-shaped batch, at several widths / orders / J,
+in train and eval mode.  (Both are separately checked against the reference's golden vectors in
+test_gpu_gnn.py; this test covers sizes the dense oracle cannot reach.)"""
+import copy
+
+import pytest
+import torch
+
+from conftest import rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+def _run(model, batch, use_engine, train=True):
+    from hgnn_b200 import engine
+    X, W, T, XL, WL, Pm, Pd, mask, mask_lg, N_batch, E_batch = batch
+    model.train(train)
+    for p in model.parameters():
+        p.grad = None
+    Xc = X.cuda().requires_grad_()
+    old = engine.supported
+    engine.supported = (lambda m: True) if use_engine else (lambda m: False)
+    try:
+        if model.dual:
+            out = model([Xc, XL.cuda(), W, WL, Pm, Pd], N_batch, mask, E_batch, mask_lg)
+        else:
+            out = model([Xc, W], N_batch, mask)
+    finally:
+        engine.supported = old
+    grads = None
+    if train:
+        y = T.squeeze(1).long().cuda() % out.shape[1]
+        torch.nn.functional.cross_entropy(out, y).backward()
+        grads = {k: v.grad.detach().clone() for k, v in model.named_parameters()}
+        grads["X"] = Xc.grad.detach().clone()
+    return out.detach().clone(), grads
+
+
+@pytest.mark.parametrize("kind,order,h,J,N", [("lg", 1, 2, 1, 300), ("lg", 2, 2, 1, 200), ("lg", 3, 4, 1, 200),
+                                              ("lg", 1, 8, 2, 60), ("simple", 0, 2, 1, 300),
+                                              ("simple", 0, 16, 2, 100), ("lg", 1, 32, 1, 100)])
+def test_engine_matches_module_path(kind, order, h, J, N):
+    import hgnn_b200  # noqa: F401
+    from hgnn_b200 import synth
+    from hgnn_b200.functions.batching import prepare_batch
+    from hgnn_b200.models.gnns.model_mnb import GNN_lg, GNN_simple
+    torch.manual_seed(order * 10 + h)
+    inst = synth.sbm_dataset(6, N=N, J=J)
+    batch = prepare_batch(inst, 0, J)
+    L = 5
+    model = (GNN_lg(0, h, L, 5, 2, J, order) if kind == "lg" else GNN_simple(0, h, L, 5, 2, J)).cuda()
+    ref_model = copy.deepcopy(model)
+    out_e, g_e = _run(model, batch, True)
+    out_m, g_m = _run(ref_model, batch, False)
+    assert rel_err(out_e.cpu(), out_m.cpu()) < 1e-4
+    fl = 0.1 * max(float(v.abs().max()) for v in g_m.values())
+    for k in g_m:
+        assert rel_err(g_e[k].cpu(), g_m[k].cpu(), fl) < 1e-4, k
+    # running statistics followed the same rule on both paths; eval outputs agree
+    for (n1, m1), (n2, m2) in zip(model.named_modules(), ref_model.named_modules()):
+        if hasattr(m1, "running_mean"):
+            assert rel_err(m1.running_mean.cpu(), m2.running_mean.cpu()) < 1e-4, n1
+            assert rel_err(m1.running_std.cpu(), m2.running_std.cpu()) < 1e-4, n1
+    with torch.no_grad():
+        oe, _ = _run(model, batch, True, train=False)
+        om, _ = _run(ref_model, batch, False, train=False)
+    assert rel_err(oe.cpu(), om.cpu()) < 1e-4
+
+
+def test_engine_grads_are_one_flat_buffer():
+    import hgnn_b200  # noqa: F401
+    from hgnn_b200 import synth
+    from hgnn_b200.dist import FlatParams
+    from hgnn_b200.functions.batching import prepare_batch
+    from hgnn_b200.models.gnns.model_mnb import GNN_lg
+    model = GNN_lg(0, 2, 4, 5, 2, 1, 1).cuda().train()
+    fp = FlatParams(model)
+    batch = prepare_batch(synth.sbm_dataset(4, N=50), 0, 1)
+    X, W, T, XL, WL, Pm, Pd, mask, mask_lg, N_batch, E_batch = batch
+    fp.zero_grad()
+    out = model([X.cuda(), XL.cuda(), W, WL, Pm, Pd], N_batch, mask, E_batch, mask_lg)
+    out.sum().backward()
+    assert fp._adopt_flat_grad()
+    assert fp.grad.numel() == fp.n and torch.isfinite(fp.grad).all()
+    assert torch.equal(fp.grad[:model.layer0.cv1.weight.numel()], model.layer0.cv1.weight.grad.reshape(-1))
