@@ -27,7 +27,8 @@ MAX_OPS = 8
 
 class OpT(ctypes.Structure):
     _fields_ = [("kind", c_int), ("diag", c_void), ("rowptr", c_void), ("col", c_void),
-                ("val", c_void)]
+                ("val", c_void), ("rng_rowptr", c_void), ("rng_id", c_void), ("rng_val", c_void),
+                ("rng_lo", c_void), ("rng_hi", c_void)]
 
 
 class SideT(ctypes.Structure):
@@ -165,7 +166,8 @@ def workspace(width, device):
 
 
 def make_ops(descs):
-    """descs: list of ('ident',) | ('diag', vec) | ('csr', rowptr, col, val) -> (OpT array, n)."""
+    """descs: list of ('ident',) | ('diag', vec) | ('csr', rowptr, col, val[, ranges]) -> (OpT array, n);
+    ranges = (rng_rowptr, rng_id, rng_val, rng_lo, rng_hi) for run-length split operators."""
     n = len(descs)
     if n < 1 or n > MAX_OPS:
         raise RuntimeError("hgnn_b200: between 1 and %d operators are supported, got %d (J too large)"
@@ -180,4 +182,8 @@ def make_ops(descs):
         else:
             arr[i].kind = OP_CSR
             arr[i].rowptr, arr[i].col, arr[i].val = iptr(d[1]), iptr(d[2]), fptr(d[3])
+            if len(d) > 4 and d[4] is not None and d[4][1].numel() > 0:
+                r = d[4]
+                arr[i].rng_rowptr, arr[i].rng_id, arr[i].rng_val = iptr(r[0]), iptr(r[1]), fptr(r[2])
+                arr[i].rng_lo, arr[i].rng_hi = iptr(r[3]), iptr(r[4])
     return arr, n

@@ -40,6 +40,11 @@ struct OpList {
     const int* rowptr[HGNN_MAX_OPS];
     const int* col[HGNN_MAX_OPS];
     const float* val[HGNN_MAX_OPS];
+    const int* rng_rowptr[HGNN_MAX_OPS];
+    const int* rng_id[HGNN_MAX_OPS];
+    const float* rng_val[HGNN_MAX_OPS];
+    const int* rng_lo[HGNN_MAX_OPS];
+    const int* rng_hi[HGNN_MAX_OPS];
 };
 
 static inline int make_oplist(const hgnn_op_t* ops, int n_ops, OpList* out) {
@@ -51,6 +56,11 @@ static inline int make_oplist(const hgnn_op_t* ops, int n_ops, OpList* out) {
         out->rowptr[i] = nullptr;
         out->col[i] = nullptr;
         out->val[i] = nullptr;
+        out->rng_rowptr[i] = nullptr;
+        out->rng_id[i] = nullptr;
+        out->rng_val[i] = nullptr;
+        out->rng_lo[i] = nullptr;
+        out->rng_hi[i] = nullptr;
     }
     for (int i = 0; i < n_ops; ++i) {
         out->kind[i] = ops[i].kind;
@@ -58,6 +68,13 @@ static inline int make_oplist(const hgnn_op_t* ops, int n_ops, OpList* out) {
         out->rowptr[i] = ops[i].rowptr;
         out->col[i] = ops[i].col;
         out->val[i] = ops[i].val;
+        if (ops[i].kind == HGNN_OP_CSR && ops[i].rng_rowptr) {
+            out->rng_rowptr[i] = ops[i].rng_rowptr;
+            out->rng_id[i] = ops[i].rng_id;
+            out->rng_val[i] = ops[i].rng_val;
+            out->rng_lo[i] = ops[i].rng_lo;
+            out->rng_hi[i] = ops[i].rng_hi;
+        }
         if (ops[i].kind == HGNN_OP_DIAG && !ops[i].diag) return -1;
         if (ops[i].kind == HGNN_OP_CSR && (!ops[i].rowptr)) return -1;
         if (ops[i].kind < 0 || ops[i].kind > HGNN_OP_CSR) return -1;

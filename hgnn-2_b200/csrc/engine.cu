@@ -150,7 +150,11 @@ __device__ __forceinline__ V<VEC> gather_op(const OpList& ops, int t, int row, c
 
 struct DeferList {
     int cnt;
+    int rng_cnt;         // rows of the tile with a run-length part (at most one push per row)
+    int rsum_id;         // range whose sum is cached in rsum (-1 = none)
     int items[ENG_MAX_DEFER];
+    int rng_items[ENG_THREADS];
+    float rsum[128];     // sum of the loader output over the cached row range, all features
 };
 __device__ __forceinline__ int defer_code(int t, int q, int r) { return (t << 24) | (q << 12) | r; }
 
@@ -158,6 +162,13 @@ template <int VEC, typename L>
 __device__ __forceinline__ void gather_or_defer(const OpList& ops, int t, int row, const L& ld_, int xo,
                                                 float* dst, DeferList* dl, int code) {
     if (ops.kind[t] == HGNN_OP_CSR) {
+        // run-length part of the row (one push per row: the range sum covers every feature chunk)
+        if (ops.rng_rowptr[t] && xo == 0 &&
+            __ldg(ops.rng_rowptr[t] + row + 1) > __ldg(ops.rng_rowptr[t] + row)) {
+            const int slot = atomicAdd(&dl->rng_cnt, 1);
+            if (slot < ENG_THREADS) dl->rng_items[slot] = code;
+            else __trap();       // more flagged (row, op) pairs than rows in a tile: impossible by construction
+        }
         const int len = __ldg(ops.rowptr[t] + row + 1) - __ldg(ops.rowptr[t] + row);
         if (len > ENG_LONG_ROW) {
             const int slot = atomicAdd(&dl->cnt, 1);
@@ -194,7 +205,8 @@ template <int VEC, typename L>
 __device__ __forceinline__ void gather_deferred(const OpList& ops, DeferList* dl, int row0, const L& ld_,
                                                 int Fblk, float* tile, int Tp, float* wpart) {
     const int nd = min(dl->cnt, ENG_MAX_DEFER);
-    if (nd == 0) return;
+    const int nr = min(dl->rng_cnt, ENG_THREADS);
+    if (nd == 0 && nr == 0) return;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
     for (int it = warp; it < nd; it += nwarps) {
         const int code = dl->items[it];
@@ -221,6 +233,48 @@ __device__ __forceinline__ void gather_deferred(const OpList& ops, DeferList* dl
             float v = 0.f;
             for (int w = 0; w < nwarps; ++w) v += wpart[w * 4 + threadIdx.x];
             tile[r * Tp + t * Fblk + xo + threadIdx.x] = v;
+        }
+    }
+    // ---- run-length parts: val * (sum of the loader output over a contiguous row range).  The
+    //      range sum is computed once by the whole CTA and cached (the flagged rows of a graph are
+    //      neighbours and share the phantom range of that graph).
+    __syncthreads();
+    for (int it = 0; it < nr; ++it) {
+        const int code = dl->rng_items[it];
+        const int t = code >> 24, r = code & 0xfff;
+        const int row = row0 + r;
+        const int e0 = __ldg(ops.rng_rowptr[t] + row), e1 = __ldg(ops.rng_rowptr[t] + row + 1);
+        for (int e = e0; e < e1; ++e) {
+            const int id = __ldg(ops.rng_id[t] + e);
+            if (id != dl->rsum_id) {
+                const int lo = __ldg(ops.rng_lo[t] + id), hi = __ldg(ops.rng_hi[t] + id);
+                for (int q = 0; q < Fblk / VEC; ++q) {
+                    V<VEC> a0 = V<VEC>::zero(), a1 = V<VEC>::zero();
+                    int rr = lo + threadIdx.x;
+                    for (; rr + (int)blockDim.x < hi; rr += 2 * blockDim.x) {
+                        a0.add(ld_(rr, q * VEC));
+                        a1.add(ld_(rr + blockDim.x, q * VEC));
+                    }
+                    if (rr < hi) a0.add(ld_(rr, q * VEC));
+                    a0.add(a1);
+                    a0.warp_reduce();
+                    __syncthreads();
+                    if (lane == 0) a0.store_scalar(wpart + warp * 4);
+                    __syncthreads();
+                    if ((int)threadIdx.x < VEC) {
+                        float v = 0.f;
+                        for (int w = 0; w < nwarps; ++w) v += wpart[w * 4 + threadIdx.x];
+                        dl->rsum[q * VEC + threadIdx.x] = v;
+                    }
+                }
+                __syncthreads();
+                if (threadIdx.x == 0) dl->rsum_id = id;
+                __syncthreads();
+            }
+            const float v = __ldg(ops.rng_val[t] + e);
+            for (int f = threadIdx.x; f < Fblk; f += blockDim.x)
+                tile[r * Tp + t * Fblk + f] = fmaf(v, dl->rsum[f], tile[r * Tp + t * Fblk + f]);
+            __syncthreads();
         }
     }
 }
@@ -339,6 +393,7 @@ fwd_kernel(const FwdArgs a) {
     }
     for (int o = tid; o < Fout; o += ENG_THREADS)
         bias[o] = (o < a.Ha) ? (a.ba ? a.ba[o] : 0.f) : (a.bb ? a.bb[o - a.Ha] : 0.f);
+    if (tid == 0) dl.rsum_id = -1;
     const bool cross = a.p_rowptr != nullptr;
     const bool aff_s = bn_vectors(a.bn_s, Fs, sc_s, sh_s, nullptr, nullptr, dtot, dscratch);
     const bool aff_c = cross ? bn_vectors(a.bn_c, Fc, sc_c, sh_c, nullptr, nullptr, dtot, dscratch) : false;
@@ -360,7 +415,7 @@ fwd_kernel(const FwdArgs a) {
     for (int tile_id = blockIdx.x; tile_id < ntiles; tile_id += gridDim.x) {
         const int row0 = tile_id * TR;
         const int trc = min(TR, a.R - row0);
-        if (tid == 0) dl.cnt = 0;
+        if (tid == 0) { dl.cnt = 0; dl.rng_cnt = 0; }
         __syncthreads();
         for (int i = tid; i < Q * TR; i += ENG_THREADS) {
             const int q = i / TR, r = i - q * TR;
@@ -537,7 +592,7 @@ __device__ __forceinline__ void bwd_part(const BwdArgs& a, const BwdPart& p, boo
     for (int tile_id = first_tile; tile_id < p.tiles; tile_id += tile_stride) {
         const int row0 = tile_id * TR;
         const int trc = min(TR, p.R - row0);
-        if (tid == 0) dl->cnt = 0;
+        if (tid == 0) { dl->cnt = 0; dl->rng_cnt = 0; }
         __syncthreads();
         for (int i = tid; i < Q * TR; i += ENG_THREADS) {
             const int q = i / TR, r = i - q * TR;
@@ -701,6 +756,8 @@ bwd_kernel(const BwdArgs a) {
     __shared__ float wpart[32];
     __shared__ __align__(16) float coef[3 * 128];
     const int Fg = a.Fg;
+    if (threadIdx.x == 0) dl.rsum_id = -1;
+    __syncthreads();
     float* c0 = coef;
     float* c1 = coef + 128;
     float* c2 = coef + 256;
@@ -904,7 +961,7 @@ extern "C" int hgnn_lg_side_bwd(const hgnn_side_bwd_t* d, hgnn_stream_t stream) 
     a.cross.R = d->R_cross;
     if (d->R_cross > 0) {
         HGNN_REQUIRE(d->pt_rowptr && d->pt_col && d->pt_pm && d->pt_pd && d->Xc && d->Fc >= 1 && d->Fc <= 128, "bad cross input");
-        hgnn_op_t cops[2];
+        hgnn_op_t cops[2] = {};
         for (int i = 0; i < 2; ++i) {
             cops[i].kind = HGNN_OP_CSR; cops[i].diag = nullptr;
             cops[i].rowptr = d->pt_rowptr; cops[i].col = d->pt_col;

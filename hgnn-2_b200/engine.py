@@ -334,7 +334,7 @@ class _ModelFunction(torch.autograd.Function):
             d.Cin = s.Cin
             d.dW_bins, d.db_bins = base + 8 * s.dW_off, base + 8 * s.db_off
             # self part
-            opsT, n = make_ops(pack.node_ops_T() if node else pack.edge_ops_T())
+            opsT, n = make_ops(pack.node_ops_T() if node else pack.edge_ops_T(split=True))
             d.R_self, d.ops_T, d.n_ops = (pack.Rn if node else pack.Rm), opsT, n
             d.Xs, d.Fs = fptr(vals[s.src_self]), s.Fs
             d.bn_self = _bn_ref(plan, s.src_self, arena, _rows_of(pack, plan, s.src_self))

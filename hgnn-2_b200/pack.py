@@ -154,6 +154,10 @@ class BatchPack(object):
             self.bt = [Csr(dev["bt_rowptr"], dev["bt_col"], dev["bt_val"])]
             self.p = Csr(dev["p_rowptr"], dev["p_col"], dev["p_pm"], dev["p_pd"])
             self.pt = Csr(dev["pt_rowptr"], dev["pt_col"], dev["pt_pm"], dev["pt_pd"])
+            # run-length split twin of bt for the engine kernels (phantom ranges stored once)
+            self.bts = Csr(dev["bts_rowptr"], dev["bts_col"], dev["bts_val"])
+            self.bts_ranges = (dev["bts_rng_rowptr"], dev["bts_rng_id"], dev["bts_rng_val"],
+                               dev["bts_rng_lo"], dev["bts_rng_hi"])
         for _ in range(1, self.J):   # A^(2^j): repeated squaring on the GPU, unclipped by default
             self.a.append(spgemm(self.a[-1], self.a[-1], clip_powers))
             self.at.append(spgemm(self.at[-1], self.at[-1], clip_powers))
@@ -218,10 +222,14 @@ class BatchPack(object):
             return [c.desc() for c in self.gen_edge]
         return [("ident",), ("diag", self.dl)] + [c.desc() for c in self.b]
 
-    def edge_ops_T(self):
+    def edge_ops_T(self, split=False):
+        """``split=True`` (engine kernels): the first-power operator as direct CSR + range entries."""
         if self.generic:
             return [c.desc() for c in self.gen_edge_T]
-        return [("ident",), ("diag", self.dl)] + [c.desc() for c in self.bt]
+        first = self.bt[0].desc()
+        if split and getattr(self, "bts", None) is not None:
+            first = self.bts.desc() + (self.bts_ranges,)
+        return [("ident",), ("diag", self.dl), first] + [c.desc() for c in self.bt[1:]]
 
     @property
     def K(self):

@@ -35,6 +35,46 @@ def _sort_coo(rows, cols, *vals):
     return (rows[order], cols[order]) + tuple(v[order] for v in vals)
 
 
+def split_runs(n_rows, rowptr, col, val, min_run=64):
+    """Run-length split of a CSR matrix: every maximal run of >= ``min_run`` consecutive columns
+    with one value inside a row is removed from the CSR and recorded as a *range entry*
+    ``(row, [lo, hi), val)`` meaning ``val * sum_{c in [lo,hi)} x[c]``.
+
+    The reference's phantom line-graph nodes (operators.py:59,68-71) make the transposed operator
+    ``AL^T`` exactly this shape: the ~deg(0) rows of the edges leaving node 0 each hold one entry per
+    phantom node, i.e. a run over the contiguous phantom range - 85 % of nnz(AL) at N=1000.  The
+    kernels evaluate a range sum once per CTA instead of once per entry.
+
+    Returns (rowptr2, col2, val2, rng_rowptr, rng_id, rng_val, rng_lo, rng_hi); ``rng_id`` indexes
+    the table of distinct ranges (rng_lo, rng_hi)."""
+    rowptr = np.asarray(rowptr, dtype=np.int64)
+    nnz = col.shape[0]
+    empty_i, empty_f = np.zeros(0, I32), np.zeros(0, F32)
+    if nnz == 0:
+        z = np.zeros(n_rows + 1, I32)
+        return z, empty_i, empty_f, z.copy(), empty_i, empty_f, empty_i, empty_i
+    rows = np.repeat(np.arange(n_rows, dtype=np.int64), np.diff(rowptr))
+    c = col.astype(np.int64)
+    brk = np.ones(nnz, dtype=bool)
+    brk[1:] = (rows[1:] != rows[:-1]) | (c[1:] != c[:-1] + 1) | (val[1:] != val[:-1])
+    run_id = np.cumsum(brk) - 1
+    run_start = np.nonzero(brk)[0]
+    run_len = np.diff(np.append(run_start, nnz))
+    long_run = run_len >= min_run
+    keep = ~long_run[run_id]
+    rp2 = np.zeros(n_rows + 1, dtype=np.int64)
+    np.add.at(rp2, rows[keep] + 1, 1)
+    ls = run_start[long_run]
+    r_rows, r_lo, r_hi, r_val = rows[ls], c[ls], c[ls] + run_len[long_run], val[ls]
+    uniq, inv = (np.unique(np.stack([r_lo, r_hi], 1), axis=0, return_inverse=True)
+                 if ls.size else (np.zeros((0, 2), np.int64), np.zeros(0, np.int64)))
+    rrp = np.zeros(n_rows + 1, dtype=np.int64)
+    np.add.at(rrp, r_rows + 1, 1)
+    return (np.cumsum(rp2).astype(I32), col[keep].astype(I32), val[keep].astype(F32),
+            np.cumsum(rrp).astype(I32), inv.reshape(-1).astype(I32), r_val.astype(F32),
+            uniq[:, 0].astype(I32), uniq[:, 1].astype(I32))
+
+
 class GraphOps(object):
     """Sparse twin of ``graph_operators([V, A], J, dual=True)`` for ONE graph (local indices).
 
@@ -47,7 +87,8 @@ class GraphOps(object):
     __slots__ = ("N", "M", "E", "a_rowptr", "a_col", "a_val", "at_rowptr", "at_col", "at_val",
                  "deg", "b_rowptr", "b_col", "b_val", "bt_rowptr", "bt_col", "bt_val", "dl",
                  "p_rowptr", "p_col", "p_pm", "p_pd", "pt_rowptr", "pt_col", "pt_pm", "pt_pd",
-                 "dual")
+                 "bts_rowptr", "bts_col", "bts_val", "bts_rng_rowptr", "bts_rng_id", "bts_rng_val",
+                 "bts_rng_lo", "bts_rng_hi", "dual")
 
     @classmethod
     def from_dense(cls, A, dual=True):
@@ -115,6 +156,9 @@ class GraphOps(object):
         self.b_rowptr, self.b_col, self.b_val = _csr_from_sorted_coo(M, m1, m2, bv)
         t1, t2, tv = _sort_coo(m2, m1, bv)
         self.bt_rowptr, self.bt_col, self.bt_val = _csr_from_sorted_coo(M, t1, t2, tv)
+        # run-length split of the transposed operator for the engine kernels (phantom ranges)
+        (self.bts_rowptr, self.bts_col, self.bts_val, self.bts_rng_rowptr, self.bts_rng_id,
+         self.bts_rng_val, self.bts_rng_lo, self.bts_rng_hi) = split_runs(M, self.bt_rowptr, self.bt_col, self.bt_val)
         dl = np.zeros(M, dtype=F32)
         np.add.at(dl, m1, bv)
         self.dl = dl
@@ -172,6 +216,7 @@ _FIELDS = {
     "bt": ("bt_rowptr", "m", "m", ("bt_col", "bt_val")),
     "p": ("p_rowptr", "n", "m", ("p_col", "p_pm", "p_pd")),
     "pt": ("pt_rowptr", "m", "n", ("pt_col", "pt_pm", "pt_pd")),
+    "bts": ("bts_rowptr", "m", "m", ("bts_col", "bts_val")),
 }
 
 
@@ -190,6 +235,20 @@ def concat_block_diagonal(graphs, dual=True):
     names = list(_FIELDS) if dual else ["a", "at"]
     if dual:
         out["dl"] = np.concatenate([g.dl for g in graphs])
+    if dual:      # run-length split twin of bt: direct CSR part + range entries
+        nr = np.array([g.bts_rng_lo.shape[0] for g in graphs], dtype=np.int64)
+        nr_off = np.concatenate([[0], np.cumsum(nr)])
+        ne = np.array([g.bts_rng_id.shape[0] for g in graphs], dtype=np.int64)
+        ne_off = np.concatenate([[0], np.cumsum(ne)])
+        out["bts_rng_rowptr"] = np.concatenate(
+            [g.bts_rng_rowptr[:-1].astype(np.int64) + ne_off[i] for i, g in enumerate(graphs)] + [ne_off[-1:]]).astype(I32)
+        out["bts_rng_id"] = np.concatenate(
+            [g.bts_rng_id.astype(np.int64) + nr_off[i] for i, g in enumerate(graphs)]).astype(I32)
+        out["bts_rng_val"] = np.concatenate([g.bts_rng_val for g in graphs]).astype(F32)
+        out["bts_rng_lo"] = np.concatenate(
+            [g.bts_rng_lo.astype(np.int64) + off["m"][i] for i, g in enumerate(graphs)]).astype(I32)
+        out["bts_rng_hi"] = np.concatenate(
+            [g.bts_rng_hi.astype(np.int64) + off["m"][i] for i, g in enumerate(graphs)]).astype(I32)
     for name in names:
         rp_name, rspace, cspace, arrs = _FIELDS[name]
         nnz = np.array([getattr(g, arrs[0]).shape[0] for g in graphs], dtype=np.int64)

@@ -43,6 +43,14 @@ typedef struct hgnn_op_t {
     const int* rowptr;   /* CSR: (R+1,) */
     const int* col;      /* CSR: (nnz,) */
     const float* val;    /* CSR: (nnz,) */
+    /* optional run-length part (engine kernels only; NULL = none): row r additionally gets
+     * sum_{k in [rng_rowptr[r], rng_rowptr[r+1])} rng_val[k] * sum_{c in [rng_lo[id], rng_hi[id])} x[c],
+     * id = rng_id[k] - long runs of equal consecutive entries stored once (sparse_ops.split_runs). */
+    const int* rng_rowptr;
+    const int* rng_id;
+    const float* rng_val;
+    const int* rng_lo;
+    const int* rng_hi;
 } hgnn_op_t;
 
 const char* hgnn_last_error(void);

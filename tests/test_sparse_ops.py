@@ -63,3 +63,33 @@ def test_block_diagonal_concat():
     seg = col[rp[4]:rp[11]]
     assert seg.size == gs[1].a_col.size and seg.min() >= 4 and seg.max() < 11
     assert np.array_equal(seg - 4, gs[1].a_col)
+
+
+def test_split_runs_reconstructs_the_operator():
+    """CSR part + range entries of the run-length split == the original transposed operator."""
+    from hgnn_b200.sparse_ops import split_runs
+    gen = torch.Generator().manual_seed(5)
+    n = 120
+    up = (torch.rand(n, n, generator=gen) < 0.08).float().triu(1)
+    up[0, 1:9] = 1.0                                  # node 0 has many forward edges -> heavy rows
+    ops = GraphOps.from_dense((up + up.t()).numpy())
+    M = ops.M
+
+    def dense(rp, col, val):
+        D = np.zeros((M, M), np.float32)
+        D[np.repeat(np.arange(M), np.diff(rp)), col] = val
+        return D
+    full = dense(ops.bt_rowptr, ops.bt_col, ops.bt_val)
+    part = dense(ops.bts_rowptr, ops.bts_col, ops.bts_val)
+    assert ops.bts_rng_id.size > 0 and ops.bts_col.size < 0.5 * ops.bt_col.size
+    rows = np.repeat(np.arange(M), np.diff(ops.bts_rng_rowptr))
+    for r, rid, v in zip(rows, ops.bts_rng_id, ops.bts_rng_val):
+        part[r, ops.bts_rng_lo[rid]:ops.bts_rng_hi[rid]] += v
+    assert np.array_equal(full, part)
+    # generic check on a hand-made matrix with two runs in one row and a short run that must stay
+    rp = np.array([0, 70, 75, 140], np.int32)
+    col = np.concatenate([np.arange(5, 75), np.arange(3, 8), np.arange(0, 65)]).astype(np.int32)
+    val = np.concatenate([np.ones(70), 2 * np.ones(5), 3 * np.ones(65)]).astype(np.float32)
+    rp2, c2, v2, rrp, rid, rv, lo, hi = split_runs(3, rp, col, val)
+    assert rp2.tolist() == [0, 0, 5, 5] and rrp.tolist() == [0, 1, 1, 2]
+    assert sorted(zip(lo.tolist(), hi.tolist())) == [(0, 65), (5, 75)] and rv.tolist() == [1.0, 3.0]
