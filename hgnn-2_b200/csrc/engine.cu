@@ -21,6 +21,7 @@
 //
 // Reference semantics are unchanged (models/layers/layers_mnb.py:52-69,189-225,256-290,322-358,
 // batch_normalization.py:34-43,65-93); parity is tested against the same golden vectors.
+#include <stdlib.h>
 #include "common.cuh"
 
 #define ENG_THREADS 256
@@ -283,11 +284,11 @@ __device__ __forceinline__ void gather_deferred(const OpList& ops, DeferList* dl
 // out[c] = sum over bins of acc[b*width + c]; all threads; `scratch` = blockDim doubles.  Ends synced.
 __device__ __forceinline__ void bins_total(const double* __restrict__ acc, int width, int nb,
                                            double* out, double* scratch) {
-    if (nb * width <= (int)blockDim.x) {
-        const int e = threadIdx.x;
-        scratch[e] = (e < nb * width) ? __ldcg(acc + e) : 0.0;
+    if (nb * width <= 256) {                     // scratch holds 256 doubles: one parallel load round
+        for (int e = threadIdx.x; e < nb * width; e += blockDim.x) scratch[e] = __ldcg(acc + e);
         __syncthreads();
-        if (e < width) {
+        if ((int)threadIdx.x < width) {
+            const int e = threadIdx.x;
             double t0 = 0.0, t1 = 0.0;
             for (int b = 0; b + 1 < nb; b += 2) {
                 t0 += scratch[b * width + e];
@@ -793,6 +794,8 @@ bwd_kernel(const BwdArgs a) {
     }
 }
 
+#include "engine_row4.cuh"
+
 }  // namespace eng
 
 // ---------------------------------------------------------------------------------------------
@@ -854,6 +857,52 @@ static eng::BnRef to_bnref(const hgnn_bn_ref_t* r) {
     return o;
 }
 
+// ---- thread-per-row fast path for width-4 states (h = 2) ---------------------------------------
+static bool eng_row4_ops(const hgnn_op_t* ops, int n_ops) {
+    if (n_ops < 3 || n_ops > 4) return false;
+    if (ops[0].kind != HGNN_OP_IDENT || ops[1].kind != HGNN_OP_DIAG) return false;
+    for (int i = 2; i < n_ops; ++i)
+        if (ops[i].kind != HGNN_OP_CSR) return false;
+    return true;
+}
+
+static bool eng_row4_disabled() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("HGNN_B200_NO_ROW4"); v = (e && e[0] == '1') ? 1 : 0; }
+    return v == 1;
+}
+
+static bool eng_try_fwd_row4(const eng::FwdArgs& g, const hgnn_side_t* side, hgnn_stream_t stream) {
+    if (eng_row4_disabled()) return false;
+    const bool cross = g.p_rowptr != nullptr;
+    if (g.Fs != 4 || g.Fout != 4 || (cross && g.Fc != 4) || !eng_row4_ops(side->ops, side->n_ops)) return false;
+    if (!eng_aligned16(g.Xs) || !eng_aligned16(g.Z) || (cross && !eng_aligned16(g.Xc))) return false;
+    for (int i = 2; i < side->n_ops; ++i) if (side->ops[i].rng_rowptr) return false;
+    eng::Fwd4Args a;
+    a.R = g.R; a.n_csr = side->n_ops - 2; a.diag = side->ops[1].diag;
+    for (int i = 0; i < 2; ++i) {
+        const bool on = i < a.n_csr;
+        a.rowptr[i] = on ? side->ops[2 + i].rowptr : nullptr;
+        a.col[i] = on ? side->ops[2 + i].col : nullptr;
+        a.val[i] = on ? side->ops[2 + i].val : nullptr;
+    }
+    a.Xs = g.Xs; a.bn_s = g.bn_s;
+    a.p_rowptr = g.p_rowptr; a.p_col = g.p_col; a.p_pm = g.p_pm; a.p_pd = g.p_pd; a.Xc = g.Xc; a.bn_c = g.bn_c;
+    a.Wa = g.Wa; a.ba = g.ba; a.Ha = g.Ha; a.Wb = g.Wb; a.bb = g.bb; a.Hb = g.Hb;
+    a.relu_from = g.relu_from; a.Cin = g.Cin; a.Z = g.Z; a.acc_out = g.acc_out;
+    cudaStream_t s = to_stream(stream);
+    const int want = ceil_div(a.R, R4_THREADS);
+#define R4_FWD(NCSR, CROSS)                                                                              \
+    {                                                                                                    \
+        int grid = min(want, eng_resident_impl((const void*)eng::fwd_row4_kernel<NCSR, CROSS>, 0, R4_THREADS)); \
+        eng::fwd_row4_kernel<NCSR, CROSS><<<grid, R4_THREADS, 0, s>>>(a);                                \
+    }
+    if (a.n_csr == 1) { if (cross) R4_FWD(1, true) else R4_FWD(1, false) }
+    else { if (cross) R4_FWD(2, true) else R4_FWD(2, false) }
+#undef R4_FWD
+    return true;
+}
+
 extern "C" int hgnn_lg_side_fwd(const hgnn_side_t* side, const hgnn_bn_ref_t* bn_self,
                                 const hgnn_bn_ref_t* bn_cross, const float* Wa, const float* ba, int Ha,
                                 const float* Wb, const float* bb, int Hb, int relu_from, float* Z,
@@ -877,6 +926,7 @@ extern "C" int hgnn_lg_side_fwd(const hgnn_side_t* side, const hgnn_bn_ref_t* bn
     if (a.R == 0) return HGNN_OK;
     a.Fout = Ha + Hb;
     a.Cin = side->n_ops * a.Fs + 2 * a.Fc;
+    if (eng_try_fwd_row4(a, side, stream)) return hgnn_check_launch("hgnn_lg_side_fwd(row4)");
     const bool vec4 = (a.Fs % 4 == 0) && (a.Fc % 4 == 0) && eng_aligned16(a.Xs) && (a.Fc == 0 || eng_aligned16(a.Xc));
     const bool vout4 = vec4 && (a.Fout % 4 == 0) && eng_aligned16(Z);
     a.Cin_pad = eng_pad(a.Cin, vec4 ? 4 : 1);
@@ -930,12 +980,58 @@ static bool eng_plan_part(eng::BwdPart& p, int Fg, bool vec4, bool& vout4, bool 
     return p.smem <= ENG_MAX_SMEM;
 }
 
+static bool eng_try_bwd_row4(const hgnn_side_bwd_t* d, hgnn_stream_t stream) {
+    if (eng_row4_disabled()) return false;
+    if (d->Fg != 4 || d->R_self <= 0 || d->Fs != 4 || !eng_row4_ops(d->ops_T, d->n_ops)) return false;
+    if (d->R_cross > 0 && d->Fc != 4) return false;
+    if (!eng_aligned16(d->gY) || (d->Z && !eng_aligned16(d->Z)) || !eng_aligned16(d->Xs) ||
+        (d->gXs && !eng_aligned16(d->gXs)) || (d->R_cross > 0 && (!eng_aligned16(d->Xc) || (d->gXc && !eng_aligned16(d->gXc)))))
+        return false;
+    for (int i = 3; i < d->n_ops; ++i) if (d->ops_T[i].rng_rowptr) return false;   // ranges only on the first CSR op
+    eng::Bwd4Args a;
+    a.gY = d->gY; a.Z = d->Z; a.relu_from = d->relu_from; a.Rg = d->Rg; a.has_bn = d->acc_b != nullptr;
+    a.acc_f = d->acc_f; a.acc_b = d->acc_b; a.bn_w = d->bn_weight;
+    a.Wa = d->Wa; a.Ha = d->Ha; a.Wb = d->Wb; a.Hb = d->Hb; a.Cin = d->Cin;
+    a.dW_bins = d->dW_bins; a.db_bins = d->db_bins;
+    a.R_self = d->R_self; a.n_csr = d->n_ops - 2; a.diag = d->ops_T[1].diag;
+    for (int i = 0; i < 2; ++i) {
+        const bool on = i < a.n_csr;
+        a.rowptr[i] = on ? d->ops_T[2 + i].rowptr : nullptr;
+        a.col[i] = on ? d->ops_T[2 + i].col : nullptr;
+        a.val[i] = on ? d->ops_T[2 + i].val : nullptr;
+    }
+    const hgnn_op_t& o2 = d->ops_T[2];
+    a.rng_rowptr = o2.rng_rowptr; a.rng_id = o2.rng_id; a.rng_val = o2.rng_val; a.rng_lo = o2.rng_lo; a.rng_hi = o2.rng_hi;
+    a.Xs = d->Xs; a.bn_s = to_bnref(&d->bn_self); a.gXs = d->gXs; a.acc_self = d->accumulate_self; a.acc_b_self = d->acc_b_self;
+    a.R_cross = d->R_cross;
+    a.pt_rowptr = d->pt_rowptr; a.pt_col = d->pt_col; a.pt_pm = d->pt_pm; a.pt_pd = d->pt_pd;
+    a.Xc = d->Xc; a.bn_c = to_bnref(&d->bn_cross); a.gXc = d->gXc; a.acc_cross = d->accumulate_cross;
+    a.acc_b_cross = d->acc_b_cross; a.col0_cross = d->n_ops * 4;
+    cudaStream_t s = to_stream(stream);
+    const long long rows = (long long)d->R_self + (d->R_cross > 0 ? d->R_cross : 0);
+#define R4_BWD(NCSR)                                                                                      \
+    {                                                                                                     \
+        const int cap = eng_resident_impl((const void*)eng::bwd_row4_kernel<NCSR>, 0, R4_THREADS);        \
+        int grid = (int)min((long long)cap, (rows + R4_THREADS - 1) / R4_THREADS);                        \
+        if (d->R_cross > 0 && grid < 2) grid = 2;                                                         \
+        int cs = d->R_cross > 0 ? (int)(((long long)grid * d->R_self + rows / 2) / rows) : grid;          \
+        if (cs < 1) cs = 1;                                                                               \
+        if (d->R_cross > 0 && cs > grid - 1) cs = grid - 1;                                               \
+        a.ctas_self = cs;                                                                                 \
+        eng::bwd_row4_kernel<NCSR><<<grid, R4_THREADS, 0, s>>>(a);                                        \
+    }
+    if (a.n_csr == 1) R4_BWD(1) else R4_BWD(2)
+#undef R4_BWD
+    return true;
+}
+
 extern "C" int hgnn_lg_side_bwd(const hgnn_side_bwd_t* d, hgnn_stream_t stream) {
     HGNN_REQUIRE(d && d->gY && d->Fg >= 1 && d->Fg <= 128, "bad argument");
     HGNN_REQUIRE(d->Ha >= 0 && d->Hb >= 0 && d->Ha + d->Hb == d->Fg, "Ha + Hb must equal the width of gY");
     HGNN_REQUIRE((d->Ha == 0 || d->Wa) && (d->Hb == 0 || d->Wb), "null weights");
     HGNN_REQUIRE(!d->acc_b || (d->acc_f && d->bn_weight && d->Z), "batch-norm backward needs acc_f, bn_weight and Z");
     HGNN_REQUIRE(d->relu_from >= d->Fg || d->Z, "ReLU backward needs Z");
+    if (eng_try_bwd_row4(d, stream)) return hgnn_check_launch("hgnn_lg_side_bwd(row4)");
     eng::BwdArgs a;
     a.gY = d->gY; a.Z = d->Z; a.Fg = d->Fg; a.relu_from = d->relu_from; a.Rg = d->Rg;
     a.acc_f = d->acc_f; a.acc_b = d->acc_b; a.bn_w = d->bn_weight;

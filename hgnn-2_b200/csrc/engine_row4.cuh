@@ -1,0 +1,509 @@
+// engine_row4.cuh -- thread-per-row engine kernels for the script-default width (h = 2: every
+// state is 4 floats = one float4 per node / line-graph node).  Included by engine.cu inside
+// namespace eng.
+//
+// At this width the generic tile kernels are instruction- and barrier-bound (profiles/README.md:
+// ~1 600 thread-instructions and four CTA barriers per row).  Here one thread owns one row from
+// the first load to the last store: all operator blocks, the concatenated x1 vector (20 floats),
+// the 20x4 mat-vec and - in the backward - the 48+32 dW accumulators live in registers; there is
+// no shared-memory tile and no barrier in the row loop.  Loads are issued in three dependent
+// rounds (row pointers -> entries -> feature rows), batches of up to 4 entries in flight.
+#pragma once
+
+#define R4_THREADS 128
+
+__device__ __forceinline__ float4 ld4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+__device__ __forceinline__ float4 f4_fma(float a, float4 x, float4 acc) {
+    acc.x = fmaf(a, x.x, acc.x); acc.y = fmaf(a, x.y, acc.y); acc.z = fmaf(a, x.z, acc.z); acc.w = fmaf(a, x.w, acc.w);
+    return acc;
+}
+__device__ __forceinline__ float4 f4_affine(float4 x, float4 s, float4 t) {
+    return make_float4(fmaf(x.x, s.x, t.x), fmaf(x.y, s.y, t.y), fmaf(x.z, s.z, t.z), fmaf(x.w, s.w, t.w));
+}
+__device__ __forceinline__ float4 f4_zero() { return make_float4(0.f, 0.f, 0.f, 0.f); }
+__device__ __forceinline__ float f4_dot(float4 a, float4 b) { return fmaf(a.x, b.x, fmaf(a.y, b.y, fmaf(a.z, b.z, a.w * b.w))); }
+
+// sum_k val[k] * X[col[k]] (raw rows) and sum_k val[k]; batches of 4 in flight
+__device__ __forceinline__ void csr_gather4(const int* __restrict__ col, const float* __restrict__ val, int k0,
+                                            int k1, const float* __restrict__ X, float4& acc, float& wsum) {
+    for (int k = k0; k < k1; k += 4) {
+        int c[4];
+        float v[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const bool on = k + j < k1;
+            c[j] = __ldg(col + (on ? k + j : k));
+            v[j] = on ? __ldg(val + k + j) : 0.f;
+        }
+        float4 x[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) x[j] = ld4(X + (size_t)c[j] * 4);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            acc = f4_fma(v[j], x[j], acc);
+            wsum += v[j];
+        }
+    }
+}
+
+// scale/shift (and mean/rstd) of a width-4 tensor into shared memory; all threads; ends synced
+__device__ __forceinline__ bool bn_vec4(const BnRef& r, float* sc, float* sh, float* mu, float* rs,
+                                        double* tot, double* scratch) {
+    return bn_vectors(r, 4, sc, sh, mu, rs, tot, scratch);
+}
+
+// ---------------------------------------------------------------------------------------------
+// forward
+// ---------------------------------------------------------------------------------------------
+struct Fwd4Args {
+    int R;
+    int n_csr;                       // K - 2 CSR operators after [IDENT, DIAG]
+    const float* diag;
+    const int* rowptr[2]; const int* col[2]; const float* val[2];
+    const float* Xs; BnRef bn_s;
+    const int* p_rowptr; const int* p_col; const float* p_pm; const float* p_pd;   // NULL: no cross part
+    const float* Xc; BnRef bn_c;
+    const float* Wa; const float* ba; int Ha;
+    const float* Wb; const float* bb; int Hb;
+    int relu_from, Cin;
+    float* Z;
+    double* acc_out;
+};
+
+template <int NCSR, bool CROSS>
+__global__ void __launch_bounds__(R4_THREADS)
+fwd_row4_kernel(const Fwd4Args a) {
+    constexpr int NB = 2 + NCSR + (CROSS ? 2 : 0);     // float4 blocks of x1
+    __shared__ __align__(16) float W[4 * NB * 4];       // [o][Cin]
+    __shared__ __align__(16) float bias[4];
+    __shared__ __align__(16) float aff[16];              // sc_s, sh_s, sc_c, sh_c
+    __shared__ double dscratch[256];
+    __shared__ double dtot[16];
+    const int tid = threadIdx.x;
+    for (int i = tid; i < 4 * NB * 4; i += R4_THREADS) {
+        const int o = i / (NB * 4), c = i - o * (NB * 4);
+        W[i] = (o < a.Ha) ? a.Wa[(size_t)o * a.Cin + c] : a.Wb[(size_t)(o - a.Ha) * a.Cin + c];
+    }
+    if (tid < 4) bias[tid] = (tid < a.Ha) ? (a.ba ? a.ba[tid] : 0.f) : (a.bb ? a.bb[tid - a.Ha] : 0.f);
+    bn_vec4(a.bn_s, aff, aff + 4, nullptr, nullptr, dtot, dscratch);
+    if (CROSS) bn_vec4(a.bn_c, aff + 8, aff + 12, nullptr, nullptr, dtot, dscratch);
+    __syncthreads();
+    const float4 sc_s = *reinterpret_cast<const float4*>(aff), sh_s = *reinterpret_cast<const float4*>(aff + 4);
+    const float4 sc_c = *reinterpret_cast<const float4*>(aff + 8), sh_c = *reinterpret_cast<const float4*>(aff + 12);
+    float s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
+
+    for (int row = blockIdx.x * R4_THREADS + tid; row < a.R; row += gridDim.x * R4_THREADS) {
+        float4 x1[NB];
+        // round 1: everything addressed by the row itself
+        const float4 xs = f4_affine(ld4(a.Xs + (size_t)row * 4), sc_s, sh_s);
+        const float d = __ldg(a.diag + row);
+        int k0[NCSR > 0 ? NCSR : 1], k1[NCSR > 0 ? NCSR : 1];
+#pragma unroll
+        for (int t = 0; t < NCSR; ++t) {
+            k0[t] = __ldg(a.rowptr[t] + row);
+            k1[t] = __ldg(a.rowptr[t] + row + 1);
+        }
+        int p0 = 0, p1 = 0;
+        if (CROSS) {
+            p0 = __ldg(a.p_rowptr + row);
+            p1 = __ldg(a.p_rowptr + row + 1);
+        }
+        x1[0] = xs;
+        x1[1] = make_float4(d * xs.x, d * xs.y, d * xs.z, d * xs.w);
+        // rounds 2+3: entries, then feature rows.  sum val*(s*z+t) = s*(sum val*z) + t*(sum val)
+#pragma unroll
+        for (int t = 0; t < NCSR; ++t) {
+            float4 acc = f4_zero();
+            float ws = 0.f;
+            csr_gather4(a.col[t], a.val[t], k0[t], k1[t], a.Xs, acc, ws);
+            x1[2 + t] = make_float4(fmaf(acc.x, sc_s.x, ws * sh_s.x), fmaf(acc.y, sc_s.y, ws * sh_s.y),
+                                    fmaf(acc.z, sc_s.z, ws * sh_s.z), fmaf(acc.w, sc_s.w, ws * sh_s.w));
+        }
+        if (CROSS) {
+            float4 am = f4_zero(), ad = f4_zero();
+            float wm = 0.f, wd = 0.f;
+            for (int k = p0; k < p1; k += 4) {
+                int c[4];
+                float vm[4], vd[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const bool on = k + j < p1;
+                    c[j] = __ldg(a.p_col + (on ? k + j : k));
+                    vm[j] = on ? __ldg(a.p_pm + k + j) : 0.f;
+                    vd[j] = on ? __ldg(a.p_pd + k + j) : 0.f;
+                }
+                float4 x[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) x[j] = ld4(a.Xc + (size_t)c[j] * 4);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    am = f4_fma(vm[j], x[j], am);
+                    ad = f4_fma(vd[j], x[j], ad);
+                    wm += vm[j];
+                    wd += vd[j];
+                }
+            }
+            x1[2 + NCSR] = make_float4(fmaf(am.x, sc_c.x, wm * sh_c.x), fmaf(am.y, sc_c.y, wm * sh_c.y),
+                                       fmaf(am.z, sc_c.z, wm * sh_c.z), fmaf(am.w, sc_c.w, wm * sh_c.w));
+            x1[3 + NCSR] = make_float4(fmaf(ad.x, sc_c.x, wd * sh_c.x), fmaf(ad.y, sc_c.y, wd * sh_c.y),
+                                       fmaf(ad.z, sc_c.z, wd * sh_c.z), fmaf(ad.w, sc_c.w, wd * sh_c.w));
+        }
+        // mat-vec: 4 outputs x (NB*4) inputs, weights broadcast from shared memory
+        float out[4];
+#pragma unroll
+        for (int o = 0; o < 4; ++o) {
+            float acc = bias[o];
+#pragma unroll
+            for (int b = 0; b < NB; ++b)
+                acc += f4_dot(x1[b], *reinterpret_cast<const float4*>(W + (o * NB + b) * 4));
+            if (o >= a.relu_from) acc = fmaxf(acc, 0.f);
+            out[o] = acc;
+            s1[o] += acc;
+            s2[o] = fmaf(acc, acc, s2[o]);
+        }
+        *reinterpret_cast<float4*>(a.Z + (size_t)row * 4) = make_float4(out[0], out[1], out[2], out[3]);
+    }
+    if (a.acc_out) {
+        const int nb = hgnn_ws_bins(8);
+#pragma unroll
+        for (int o = 0; o < 4; ++o) {
+            const double x = cta_reduce_mod((double)s1[o], 1, dscratch);
+            const double y = cta_reduce_mod((double)s2[o], 1, dscratch);
+            if (tid == 0) {
+                accum_add(a.acc_out, 8, nb, o, x);
+                accum_add(a.acc_out, 8, nb, 4 + o, y);
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// backward
+// ---------------------------------------------------------------------------------------------
+struct Bwd4Args {
+    // side being differentiated (width 4)
+    const float* gY; const float* Z; int relu_from; int Rg; int has_bn;
+    const double* acc_f; const double* acc_b; const float* bn_w;
+    const float* Wa; int Ha; const float* Wb; int Hb; int Cin;
+    double* dW_bins; double* db_bins;
+    // self part: transposed [IDENT, DIAG, CSR...]
+    int R_self, n_csr;
+    const float* diag;
+    const int* rowptr[2]; const int* col[2]; const float* val[2];
+    const int* rng_rowptr; const int* rng_id; const float* rng_val; const int* rng_lo; const int* rng_hi;  // op 0 only
+    const float* Xs; BnRef bn_s; float* gXs; int acc_self; double* acc_b_self;
+    // cross part: Pm^T / Pd^T pattern with rows = rows of the cross tensor
+    int R_cross;
+    const int* pt_rowptr; const int* pt_col; const float* pt_pm; const float* pt_pd;
+    const float* Xc; BnRef bn_c; float* gXc; int acc_cross; double* acc_b_cross;
+    int col0_cross;
+    int ctas_self;        // CTAs [0, ctas_self) work on the self rows
+};
+
+struct Gpre4 {
+    float4 c0, c1, c2;
+    int relu_from;
+    bool bn, need_z;
+    const float* G;
+    const float* Z;
+    __device__ __forceinline__ float4 operator()(int row) const {
+        float4 g = ld4(G + (size_t)row * 4);
+        if (!need_z) return g;
+        const float4 z = ld4(Z + (size_t)row * 4);
+        if (bn) g = make_float4(fmaf(c2.x, z.x, fmaf(c0.x, g.x, c1.x)), fmaf(c2.y, z.y, fmaf(c0.y, g.y, c1.y)),
+                                fmaf(c2.z, z.z, fmaf(c0.z, g.z, c1.z)), fmaf(c2.w, z.w, fmaf(c0.w, g.w, c1.w)));
+        if (0 >= relu_from && !(z.x > 0.f)) g.x = 0.f;
+        if (1 >= relu_from && !(z.y > 0.f)) g.y = 0.f;
+        if (2 >= relu_from && !(z.z > 0.f)) g.z = 0.f;
+        if (3 >= relu_from && !(z.w > 0.f)) g.w = 0.f;
+        return g;
+    }
+};
+
+// sum_k val[k] * gpre(col[k]); batches of 2 (two loads per entry)
+__device__ __forceinline__ float4 gpre_gather(const Gpre4& gp, const int* __restrict__ col,
+                                              const float* __restrict__ val, int k0, int k1) {
+    float4 acc = f4_zero();
+    for (int k = k0; k < k1; k += 2) {
+        const bool on = k + 1 < k1;
+        const int c0 = __ldg(col + k), c1 = __ldg(col + (on ? k + 1 : k));
+        const float v0 = __ldg(val + k), v1 = on ? __ldg(val + k + 1) : 0.f;
+        const float4 g0 = gp(c0), g1 = gp(c1);
+        acc = f4_fma(v0, g0, acc);
+        acc = f4_fma(v1, g1, acc);
+    }
+    return acc;
+}
+
+#define R4_MAX_FLAGGED 64
+
+template <int NCSR>
+__global__ void __launch_bounds__(R4_THREADS)
+bwd_row4_kernel(const Bwd4Args a) {
+    constexpr int NT = 2 + NCSR;                          // self blocks
+    __shared__ __align__(16) float Ws[NT * 4 * 4];        // [t][o][f] = W[o][t*4+f]
+    __shared__ __align__(16) float Wc[2 * 4 * 4];         // [t][o][f] = W[o][col0 + t*4 + f]
+    __shared__ __align__(16) float vec[16];                // sc, sh, mu, rs of the part's input
+    __shared__ __align__(16) float coef[12];
+    __shared__ double dscratch[256];
+    __shared__ double dtot[32];
+    __shared__ float red[(R4_THREADS / 32) * 64];
+    __shared__ int flagged[R4_MAX_FLAGGED];
+    __shared__ int n_flagged;
+    __shared__ float rsum[4];
+    __shared__ int rsum_id;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const bool is_self = (int)blockIdx.x < a.ctas_self;
+    if (tid == 0) { n_flagged = 0; rsum_id = -1; }
+    // ---- coefficients of this side's BN + ReLU backward
+    if (a.has_bn) {
+        bins_total(a.acc_f, 8, hgnn_ws_bins(8), dtot, dscratch);
+        bins_total(a.acc_b, 8, hgnn_ws_bins(8), dtot + 8, dscratch);
+        if (tid < 4) {
+            const double w = a.bn_w[0], n = (double)a.Rg;
+            const double m = dtot[tid] / n;
+            double var = dtot[4 + tid] / n - m * m;
+            if (var < 0.0) var = 0.0;
+            const double sd = sqrt(var + ENG_BN_EPS);
+            const double k0 = w / sd, k2 = -k0 * dtot[12 + tid] / (n * sd);
+            coef[tid] = (float)k0;
+            coef[8 + tid] = (float)k2;
+            coef[4 + tid] = (float)(-k0 * dtot[8 + tid] / n - k2 * m);
+        }
+    } else if (tid < 4) {
+        coef[tid] = 1.f; coef[4 + tid] = 0.f; coef[8 + tid] = 0.f;
+    }
+    for (int i = tid; i < NT * 16; i += R4_THREADS) {
+        const int t = i >> 4, o = (i >> 2) & 3, f = i & 3;
+        const float* wrow = (o < a.Ha) ? a.Wa + (size_t)o * a.Cin : a.Wb + (size_t)(o - a.Ha) * a.Cin;
+        Ws[i] = wrow[t * 4 + f];
+    }
+    if (a.R_cross > 0)
+        for (int i = tid; i < 32; i += R4_THREADS) {
+            const int t = i >> 4, o = (i >> 2) & 3, f = i & 3;
+            const float* wrow = (o < a.Ha) ? a.Wa + (size_t)o * a.Cin : a.Wb + (size_t)(o - a.Ha) * a.Cin;
+            Wc[i] = wrow[a.col0_cross + t * 4 + f];
+        }
+    const BnRef& bref = is_self ? a.bn_s : a.bn_c;
+    const bool x_aff = bn_vec4(bref, vec, vec + 4, vec + 8, vec + 12, dtot + 16, dscratch);
+    __syncthreads();
+    Gpre4 gp;
+    gp.c0 = *reinterpret_cast<const float4*>(coef);
+    gp.c1 = *reinterpret_cast<const float4*>(coef + 4);
+    gp.c2 = *reinterpret_cast<const float4*>(coef + 8);
+    gp.relu_from = a.relu_from; gp.bn = a.has_bn != 0; gp.need_z = a.has_bn != 0 || a.relu_from < 4;
+    gp.G = a.gY; gp.Z = a.Z;
+    const float4 sc = x_aff ? *reinterpret_cast<const float4*>(vec) : make_float4(1.f, 1.f, 1.f, 1.f);
+    const float4 sh = x_aff ? *reinterpret_cast<const float4*>(vec + 4) : f4_zero();
+    const float4 mu = *reinterpret_cast<const float4*>(vec + 8), rs = *reinterpret_cast<const float4*>(vec + 12);
+
+    // per-thread accumulators: dW (NT or 2 blocks of 4x4), dbias (4), (sum g, sum g*xhat) (8)
+    float dw[NT * 16];
+#pragma unroll
+    for (int i = 0; i < NT * 16; ++i) dw[i] = 0.f;
+    float db[4] = {0.f, 0.f, 0.f, 0.f};
+    float sg[4] = {0.f, 0.f, 0.f, 0.f}, sgx[4] = {0.f, 0.f, 0.f, 0.f};
+
+    if (is_self) {
+        float* const gX = a.gXs;
+        const bool stats = a.acc_b_self != nullptr && gX != nullptr;
+        for (int row = blockIdx.x * R4_THREADS + tid; row < a.R_self; row += a.ctas_self * R4_THREADS) {
+            float4 T[NT];
+            T[0] = gp(row);
+            const float d = __ldg(a.diag + row);
+            T[1] = make_float4(d * T[0].x, d * T[0].y, d * T[0].z, d * T[0].w);
+#pragma unroll
+            for (int t = 0; t < NCSR; ++t)
+                T[2 + t] = gpre_gather(gp, a.col[t], a.val[t], __ldg(a.rowptr[t] + row), __ldg(a.rowptr[t] + row + 1));
+            if (NCSR > 0 && a.rng_rowptr && __ldg(a.rng_rowptr + row + 1) > __ldg(a.rng_rowptr + row)) {
+                const int slot = atomicAdd(&n_flagged, 1);
+                if (slot < R4_MAX_FLAGGED) {
+                    flagged[slot] = row;
+                } else {            // list full: add the run-length part serially (correct, slow, rare)
+                    for (int e = __ldg(a.rng_rowptr + row); e < __ldg(a.rng_rowptr + row + 1); ++e) {
+                        const int id = __ldg(a.rng_id + e);
+                        const float v = __ldg(a.rng_val + e);
+                        for (int rr = __ldg(a.rng_lo + id); rr < __ldg(a.rng_hi + id); ++rr) T[2] = f4_fma(v, gp(rr), T[2]);
+                    }
+                }
+            }
+            const float4 xr = ld4(a.Xs + (size_t)row * 4);
+            const float4 xn = f4_affine(xr, sc, sh);
+            float g[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+            for (int t = 0; t < NT; ++t) {
+                const float Tv[4] = {T[t].x, T[t].y, T[t].z, T[t].w};
+#pragma unroll
+                for (int o = 0; o < 4; ++o) {
+                    const float4 w = *reinterpret_cast<const float4*>(Ws + (t * 4 + o) * 4);
+                    g[0] = fmaf(Tv[o], w.x, g[0]); g[1] = fmaf(Tv[o], w.y, g[1]);
+                    g[2] = fmaf(Tv[o], w.z, g[2]); g[3] = fmaf(Tv[o], w.w, g[3]);
+                    dw[(t * 4 + o) * 4 + 0] = fmaf(Tv[o], xn.x, dw[(t * 4 + o) * 4 + 0]);
+                    dw[(t * 4 + o) * 4 + 1] = fmaf(Tv[o], xn.y, dw[(t * 4 + o) * 4 + 1]);
+                    dw[(t * 4 + o) * 4 + 2] = fmaf(Tv[o], xn.z, dw[(t * 4 + o) * 4 + 2]);
+                    dw[(t * 4 + o) * 4 + 3] = fmaf(Tv[o], xn.w, dw[(t * 4 + o) * 4 + 3]);
+                }
+            }
+            db[0] += T[0].x; db[1] += T[0].y; db[2] += T[0].z; db[3] += T[0].w;
+            if (gX) {
+                float4 o4 = make_float4(g[0], g[1], g[2], g[3]);
+                if (a.acc_self) {
+                    const float4 old = *reinterpret_cast<const float4*>(gX + (size_t)row * 4);
+                    o4.x += old.x; o4.y += old.y; o4.z += old.z; o4.w += old.w;
+                }
+                *reinterpret_cast<float4*>(gX + (size_t)row * 4) = o4;
+                if (stats) {
+                    const float xh[4] = {(xr.x - mu.x) * rs.x, (xr.y - mu.y) * rs.y, (xr.z - mu.z) * rs.z, (xr.w - mu.w) * rs.w};
+#pragma unroll
+                    for (int f = 0; f < 4; ++f) { sg[f] += g[f]; sgx[f] = fmaf(g[f], xh[f], sgx[f]); }
+                }
+            }
+        }
+        // ---- run-length parts of the flagged rows: range sum once per CTA (cached), then the delta
+        //      of everything that is linear in T[2]
+        __syncthreads();
+        const int nf = min(n_flagged, R4_MAX_FLAGGED);
+        for (int it = 0; it < nf; ++it) {
+            const int row = flagged[it];
+            for (int e = __ldg(a.rng_rowptr + row); e < __ldg(a.rng_rowptr + row + 1); ++e) {
+                const int id = __ldg(a.rng_id + e);
+                if (id != rsum_id) {               // uniform
+                    const int lo = __ldg(a.rng_lo + id), hi = __ldg(a.rng_hi + id);
+                    float4 acc = f4_zero();
+                    for (int rr = lo + tid; rr < hi; rr += R4_THREADS) {
+                        const float4 gv = gp(rr);
+                        acc.x += gv.x; acc.y += gv.y; acc.z += gv.z; acc.w += gv.w;
+                    }
+                    acc.x = warp_sum(acc.x); acc.y = warp_sum(acc.y); acc.z = warp_sum(acc.z); acc.w = warp_sum(acc.w);
+                    __syncthreads();
+                    if (lane == 0) { red[warp * 4] = acc.x; red[warp * 4 + 1] = acc.y; red[warp * 4 + 2] = acc.z; red[warp * 4 + 3] = acc.w; }
+                    __syncthreads();
+                    if (tid < 4) {
+                        float v = 0.f;
+                        for (int w = 0; w < R4_THREADS / 32; ++w) v += red[w * 4 + tid];
+                        rsum[tid] = v;
+                    }
+                    if (tid == 0) rsum_id = id;
+                    __syncthreads();
+                }
+                if (tid == 0) {                    // one thread finishes the row
+                    const float v = __ldg(a.rng_val + e);
+                    const float dT[4] = {v * rsum[0], v * rsum[1], v * rsum[2], v * rsum[3]};
+                    const float4 xr = ld4(a.Xs + (size_t)row * 4);
+                    const float4 xn = f4_affine(xr, sc, sh);
+                    float g[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+                    for (int o = 0; o < 4; ++o) {
+                        const float4 w = *reinterpret_cast<const float4*>(Ws + (2 * 4 + o) * 4);
+                        g[0] = fmaf(dT[o], w.x, g[0]); g[1] = fmaf(dT[o], w.y, g[1]);
+                        g[2] = fmaf(dT[o], w.z, g[2]); g[3] = fmaf(dT[o], w.w, g[3]);
+                        dw[(2 * 4 + o) * 4 + 0] = fmaf(dT[o], xn.x, dw[(2 * 4 + o) * 4 + 0]);
+                        dw[(2 * 4 + o) * 4 + 1] = fmaf(dT[o], xn.y, dw[(2 * 4 + o) * 4 + 1]);
+                        dw[(2 * 4 + o) * 4 + 2] = fmaf(dT[o], xn.z, dw[(2 * 4 + o) * 4 + 2]);
+                        dw[(2 * 4 + o) * 4 + 3] = fmaf(dT[o], xn.w, dw[(2 * 4 + o) * 4 + 3]);
+                    }
+                    if (gX) {
+                        float4 old = __ldcg(reinterpret_cast<const float4*>(gX + (size_t)row * 4));
+                        old.x += g[0]; old.y += g[1]; old.z += g[2]; old.w += g[3];
+                        *reinterpret_cast<float4*>(gX + (size_t)row * 4) = old;
+                        if (stats) {
+                            const float xh[4] = {(xr.x - mu.x) * rs.x, (xr.y - mu.y) * rs.y, (xr.z - mu.z) * rs.z, (xr.w - mu.w) * rs.w};
+#pragma unroll
+                            for (int f = 0; f < 4; ++f) { sg[f] += g[f]; sgx[f] = fmaf(g[f], xh[f], sgx[f]); }
+                        }
+                    }
+                }
+            }
+        }
+    } else {
+        float* const gX = a.gXc;
+        const bool stats = a.acc_b_cross != nullptr && gX != nullptr;
+        const int ncta = gridDim.x - a.ctas_self;
+        for (int row = (blockIdx.x - a.ctas_self) * R4_THREADS + tid; row < a.R_cross; row += ncta * R4_THREADS) {
+            float4 Tm = f4_zero(), Td = f4_zero();
+            const int k0 = __ldg(a.pt_rowptr + row), k1 = __ldg(a.pt_rowptr + row + 1);
+            for (int k = k0; k < k1; k += 2) {
+                const bool on = k + 1 < k1;
+                const int c0 = __ldg(a.pt_col + k), c1 = __ldg(a.pt_col + (on ? k + 1 : k));
+                const float m0 = __ldg(a.pt_pm + k), d0 = __ldg(a.pt_pd + k);
+                const float m1 = on ? __ldg(a.pt_pm + k + 1) : 0.f, d1 = on ? __ldg(a.pt_pd + k + 1) : 0.f;
+                const float4 g0 = gp(c0), g1 = gp(c1);
+                Tm = f4_fma(m0, g0, Tm); Td = f4_fma(d0, g0, Td);
+                Tm = f4_fma(m1, g1, Tm); Td = f4_fma(d1, g1, Td);
+            }
+            const float4 xr = ld4(a.Xc + (size_t)row * 4);
+            const float4 xn = f4_affine(xr, sc, sh);
+            float g[4] = {0.f, 0.f, 0.f, 0.f};
+            const float4 T[2] = {Tm, Td};
+#pragma unroll
+            for (int t = 0; t < 2; ++t) {
+                const float Tv[4] = {T[t].x, T[t].y, T[t].z, T[t].w};
+#pragma unroll
+                for (int o = 0; o < 4; ++o) {
+                    const float4 w = *reinterpret_cast<const float4*>(Wc + (t * 4 + o) * 4);
+                    g[0] = fmaf(Tv[o], w.x, g[0]); g[1] = fmaf(Tv[o], w.y, g[1]);
+                    g[2] = fmaf(Tv[o], w.z, g[2]); g[3] = fmaf(Tv[o], w.w, g[3]);
+                    dw[(t * 4 + o) * 4 + 0] = fmaf(Tv[o], xn.x, dw[(t * 4 + o) * 4 + 0]);
+                    dw[(t * 4 + o) * 4 + 1] = fmaf(Tv[o], xn.y, dw[(t * 4 + o) * 4 + 1]);
+                    dw[(t * 4 + o) * 4 + 2] = fmaf(Tv[o], xn.z, dw[(t * 4 + o) * 4 + 2]);
+                    dw[(t * 4 + o) * 4 + 3] = fmaf(Tv[o], xn.w, dw[(t * 4 + o) * 4 + 3]);
+                }
+            }
+            if (gX) {
+                float4 o4 = make_float4(g[0], g[1], g[2], g[3]);
+                if (a.acc_cross) {
+                    const float4 old = *reinterpret_cast<const float4*>(gX + (size_t)row * 4);
+                    o4.x += old.x; o4.y += old.y; o4.z += old.z; o4.w += old.w;
+                }
+                *reinterpret_cast<float4*>(gX + (size_t)row * 4) = o4;
+                if (stats) {
+                    const float xh[4] = {(xr.x - mu.x) * rs.x, (xr.y - mu.y) * rs.y, (xr.z - mu.z) * rs.z, (xr.w - mu.w) * rs.w};
+#pragma unroll
+                    for (int f = 0; f < 4; ++f) { sg[f] += g[f]; sgx[f] = fmaf(g[f], xh[f], sgx[f]); }
+                }
+            }
+        }
+    }
+    // ---- flush: warp shuffle tree -> per-warp rows in shared memory -> one fp64 atomic per value
+    const int nvals = is_self ? NT * 16 : 32;
+    const int nbw = hgnn_ws_bins(4 * a.Cin);
+    const int col_base = is_self ? 0 : a.col0_cross;
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < NT * 16; ++i) {
+        if (i < nvals) {
+            const float v = warp_sum(dw[i]);
+            if (lane == 0) red[warp * 64 + i] = v;
+        }
+    }
+    __syncthreads();
+    if (a.dW_bins)
+        for (int i = tid; i < nvals; i += R4_THREADS) {
+            float v = 0.f;
+            for (int w = 0; w < R4_THREADS / 32; ++w) v += red[w * 64 + i];
+            const int t = i >> 4, o = (i >> 2) & 3, f = i & 3;
+            accum_add(a.dW_bins, 4 * a.Cin, nbw, o * a.Cin + col_base + t * 4 + f, (double)v);
+        }
+    __syncthreads();
+    // dbias (self only) and the BN sums of the produced gradient
+    float extra[12];
+#pragma unroll
+    for (int f = 0; f < 4; ++f) { extra[f] = db[f]; extra[4 + f] = sg[f]; extra[8 + f] = sgx[f]; }
+#pragma unroll
+    for (int i = 0; i < 12; ++i) {
+        const float v = warp_sum(extra[i]);
+        if (lane == 0) red[warp * 64 + i] = v;
+    }
+    __syncthreads();
+    if (tid < 12) {
+        double v = 0.0;
+        for (int w = 0; w < R4_THREADS / 32; ++w) v += (double)red[w * 64 + tid];
+        if (tid < 4) {
+            if (is_self && a.db_bins) accum_add(a.db_bins, 4, hgnn_ws_bins(4), tid, v);
+        } else {
+            double* accb = is_self ? a.acc_b_self : a.acc_b_cross;
+            float* gXp = is_self ? a.gXs : a.gXc;
+            if (accb && gXp) accum_add(accb, 8, hgnn_ws_bins(8), tid - 4, v);
+        }
+    }
+}
