@@ -191,45 +191,30 @@ def lgnn_layer_algorithmic_bytes(pack, F):
     return gmul_b + pmul_e, gmul_a + pmul_n
 
 
-def time_dominant_kernel(a, model, pack, reps=30):
-    """The fused edge-side update of a middle layer (csrc/side.cu side_fwd_kernel), timed alone on the
-    current stream with CUDA events, L2 flushed before every launch."""
-    import ctypes
+def profile_step(train_step, resident, flush, reps=5):
+    """Per-launch device time of every C-ABI call inside real (eager) training steps: CUDA events
+    recorded on the launching stream right before / after each call, L2 flushed before each step.
+    Returns {(entry point, side kind): [n_launches_per_step, mean_us, total_us_per_step]}."""
     from hgnn_b200 import _lib
-    from hgnn_b200.models.layers import layers_mnb
-    from hgnn_b200.ops import _side_struct
-    layer = model._modules["layer1"]
-    _, edge = layers_mnb._side_cfgs(pack)
-    F = 2 * a.h
-    dev = pack.device
-    g = torch.Generator(device="cuda").manual_seed(1)
-    XL = torch.randn(pack.Rm, F, device=dev, generator=g)
-    Xn = torch.randn(pack.Rn, F, device=dev, generator=g)
-    Z = torch.empty(pack.Rm, F, device=dev)
-    stats = torch.empty(4 * F, device=dev)
-    side, keep = _side_struct(edge, XL, Xn)
-    Wa, Wb = layer.cv4.weight.detach().view(a.h, -1), layer.cv3.weight.detach().view(a.h, -1)
-    ws, wsb = _lib.workspace(2 * F, dev)
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-    rm, rs = torch.zeros(F, device=dev), torch.zeros(F, device=dev)
-
-    def launch():
-        _lib.call("hgnn_side_fwd", ctypes.byref(side), _lib.fptr(Wa), _lib.fptr(layer.cv4.bias.detach()),
-                  a.h, _lib.fptr(Wb), _lib.fptr(layer.cv3.bias.detach()), a.h, a.h, _lib.fptr(Z),
-                  _lib.fptr(layer.bn2.weight.detach()), _lib.fptr(layer.bn2.bias.detach()),
-                  _lib.fptr(rm), _lib.fptr(rs), 0.1, _lib.fptr(stats), ws, wsb, _lib.stream())
-    for _ in range(3):
-        launch()
-    times = []
+    agg = {}
     for _ in range(reps):
         flush.zero_()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        launch()
-        e1.record()
-        e1.synchronize()
-        times.append(e0.elapsed_time(e1) * 1e-3)
-    return statistics.mean(times), min(times)
+        torch.cuda.synchronize()
+        _lib.timing = []
+        train_step(resident)
+        torch.cuda.synchronize()
+        rec, _lib.timing = _lib.timing, None
+        for name, tag, e0, e1 in rec:
+            kind = "edge" if tag.endswith(".edge") else "node" if tag.endswith(".node") else tag
+            if tag.startswith("L0."):
+                kind = "layer0." + kind          # layer 0 has different widths (5 / 1 input features)
+            key = (name, kind if name.startswith("hgnn_lg_side") else "")
+            agg.setdefault(key, []).append(e0.elapsed_time(e1) * 1e3)
+    out = {}
+    for key, v in agg.items():
+        n = len(v) / reps
+        out[key] = [n, sum(v) / len(v), sum(v) / reps]
+    return out
 
 
 def run_ours(a):
@@ -378,16 +363,34 @@ def run_ours(a):
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
     peak_kind = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6.65 TB/s"
-    t_mean, t_min = time_dominant_kernel(a, model, pack)
+    prof = profile_step(train_step, resident, flush)
     edge_bytes, node_bytes = lgnn_layer_algorithmic_bytes(pack, 2 * a.h)
-    achieved = edge_bytes / t_mean / 1e9
-    roofline = {"bound": "hbm", "kernel": "side_fwd_kernel<4> (fused edge-side update: gmul(B) + Pm^T/Pd^T "
-                                          "+ cv3/cv4 + ReLU + BN stats)",
+    step_us = sum(v[2] for v in prof.values())
+    breakdown = sorted(([k[0] + ("[" + k[1] + "]" if k[1] else ""), round(v[0], 1), round(v[1], 2),
+                         round(100 * v[2] / step_us, 1)] for k, v in prof.items()), key=lambda r: -r[3])
+    # the dominant kernel = the C-ABI entry point / side with the largest share of the step
+    dom = max((k for k in prof if k[0].startswith("hgnn_lg_side") and not k[1].startswith("layer0")
+               and k[1] in ("edge", "node")), key=lambda k: prof[k][2])
+    dom_bytes = edge_bytes if dom[1] == "edge" else node_bytes
+    t_mean = prof[dom][1] * 1e-6
+    achieved = dom_bytes / t_mean / 1e9
+    traffic = None
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get("%s[%s]" % dom)
+    except Exception:
+        pass
+    roofline = {"bound": "hbm",
+                "kernel": "%s [%s side of a middle layer]: fused gather (multi-operator + Pm/Pd) + conv + ReLU + BN "
+                          "(forward) / its transposed-gather backward" % dom,
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "peak_kind": peak_kind, "algorithmic_bytes_per_launch": edge_bytes,
-                "launch_us_mean": t_mean * 1e6, "launch_us_min": t_min * 1e6,
-                "note": "L2 flushed before each launch; at h=2 the per-launch working set (~%d MB) is "
-                        "L2-sized and the kernel is latency-bound (SURVEY.md 8d)" % (edge_bytes // 1000000)}
+                "traffic": traffic, "peak_kind": peak_kind, "algorithmic_bytes_per_launch": dom_bytes,
+                "launch_us_mean": t_mean * 1e6, "share_of_step_pct": round(100 * prof[dom][2] / step_us, 1),
+                "how": "CUDA events around every launch of 5 eager training steps (L2 flushed before each "
+                       "step); algorithmic bytes per SURVEY.md 8(d); backward counts the forward's bytes",
+                "per_kernel": {"columns": ["entry point [side]", "launches/step", "mean us", "% of step"],
+                               "rows": breakdown[:8]},
+                "note": "h=2: <= %d MB per launch, latency-bound (3 dependent memory rounds per row); the "
+                        "fraction is bounded by launch latency, not by HBM" % (dom_bytes // 1000000)}
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps,
             "warmup": a.warmup, "ms_per_step": elapsed * 1e3 / a.steps, "higher_is_better": True,

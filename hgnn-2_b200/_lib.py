@@ -109,12 +109,22 @@ lib.hgnn_bins_for.argtypes = [c_int]
 
 # number of kernel launches issued through the C ABI (bench.py reports it as gpu_launches)
 launch_count = 0
+# optional per-call CUDA-event timing (bench.py): list of (name, tag, start_event, end_event)
+timing = None
+tag = ""
 
 
 def call(name, *args):
     """Invoke one C-ABI entry point; raise on a non-zero status."""
     global launch_count
-    rc = getattr(lib, name)(*args)
+    if timing is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        rc = getattr(lib, name)(*args)
+        e1.record()
+        timing.append((name, tag, e0, e1))
+    else:
+        rc = getattr(lib, name)(*args)
     if rc != 0:
         raise RuntimeError("%s failed (%d): %s" % (name, rc, lib.hgnn_last_error().decode()))
     launch_count += 1

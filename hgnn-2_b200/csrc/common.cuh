@@ -90,10 +90,14 @@ static inline int make_oplist(const hgnn_op_t* ops, int n_ops, OpList* out) {
 // runs the finalizer in the same launch.
 #define HGNN_WS_HEADER 256
 
-// number of accumulator bins for a reduction of `width` values (host and device agree on this)
+// number of accumulator bins for a reduction of `width` values (host and device agree on this):
+// 32 / width rounded down to a power of two, at least 1 - i.e. small reductions (the 2F batch-norm
+// sums) spread over a few bins so that nb*width = 32 doubles = one load per lane of a warp, wide
+// ones (dW) use a single bin: same-address fp64 RED throughput (~1 op/clk at the L2 slice) is ample
+// for the <= ~1000 CTAs of a launch.
 __host__ __device__ inline int hgnn_ws_bins(int width) {
-    int nb = 32;
-    while (nb > 1 && (long long)nb * width > 4096) nb >>= 1;
+    int nb = 1;
+    while (nb * 2 * width <= 32) nb *= 2;
     return nb;
 }
 

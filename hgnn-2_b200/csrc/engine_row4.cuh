@@ -46,10 +46,64 @@ __device__ __forceinline__ void csr_gather4(const int* __restrict__ col, const f
     }
 }
 
-// scale/shift (and mean/rstd) of a width-4 tensor into shared memory; all threads; ends synced
-__device__ __forceinline__ bool bn_vec4(const BnRef& r, float* sc, float* sh, float* mu, float* rs,
-                                        double* tot, double* scratch) {
-    return bn_vectors(r, 4, sc, sh, mu, rs, tot, scratch);
+// ---- warp-level batch-norm prologue for width-4 tensors: the binned (sum, sum^2) accumulators are
+// hgnn_ws_bins(8) x 8 = 32 doubles = one load per lane; two shuffles fold the bins, eight more
+// broadcast the totals, and every thread derives the vectors in registers - no shared memory and
+// no block barrier.
+__device__ __forceinline__ void warp_totals8(const double* __restrict__ acc, double tot[8]) {
+    const int lane = threadIdx.x & 31;
+    double v = __ldcg(acc + lane);            // nb * 8 == 32 by construction (hgnn_ws_bins(8) == 4)
+    v += __shfl_xor_sync(0xffffffffu, v, 8);
+    v += __shfl_xor_sync(0xffffffffu, v, 16);
+#pragma unroll
+    for (int c = 0; c < 8; ++c) tot[c] = __shfl_sync(0xffffffffu, v, c);
+}
+
+struct Bn4 {
+    float4 sc, sh, mu, rs;
+    bool on;
+};
+
+__device__ __forceinline__ Bn4 bn4_from_ref(const BnRef& r) {
+    Bn4 o;
+    o.on = true;
+    if (r.affine) {
+        o.sc = ld4(r.affine);
+        o.sh = ld4(r.affine + 4);
+        o.mu = f4_zero();
+        o.rs = make_float4(1.f, 1.f, 1.f, 1.f);
+        return o;
+    }
+    if (!r.acc) {
+        o.on = false;
+        o.sc = make_float4(1.f, 1.f, 1.f, 1.f);
+        o.sh = f4_zero();
+        o.mu = f4_zero();
+        o.rs = make_float4(1.f, 1.f, 1.f, 1.f);
+        return o;
+    }
+    double tot[8];
+    warp_totals8(r.acc, tot);
+    // E[x^2] - mean^2 in fp64 (the only cancellation-prone step); everything after in fp32 - fp64
+    // divide / sqrt are long software sequences and every thread runs this prologue
+    const float w = r.w[0], b = r.b[0];
+    const double inv_n = 1.0 / (double)r.n;
+    float sc[4], sh[4], mu[4], rs[4];
+#pragma unroll
+    for (int f = 0; f < 4; ++f) {
+        const double m = tot[f] * inv_n;
+        const double var = fma(-m, m, tot[4 + f] * inv_n);
+        const float r_ = 1.0f / sqrtf(fmaxf((float)var, 0.f) + (float)ENG_BN_EPS);
+        mu[f] = (float)m;
+        rs[f] = r_;
+        sc[f] = w * r_;
+        sh[f] = b - w * mu[f] * r_;
+    }
+    o.sc = make_float4(sc[0], sc[1], sc[2], sc[3]);
+    o.sh = make_float4(sh[0], sh[1], sh[2], sh[3]);
+    o.mu = make_float4(mu[0], mu[1], mu[2], mu[3]);
+    o.rs = make_float4(rs[0], rs[1], rs[2], rs[3]);
+    return o;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -76,20 +130,18 @@ fwd_row4_kernel(const Fwd4Args a) {
     constexpr int NB = 2 + NCSR + (CROSS ? 2 : 0);     // float4 blocks of x1
     __shared__ __align__(16) float W[4 * NB * 4];       // [o][Cin]
     __shared__ __align__(16) float bias[4];
-    __shared__ __align__(16) float aff[16];              // sc_s, sh_s, sc_c, sh_c
-    __shared__ double dscratch[256];
-    __shared__ double dtot[16];
+    __shared__ double red[(R4_THREADS / 32) * 8];
     const int tid = threadIdx.x;
     for (int i = tid; i < 4 * NB * 4; i += R4_THREADS) {
         const int o = i / (NB * 4), c = i - o * (NB * 4);
         W[i] = (o < a.Ha) ? a.Wa[(size_t)o * a.Cin + c] : a.Wb[(size_t)(o - a.Ha) * a.Cin + c];
     }
     if (tid < 4) bias[tid] = (tid < a.Ha) ? (a.ba ? a.ba[tid] : 0.f) : (a.bb ? a.bb[tid - a.Ha] : 0.f);
-    bn_vec4(a.bn_s, aff, aff + 4, nullptr, nullptr, dtot, dscratch);
-    if (CROSS) bn_vec4(a.bn_c, aff + 8, aff + 12, nullptr, nullptr, dtot, dscratch);
-    __syncthreads();
-    const float4 sc_s = *reinterpret_cast<const float4*>(aff), sh_s = *reinterpret_cast<const float4*>(aff + 4);
-    const float4 sc_c = *reinterpret_cast<const float4*>(aff + 8), sh_c = *reinterpret_cast<const float4*>(aff + 12);
+    const Bn4 bs4 = bn4_from_ref(a.bn_s);
+    Bn4 bc4 = bs4;
+    if (CROSS) bc4 = bn4_from_ref(a.bn_c);
+    __syncthreads();                                   // weights in shared memory
+    const float4 sc_s = bs4.sc, sh_s = bs4.sh, sc_c = bc4.sc, sh_c = bc4.sh;
     float s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
 
     for (int row = blockIdx.x * R4_THREADS + tid; row < a.R; row += gridDim.x * R4_THREADS) {
@@ -163,16 +215,18 @@ fwd_row4_kernel(const Fwd4Args a) {
         }
         *reinterpret_cast<float4*>(a.Z + (size_t)row * 4) = make_float4(out[0], out[1], out[2], out[3]);
     }
-    if (a.acc_out) {
-        const int nb = hgnn_ws_bins(8);
+    if (a.acc_out) {       // warp shuffle tree -> one row per warp in shared memory -> 8 fp64 atomics per CTA
+        const int lane = tid & 31, warp = tid >> 5;
 #pragma unroll
         for (int o = 0; o < 4; ++o) {
-            const double x = cta_reduce_mod((double)s1[o], 1, dscratch);
-            const double y = cta_reduce_mod((double)s2[o], 1, dscratch);
-            if (tid == 0) {
-                accum_add(a.acc_out, 8, nb, o, x);
-                accum_add(a.acc_out, 8, nb, 4 + o, y);
-            }
+            const double x = warp_sum_d((double)s1[o]), y = warp_sum_d((double)s2[o]);
+            if (lane == 0) { red[warp * 8 + o] = x; red[warp * 8 + 4 + o] = y; }
+        }
+        __syncthreads();
+        if (tid < 8) {
+            double v = 0.0;
+            for (int w = 0; w < R4_THREADS / 32; ++w) v += red[w * 8 + tid];
+            accum_add(a.acc_out, 8, hgnn_ws_bins(8), tid, v);
         }
     }
 }
@@ -243,10 +297,6 @@ bwd_row4_kernel(const Bwd4Args a) {
     constexpr int NT = 2 + NCSR;                          // self blocks
     __shared__ __align__(16) float Ws[NT * 4 * 4];        // [t][o][f] = W[o][t*4+f]
     __shared__ __align__(16) float Wc[2 * 4 * 4];         // [t][o][f] = W[o][col0 + t*4 + f]
-    __shared__ __align__(16) float vec[16];                // sc, sh, mu, rs of the part's input
-    __shared__ __align__(16) float coef[12];
-    __shared__ double dscratch[256];
-    __shared__ double dtot[32];
     __shared__ float red[(R4_THREADS / 32) * 64];
     __shared__ int flagged[R4_MAX_FLAGGED];
     __shared__ int n_flagged;
@@ -255,24 +305,6 @@ bwd_row4_kernel(const Bwd4Args a) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const bool is_self = (int)blockIdx.x < a.ctas_self;
     if (tid == 0) { n_flagged = 0; rsum_id = -1; }
-    // ---- coefficients of this side's BN + ReLU backward
-    if (a.has_bn) {
-        bins_total(a.acc_f, 8, hgnn_ws_bins(8), dtot, dscratch);
-        bins_total(a.acc_b, 8, hgnn_ws_bins(8), dtot + 8, dscratch);
-        if (tid < 4) {
-            const double w = a.bn_w[0], n = (double)a.Rg;
-            const double m = dtot[tid] / n;
-            double var = dtot[4 + tid] / n - m * m;
-            if (var < 0.0) var = 0.0;
-            const double sd = sqrt(var + ENG_BN_EPS);
-            const double k0 = w / sd, k2 = -k0 * dtot[12 + tid] / (n * sd);
-            coef[tid] = (float)k0;
-            coef[8 + tid] = (float)k2;
-            coef[4 + tid] = (float)(-k0 * dtot[8 + tid] / n - k2 * m);
-        }
-    } else if (tid < 4) {
-        coef[tid] = 1.f; coef[4 + tid] = 0.f; coef[8 + tid] = 0.f;
-    }
     for (int i = tid; i < NT * 16; i += R4_THREADS) {
         const int t = i >> 4, o = (i >> 2) & 3, f = i & 3;
         const float* wrow = (o < a.Ha) ? a.Wa + (size_t)o * a.Cin : a.Wb + (size_t)(o - a.Ha) * a.Cin;
@@ -284,18 +316,39 @@ bwd_row4_kernel(const Bwd4Args a) {
             const float* wrow = (o < a.Ha) ? a.Wa + (size_t)o * a.Cin : a.Wb + (size_t)(o - a.Ha) * a.Cin;
             Wc[i] = wrow[a.col0_cross + t * 4 + f];
         }
-    const BnRef& bref = is_self ? a.bn_s : a.bn_c;
-    const bool x_aff = bn_vec4(bref, vec, vec + 4, vec + 8, vec + 12, dtot + 16, dscratch);
-    __syncthreads();
+    // ---- coefficients of this side's BN + ReLU backward, and the input's BN vectors: warp-level
     Gpre4 gp;
-    gp.c0 = *reinterpret_cast<const float4*>(coef);
-    gp.c1 = *reinterpret_cast<const float4*>(coef + 4);
-    gp.c2 = *reinterpret_cast<const float4*>(coef + 8);
     gp.relu_from = a.relu_from; gp.bn = a.has_bn != 0; gp.need_z = a.has_bn != 0 || a.relu_from < 4;
     gp.G = a.gY; gp.Z = a.Z;
-    const float4 sc = x_aff ? *reinterpret_cast<const float4*>(vec) : make_float4(1.f, 1.f, 1.f, 1.f);
-    const float4 sh = x_aff ? *reinterpret_cast<const float4*>(vec + 4) : f4_zero();
-    const float4 mu = *reinterpret_cast<const float4*>(vec + 8), rs = *reinterpret_cast<const float4*>(vec + 12);
+    if (a.has_bn) {
+        double tf[8], tb[8];
+        warp_totals8(a.acc_f, tf);
+        warp_totals8(a.acc_b, tb);
+        const float w = a.bn_w[0];
+        const double inv_n = 1.0 / (double)a.Rg;
+        float c0[4], c1[4], c2[4];
+#pragma unroll
+        for (int f = 0; f < 4; ++f) {
+            const double m = tf[f] * inv_n;
+            const double var = fma(-m, m, tf[4 + f] * inv_n);
+            const float r_ = 1.0f / sqrtf(fmaxf((float)var, 0.f) + (float)ENG_BN_EPS);
+            const float k0 = w * r_;
+            const float k2 = -k0 * (float)(tb[4 + f] * inv_n) * r_;
+            c0[f] = k0;
+            c2[f] = k2;
+            c1[f] = -k0 * (float)(tb[f] * inv_n) - k2 * (float)m;
+        }
+        gp.c0 = make_float4(c0[0], c0[1], c0[2], c0[3]);
+        gp.c1 = make_float4(c1[0], c1[1], c1[2], c1[3]);
+        gp.c2 = make_float4(c2[0], c2[1], c2[2], c2[3]);
+    } else {
+        gp.c0 = make_float4(1.f, 1.f, 1.f, 1.f);
+        gp.c1 = f4_zero();
+        gp.c2 = f4_zero();
+    }
+    const Bn4 bx = bn4_from_ref(is_self ? a.bn_s : a.bn_c);
+    __syncthreads();                                   // weights in shared memory
+    const float4 sc = bx.sc, sh = bx.sh, mu = bx.mu, rs = bx.rs;
 
     // per-thread accumulators: dW (NT or 2 blocks of 4x4), dbias (4), (sum g, sum g*xhat) (8)
     float dw[NT * 16];
@@ -422,14 +475,24 @@ bwd_row4_kernel(const Bwd4Args a) {
         for (int row = (blockIdx.x - a.ctas_self) * R4_THREADS + tid; row < a.R_cross; row += ncta * R4_THREADS) {
             float4 Tm = f4_zero(), Td = f4_zero();
             const int k0 = __ldg(a.pt_rowptr + row), k1 = __ldg(a.pt_rowptr + row + 1);
-            for (int k = k0; k < k1; k += 2) {
-                const bool on = k + 1 < k1;
-                const int c0 = __ldg(a.pt_col + k), c1 = __ldg(a.pt_col + (on ? k + 1 : k));
-                const float m0 = __ldg(a.pt_pm + k), d0 = __ldg(a.pt_pd + k);
-                const float m1 = on ? __ldg(a.pt_pm + k + 1) : 0.f, d1 = on ? __ldg(a.pt_pd + k + 1) : 0.f;
-                const float4 g0 = gp(c0), g1 = gp(c1);
-                Tm = f4_fma(m0, g0, Tm); Td = f4_fma(d0, g0, Td);
-                Tm = f4_fma(m1, g1, Tm); Td = f4_fma(d1, g1, Td);
+            for (int k = k0; k < k1; k += 4) {          // 4 entries (8 row loads) in flight
+                int c[4];
+                float vm[4], vd[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const bool on = k + j < k1;
+                    c[j] = __ldg(a.pt_col + (on ? k + j : k));
+                    vm[j] = on ? __ldg(a.pt_pm + k + j) : 0.f;
+                    vd[j] = on ? __ldg(a.pt_pd + k + j) : 0.f;
+                }
+                float4 gv[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) gv[j] = gp(c[j]);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    Tm = f4_fma(vm[j], gv[j], Tm);
+                    Td = f4_fma(vd[j], gv[j], Td);
+                }
             }
             const float4 xr = ld4(a.Xc + (size_t)row * 4);
             const float4 xn = f4_affine(xr, sc, sh);

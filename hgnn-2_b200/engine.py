@@ -261,6 +261,7 @@ def _forward(plan, pack, Xp, XLp, training, arena):
         Ha = s.conv_a.weight.shape[0]
         Hb = s.conv_b.weight.shape[0] if s.conv_b is not None else 0
         Z = torch.empty(st.R, s.Fout, device=dev)
+        _lib.tag = s.name
         acc_out = None
         if s.out is not None and training:
             acc_out = arena.data_ptr() + 8 * plan.tensors[s.out]["acc_f"]
@@ -361,6 +362,7 @@ class _ModelFunction(torch.autograd.Function):
                     started.add(s.src_cross)
             else:
                 d.R_cross = 0
+            _lib.tag = s.name
             call("hgnn_lg_side_bwd", ctypes.byref(d), stream())
         offs, nbs, strides, cnts = plan.tables(dev)
         gflat = torch.empty(plan.n_flat, device=dev)
