@@ -302,13 +302,16 @@ def run_ours(a):
         h2d = W.pack.nbytes + sum(t.numel() * t.element_size() for t in staged)
         return (Xd, XLd, W, WL, Pm, Pd, mask, mask_lg, N_batch, E_batch, yd), h2d
 
-    def train_step(dbatch):
+    def train_step(dbatch, collective=True):
         Xd, XLd, W, WL, Pm, Pd, mask, mask_lg, N_batch, E_batch, yd = dbatch
         fp.zero_grad()
         out = model([Xd, XLd, W, WL, Pm, Pd], N_batch, mask, E_batch, mask_lg)
         loss = torch.nn.functional.cross_entropy(out, yd)
         loss.backward()
-        fp.all_reduce_grad()
+        if collective:
+            fp.all_reduce_grad()        # the only collective of the step
+        else:
+            fp.gather_grad()
         opt.step(grad_scale=1.0 / world)
         return loss
 
@@ -397,10 +400,24 @@ def run_ours(a):
                "path": "prepare_batch(host instances) -> pinned H2D -> GNN_lg fwd -> CE loss -> bwd -> "
                        "all-reduce -> fused Adamax -> loss.item()"}
 
+    def finish():
+        """End of the run for world > 1.  The captured CUDA graph holds NCCL kernels, and tearing the
+        process group down under it can hang, so: rank 0 announces completion through the rendezvous
+        store (no NCCL), everybody leaves with os._exit."""
+        if world == 1:
+            return
+        import datetime
+        store = dist.distributed_c10d._get_default_store()
+        if rank == 0:
+            store.set("bench_done", "1")
+        else:
+            store.wait(["bench_done"], datetime.timedelta(minutes=15))
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
+
     if rank != 0:
-        if world > 1:
-            dist.barrier()
-            dist.destroy_process_group()
+        finish()
         return
 
     # ---- roofline of the dominant aggregation kernel
@@ -411,7 +428,7 @@ def run_ours(a):
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
     peak_kind = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6.65 TB/s"
-    prof = profile_step(train_step, resident, flush)
+    prof = profile_step(lambda b: train_step(b, collective=False), resident, flush)   # rank 0 only: no collective
     edge_bytes, node_bytes = lgnn_layer_algorithmic_bytes(pack, 2 * a.h)
     step_us = sum(v["n"] * v["warm_us"] for v in prof.values())
     breakdown = sorted(([k[0] + ("[" + k[1] + "]" if k[1] else ""), v["n"], round(v["warm_us"], 2),
@@ -453,9 +470,7 @@ def run_ours(a):
     if not a.skip_cpu:
         line["cpu_baseline"] = {k: v for k, v in cpu_baseline(a).items() if k != "ms_per_step"}
     print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
+    finish()
 
 
 def main():

@@ -84,3 +84,18 @@ def test_engine_grads_are_one_flat_buffer():
     assert fp._adopt_flat_grad()
     assert fp.grad.numel() == fp.n and torch.isfinite(fp.grad).all()
     assert torch.equal(fp.grad[:model.layer0.cv1.weight.numel()], model.layer0.cv1.weight.grad.reshape(-1))
+
+
+def test_generic_engine_kernels_at_width4():
+    """The thread-per-row fast path hides the generic tile kernels at h=2: run the same comparison in a
+    subprocess with HGNN_B200_NO_ROW4=1 so that both engine code paths stay covered."""
+    import os
+    import subprocess
+    import sys
+    env = dict(os.environ, HGNN_B200_NO_ROW4="1")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "pytest", "-q", "-x", "-m", "gpu",
+                        os.path.join(root, "tests", "test_gpu_engine.py"), "-k",
+                        "matches_module_path and (lg-1-2-1-300 or lg-2-2-1-200 or simple-0-2-1-300)"],
+                       env=env, capture_output=True, text=True, cwd=root, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
