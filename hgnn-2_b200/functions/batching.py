@@ -79,14 +79,17 @@ def prepare_batch(batch, task, J=1, sparse=None, device="cuda"):
     N_batch = torch.tensor([g.N for g in graphs], dtype=torch.int64)
     E_batch = torch.tensor([g.M for g in graphs], dtype=torch.int64)
     Nmax, Emax = int(N_batch.max()), int(E_batch.max())
-    X = torch.zeros(bs, n_feat, Nmax)
-    XL = torch.zeros(bs, 1, Emax)
+    # host tensors in pinned memory (when CUDA is there) so that the caller's .cuda() is one DMA each
+    pin = torch.cuda.is_available()
+    X = torch.zeros(bs, n_feat, Nmax, pin_memory=pin)
+    XL = torch.zeros(bs, 1, Emax, pin_memory=pin)
     T = torch.zeros(bs, 1)
+    Xn, XLn = X.numpy(), XL.numpy()
     for i, inst in enumerate(batch):
         g = graphs[i]
-        X[i, :, :g.N] = inst[0].t()
-        XL[i, 0, :g.M] = torch.from_numpy(g.dl)
-        T[i, 0] = inst[2][task]
+        Xn[i, :, :g.N] = inst[0].numpy().T
+        XLn[i, 0, :g.M] = g.dl
+        T[i, 0] = float(inst[2][task])
     pack = BatchPack.from_graphs(graphs, J, dual=True, device=device)
     W, WL = OperatorHandle(pack, "W"), OperatorHandle(pack, "WL")
     Pm, Pd = OperatorHandle(pack, "Pm"), OperatorHandle(pack, "Pd")

@@ -16,7 +16,7 @@ import torch
 
 from . import _lib
 from ._lib import call, fptr, iptr, stream
-from .sparse_ops import GraphOps, concat_block_diagonal
+from .sparse_ops import GraphOps, concat_block_diagonal  # noqa: F401
 
 
 class Csr(object):
@@ -35,22 +35,22 @@ class Csr(object):
         return ("csr", self.rowptr, self.col, self.val2 if second else self.val)
 
 
-def _upload(arrays, device):
-    """One pinned staging buffer + one H2D copy for a dict of int32/float32 numpy arrays."""
-    offs, total = {}, 0
-    for k, a in arrays.items():
-        offs[k] = total
-        total += (a.nbytes + 15) & ~15
-    host = torch.empty(max(total, 16), dtype=torch.uint8, pin_memory=True)
-    hv = host.numpy()
-    for k, a in arrays.items():
-        hv[offs[k]:offs[k] + a.nbytes] = a.view(np.uint8).reshape(-1)
-    dev = host.to(device, non_blocking=True)
+def _pinned_alloc(holder):
+    """alloc(nbytes) -> numpy uint8 view of a pinned torch buffer (kept alive in ``holder``)."""
+    def alloc(nbytes):
+        holder["host"] = torch.empty(nbytes, dtype=torch.uint8, pin_memory=torch.cuda.is_available())
+        return holder["host"].numpy()
+    return alloc
+
+
+def _device_views(host_tensor, layout, device):
+    """One H2D copy of the staging buffer; the arrays become views of the device buffer."""
+    dev = host_tensor.to(device, non_blocking=True)
     out = {}
-    for k, a in arrays.items():
-        dt = torch.int32 if a.dtype == np.int32 else torch.float32
-        out[k] = dev[offs[k]:offs[k] + a.nbytes].view(dt)
-    return out, dev, total
+    for k, (o, dt, length) in layout.items():
+        tdt = torch.int32 if dt is np.int32 else torch.float32
+        out[k] = dev[o:o + 4 * length].view(tdt)
+    return out, dev
 
 
 def exclusive_scan(counts):
@@ -134,15 +134,21 @@ class BatchPack(object):
         self = cls()
         device = torch.device(device)
         self.J, self.dual, self.device = int(J), bool(dual), device
-        host = concat_block_diagonal(graphs, dual=dual)
+        # The full transposed line-graph operator is only needed by the layer-level kernels and by
+        # the powers; the engine uses its run-length split twin.  It is uploaded on first use.
+        lazy_bt = dual and self.J == 1
+        holder = {}
+        _, _, layout = host = concat_block_diagonal(graphs, dual=dual, skip=("bt",) if lazy_bt else (),
+                                                    alloc=_pinned_alloc(holder))
         self.bs = len(graphs)
         self.n_nodes = np.array([g.N for g in graphs], dtype=np.int64)
         self.n_edges = np.array([g.M for g in graphs], dtype=np.int64)
         self.Nmax = int(self.n_nodes.max())
         self.Emax = int(self.n_edges.max()) if dual else 0
         self.Rn, self.Rm = int(self.n_nodes.sum()), int(self.n_edges.sum())
-        host["pad_n"] = (self.Nmax - self.n_nodes).astype(np.float32)
-        dev, self._buffer, self.nbytes = _upload(host, device)
+        dev, self._buffer = _device_views(holder["host"], layout, device)
+        self.nbytes = holder["host"].numel()
+        self._host_graphs = graphs if lazy_bt else None
         self.node_off, self.edge_off = dev["node_off"], dev["edge_off"]
         self.pad_n = dev["pad_n"]
         self.deg = dev["deg"]
@@ -151,7 +157,7 @@ class BatchPack(object):
         if dual:
             self.dl = dev["dl"]
             self.b = [Csr(dev["b_rowptr"], dev["b_col"], dev["b_val"])]
-            self.bt = [Csr(dev["bt_rowptr"], dev["bt_col"], dev["bt_val"])]
+            self._bt = None if lazy_bt else [Csr(dev["bt_rowptr"], dev["bt_col"], dev["bt_val"])]
             self.p = Csr(dev["p_rowptr"], dev["p_col"], dev["p_pm"], dev["p_pd"])
             self.pt = Csr(dev["pt_rowptr"], dev["pt_col"], dev["pt_pm"], dev["pt_pd"])
             # run-length split twin of bt for the engine kernels (phantom ranges stored once)
@@ -165,6 +171,21 @@ class BatchPack(object):
                 self.b.append(spgemm(self.b[-1], self.b[-1], clip_powers))
                 self.bt.append(spgemm(self.bt[-1], self.bt[-1], clip_powers))
         return self
+
+    @property
+    def bt(self):
+        """Transposed line-graph operator(s) as full CSR; uploaded lazily when J == 1."""
+        if self._bt is None:
+            gs = self._host_graphs
+            nnz = np.concatenate([[0], np.cumsum([g.bt_col.shape[0] for g in gs])])
+            eoff = np.concatenate([[0], np.cumsum([g.M for g in gs])])
+            rp = np.concatenate([g.bt_rowptr[:-1].astype(np.int64) + nnz[i] for i, g in enumerate(gs)] + [nnz[-1:]])
+            col = np.concatenate([g.bt_col.astype(np.int64) + eoff[i] for i, g in enumerate(gs)])
+            val = np.concatenate([g.bt_val for g in gs])
+            d = self.device
+            self._bt = [Csr(torch.from_numpy(rp.astype(np.int32)).to(d), torch.from_numpy(col.astype(np.int32)).to(d),
+                            torch.from_numpy(val.astype(np.float32)).to(d))]
+        return self._bt
 
     # ---- construction from the reference's dense tensors (compatibility path) --------------
     @classmethod
@@ -226,10 +247,10 @@ class BatchPack(object):
         """``split=True`` (engine kernels): the first-power operator as direct CSR + range entries."""
         if self.generic:
             return [c.desc() for c in self.gen_edge_T]
-        first = self.bt[0].desc()
         if split and getattr(self, "bts", None) is not None:
-            first = self.bts.desc() + (self.bts_ranges,)
-        return [("ident",), ("diag", self.dl), first] + [c.desc() for c in self.bt[1:]]
+            rest = self._bt[1:] if self._bt is not None else []      # J == 1: the full bt stays on the host
+            return [("ident",), ("diag", self.dl), self.bts.desc() + (self.bts_ranges,)] + [c.desc() for c in rest]
+        return [("ident",), ("diag", self.dl)] + [c.desc() for c in self.bt]
 
     @property
     def K(self):

@@ -220,44 +220,70 @@ _FIELDS = {
 }
 
 
-def concat_block_diagonal(graphs, dual=True):
+def concat_block_diagonal(graphs, dual=True, skip=(), alloc=None):
     """Block-diagonal batch of ``GraphOps``: global row/col indices, per-graph offsets.
 
-    Returns a dict of numpy arrays: ``node_off``/``edge_off`` (bs+1), ``deg``, ``dl`` and, for each
-    operator in ``a, at[, b, bt, p, pt]``, ``<op>_rowptr`` and its index/value arrays."""
+    Every output array is written ONCE, straight into one contiguous staging buffer (16-byte aligned
+    sub-arrays; index arrays get their row / column / nnz offset added on the way in, in int32).
+    ``alloc(nbytes)`` supplies that buffer as a numpy uint8 array (``pack.py`` passes pinned memory,
+    so the staging buffer IS the host->device copy source); default: ordinary numpy memory.
+    ``skip`` lists operators to leave out (``pack.py`` skips the full ``bt`` when only the
+    run-length split ``bts`` is needed).
+
+    Returns ``(arrays, buffer, layout)``: ``arrays`` = dict of numpy views (``node_off``/``edge_off``
+    (bs+1), ``deg``, ``dl``, ``pad_n`` and, per operator, ``<op>_rowptr`` + index/value arrays),
+    ``layout`` = {name: (byte offset, dtype, length)}."""
     bs = len(graphs)
     n = np.array([g.N for g in graphs], dtype=np.int64)
     m = np.array([g.M for g in graphs], dtype=np.int64)
-    out = {"node_off": np.concatenate([[0], np.cumsum(n)]).astype(I32),
-           "edge_off": np.concatenate([[0], np.cumsum(m)]).astype(I32),
-           "deg": np.concatenate([g.deg for g in graphs]) if bs else np.zeros(0, F32)}
-    off = {"n": out["node_off"].astype(np.int64), "m": out["edge_off"].astype(np.int64)}
-    names = list(_FIELDS) if dual else ["a", "at"]
+    node_off = np.concatenate([[0], np.cumsum(n)])
+    edge_off = np.concatenate([[0], np.cumsum(m)])
+    off = {"n": node_off, "m": edge_off}
+    # spec: name -> (dtype, [(source array, offset to add, drop last element)], optional tail value)
+    spec = {"node_off": (I32, [(node_off.astype(I32), 0, False)], None),
+            "edge_off": (I32, [(edge_off.astype(I32), 0, False)], None),
+            "pad_n": (F32, [((int(n.max()) - n).astype(F32) if bs else np.zeros(0, F32), 0, False)], None),
+            "deg": (F32, [(g.deg, 0, False) for g in graphs], None)}
+    names = [k for k in (list(_FIELDS) if dual else ["a", "at"]) if k not in skip]
     if dual:
-        out["dl"] = np.concatenate([g.dl for g in graphs])
-    if dual:      # run-length split twin of bt: direct CSR part + range entries
-        nr = np.array([g.bts_rng_lo.shape[0] for g in graphs], dtype=np.int64)
-        nr_off = np.concatenate([[0], np.cumsum(nr)])
-        ne = np.array([g.bts_rng_id.shape[0] for g in graphs], dtype=np.int64)
-        ne_off = np.concatenate([[0], np.cumsum(ne)])
-        out["bts_rng_rowptr"] = np.concatenate(
-            [g.bts_rng_rowptr[:-1].astype(np.int64) + ne_off[i] for i, g in enumerate(graphs)] + [ne_off[-1:]]).astype(I32)
-        out["bts_rng_id"] = np.concatenate(
-            [g.bts_rng_id.astype(np.int64) + nr_off[i] for i, g in enumerate(graphs)]).astype(I32)
-        out["bts_rng_val"] = np.concatenate([g.bts_rng_val for g in graphs]).astype(F32)
-        out["bts_rng_lo"] = np.concatenate(
-            [g.bts_rng_lo.astype(np.int64) + off["m"][i] for i, g in enumerate(graphs)]).astype(I32)
-        out["bts_rng_hi"] = np.concatenate(
-            [g.bts_rng_hi.astype(np.int64) + off["m"][i] for i, g in enumerate(graphs)]).astype(I32)
+        spec["dl"] = (F32, [(g.dl, 0, False) for g in graphs], None)
+        nr_off = np.concatenate([[0], np.cumsum([g.bts_rng_lo.shape[0] for g in graphs])])
+        ne_off = np.concatenate([[0], np.cumsum([g.bts_rng_id.shape[0] for g in graphs])])
+        spec["bts_rng_rowptr"] = (I32, [(g.bts_rng_rowptr, int(ne_off[i]), True) for i, g in enumerate(graphs)],
+                                  int(ne_off[-1]))
+        spec["bts_rng_id"] = (I32, [(g.bts_rng_id, int(nr_off[i]), False) for i, g in enumerate(graphs)], None)
+        spec["bts_rng_val"] = (F32, [(g.bts_rng_val, 0, False) for g in graphs], None)
+        spec["bts_rng_lo"] = (I32, [(g.bts_rng_lo, int(edge_off[i]), False) for i, g in enumerate(graphs)], None)
+        spec["bts_rng_hi"] = (I32, [(g.bts_rng_hi, int(edge_off[i]), False) for i, g in enumerate(graphs)], None)
     for name in names:
         rp_name, rspace, cspace, arrs = _FIELDS[name]
-        nnz = np.array([getattr(g, arrs[0]).shape[0] for g in graphs], dtype=np.int64)
-        nnz_off = np.concatenate([[0], np.cumsum(nnz)])
-        rp = [getattr(g, rp_name)[:-1].astype(np.int64) + nnz_off[i] for i, g in enumerate(graphs)]
-        out[rp_name] = np.concatenate(rp + [nnz_off[-1:]]).astype(I32)
-        out[arrs[0]] = np.concatenate(
-            [getattr(g, arrs[0]).astype(np.int64) + off[cspace][i] for i, g in enumerate(graphs)]
-        ).astype(I32)
+        nnz_off = np.concatenate([[0], np.cumsum([getattr(g, arrs[0]).shape[0] for g in graphs])])
+        spec[rp_name] = (I32, [(getattr(g, rp_name), int(nnz_off[i]), True) for i, g in enumerate(graphs)],
+                         int(nnz_off[-1]))
+        spec[arrs[0]] = (I32, [(getattr(g, arrs[0]), int(off[cspace][i]), False) for i, g in enumerate(graphs)], None)
         for a in arrs[1:]:
-            out[a] = np.concatenate([getattr(g, a) for g in graphs]).astype(F32)
-    return out
+            spec[a] = (F32, [(getattr(g, a), 0, False) for g in graphs], None)
+    # layout
+    layout, total = {}, 0
+    for key, (dt, parts, tail) in spec.items():
+        length = sum(p[0].shape[0] - (1 if p[2] else 0) for p in parts) + (1 if tail is not None else 0)
+        layout[key] = (total, dt, length)
+        total += (4 * length + 15) & ~15
+    buf = alloc(max(total, 16)) if alloc is not None else np.empty(max(total, 16), dtype=np.uint8)
+    arrays = {}
+    for key, (dt, parts, tail) in spec.items():
+        o, _, length = layout[key]
+        view = buf[o:o + 4 * length].view(dt)
+        pos = 0
+        for src, add, drop in parts:
+            k = src.shape[0] - (1 if drop else 0)
+            if k:
+                if dt is I32 and add:
+                    np.add(src[:k], I32(add), out=view[pos:pos + k], casting="unsafe")
+                else:
+                    view[pos:pos + k] = src[:k]
+            pos += k
+        if tail is not None:
+            view[pos] = tail
+        arrays[key] = view
+    return arrays, buf, layout

@@ -52,7 +52,8 @@ def test_block_diagonal_concat():
     for n in (4, 7, 1, 5):
         up = (torch.rand(n, n, generator=gen) < 0.5).float().triu(1)
         gs.append(GraphOps.from_dense((up + up.t()).numpy()))
-    b = concat_block_diagonal(gs)
+    b, buf, layout = concat_block_diagonal(gs)
+    assert all(o % 16 == 0 for o, _, _ in layout.values()) and buf.dtype == np.uint8
     assert b["node_off"].tolist() == [0, 4, 11, 12, 17]
     assert b["edge_off"][-1] == sum(g.M for g in gs)
     for name, rows in (("a", 17), ("b", b["edge_off"][-1]), ("p", 17), ("pt", b["edge_off"][-1])):
