@@ -51,13 +51,15 @@ class SideBwdT(ctypes.Structure):
                 ("acc_b_self", c_void),
                 ("R_cross", c_int), ("pt_rowptr", c_void), ("pt_col", c_void), ("pt_pm", c_void),
                 ("pt_pd", c_void), ("Xc", c_void), ("Fc", c_int), ("bn_cross", BnRefT), ("gXc", c_void),
-                ("accumulate_cross", c_int), ("acc_b_cross", c_void)]
+                ("accumulate_cross", c_int), ("acc_b_cross", c_void), ("skip_dw", c_int)]
 
 
 _P = c_void
 _SIGS = {
     "hgnn_lg_side_fwd": [ctypes.POINTER(SideT), ctypes.POINTER(BnRefT), ctypes.POINTER(BnRefT), _P, _P, c_int,
-                         _P, _P, c_int, c_int, _P, _P, _P],
+                         _P, _P, c_int, c_int, _P, _P, _P, _P],
+    "hgnn_lg_row4_eligible": [ctypes.POINTER(OpT), c_int, c_int, c_int, c_int],
+    "hgnn_lg_side_dw": [_P, _P, c_int, c_int, _P, _P, _P, _P, c_int, _P, _P, _P],
     "hgnn_lg_side_bwd": [ctypes.POINTER(SideBwdT), _P],
     "hgnn_bins_reduce": [_P, _P, _P, _P, _P, c_int, _P, _P],
     "hgnn_bn_running_update": [_P, _P, _P, _P, _P, c_int, c_float, _P, _P],

@@ -366,6 +366,7 @@ struct FwdArgs {
     int relu_from;
     float* Z;
     double* acc_out;     // binned (sum z, sum z^2) of Z, or NULL
+    float* X1;           // row4 path only: save the concatenated x1 rows for the dW pass
     int TR, Cin, Cin_pad, Fout;
 };
 
@@ -872,12 +873,18 @@ static bool eng_row4_disabled() {
     return v == 1;
 }
 
+extern "C" int hgnn_lg_row4_eligible(const hgnn_op_t* ops, int n_ops, int Fs, int Fc, int Fout) {
+    if (eng_row4_disabled()) return 0;
+    if (Fs != 4 || Fout != 4 || (Fc != 0 && Fc != 4) || !ops || !eng_row4_ops(ops, n_ops)) return 0;
+    for (int i = 2; i < n_ops; ++i) if (ops[i].rng_rowptr) return 0;
+    return 1;
+}
+
 static bool eng_try_fwd_row4(const eng::FwdArgs& g, const hgnn_side_t* side, hgnn_stream_t stream) {
-    if (eng_row4_disabled()) return false;
     const bool cross = g.p_rowptr != nullptr;
-    if (g.Fs != 4 || g.Fout != 4 || (cross && g.Fc != 4) || !eng_row4_ops(side->ops, side->n_ops)) return false;
-    if (!eng_aligned16(g.Xs) || !eng_aligned16(g.Z) || (cross && !eng_aligned16(g.Xc))) return false;
-    for (int i = 2; i < side->n_ops; ++i) if (side->ops[i].rng_rowptr) return false;
+    if (!hgnn_lg_row4_eligible(side->ops, side->n_ops, g.Fs, cross ? g.Fc : 0, g.Fout)) return false;
+    if (!eng_aligned16(g.Xs) || !eng_aligned16(g.Z) || (cross && !eng_aligned16(g.Xc)) ||
+        (g.X1 && !eng_aligned16(g.X1))) return false;
     eng::Fwd4Args a;
     a.R = g.R; a.n_csr = side->n_ops - 2; a.diag = side->ops[1].diag;
     for (int i = 0; i < 2; ++i) {
@@ -889,7 +896,7 @@ static bool eng_try_fwd_row4(const eng::FwdArgs& g, const hgnn_side_t* side, hgn
     a.Xs = g.Xs; a.bn_s = g.bn_s;
     a.p_rowptr = g.p_rowptr; a.p_col = g.p_col; a.p_pm = g.p_pm; a.p_pd = g.p_pd; a.Xc = g.Xc; a.bn_c = g.bn_c;
     a.Wa = g.Wa; a.ba = g.ba; a.Ha = g.Ha; a.Wb = g.Wb; a.bb = g.bb; a.Hb = g.Hb;
-    a.relu_from = g.relu_from; a.Cin = g.Cin; a.Z = g.Z; a.acc_out = g.acc_out;
+    a.relu_from = g.relu_from; a.Cin = g.Cin; a.Z = g.Z; a.acc_out = g.acc_out; a.X1 = g.X1;
     cudaStream_t s = to_stream(stream);
     const int want = ceil_div(a.R, R4_THREADS);
 #define R4_FWD(NCSR, CROSS)                                                                              \
@@ -906,9 +913,10 @@ static bool eng_try_fwd_row4(const eng::FwdArgs& g, const hgnn_side_t* side, hgn
 extern "C" int hgnn_lg_side_fwd(const hgnn_side_t* side, const hgnn_bn_ref_t* bn_self,
                                 const hgnn_bn_ref_t* bn_cross, const float* Wa, const float* ba, int Ha,
                                 const float* Wb, const float* bb, int Hb, int relu_from, float* Z,
-                                double* acc_out, hgnn_stream_t stream) {
+                                double* acc_out, float* X1, hgnn_stream_t stream) {
     HGNN_REQUIRE(side && Z, "null argument");
     eng::FwdArgs a;
+    a.X1 = X1;
     HGNN_REQUIRE(make_oplist(side->ops, side->n_ops, &a.ops) == 0 && side->n_ops >= 1, "bad operator list");
     a.R = side->R;
     a.Xs = side->Xs; a.Fs = side->Fs; a.bn_s = to_bnref(bn_self);
@@ -927,6 +935,7 @@ extern "C" int hgnn_lg_side_fwd(const hgnn_side_t* side, const hgnn_bn_ref_t* bn
     a.Fout = Ha + Hb;
     a.Cin = side->n_ops * a.Fs + 2 * a.Fc;
     if (eng_try_fwd_row4(a, side, stream)) return hgnn_check_launch("hgnn_lg_side_fwd(row4)");
+    HGNN_REQUIRE(!X1, "x1 rows can only be saved by the width-4 fast path (check hgnn_lg_row4_eligible)");
     const bool vec4 = (a.Fs % 4 == 0) && (a.Fc % 4 == 0) && eng_aligned16(a.Xs) && (a.Fc == 0 || eng_aligned16(a.Xc));
     const bool vout4 = vec4 && (a.Fout % 4 == 0) && eng_aligned16(Z);
     a.Cin_pad = eng_pad(a.Cin, vec4 ? 4 : 1);
@@ -1009,29 +1018,56 @@ static bool eng_try_bwd_row4(const hgnn_side_bwd_t* d, hgnn_stream_t stream) {
     a.acc_b_cross = d->acc_b_cross; a.col0_cross = d->n_ops * 4;
     cudaStream_t s = to_stream(stream);
     const long long rows = (long long)d->R_self + (d->R_cross > 0 ? d->R_cross : 0);
-#define R4_BWD(NCSR)                                                                                      \
+#define R4_BWD(NCSR, DW)                                                                                  \
     {                                                                                                     \
-        const int cap = eng_resident_impl((const void*)eng::bwd_row4_kernel<NCSR>, 0, R4_THREADS);        \
+        const int cap = eng_resident_impl((const void*)eng::bwd_row4_kernel<NCSR, DW>, 0, R4_THREADS);    \
         int grid = (int)min((long long)cap, (rows + R4_THREADS - 1) / R4_THREADS);                        \
         if (d->R_cross > 0 && grid < 2) grid = 2;                                                         \
         int cs = d->R_cross > 0 ? (int)(((long long)grid * d->R_self + rows / 2) / rows) : grid;          \
         if (cs < 1) cs = 1;                                                                               \
         if (d->R_cross > 0 && cs > grid - 1) cs = grid - 1;                                               \
         a.ctas_self = cs;                                                                                 \
-        eng::bwd_row4_kernel<NCSR><<<grid, R4_THREADS, 0, s>>>(a);                                        \
+        eng::bwd_row4_kernel<NCSR, DW><<<grid, R4_THREADS, 0, s>>>(a);                                    \
     }
-    if (a.n_csr == 1) R4_BWD(1) else R4_BWD(2)
+    if (d->skip_dw) { if (a.n_csr == 1) R4_BWD(1, false) else R4_BWD(2, false) }
+    else { if (a.n_csr == 1) R4_BWD(1, true) else R4_BWD(2, true) }
 #undef R4_BWD
     return true;
 }
 
+extern "C" int hgnn_lg_side_dw(const float* gY, const float* Z, int R, int relu_from, const double* acc_f,
+                               const double* acc_b, const float* bn_weight, const float* X1, int Cin,
+                               double* dW_bins, double* db_bins, hgnn_stream_t stream) {
+    HGNN_REQUIRE(gY && X1 && dW_bins && R >= 0 && Cin % 4 == 0 && Cin >= 8 && Cin <= 24, "bad argument");
+    HGNN_REQUIRE(!acc_b || (acc_f && bn_weight && Z), "batch-norm backward needs acc_f, bn_weight and Z");
+    HGNN_REQUIRE(relu_from >= 4 || Z, "ReLU backward needs Z");
+    HGNN_REQUIRE(eng_aligned16(gY) && eng_aligned16(X1) && (!Z || eng_aligned16(Z)), "misaligned rows");
+    if (R == 0) return HGNN_OK;
+    eng::Dw4Args a;
+    a.gY = gY; a.Z = Z; a.relu_from = relu_from; a.R = R; a.has_bn = acc_b != nullptr;
+    a.acc_f = acc_f; a.acc_b = acc_b; a.bn_w = bn_weight; a.X1 = X1; a.Cin = Cin;
+    a.dW_bins = dW_bins; a.db_bins = db_bins;
+    cudaStream_t s = to_stream(stream);
+    const int grid = min(ceil_div(R, R4_THREADS), HGNN_SM_COUNT * 4);
+    switch (Cin / 4) {
+        case 2: eng::dw_row4_kernel<2><<<grid, R4_THREADS, 0, s>>>(a); break;
+        case 3: eng::dw_row4_kernel<3><<<grid, R4_THREADS, 0, s>>>(a); break;
+        case 4: eng::dw_row4_kernel<4><<<grid, R4_THREADS, 0, s>>>(a); break;
+        case 5: eng::dw_row4_kernel<5><<<grid, R4_THREADS, 0, s>>>(a); break;
+        default: eng::dw_row4_kernel<6><<<grid, R4_THREADS, 0, s>>>(a); break;
+    }
+    return hgnn_check_launch("hgnn_lg_side_dw");
+}
+
 extern "C" int hgnn_lg_side_bwd(const hgnn_side_bwd_t* d, hgnn_stream_t stream) {
     HGNN_REQUIRE(d && d->gY && d->Fg >= 1 && d->Fg <= 128, "bad argument");
+    HGNN_REQUIRE(!d->skip_dw || (d->Fg == 4 && d->Fs == 4), "skip_dw is only valid on the width-4 fast path");
     HGNN_REQUIRE(d->Ha >= 0 && d->Hb >= 0 && d->Ha + d->Hb == d->Fg, "Ha + Hb must equal the width of gY");
     HGNN_REQUIRE((d->Ha == 0 || d->Wa) && (d->Hb == 0 || d->Wb), "null weights");
     HGNN_REQUIRE(!d->acc_b || (d->acc_f && d->bn_weight && d->Z), "batch-norm backward needs acc_f, bn_weight and Z");
     HGNN_REQUIRE(d->relu_from >= d->Fg || d->Z, "ReLU backward needs Z");
     if (eng_try_bwd_row4(d, stream)) return hgnn_check_launch("hgnn_lg_side_bwd(row4)");
+    HGNN_REQUIRE(!d->skip_dw, "skip_dw needs the width-4 fast path (check hgnn_lg_row4_eligible)");
     eng::BwdArgs a;
     a.gY = d->gY; a.Z = d->Z; a.Fg = d->Fg; a.relu_from = d->relu_from; a.Rg = d->Rg;
     a.acc_f = d->acc_f; a.acc_b = d->acc_b; a.bn_w = d->bn_weight;

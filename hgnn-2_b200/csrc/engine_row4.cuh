@@ -122,6 +122,7 @@ struct Fwd4Args {
     int relu_from, Cin;
     float* Z;
     double* acc_out;
+    float* X1;                       // optional: the concatenated x1 rows (R, Cin) for the dW pass
 };
 
 template <int NCSR, bool CROSS>
@@ -199,6 +200,10 @@ fwd_row4_kernel(const Fwd4Args a) {
                                        fmaf(am.z, sc_c.z, wm * sh_c.z), fmaf(am.w, sc_c.w, wm * sh_c.w));
             x1[3 + NCSR] = make_float4(fmaf(ad.x, sc_c.x, wd * sh_c.x), fmaf(ad.y, sc_c.y, wd * sh_c.y),
                                        fmaf(ad.z, sc_c.z, wd * sh_c.z), fmaf(ad.w, sc_c.w, wd * sh_c.w));
+        }
+        if (a.X1) {
+#pragma unroll
+            for (int b = 0; b < NB; ++b) *reinterpret_cast<float4*>(a.X1 + ((size_t)row * NB + b) * 4) = x1[b];
         }
         // mat-vec: 4 outputs x (NB*4) inputs, weights broadcast from shared memory
         float out[4];
@@ -291,7 +296,9 @@ __device__ __forceinline__ float4 gpre_gather(const Gpre4& gp, const int* __rest
 
 #define R4_MAX_FLAGGED 64
 
-template <int NCSR>
+// DW = false: the gather-only variant (the weight gradients come from dw_row4_kernel, which streams
+// over the x1 rows saved by the forward on a parallel graph branch): ~48 fewer live registers.
+template <int NCSR, bool DW>
 __global__ void __launch_bounds__(R4_THREADS)
 bwd_row4_kernel(const Bwd4Args a) {
     constexpr int NT = 2 + NCSR;                          // self blocks
@@ -391,13 +398,15 @@ bwd_row4_kernel(const Bwd4Args a) {
                     const float4 w = *reinterpret_cast<const float4*>(Ws + (t * 4 + o) * 4);
                     g[0] = fmaf(Tv[o], w.x, g[0]); g[1] = fmaf(Tv[o], w.y, g[1]);
                     g[2] = fmaf(Tv[o], w.z, g[2]); g[3] = fmaf(Tv[o], w.w, g[3]);
-                    dw[(t * 4 + o) * 4 + 0] = fmaf(Tv[o], xn.x, dw[(t * 4 + o) * 4 + 0]);
-                    dw[(t * 4 + o) * 4 + 1] = fmaf(Tv[o], xn.y, dw[(t * 4 + o) * 4 + 1]);
-                    dw[(t * 4 + o) * 4 + 2] = fmaf(Tv[o], xn.z, dw[(t * 4 + o) * 4 + 2]);
-                    dw[(t * 4 + o) * 4 + 3] = fmaf(Tv[o], xn.w, dw[(t * 4 + o) * 4 + 3]);
+                    if (DW) {
+                        dw[(t * 4 + o) * 4 + 0] = fmaf(Tv[o], xn.x, dw[(t * 4 + o) * 4 + 0]);
+                        dw[(t * 4 + o) * 4 + 1] = fmaf(Tv[o], xn.y, dw[(t * 4 + o) * 4 + 1]);
+                        dw[(t * 4 + o) * 4 + 2] = fmaf(Tv[o], xn.z, dw[(t * 4 + o) * 4 + 2]);
+                        dw[(t * 4 + o) * 4 + 3] = fmaf(Tv[o], xn.w, dw[(t * 4 + o) * 4 + 3]);
+                    }
                 }
             }
-            db[0] += T[0].x; db[1] += T[0].y; db[2] += T[0].z; db[3] += T[0].w;
+            if (DW) { db[0] += T[0].x; db[1] += T[0].y; db[2] += T[0].z; db[3] += T[0].w; }
             if (gX) {
                 float4 o4 = make_float4(g[0], g[1], g[2], g[3]);
                 if (a.acc_self) {
@@ -450,10 +459,12 @@ bwd_row4_kernel(const Bwd4Args a) {
                         const float4 w = *reinterpret_cast<const float4*>(Ws + (2 * 4 + o) * 4);
                         g[0] = fmaf(dT[o], w.x, g[0]); g[1] = fmaf(dT[o], w.y, g[1]);
                         g[2] = fmaf(dT[o], w.z, g[2]); g[3] = fmaf(dT[o], w.w, g[3]);
-                        dw[(2 * 4 + o) * 4 + 0] = fmaf(dT[o], xn.x, dw[(2 * 4 + o) * 4 + 0]);
-                        dw[(2 * 4 + o) * 4 + 1] = fmaf(dT[o], xn.y, dw[(2 * 4 + o) * 4 + 1]);
-                        dw[(2 * 4 + o) * 4 + 2] = fmaf(dT[o], xn.z, dw[(2 * 4 + o) * 4 + 2]);
-                        dw[(2 * 4 + o) * 4 + 3] = fmaf(dT[o], xn.w, dw[(2 * 4 + o) * 4 + 3]);
+                        if (DW) {
+                            dw[(2 * 4 + o) * 4 + 0] = fmaf(dT[o], xn.x, dw[(2 * 4 + o) * 4 + 0]);
+                            dw[(2 * 4 + o) * 4 + 1] = fmaf(dT[o], xn.y, dw[(2 * 4 + o) * 4 + 1]);
+                            dw[(2 * 4 + o) * 4 + 2] = fmaf(dT[o], xn.z, dw[(2 * 4 + o) * 4 + 2]);
+                            dw[(2 * 4 + o) * 4 + 3] = fmaf(dT[o], xn.w, dw[(2 * 4 + o) * 4 + 3]);
+                        }
                     }
                     if (gX) {
                         float4 old = __ldcg(reinterpret_cast<const float4*>(gX + (size_t)row * 4));
@@ -506,10 +517,12 @@ bwd_row4_kernel(const Bwd4Args a) {
                     const float4 w = *reinterpret_cast<const float4*>(Wc + (t * 4 + o) * 4);
                     g[0] = fmaf(Tv[o], w.x, g[0]); g[1] = fmaf(Tv[o], w.y, g[1]);
                     g[2] = fmaf(Tv[o], w.z, g[2]); g[3] = fmaf(Tv[o], w.w, g[3]);
-                    dw[(t * 4 + o) * 4 + 0] = fmaf(Tv[o], xn.x, dw[(t * 4 + o) * 4 + 0]);
-                    dw[(t * 4 + o) * 4 + 1] = fmaf(Tv[o], xn.y, dw[(t * 4 + o) * 4 + 1]);
-                    dw[(t * 4 + o) * 4 + 2] = fmaf(Tv[o], xn.z, dw[(t * 4 + o) * 4 + 2]);
-                    dw[(t * 4 + o) * 4 + 3] = fmaf(Tv[o], xn.w, dw[(t * 4 + o) * 4 + 3]);
+                    if (DW) {
+                        dw[(t * 4 + o) * 4 + 0] = fmaf(Tv[o], xn.x, dw[(t * 4 + o) * 4 + 0]);
+                        dw[(t * 4 + o) * 4 + 1] = fmaf(Tv[o], xn.y, dw[(t * 4 + o) * 4 + 1]);
+                        dw[(t * 4 + o) * 4 + 2] = fmaf(Tv[o], xn.z, dw[(t * 4 + o) * 4 + 2]);
+                        dw[(t * 4 + o) * 4 + 3] = fmaf(Tv[o], xn.w, dw[(t * 4 + o) * 4 + 3]);
+                    }
                 }
             }
             if (gX) {
@@ -532,15 +545,17 @@ bwd_row4_kernel(const Bwd4Args a) {
     const int nbw = hgnn_ws_bins(4 * a.Cin);
     const int col_base = is_self ? 0 : a.col0_cross;
     __syncthreads();
+    if (DW) {
 #pragma unroll
-    for (int i = 0; i < NT * 16; ++i) {
-        if (i < nvals) {
-            const float v = warp_sum(dw[i]);
-            if (lane == 0) red[warp * 64 + i] = v;
+        for (int i = 0; i < NT * 16; ++i) {
+            if (i < nvals) {
+                const float v = warp_sum(dw[i]);
+                if (lane == 0) red[warp * 64 + i] = v;
+            }
         }
     }
     __syncthreads();
-    if (a.dW_bins)
+    if (DW && a.dW_bins)
         for (int i = tid; i < nvals; i += R4_THREADS) {
             float v = 0.f;
             for (int w = 0; w < R4_THREADS / 32; ++w) v += red[w * 64 + i];
@@ -562,11 +577,97 @@ bwd_row4_kernel(const Bwd4Args a) {
         double v = 0.0;
         for (int w = 0; w < R4_THREADS / 32; ++w) v += (double)red[w * 64 + tid];
         if (tid < 4) {
-            if (is_self && a.db_bins) accum_add(a.db_bins, 4, hgnn_ws_bins(4), tid, v);
+            if (DW && is_self && a.db_bins) accum_add(a.db_bins, 4, hgnn_ws_bins(4), tid, v);
         } else {
             double* accb = is_self ? a.acc_b_self : a.acc_b_cross;
             float* gXp = is_self ? a.gXs : a.gXc;
             if (accb && gXp) accum_add(accb, 8, hgnn_ws_bins(8), tid - 4, v);
         }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// weight gradients as a streaming pass:  dW[o][c] = sum_rows gPre[row][o] * x1[row][c],
+// dbias[o] = sum_rows gPre[row][o], with x1 saved by the forward.  No gathers, no dependent loads;
+// runs on a parallel graph branch, off the critical path of the backward chain.
+// ---------------------------------------------------------------------------------------------
+struct Dw4Args {
+    const float* gY; const float* Z; int relu_from; int R; int has_bn;
+    const double* acc_f; const double* acc_b; const float* bn_w;
+    const float* X1; int Cin;
+    double* dW_bins; double* db_bins;
+};
+
+template <int NB>
+__global__ void __launch_bounds__(R4_THREADS)
+dw_row4_kernel(const Dw4Args a) {
+    __shared__ float red[(R4_THREADS / 32) * (16 * NB + 4)];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    Gpre4 gp;
+    gp.relu_from = a.relu_from; gp.bn = a.has_bn != 0; gp.need_z = a.has_bn != 0 || a.relu_from < 4;
+    gp.G = a.gY; gp.Z = a.Z;
+    if (a.has_bn) {
+        double tf[8], tb[8];
+        warp_totals8(a.acc_f, tf);
+        warp_totals8(a.acc_b, tb);
+        const float w = a.bn_w[0];
+        const double inv_n = 1.0 / (double)a.R;
+        float c0[4], c1[4], c2[4];
+#pragma unroll
+        for (int f = 0; f < 4; ++f) {
+            const double m = tf[f] * inv_n;
+            const double var = fma(-m, m, tf[4 + f] * inv_n);
+            const float r_ = 1.0f / sqrtf(fmaxf((float)var, 0.f) + (float)ENG_BN_EPS);
+            const float k0 = w * r_;
+            const float k2 = -k0 * (float)(tb[4 + f] * inv_n) * r_;
+            c0[f] = k0; c2[f] = k2;
+            c1[f] = -k0 * (float)(tb[f] * inv_n) - k2 * (float)m;
+        }
+        gp.c0 = make_float4(c0[0], c0[1], c0[2], c0[3]);
+        gp.c1 = make_float4(c1[0], c1[1], c1[2], c1[3]);
+        gp.c2 = make_float4(c2[0], c2[1], c2[2], c2[3]);
+    } else {
+        gp.c0 = make_float4(1.f, 1.f, 1.f, 1.f); gp.c1 = f4_zero(); gp.c2 = f4_zero();
+    }
+    float dw[16 * NB];
+#pragma unroll
+    for (int i = 0; i < 16 * NB; ++i) dw[i] = 0.f;
+    float db[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int row = blockIdx.x * R4_THREADS + tid; row < a.R; row += gridDim.x * R4_THREADS) {
+        const float4 g = gp(row);
+        float4 x1[NB];
+#pragma unroll
+        for (int b = 0; b < NB; ++b) x1[b] = ld4(a.X1 + ((size_t)row * NB + b) * 4);
+        const float gv[4] = {g.x, g.y, g.z, g.w};
+#pragma unroll
+        for (int o = 0; o < 4; ++o) {
+            db[o] += gv[o];
+#pragma unroll
+            for (int b = 0; b < NB; ++b) {
+                dw[(o * NB + b) * 4 + 0] = fmaf(gv[o], x1[b].x, dw[(o * NB + b) * 4 + 0]);
+                dw[(o * NB + b) * 4 + 1] = fmaf(gv[o], x1[b].y, dw[(o * NB + b) * 4 + 1]);
+                dw[(o * NB + b) * 4 + 2] = fmaf(gv[o], x1[b].z, dw[(o * NB + b) * 4 + 2]);
+                dw[(o * NB + b) * 4 + 3] = fmaf(gv[o], x1[b].w, dw[(o * NB + b) * 4 + 3]);
+            }
+        }
+    }
+    constexpr int NV = 16 * NB + 4;
+#pragma unroll
+    for (int i = 0; i < 16 * NB; ++i) {
+        const float v = warp_sum(dw[i]);
+        if (lane == 0) red[warp * NV + i] = v;
+    }
+#pragma unroll
+    for (int o = 0; o < 4; ++o) {
+        const float v = warp_sum(db[o]);
+        if (lane == 0) red[warp * NV + 16 * NB + o] = v;
+    }
+    __syncthreads();
+    const int nbw = hgnn_ws_bins(4 * a.Cin);
+    for (int i = tid; i < NV; i += R4_THREADS) {
+        double v = 0.0;
+        for (int w = 0; w < R4_THREADS / 32; ++w) v += (double)red[w * NV + i];
+        if (i < 16 * NB) accum_add(a.dW_bins, 4 * a.Cin, nbw, i, v);      // i = o*Cin + c  (Cin = 4*NB)
+        else if (a.db_bins) accum_add(a.db_bins, 4, hgnn_ws_bins(4), i - 16 * NB, v);
     }
 }

@@ -27,6 +27,22 @@ from . import _lib
 from ._lib import BnRefT, SideBwdT, SideT, call, fptr, iptr, make_ops, stream
 
 
+# Optional: split the weight gradients of width-4 sides off the backward gather chain (x1 rows saved
+# by the forward, streaming hgnn_lg_side_dw on a parallel stream).  Measured on the C2 workload it
+# shortens the gather kernels (21.7 -> 17.7 us, 16.9 -> 13.3 us) but the extra launches share the SMs
+# with the chain and the step does not get faster (1.38 vs 1.30 ms), so it is off by default; kept,
+# tested, for the multi-side variant planned in profiles/README.md.
+SPLIT_DW = False
+_side_streams = {}
+
+
+def _side_stream(device):
+    key = device.index if device.index is not None else torch.cuda.current_device()
+    if key not in _side_streams:
+        _side_streams[key] = torch.cuda.Stream(device=device)
+    return _side_streams[key]
+
+
 def _bins(width):
     return int(_lib.lib.hgnn_bins_for(int(width)))
 
@@ -237,7 +253,7 @@ def _rows_of(pack, plan, tname):
     return pack.Rn if plan.tensors[tname]["rows"] == "n" else pack.Rm
 
 
-def _forward(plan, pack, Xp, XLp, training, arena):
+def _forward(plan, pack, Xp, XLp, training, arena, save_x1=False):
     """Runs every side; returns (dict of raw tensors, model output)."""
     dev = Xp.device
     vals = {"X": Xp, "XL": XLp}
@@ -265,10 +281,17 @@ def _forward(plan, pack, Xp, XLp, training, arena):
         acc_out = None
         if s.out is not None and training:
             acc_out = arena.data_ptr() + 8 * plan.tensors[s.out]["acc_f"]
+        # width-4 fast path in training: save the concatenated x1 rows so that the weight gradients
+        # become a streaming pass on a parallel branch (hgnn_lg_side_dw) instead of 48+32 register
+        # accumulators inside the latency-bound backward gather
+        X1 = None
+        if save_x1 and s.out is not None and _lib.lib.hgnn_lg_row4_eligible(keep, st.n_ops, s.Fs, s.Fc, s.Fout):
+            X1 = torch.empty(st.R, s.Cin, device=dev)
+            vals["x1:" + s.name] = X1
         call("hgnn_lg_side_fwd", ctypes.byref(st), ctypes.byref(bs_), ctypes.byref(bc_) if bc_ is not None else None,
              fptr(s.conv_a.weight), fptr(s.conv_a.bias), Ha,
              fptr(s.conv_b.weight) if Hb else None, fptr(s.conv_b.bias) if Hb else None, Hb,
-             s.relu_from, fptr(Z), acc_out, stream())
+             s.relu_from, fptr(Z), acc_out, fptr(X1), stream())
         if s.out is not None:
             vals[s.out] = Z
         else:     # readout: sum over all Nmax slots, padded slots add fc.bias (layers_mnb.py:92,:386)
@@ -285,7 +308,7 @@ class _ModelFunction(torch.autograd.Function):
         plan = get_plan(model)
         dev = Xp.device
         arena = torch.zeros(max(plan.arena_size, 1), dtype=torch.float64, device=dev)
-        vals, out = _forward(plan, pack, Xp, XLp, True, arena)
+        vals, out = _forward(plan, pack, Xp, XLp, True, arena, save_x1=SPLIT_DW and any(ctx.needs_input_grad))
         run = plan.running_flat(dev)
         if run[0] is not None:
             flat, (acc_off, Fs, run_off) = run
@@ -303,6 +326,7 @@ class _ModelFunction(torch.autograd.Function):
         g_out = g_out.contiguous().float()
         grads, started = {}, set()
         base = arena.data_ptr()
+        main, side_stream, forked = torch.cuda.current_stream(), None, False
 
         def grad_buf(name):
             if name not in grads:
@@ -363,7 +387,23 @@ class _ModelFunction(torch.autograd.Function):
             else:
                 d.R_cross = 0
             _lib.tag = s.name
+            X1 = vals.get("x1:" + s.name)
+            d.skip_dw = 0
+            if X1 is not None:
+                # gY of this side is complete here: fork the streaming dW pass onto the side stream
+                d.skip_dw = 1
+                if side_stream is None:
+                    side_stream = _side_stream(dev)
+                ev = torch.cuda.Event()
+                ev.record(main)
+                side_stream.wait_event(ev)
+                with torch.cuda.stream(side_stream):
+                    call("hgnn_lg_side_dw", d.gY, d.Z, d.Rg, s.relu_from, d.acc_f, d.acc_b, d.bn_weight,
+                         fptr(X1), s.Cin, base + 8 * s.dW_off, base + 8 * s.db_off, stream())
+                forked = True
             call("hgnn_lg_side_bwd", ctypes.byref(d), stream())
+        if forked:
+            main.wait_stream(side_stream)       # join before the accumulators are read
         offs, nbs, strides, cnts = plan.tables(dev)
         gflat = torch.empty(plan.n_flat, device=dev)
         call("hgnn_bins_reduce", arena.data_ptr(), offs.data_ptr(), iptr(nbs), iptr(strides), iptr(cnts),

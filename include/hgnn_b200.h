@@ -193,10 +193,20 @@ typedef struct hgnn_bn_ref_t {
 /* Forward of one layer side like hgnn_side_fwd, but inputs are normalised on load (bn_self /
  * bn_cross, NULL = identity), Z is written RAW and its (sum z, sum z^2) are added to the binned
  * accumulators acc_out (hgnn_ws_bins(2*Fout) x 2*Fout doubles, zeroed by the caller; NULL = no BN).
- * No ticket, no finalisation: the consumers derive mean/std themselves. */
+ * No ticket, no finalisation: the consumers derive mean/std themselves.  X1 != NULL (width-4 fast
+ * path only) additionally saves the concatenated, normalised input rows for hgnn_lg_side_dw. */
 int hgnn_lg_side_fwd(const hgnn_side_t* side, const hgnn_bn_ref_t* bn_self, const hgnn_bn_ref_t* bn_cross,
                      const float* Wa, const float* ba, int Ha, const float* Wb, const float* bb, int Hb,
-                     int relu_from, float* Z, double* acc_out, hgnn_stream_t stream);
+                     int relu_from, float* Z, double* acc_out, float* X1, hgnn_stream_t stream);
+/* 1 if the (ops, widths) combination runs on the thread-per-row width-4 kernels (engine_row4.cuh);
+ * only then may X1 (the saved concatenated input rows, (R, Cin)) and skip_dw be used. */
+int hgnn_lg_row4_eligible(const hgnn_op_t* ops, int n_ops, int Fs, int Fc, int Fout);
+/* Weight gradients of a width-4 side as a streaming pass over the saved x1 rows:
+ * dW[o][c] += sum_r gPre[r][o] x1[r][c], dbias[o] += sum_r gPre[r][o] (gPre as in hgnn_lg_side_bwd).
+ * Independent of hgnn_lg_side_bwd(skip_dw=1): the host layer runs it on a parallel stream. */
+int hgnn_lg_side_dw(const float* gY, const float* Z, int R, int relu_from, const double* acc_f,
+                    const double* acc_b, const float* bn_weight, const float* X1, int Cin,
+                    double* dW_bins, double* db_bins, hgnn_stream_t stream);
 
 /* Backward of one layer side in ONE launch.  gY = gradient w.r.t. the NORMALISED output of the side
  * (R_g x Fg, complete), Z its raw output.  gPre = (c0 gY + c1 + c2 Z) * relu_mask is evaluated on the
@@ -215,6 +225,7 @@ typedef struct hgnn_side_bwd_t {
     /* cross part (R_cross = 0: absent) */
     int R_cross; const int* pt_rowptr; const int* pt_col; const float* pt_pm; const float* pt_pd;
     const float* Xc; int Fc; hgnn_bn_ref_t bn_cross; float* gXc; int accumulate_cross; double* acc_b_cross;
+    int skip_dw; /* 1: leave dW / dbias to hgnn_lg_side_dw (width-4 fast path only) */
 } hgnn_side_bwd_t;
 int hgnn_lg_side_bwd(const hgnn_side_bwd_t* desc, hgnn_stream_t stream);
 

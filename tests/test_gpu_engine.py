@@ -68,6 +68,29 @@ def test_engine_matches_module_path(kind, order, h, J, N):
     assert rel_err(oe.cpu(), om.cpu()) < 1e-4
 
 
+def test_split_dw_variant_matches():
+    """engine.SPLIT_DW = True (x1 saved by the forward, streaming dW pass on a side stream) gives the
+    same gradients as the fused backward."""
+    import hgnn_b200  # noqa: F401
+    from hgnn_b200 import engine, synth
+    from hgnn_b200.functions.batching import prepare_batch
+    from hgnn_b200.models.gnns.model_mnb import GNN_lg
+    torch.manual_seed(3)
+    batch = prepare_batch(synth.sbm_dataset(6, N=300), 0, 1)
+    model = GNN_lg(0, 2, 5, 5, 2, 1, 1).cuda()
+    twin = copy.deepcopy(model)
+    out_a, g_a = _run(model, batch, True)
+    engine.SPLIT_DW = True
+    try:
+        out_b, g_b = _run(twin, batch, True)
+    finally:
+        engine.SPLIT_DW = False
+    assert rel_err(out_b.cpu(), out_a.cpu()) < 1e-6
+    fl = 0.1 * max(float(v.abs().max()) for v in g_a.values())
+    for k in g_a:
+        assert rel_err(g_b[k].cpu(), g_a[k].cpu(), fl) < 1e-4, k
+
+
 def test_engine_grads_are_one_flat_buffer():
     import hgnn_b200  # noqa: F401
     from hgnn_b200 import synth
