@@ -71,6 +71,7 @@ _SIGS = {
     "hgnn_exclusive_scan_i32": [_P, _P, c_int, _P],
     "hgnn_csr_to_dense": [_P, _P, _P, c_int, _P, _P, _P, c_ll, c_ll, c_ll, _P],
     "hgnn_csr_row_sums": [_P, _P, c_int, _P, _P],
+    "hgnn_fixup_offsets": [_P, _P, c_int, c_int, _P],
     "hgnn_spgemm_count_products": [c_int, _P, _P, _P, _P, _P],
     "hgnn_spgemm_expand": [c_int, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P],
     "hgnn_spgemm_fill": [c_int, _P, _P, _P, _P, _P, _P, _P, c_int, _P],

@@ -334,3 +334,29 @@ extern "C" int hgnn_segment_bcast(const float* g, int bs, int F, const int* off,
     segment_bcast_kernel<<<grid, 256, 0, to_stream(stream)>>>(g, bs, F, off, G);
     return hgnn_check_launch("hgnn_segment_bcast");
 }
+
+// ---------------------------------------------------------------------------------------------
+// block-diagonal fix-up: the host copies every graph's index arrays RAW into the staging buffer;
+// this adds the per-graph row / column / nnz offsets in place after the H2D copy.
+// table[e] = (array offset, length, segment-pointer offset, segment-addend offset), in 4-byte words
+// from `base`;  arr[i] += addend[g] for i in [segptr[g], segptr[g+1]).
+// ---------------------------------------------------------------------------------------------
+__global__ void fixup_offsets_kernel(int* __restrict__ base, const int* __restrict__ table, int n_seg) {
+    const int e = blockIdx.z, g = blockIdx.y;
+    const int4 t = *reinterpret_cast<const int4*>(table + 4 * e);
+    int* arr = base + t.x;
+    const int* segp = base + t.z;
+    const int add = base[t.w + g];
+    const int lo = segp[g], hi = min(segp[g + 1], t.y);
+    if (add == 0) return;
+    for (int i = lo + blockIdx.x * blockDim.x + threadIdx.x; i < hi; i += gridDim.x * blockDim.x) arr[i] += add;
+}
+
+extern "C" int hgnn_fixup_offsets(int* base, const int* table, int n_entries, int n_seg, hgnn_stream_t stream) {
+    HGNN_REQUIRE(base && table && n_entries >= 0 && n_seg >= 0, "bad argument");
+    if (n_entries == 0 || n_seg == 0) return HGNN_OK;
+    HGNN_REQUIRE(n_seg <= 65535 && n_entries <= 65535, "too many segments");
+    dim3 grid(8, n_seg, n_entries);
+    fixup_offsets_kernel<<<grid, 256, 0, to_stream(stream)>>>(base, table, n_seg);
+    return hgnn_check_launch("hgnn_fixup_offsets");
+}

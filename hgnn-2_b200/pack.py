@@ -138,8 +138,10 @@ class BatchPack(object):
         # the powers; the engine uses its run-length split twin.  It is uploaded on first use.
         lazy_bt = dual and self.J == 1
         holder = {}
-        _, _, layout = host = concat_block_diagonal(graphs, dual=dual, skip=("bt",) if lazy_bt else (),
-                                                    alloc=_pinned_alloc(holder))
+        # raw per-graph arrays -> pinned staging (one np.concatenate per field); the per-graph index
+        # offsets are added on the GPU after the copy (hgnn_fixup_offsets)
+        _, _, layout = concat_block_diagonal(graphs, dual=dual, skip=("bt",) if lazy_bt else (),
+                                             alloc=_pinned_alloc(holder), defer_offsets=True)
         self.bs = len(graphs)
         self.n_nodes = np.array([g.N for g in graphs], dtype=np.int64)
         self.n_edges = np.array([g.M for g in graphs], dtype=np.int64)
@@ -148,6 +150,8 @@ class BatchPack(object):
         self.Rn, self.Rm = int(self.n_nodes.sum()), int(self.n_edges.sum())
         dev, self._buffer = _device_views(holder["host"], layout, device)
         self.nbytes = holder["host"].numel()
+        call("hgnn_fixup_offsets", self._buffer.data_ptr(), iptr(dev["fixup"]), dev["fixup"].numel() // 4,
+             len(graphs), stream())
         self._host_graphs = graphs if lazy_bt else None
         self.node_off, self.edge_off = dev["node_off"], dev["edge_off"]
         self.pad_n = dev["pad_n"]

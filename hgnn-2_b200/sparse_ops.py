@@ -220,15 +220,22 @@ _FIELDS = {
 }
 
 
-def concat_block_diagonal(graphs, dual=True, skip=(), alloc=None):
+def concat_block_diagonal(graphs, dual=True, skip=(), alloc=None, defer_offsets=False):
     """Block-diagonal batch of ``GraphOps``: global row/col indices, per-graph offsets.
 
     Every output array is written ONCE, straight into one contiguous staging buffer (16-byte aligned
-    sub-arrays; index arrays get their row / column / nnz offset added on the way in, in int32).
-    ``alloc(nbytes)`` supplies that buffer as a numpy uint8 array (``pack.py`` passes pinned memory,
-    so the staging buffer IS the host->device copy source); default: ordinary numpy memory.
-    ``skip`` lists operators to leave out (``pack.py`` skips the full ``bt`` when only the
-    run-length split ``bts`` is needed).
+    sub-arrays).  ``alloc(nbytes)`` supplies that buffer as a numpy uint8 array (``pack.py`` passes
+    pinned memory, so the staging buffer IS the host->device copy source); default: numpy memory.
+    ``skip`` lists operators to leave out (``pack.py`` skips the full ``bt`` when only the run-length
+    split ``bts`` is needed).
+
+    ``defer_offsets=False``: index arrays get their row / column / nnz offset added on the host.
+    ``defer_offsets=True`` (the fast path): the per-graph arrays are copied RAW (one
+    ``np.concatenate`` per field - no per-graph arithmetic on the host) and the buffer additionally
+    carries a fix-up table ``fixup`` (n_entries x 4 int32: array offset, length, segment-pointer
+    offset, segment-addend offset, all in 4-byte elements from the buffer start) plus the segment
+    tables it refers to; ``hgnn_fixup_offsets`` applies it on the GPU after the copy
+    (``apply_fixups`` is the numpy twin used by the CPU tests).
 
     Returns ``(arrays, buffer, layout)``: ``arrays`` = dict of numpy views (``node_off``/``edge_off``
     (bs+1), ``deg``, ``dl``, ``pad_n`` and, per operator, ``<op>_rowptr`` + index/value arrays),
@@ -239,51 +246,92 @@ def concat_block_diagonal(graphs, dual=True, skip=(), alloc=None):
     node_off = np.concatenate([[0], np.cumsum(n)])
     edge_off = np.concatenate([[0], np.cumsum(m)])
     off = {"n": node_off, "m": edge_off}
-    # spec: name -> (dtype, [(source array, offset to add, drop last element)], optional tail value)
-    spec = {"node_off": (I32, [(node_off.astype(I32), 0, False)], None),
-            "edge_off": (I32, [(edge_off.astype(I32), 0, False)], None),
-            "pad_n": (F32, [((int(n.max()) - n).astype(F32) if bs else np.zeros(0, F32), 0, False)], None),
-            "deg": (F32, [(g.deg, 0, False) for g in graphs], None)}
+    # spec: name -> (dtype, [source arrays], drop last element of each, per-graph addend or None, tail)
+    spec = {"node_off": (I32, [node_off.astype(I32)], False, None, None),
+            "edge_off": (I32, [edge_off.astype(I32)], False, None, None),
+            "pad_n": (F32, [(int(n.max()) - n).astype(F32) if bs else np.zeros(0, F32)], False, None, None),
+            "deg": (F32, [g.deg for g in graphs], False, None, None)}
+    seg = {"n": "node_off", "m": "edge_off"}            # segment-pointer arrays by name
+    fix = []                                            # (array, segment pointers, addends)
+
+    def seg_table(name, values):
+        spec[name] = (I32, [np.asarray(values, dtype=I32)], False, None, None)
+        return name
+
     names = [k for k in (list(_FIELDS) if dual else ["a", "at"]) if k not in skip]
     if dual:
-        spec["dl"] = (F32, [(g.dl, 0, False) for g in graphs], None)
+        spec["dl"] = (F32, [g.dl for g in graphs], False, None, None)
         nr_off = np.concatenate([[0], np.cumsum([g.bts_rng_lo.shape[0] for g in graphs])])
         ne_off = np.concatenate([[0], np.cumsum([g.bts_rng_id.shape[0] for g in graphs])])
-        spec["bts_rng_rowptr"] = (I32, [(g.bts_rng_rowptr, int(ne_off[i]), True) for i, g in enumerate(graphs)],
-                                  int(ne_off[-1]))
-        spec["bts_rng_id"] = (I32, [(g.bts_rng_id, int(nr_off[i]), False) for i, g in enumerate(graphs)], None)
-        spec["bts_rng_val"] = (F32, [(g.bts_rng_val, 0, False) for g in graphs], None)
-        spec["bts_rng_lo"] = (I32, [(g.bts_rng_lo, int(edge_off[i]), False) for i, g in enumerate(graphs)], None)
-        spec["bts_rng_hi"] = (I32, [(g.bts_rng_hi, int(edge_off[i]), False) for i, g in enumerate(graphs)], None)
+        seg_table("_seg_rng_entries", ne_off)
+        seg_table("_seg_rng_ranges", nr_off)
+        spec["bts_rng_rowptr"] = (I32, [g.bts_rng_rowptr for g in graphs], True, ne_off[:-1], int(ne_off[-1]))
+        fix.append(("bts_rng_rowptr", "edge_off", "_seg_rng_entries"))
+        spec["bts_rng_id"] = (I32, [g.bts_rng_id for g in graphs], False, nr_off[:-1], None)
+        fix.append(("bts_rng_id", "_seg_rng_entries", "_seg_rng_ranges"))
+        spec["bts_rng_val"] = (F32, [g.bts_rng_val for g in graphs], False, None, None)
+        for k in ("bts_rng_lo", "bts_rng_hi"):
+            spec[k] = (I32, [getattr(g, k) for g in graphs], False, edge_off[:-1], None)
+            fix.append((k, "_seg_rng_ranges", "edge_off"))
     for name in names:
         rp_name, rspace, cspace, arrs = _FIELDS[name]
         nnz_off = np.concatenate([[0], np.cumsum([getattr(g, arrs[0]).shape[0] for g in graphs])])
-        spec[rp_name] = (I32, [(getattr(g, rp_name), int(nnz_off[i]), True) for i, g in enumerate(graphs)],
-                         int(nnz_off[-1]))
-        spec[arrs[0]] = (I32, [(getattr(g, arrs[0]), int(off[cspace][i]), False) for i, g in enumerate(graphs)], None)
+        seg_nnz = seg_table("_seg_nnz_" + name, nnz_off)
+        spec[rp_name] = (I32, [getattr(g, rp_name) for g in graphs], True, nnz_off[:-1], int(nnz_off[-1]))
+        fix.append((rp_name, seg[rspace], seg_nnz))
+        spec[arrs[0]] = (I32, [getattr(g, arrs[0]) for g in graphs], False, off[cspace][:-1], None)
+        fix.append((arrs[0], seg_nnz, seg[cspace]))
         for a in arrs[1:]:
-            spec[a] = (F32, [(getattr(g, a), 0, False) for g in graphs], None)
+            spec[a] = (F32, [getattr(g, a) for g in graphs], False, None, None)
     # layout
     layout, total = {}, 0
-    for key, (dt, parts, tail) in spec.items():
-        length = sum(p[0].shape[0] - (1 if p[2] else 0) for p in parts) + (1 if tail is not None else 0)
+    for key, (dt, parts, drop, add, tail) in spec.items():
+        length = sum(p.shape[0] - (1 if drop else 0) for p in parts) + (1 if tail is not None else 0)
         layout[key] = (total, dt, length)
         total += (4 * length + 15) & ~15
+    if defer_offsets:
+        layout["fixup"] = (total, I32, 4 * len(fix))
+        total += (16 * len(fix) + 15) & ~15
     buf = alloc(max(total, 16)) if alloc is not None else np.empty(max(total, 16), dtype=np.uint8)
     arrays = {}
-    for key, (dt, parts, tail) in spec.items():
+    for key, (dt, parts, drop, add, tail) in spec.items():
         o, _, length = layout[key]
         view = buf[o:o + 4 * length].view(dt)
-        pos = 0
-        for src, add, drop in parts:
-            k = src.shape[0] - (1 if drop else 0)
-            if k:
-                if dt is I32 and add:
-                    np.add(src[:k], I32(add), out=view[pos:pos + k], casting="unsafe")
-                else:
-                    view[pos:pos + k] = src[:k]
-            pos += k
+        body = length - (1 if tail is not None else 0)
+        if defer_offsets or add is None:
+            srcs = [p[:-1] for p in parts] if drop else parts
+            if len(srcs) == 1:
+                view[:body] = srcs[0]
+            elif body:
+                np.concatenate(srcs, out=view[:body])
+        else:
+            pos = 0
+            for src, ad in zip(parts, add):
+                k = src.shape[0] - (1 if drop else 0)
+                if k:
+                    np.add(src[:k], I32(ad), out=view[pos:pos + k], casting="unsafe")
+                pos += k
         if tail is not None:
-            view[pos] = tail
+            view[body] = tail
         arrays[key] = view
+    if defer_offsets:
+        o, _, length = layout["fixup"]
+        table = buf[o:o + 4 * length].view(I32).reshape(-1, 4)
+        for i, (arr, segp, sadd) in enumerate(fix):
+            n_body = layout[arr][2] - (1 if spec[arr][4] is not None else 0)
+            table[i] = (layout[arr][0] // 4, n_body, layout[segp][0] // 4, layout[sadd][0] // 4)
+        arrays["fixup"] = table
     return arrays, buf, layout
+
+
+def apply_fixups(buf, layout, n_graphs):
+    """numpy twin of ``hgnn_fixup_offsets``: arr[i] += addend[g] for i in [segptr[g], segptr[g+1])."""
+    o, _, length = layout["fixup"]
+    words = buf.view(I32)
+    table = buf[o:o + 4 * length].view(I32).reshape(-1, 4)
+    for arr_off, n_body, seg_off, add_off in table:
+        segp = words[seg_off:seg_off + n_graphs + 1]
+        addend = words[add_off:add_off + n_graphs]
+        arr = words[arr_off:arr_off + n_body]
+        for g in range(n_graphs):
+            arr[segp[g]:segp[g + 1]] += addend[g]

@@ -83,6 +83,11 @@ int hgnn_exclusive_scan_i32(const int* in, int* out, int n, hgnn_stream_t stream
 int hgnn_csr_to_dense(const int* rowptr, const int* col, const float* val, int bs,
                       const int* row_off, const int* col_off, float* D, long long sb, long long sr,
                       long long sc, hgnn_stream_t stream);
+/* Block-diagonal fix-up after the raw H2D copy of a batch (hgnn-2_b200/sparse_ops.py
+ * concat_block_diagonal(defer_offsets=True)): table = n_entries x (array offset, length,
+ * segment-pointer offset, segment-addend offset) in 4-byte words from `base`;
+ * arr[i] += addend[g] for i in [segptr[g], segptr[g+1]), g < n_seg. */
+int hgnn_fixup_offsets(int* base, const int* table, int n_entries, int n_seg, hgnn_stream_t stream);
 /* out[r] = sum of row r's values (weighted degree, functions/operators.py:22,74). */
 int hgnn_csr_row_sums(const int* rowptr, const float* val, int R, float* out, hgnn_stream_t stream);
 

@@ -94,3 +94,21 @@ def test_split_runs_reconstructs_the_operator():
     rp2, c2, v2, rrp, rid, rv, lo, hi = split_runs(3, rp, col, val)
     assert rp2.tolist() == [0, 0, 5, 5] and rrp.tolist() == [0, 1, 1, 2]
     assert sorted(zip(lo.tolist(), hi.tolist())) == [(0, 65), (5, 75)] and rv.tolist() == [1.0, 3.0]
+
+
+def test_deferred_offsets_equal_host_offsets():
+    """The raw copy + fix-up table (applied on the GPU by hgnn_fixup_offsets; here by its numpy twin)
+    gives exactly the arrays of the host-side offset path."""
+    from hgnn_b200.sparse_ops import apply_fixups
+    gen = torch.Generator().manual_seed(9)
+    gs = []
+    for n in (90, 5, 140, 1, 64):
+        up = (torch.rand(n, n, generator=gen) < 0.1).float().triu(1)
+        if n > 20:
+            up[0, 1:12] = 1.0
+        gs.append(GraphOps.from_dense((up + up.t()).numpy()))
+    ref, _, _ = concat_block_diagonal(gs)
+    got, buf, layout = concat_block_diagonal(gs, defer_offsets=True)
+    apply_fixups(buf, layout, len(gs))
+    for k, v in ref.items():
+        assert np.array_equal(got[k], v), k
