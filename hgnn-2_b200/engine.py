@@ -201,8 +201,11 @@ class _Plan(object):
 
 
 def get_plan(model):
+    """The cached plan; rebuilt when the parameter objects were replaced (checked on two of them -
+    walking all ~230 parameters costs more than a kernel launch)."""
     plan = model.__dict__.get("_engine_plan")
-    if plan is None or [id(p) for p in plan.params] != [id(p) for p in model.parameters()]:
+    if (plan is None or plan.params[0] is not model.layer0.cv1.weight
+            or plan.params[-1] is not model.layerlast.fc.bias):
         plan = _Plan(model)
         model.__dict__["_engine_plan"] = plan
     return plan
@@ -217,31 +220,54 @@ def _rows_table(pack, plan, device):
     return cache[key]
 
 
+def _pack_cache(pack):
+    """ctypes operator arrays and raw pointers of a pack, built once (host overhead matters: an eager
+    step is ~90 C-ABI calls)."""
+    c = pack.__dict__.get("_engine_cache")
+    if c is None:
+        c = {"node": make_ops(pack.node_ops()), "nodeT": make_ops(pack.node_ops_T())}
+        if pack.dual:
+            c["edge"] = make_ops(pack.edge_ops())
+            c["edgeT"] = make_ops(pack.edge_ops_T(split=True))
+            for k, p in (("p", pack.p), ("pt", pack.pt)):
+                c[k] = (iptr(p.rowptr), iptr(p.col), fptr(p.val), fptr(p.val2))
+        c["node_off"], c["pad_n"] = iptr(pack.node_off), fptr(pack.pad_n)
+        pack.__dict__["_engine_cache"] = c
+    return c
+
+
 def _side_struct(pack, side, Xs, Xc):
     node = side.kind == "node"
-    descs = pack.node_ops() if node else pack.edge_ops()
-    ops, n = make_ops(descs)
+    pc = _pack_cache(pack)
+    ops, n = pc["node" if node else "edge"]
     s = SideT()
     s.R, s.ops, s.n_ops = (pack.Rn if node else pack.Rm), ops, n
-    s.Xs, s.Fs = fptr(Xs), Xs.shape[1]
+    s.Xs, s.Fs = Xs.data_ptr(), Xs.shape[1]
     if Xc is not None:
-        p = pack.p if node else pack.pt
-        s.p_rowptr, s.p_col, s.p_pm, s.p_pd = iptr(p.rowptr), iptr(p.col), fptr(p.val), fptr(p.val2)
-        s.Xc, s.Fc = fptr(Xc), Xc.shape[1]
+        s.p_rowptr, s.p_col, s.p_pm, s.p_pd = pc["p" if node else "pt"]
+        s.Xc, s.Fc = Xc.data_ptr(), Xc.shape[1]
     else:
         s.p_rowptr = s.p_col = s.p_pm = s.p_pd = s.Xc = None
         s.Fc = 0
     return s, ops
 
 
-def _bn_ref(plan, tname, arena, rows, affine=None):
+def _param_ptrs(plan):
+    """{id(parameter): device pointer}, validated once per call (CUDA, fp32, contiguous)."""
+    out = {}
+    for p in plan.params:
+        out[id(p)] = fptr(p)
+    return out
+
+
+def _bn_ref(plan, tname, arena, rows, affine=None, pp=None):
     t = plan.tensors[tname]
     r = BnRefT()
     if t["bn"] is None:
         r.acc = r.affine = r.weight = r.bias = None
         r.n_rows = 0
         return r
-    r.weight, r.bias, r.n_rows = fptr(t["bn"].weight), fptr(t["bn"].bias), rows
+    r.weight, r.bias, r.n_rows = pp[id(t["bn"].weight)], pp[id(t["bn"].bias)], rows
     if affine is not None:
         r.acc, r.affine = None, affine[tname].data_ptr()
     else:
@@ -257,6 +283,10 @@ def _forward(plan, pack, Xp, XLp, training, arena, save_x1=False):
     """Runs every side; returns (dict of raw tensors, model output)."""
     dev = Xp.device
     vals = {"X": Xp, "XL": XLp}
+    pp = _param_ptrs(plan)
+    pc = _pack_cache(pack)
+    cur = stream()
+    arena_ptr = arena.data_ptr()
     affine = None
     if not training:      # eval: normalise with the running statistics (batch_normalization.py:39-41)
         affine = {}
@@ -272,15 +302,15 @@ def _forward(plan, pack, Xp, XLp, training, arena, save_x1=False):
         Xs = vals[s.src_self]
         Xc = vals[s.src_cross] if s.src_cross else None
         st, keep = _side_struct(pack, s, Xs, Xc)
-        bs_ = _bn_ref(plan, s.src_self, arena, _rows_of(pack, plan, s.src_self), affine)
-        bc_ = _bn_ref(plan, s.src_cross, arena, _rows_of(pack, plan, s.src_cross), affine) if s.src_cross else None
+        bs_ = _bn_ref(plan, s.src_self, arena, _rows_of(pack, plan, s.src_self), affine, pp)
+        bc_ = _bn_ref(plan, s.src_cross, arena, _rows_of(pack, plan, s.src_cross), affine, pp) if s.src_cross else None
         Ha = s.conv_a.weight.shape[0]
         Hb = s.conv_b.weight.shape[0] if s.conv_b is not None else 0
         Z = torch.empty(st.R, s.Fout, device=dev)
         _lib.tag = s.name
         acc_out = None
         if s.out is not None and training:
-            acc_out = arena.data_ptr() + 8 * plan.tensors[s.out]["acc_f"]
+            acc_out = arena_ptr + 8 * plan.tensors[s.out]["acc_f"]
         # width-4 fast path in training: save the concatenated x1 rows so that the weight gradients
         # become a streaming pass on a parallel branch (hgnn_lg_side_dw) instead of 48+32 register
         # accumulators inside the latency-bound backward gather
@@ -289,15 +319,15 @@ def _forward(plan, pack, Xp, XLp, training, arena, save_x1=False):
             X1 = torch.empty(st.R, s.Cin, device=dev)
             vals["x1:" + s.name] = X1
         call("hgnn_lg_side_fwd", ctypes.byref(st), ctypes.byref(bs_), ctypes.byref(bc_) if bc_ is not None else None,
-             fptr(s.conv_a.weight), fptr(s.conv_a.bias), Ha,
-             fptr(s.conv_b.weight) if Hb else None, fptr(s.conv_b.bias) if Hb else None, Hb,
-             s.relu_from, fptr(Z), acc_out, fptr(X1), stream())
+             pp[id(s.conv_a.weight)], pp[id(s.conv_a.bias)], Ha,
+             pp[id(s.conv_b.weight)] if Hb else None, pp[id(s.conv_b.bias)] if Hb else None, Hb,
+             s.relu_from, Z.data_ptr(), acc_out, X1.data_ptr() if X1 is not None else None, cur)
         if s.out is not None:
             vals[s.out] = Z
         else:     # readout: sum over all Nmax slots, padded slots add fc.bias (layers_mnb.py:92,:386)
             out = torch.empty(pack.bs, s.Fout, device=dev)
-            call("hgnn_segment_sum", fptr(Z), pack.bs, s.Fout, iptr(pack.node_off), fptr(pack.pad_n),
-                 fptr(s.conv_a.bias), fptr(out), stream())
+            call("hgnn_segment_sum", Z.data_ptr(), pack.bs, s.Fout, pc["node_off"], pc["pad_n"],
+                 pp[id(s.conv_a.bias)], out.data_ptr(), cur)
     return vals, out
 
 
@@ -327,6 +357,9 @@ class _ModelFunction(torch.autograd.Function):
         grads, started = {}, set()
         base = arena.data_ptr()
         main, side_stream, forked = torch.cuda.current_stream(), None, False
+        pp = _param_ptrs(plan)
+        pc = _pack_cache(pack)
+        cur = stream()
 
         def grad_buf(name):
             if name not in grads:
@@ -340,46 +373,45 @@ class _ModelFunction(torch.autograd.Function):
             Hb = s.conv_b.weight.shape[0] if s.conv_b is not None else 0
             if s.out is None:       # readout: gPre = g_out broadcast over the rows of each graph
                 G = torch.empty(pack.Rn, s.Fout, device=dev)
-                call("hgnn_readout_bwd_prep", fptr(g_out), pack.bs, s.Fout, iptr(pack.node_off), fptr(pack.pad_n),
-                     fptr(G), base + 8 * s.db_off, stream())
-                d.gY, d.Z, d.acc_f, d.acc_b, d.bn_weight = fptr(G), None, None, None, None
+                call("hgnn_readout_bwd_prep", fptr(g_out), pack.bs, s.Fout, pc["node_off"], pc["pad_n"],
+                     G.data_ptr(), base + 8 * s.db_off, cur)
+                d.gY, d.Z, d.acc_f, d.acc_b, d.bn_weight = G.data_ptr(), None, None, None, None
                 d.Rg = pack.Rn
                 keep_g = G
             else:
                 t = plan.tensors[s.out]
                 if s.out not in grads:          # output never used downstream: zero gradient
                     grads[s.out] = torch.zeros_like(vals[s.out])
-                d.gY, d.Z = fptr(grads[s.out]), fptr(vals[s.out])
+                d.gY, d.Z = grads[s.out].data_ptr(), vals[s.out].data_ptr()
                 d.acc_f, d.acc_b = base + 8 * t["acc_f"], base + 8 * t["acc_b"]
-                d.bn_weight = fptr(t["bn"].weight)
+                d.bn_weight = pp[id(t["bn"].weight)]
                 d.Rg = _rows_of(pack, plan, s.out)
             d.Fg, d.relu_from = s.Fout, s.relu_from
-            d.Wa, d.Ha = fptr(s.conv_a.weight), Ha
-            d.Wb, d.Hb = (fptr(s.conv_b.weight) if Hb else None), Hb
+            d.Wa, d.Ha = pp[id(s.conv_a.weight)], Ha
+            d.Wb, d.Hb = (pp[id(s.conv_b.weight)] if Hb else None), Hb
             d.Cin = s.Cin
             d.dW_bins, d.db_bins = base + 8 * s.dW_off, base + 8 * s.db_off
             # self part
-            opsT, n = make_ops(pack.node_ops_T() if node else pack.edge_ops_T(split=True))
+            opsT, n = pc["nodeT" if node else "edgeT"]
             d.R_self, d.ops_T, d.n_ops = (pack.Rn if node else pack.Rm), opsT, n
-            d.Xs, d.Fs = fptr(vals[s.src_self]), s.Fs
-            d.bn_self = _bn_ref(plan, s.src_self, arena, _rows_of(pack, plan, s.src_self))
+            d.Xs, d.Fs = vals[s.src_self].data_ptr(), s.Fs
+            d.bn_self = _bn_ref(plan, s.src_self, arena, _rows_of(pack, plan, s.src_self), None, pp)
             ts = plan.tensors[s.src_self]
             need_self = ts["bn"] is not None or (s.src_self == "X" and ctx.need_x)
-            d.gXs = fptr(grad_buf(s.src_self)) if need_self else None
+            d.gXs = grad_buf(s.src_self).data_ptr() if need_self else None
             d.accumulate_self = 1 if s.src_self in started else 0
             d.acc_b_self = (base + 8 * ts["acc_b"]) if ts["bn"] is not None else None
             if need_self:
                 started.add(s.src_self)
             # cross part
             if s.src_cross:
-                pt = pack.pt if node else pack.p      # rows = the cross tensor's rows
                 tc = plan.tensors[s.src_cross]
                 d.R_cross = _rows_of(pack, plan, s.src_cross)
-                d.pt_rowptr, d.pt_col, d.pt_pm, d.pt_pd = iptr(pt.rowptr), iptr(pt.col), fptr(pt.val), fptr(pt.val2)
-                d.Xc, d.Fc = fptr(vals[s.src_cross]), s.Fc
-                d.bn_cross = _bn_ref(plan, s.src_cross, arena, d.R_cross)
+                d.pt_rowptr, d.pt_col, d.pt_pm, d.pt_pd = pc["pt" if node else "p"]   # rows = the cross tensor's rows
+                d.Xc, d.Fc = vals[s.src_cross].data_ptr(), s.Fc
+                d.bn_cross = _bn_ref(plan, s.src_cross, arena, d.R_cross, None, pp)
                 need_cross = tc["bn"] is not None or (s.src_cross == "X" and ctx.need_x)
-                d.gXc = fptr(grad_buf(s.src_cross)) if need_cross else None
+                d.gXc = grad_buf(s.src_cross).data_ptr() if need_cross else None
                 d.accumulate_cross = 1 if s.src_cross in started else 0
                 d.acc_b_cross = (base + 8 * tc["acc_b"]) if tc["bn"] is not None else None
                 if need_cross:
@@ -401,7 +433,7 @@ class _ModelFunction(torch.autograd.Function):
                     call("hgnn_lg_side_dw", d.gY, d.Z, d.Rg, s.relu_from, d.acc_f, d.acc_b, d.bn_weight,
                          fptr(X1), s.Cin, base + 8 * s.dW_off, base + 8 * s.db_off, stream())
                 forked = True
-            call("hgnn_lg_side_bwd", ctypes.byref(d), stream())
+            call("hgnn_lg_side_bwd", ctypes.byref(d), cur)
         if forked:
             main.wait_stream(side_stream)       # join before the accumulators are read
         offs, nbs, strides, cnts = plan.tables(dev)
