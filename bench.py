@@ -265,6 +265,11 @@ def profile_step(train_step, resident, flush, reps=20):
     return out
 
 
+def _trace(msg):
+    if os.environ.get("HGNN_BENCH_TRACE"):
+        print("[rank %s] %s" % (os.environ.get("RANK", "0"), msg), file=sys.stderr, flush=True)
+
+
 def run_ours(a):
     import torch.distributed as dist
     import hgnn_b200
@@ -291,7 +296,9 @@ def run_ours(a):
     torch.manual_seed(0)
     model = GNN_lg(0, a.h, a.layers, 5, 2, a.J, a.order).to(dev).train()
     fp = FlatParams(model)
+    _trace("model built, broadcasting parameters")
     fp.broadcast(0)
+    _trace("broadcast done")
     opt = FusedAdamax(fp, lr=1e-3)
 
     def to_device(batch):
@@ -318,6 +325,7 @@ def run_ours(a):
     resident, h2d_bytes = to_device(prepare_batch(host_batches[0], 0, a.J))
     pack = resident[2].pack
     torch.cuda.synchronize()
+    _trace("batch resident, eager warm-up")
 
     # ---- warm-up (eager), then capture the whole step in a CUDA graph
     launches0 = hgnn_b200.launch_count()
@@ -330,10 +338,12 @@ def run_ours(a):
     torch.cuda.synchronize()
     launches_per_step = (hgnn_b200.launch_count() - launches0) // max(3, a.warmup)
     graph = None
+    _trace("eager warm-up done, capturing the step")
     if not a.no_graph:
         graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(graph):
             static_loss = train_step(resident)
+    _trace("capture done")
 
     def step():
         if graph is not None:
@@ -361,9 +371,10 @@ def run_ours(a):
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
-        # keep the sampler alive for at least a few samples under load
-        t_end = time.time() + 0.5
-        while time.time() < t_end:
+        # keep the GPU busy a little longer so that the clock sampler sees it under load.  A FIXED number
+        # of extra steps: every replay contains the gradient all-reduce, so all ranks must issue the
+        # same count (a time-based loop would leave unmatched collectives behind).
+        for _ in range(300):
             step()
         torch.cuda.synchronize()
     elapsed = sum(e0.elapsed_time(e1) for e0, e1 in events) * 1e-3
@@ -371,6 +382,7 @@ def run_ours(a):
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     elapsed = float(t.item())
+    _trace("timed region done")
     value = a.bs * world * a.steps / elapsed
     final_loss = float(loss.item())
 
