@@ -12,8 +12,9 @@ defaults (scripts/main_gnn.py:59,75-77), fp32.
 Printed JSON (one line, rank 0):
   value   graphs/s with the batch already packed in HBM (CUDA-graph replay of the whole step, CUDA
           events per step, L2 flushed between steps, max over ranks);
-  e2e     graphs/s through the public API from HOST instances: prepare_batch (block-diagonal CSR
-          concat + one pinned H2D copy) -> model -> loss -> backward -> optimizer -> loss.item();
+  e2e     graphs/s through the public API from HOST instances: prepare_batch (per-graph DMA out of the
+          pinned dataset + GPU gather into block-diagonal CSR) -> model -> loss -> backward -> optimizer
+          -> loss.item(); e2e.prefetch = the same loop fed by functions.batching.BatchLoader;
   roofline  the dominant aggregation kernel (fused edge-side update) timed alone with CUDA events,
           algorithmic bytes per SURVEY.md 8(d) / DESIGN.md, against MEASURED_PEAKS.json;
   cpu_baseline  the CPU oracle port (oracle/hgnn_oracle.py = the reference's dense torch.mm loops)
@@ -209,10 +210,13 @@ def profile_step(train_step, resident, flush, reps=20):
         return orig(name, *args)
 
     _lib.call = engine.call = rec
+    use_program = engine.USE_PROGRAM
+    engine.USE_PROGRAM = False      # the per-side Python loop issues the same launches one visible call at a time
     try:
         train_step(resident)
     finally:
         _lib.call = engine.call = orig
+        engine.USE_PROGRAM = use_program
     torch.cuda.synchronize()
 
     def kind_of(name, tag):
@@ -389,8 +393,8 @@ def run_ours(a):
     # ---- end to end through the public API: host instances -> prepare_batch -> step -> loss.item()
     e2e = None
     if not a.skip_e2e:
-        e2e_steps = max(3, min(a.steps, 10))
-        for k in range(2):
+        e2e_steps = max(3, min(a.steps, 20))
+        for k in range(6):      # warm-up: pinned slabs / staging slots / allocator pools reach steady state
             db, _ = to_device(prepare_batch(host_batches[k % n_host_batches], 0, a.J))
             train_step(db).item()
         torch.cuda.synchronize()
@@ -409,8 +413,33 @@ def run_ours(a):
         e2e = {"value": a.bs * world * e2e_steps / float(dt.item()), "unit": UNIT,
                "h2d_bytes_per_step": h2d_tot // e2e_steps, "d2h_bytes_per_step": 4,
                "steps": e2e_steps, "ms_per_step": float(dt.item()) * 1e3 / e2e_steps,
-               "path": "prepare_batch(host instances) -> pinned H2D -> GNN_lg fwd -> CE loss -> bwd -> "
-                       "all-reduce -> fused Adamax -> loss.item()"}
+               "path": "the reference's loop shape (scripts/train_mnb.py:43-70), synchronous: prepare_batch(host "
+                       "instances) -> pinned H2D -> GNN_lg fwd -> CE loss -> bwd -> all-reduce -> fused Adamax -> "
+                       "loss.item()"}
+        # same loop fed by functions.batching.BatchLoader (prepare_batch of batch k+1 on a background
+        # thread + copy stream while batch k trains); every step still copies its inputs from pinned
+        # host memory and reads the loss back
+        from hgnn_b200.functions.batching import BatchLoader
+        data = [inst for hb in host_batches for inst in hb]
+        idx_lists = [list(range((k % n_host_batches) * a.bs, (k % n_host_batches + 1) * a.bs))
+                     for k in range(e2e_steps + 4)]
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        t0 = None
+        for k, batch in enumerate(BatchLoader(data, idx_lists, 0, a.J, device=dev)):
+            if k == 4:
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+            db, _ = to_device(batch)
+            train_step(db).item()
+        torch.cuda.synchronize()
+        dt2 = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(dt2, op=dist.ReduceOp.MAX)
+        e2e["prefetch"] = {"value": a.bs * world * e2e_steps / float(dt2.item()), "unit": UNIT,
+                           "ms_per_step": float(dt2.item()) * 1e3 / e2e_steps,
+                           "path": "same loop over functions.batching.BatchLoader (one batch of look-ahead)"}
 
     def finish():
         """End of the run for world > 1.  The captured CUDA graph holds NCCL kernels, and tearing the

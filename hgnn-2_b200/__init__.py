@@ -44,4 +44,4 @@ def install_aliases(force=False):
 
 def launch_count():
     """Number of kernels launched through the C ABI so far (bench.py's ``gpu_launches``)."""
-    return _lib.launch_count
+    return _lib.total_launches()

@@ -54,8 +54,43 @@ class SideBwdT(ctypes.Structure):
                 ("accumulate_cross", c_int), ("acc_b_cross", c_void), ("skip_dw", c_int)]
 
 
+class ProgTensorT(ctypes.Structure):
+    _fields_ = [("F", c_int), ("rows", c_int), ("bn_weight", c_int), ("bn_bias", c_int),
+                ("acc_f", c_ll), ("acc_b", c_ll)]
+
+
+class ProgSideT(ctypes.Structure):
+    _fields_ = [("kind", c_int), ("src_self", c_int), ("src_cross", c_int), ("out", c_int),
+                ("Wa", c_int), ("ba", c_int), ("Ha", c_int), ("Wb", c_int), ("bb", c_int), ("Hb", c_int),
+                ("relu_from", c_int), ("dW_off", c_ll), ("db_off", c_ll)]
+
+
+class ProgramT(ctypes.Structure):
+    _fields_ = [("n_tensors", c_int), ("tensors", ctypes.POINTER(ProgTensorT)),
+                ("n_sides", c_int), ("sides", ctypes.POINTER(ProgSideT)),
+                ("dual", c_int), ("arena_doubles", c_ll),
+                ("n_flat", c_int), ("red_off", c_void), ("red_nb", c_void), ("red_stride", c_void),
+                ("red_cnt", c_void),
+                ("n_bn", c_int), ("bn_acc_off", c_void), ("bn_F", c_void), ("bn_rows_kind", c_void),
+                ("bn_run_off", c_void), ("momentum", c_float)]
+
+
+class BatchT(ctypes.Structure):
+    _fields_ = [("bs", c_int), ("Rn", c_int), ("Rm", c_int), ("n_ops", c_int),
+                ("node_ops", ctypes.POINTER(OpT)), ("node_ops_T", ctypes.POINTER(OpT)),
+                ("edge_ops", ctypes.POINTER(OpT)), ("edge_ops_T", ctypes.POINTER(OpT)),
+                ("p_rowptr", c_void), ("p_col", c_void), ("p_pm", c_void), ("p_pd", c_void),
+                ("pt_rowptr", c_void), ("pt_col", c_void), ("pt_pm", c_void), ("pt_pd", c_void),
+                ("node_off", c_void), ("pad_n", c_void)]
+
+
 _P = c_void
 _SIGS = {
+    "hgnn_program_fwd": [ctypes.POINTER(ProgramT), ctypes.POINTER(BatchT), _P, _P, _P, _P, _P, _P, _P, _P],
+    "hgnn_program_bwd": [ctypes.POINTER(ProgramT), ctypes.POINTER(BatchT), _P, _P, _P, _P, _P, _P, _P, _P, _P, _P],
+    "hgnn_bn_running_update_k": [_P, _P, _P, _P, c_int, c_int, _P, c_int, c_float, _P, _P],
+    "hgnn_host_pack_fill": [c_int, _P, c_int, c_int, _P, _P, c_int],
+    "hgnn_pack_device_upload": [c_int, _P, c_int, c_int, _P, _P, _P, _P, _P],
     "hgnn_lg_side_fwd": [ctypes.POINTER(SideT), ctypes.POINTER(BnRefT), ctypes.POINTER(BnRefT), _P, _P, c_int,
                          _P, _P, c_int, c_int, _P, _P, _P, _P],
     "hgnn_lg_row4_eligible": [ctypes.POINTER(OpT), c_int, c_int, c_int, c_int],
@@ -96,7 +131,10 @@ _SIGS = {
     "hgnn_ccn1_update_bwd": [c_int, c_int, _P, _P, _P, c_int, _P, c_int, _P, _P, _P, _P, _P, _P, c_ll, _P],
     "hgnn_adamax_step": [_P, _P, _P, _P, c_ll, c_float, c_float, c_float, c_float, c_float, _P, _P],
 }
-EXPORTS = sorted(list(_SIGS) + ["hgnn_last_error", "hgnn_version", "hgnn_workspace_bytes", "hgnn_bins_for"])
+EXPORTS = sorted(list(_SIGS) + ["hgnn_last_error", "hgnn_version", "hgnn_workspace_bytes", "hgnn_bins_for",
+                                "hgnn_program_work_floats", "hgnn_program_launches", "hgnn_host_pack_n_keys",
+                                "hgnn_host_pack_key", "hgnn_host_pack_layout", "hgnn_host_pack_last_ns",
+                                "hgnn_pack_device_plan"])
 
 for _name, _args in _SIGS.items():
     _fn = getattr(lib, _name)
@@ -109,6 +147,20 @@ lib.hgnn_workspace_bytes.restype = c_ll
 lib.hgnn_workspace_bytes.argtypes = [c_int]
 lib.hgnn_bins_for.restype = c_int
 lib.hgnn_bins_for.argtypes = [c_int]
+lib.hgnn_program_work_floats.restype = c_ll
+lib.hgnn_program_work_floats.argtypes = [ctypes.POINTER(ProgramT), c_int, c_int]
+lib.hgnn_program_launches.restype = c_ll
+lib.hgnn_program_launches.argtypes = []
+lib.hgnn_host_pack_last_ns.restype = c_ll
+lib.hgnn_host_pack_last_ns.argtypes = [c_int]
+lib.hgnn_pack_device_plan.restype = c_ll
+lib.hgnn_pack_device_plan.argtypes = [c_int, _P, c_int, c_int, _P, _P, _P]
+lib.hgnn_host_pack_n_keys.restype = c_int
+lib.hgnn_host_pack_n_keys.argtypes = []
+lib.hgnn_host_pack_key.restype = ctypes.c_char_p
+lib.hgnn_host_pack_key.argtypes = [c_int]
+lib.hgnn_host_pack_layout.restype = c_ll
+lib.hgnn_host_pack_layout.argtypes = [c_int, _P, c_int, c_int, _P]
 
 # number of kernel launches issued through the C ABI (bench.py reports it as gpu_launches)
 launch_count = 0
@@ -131,6 +183,18 @@ def call(name, *args):
     if rc != 0:
         raise RuntimeError("%s failed (%d): %s" % (name, rc, lib.hgnn_last_error().decode()))
     launch_count += 1
+
+
+def call_program(name, *args):
+    """A hgnn_program_* entry point: the kernels it launches are counted on the C side
+    (``hgnn_program_launches``), so the call itself is not added to ``launch_count``."""
+    rc = getattr(lib, name)(*args)
+    if rc != 0:
+        raise RuntimeError("%s failed (%d): %s" % (name, rc, lib.hgnn_last_error().decode()))
+
+
+def total_launches():
+    return launch_count + int(lib.hgnn_program_launches())
 
 
 def require_cuda():

@@ -370,8 +370,11 @@ struct FwdArgs {
     int TR, Cin, Cin_pad, Fout;
 };
 
-template <int VEC, int VOUT>
-__global__ void __launch_bounds__(ENG_THREADS, 4)
+// WIDE (states of 16+ features, VEC = VOUT = 4): a warp's lanes walk the feature chunks of ONE row in the
+// gather (coalesced 16 B x 32 lanes, CSR entries broadcast), and the linear is register-tiled 4 rows x 4
+// outputs per thread (8 FMA per shared-memory load instead of 3.2).
+template <int VEC, int VOUT, bool WIDE>
+__global__ void __launch_bounds__(ENG_THREADS, WIDE ? 2 : 4)
 fwd_kernel(const FwdArgs a) {
     extern __shared__ __align__(16) float smem[];
     __shared__ double dscratch[ENG_THREADS];
@@ -420,7 +423,7 @@ fwd_kernel(const FwdArgs a) {
         if (tid == 0) { dl.cnt = 0; dl.rng_cnt = 0; }
         __syncthreads();
         for (int i = tid; i < Q * TR; i += ENG_THREADS) {
-            const int q = i / TR, r = i - q * TR;
+            const int q = WIDE ? i % Q : i / TR, r = WIDE ? i / Q : i - q * TR;
             if (r >= trc) continue;
             const int row = row0 + r;
             float* trow = tile + r * Cp;
@@ -458,7 +461,56 @@ fwd_kernel(const FwdArgs a) {
         __syncthreads();
         gather_deferred<VEC>(a.ops, &dl, row0, ls, Fs, tile, Cp, wpart);
         __syncthreads();
-        if (owner) {
+        if (WIDE) {
+            if (owner) {
+                const float* w = Wt + oq * 4;
+                const float4 b4 = *reinterpret_cast<const float4*>(bias + oq * 4);
+                for (int rb = rg; rb < trc; rb += 4 * rows_per_pass) {
+                    float acc[4][4];
+                    const float* t[4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        acc[j][0] = b4.x; acc[j][1] = b4.y; acc[j][2] = b4.z; acc[j][3] = b4.w;
+                        const int r = rb + j * rows_per_pass;
+                        t[j] = tile + (r < trc ? r : rb) * Cp;
+                    }
+                    for (int c = 0; c < Cin; c += 4) {
+                        float x[4][4];
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const float4 v = *reinterpret_cast<const float4*>(t[j] + c);
+                            x[j][0] = v.x; x[j][1] = v.y; x[j][2] = v.z; x[j][3] = v.w;
+                        }
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            const float4 wv = *reinterpret_cast<const float4*>(w + (c + u) * Fout);
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                acc[j][0] = fmaf(x[j][u], wv.x, acc[j][0]);
+                                acc[j][1] = fmaf(x[j][u], wv.y, acc[j][1]);
+                                acc[j][2] = fmaf(x[j][u], wv.z, acc[j][2]);
+                                acc[j][3] = fmaf(x[j][u], wv.w, acc[j][3]);
+                            }
+                        }
+                    }
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const int r = rb + j * rows_per_pass;
+                        if (r >= trc) continue;
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            float v = acc[j][k];
+                            if (oq * 4 + k >= a.relu_from) v = fmaxf(v, 0.f);
+                            acc[j][k] = v;
+                            s1[k % VOUT] += v;
+                            s2[k % VOUT] = fmaf(v, v, s2[k % VOUT]);
+                        }
+                        *reinterpret_cast<float4*>(a.Z + (size_t)(row0 + r) * Fout + oq * 4) =
+                            make_float4(acc[j][0], acc[j][1], acc[j][2], acc[j][3]);
+                    }
+                }
+            }
+        } else if (owner) {
             for (int r = rg; r < trc; r += rows_per_pass) {
                 float acc[VOUT];
 #pragma unroll
@@ -551,7 +603,7 @@ struct BwdArgs {
     BwdPart self, cross;
 };
 
-template <int VEC, int VOUT>
+template <int VEC, int VOUT, bool WIDE>
 __device__ __forceinline__ void bwd_part(const BwdArgs& a, const BwdPart& p, bool is_self, int first_tile,
                                          int tile_stride, float* smem, double* dscratch, double* dtot, DeferList* dl,
                                          float* wpart, const float* c0, const float* c1, const float* c2,
@@ -597,7 +649,7 @@ __device__ __forceinline__ void bwd_part(const BwdArgs& a, const BwdPart& p, boo
         if (tid == 0) { dl->cnt = 0; dl->rng_cnt = 0; }
         __syncthreads();
         for (int i = tid; i < Q * TR; i += ENG_THREADS) {
-            const int q = i / TR, r = i - q * TR;
+            const int q = WIDE ? i % Q : i / TR, r = WIDE ? i / Q : i - q * TR;
             if (r >= trc) continue;
             const int xo = q * VEC;
             float* trow = tile + r * Tp;
@@ -621,7 +673,62 @@ __device__ __forceinline__ void bwd_part(const BwdArgs& a, const BwdPart& p, boo
         gather_deferred<VEC>(p.ops, dl, row0, lg, Fg, tile, Tp, wpart);
         __syncthreads();
         // ---- gX = W^T T  (+ statistics of what was produced, for the input's own BN backward)
-        if (p.gX && owner) {
+        if (WIDE) {
+            if (p.gX && owner) {
+                const float* w = Wsm + fq * 4;
+                for (int rb = rg; rb < trc; rb += 4 * rows_per_pass) {
+                    float acc[4][4];
+                    const float* t[4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.f;
+                        const int r = rb + j * rows_per_pass;
+                        t[j] = tile + (r < trc ? r : rb) * Tp;
+                    }
+                    for (int c = 0; c < nT; c += 4) {
+                        float x[4][4];
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const float4 v = *reinterpret_cast<const float4*>(t[j] + c);
+                            x[j][0] = v.x; x[j][1] = v.y; x[j][2] = v.z; x[j][3] = v.w;
+                        }
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            const float4 wv = *reinterpret_cast<const float4*>(w + (c + u) * Fx);
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                acc[j][0] = fmaf(x[j][u], wv.x, acc[j][0]);
+                                acc[j][1] = fmaf(x[j][u], wv.y, acc[j][1]);
+                                acc[j][2] = fmaf(x[j][u], wv.z, acc[j][2]);
+                                acc[j][3] = fmaf(x[j][u], wv.w, acc[j][3]);
+                            }
+                        }
+                    }
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const int r = rb + j * rows_per_pass;
+                        if (r >= trc) continue;
+                        if (p.acc_b) {
+                            const float4 xr = *reinterpret_cast<const float4*>(xt + r * Xp + fq * 4);
+                            const float xv[4] = {xr.x, xr.y, xr.z, xr.w};
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) {
+                                const int f = fq * 4 + k;
+                                sg[k % VOUT] += acc[j][k];
+                                sgx[k % VOUT] = fmaf(acc[j][k], (xv[k] - mu[f]) * rs[f], sgx[k % VOUT]);
+                            }
+                        }
+                        float* dst = p.gX + (size_t)(row0 + r) * Fx + fq * 4;
+                        float4 o = make_float4(acc[j][0], acc[j][1], acc[j][2], acc[j][3]);
+                        if (p.accumulate) {
+                            const float4 old = *reinterpret_cast<const float4*>(dst);
+                            o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
+                        }
+                        *reinterpret_cast<float4*>(dst) = o;
+                    }
+                }
+            }
+        } else if (p.gX && owner) {
             for (int r = rg; r < trc; r += rows_per_pass) {
                 float acc[VOUT];
 #pragma unroll
@@ -672,7 +779,54 @@ __device__ __forceinline__ void bwd_part(const BwdArgs& a, const BwdPart& p, boo
             }
         }
         // ---- dW[c][f] += sum_r T[r][c] * xnorm[r][f]  and (self) dbias[o] += sum_r gPre[r][o]
-        if (want_dw) {
+        if (want_dw && WIDE) {
+            // 4x4 register blocks of dW (4 tile columns x 4 input features), rows strided over NG groups
+            const int NB = (nT >> 2) * NQ;
+            for (int sidx = tid; sidx < NG * NB; sidx += ENG_THREADS) {
+                const int g = sidx / NB, b = sidx - g * NB;
+                const int c4 = b / NQ, f4 = b - c4 * NQ;
+                float4 scv = make_float4(1.f, 1.f, 1.f, 1.f), shv = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (x_aff) {
+                    scv = *reinterpret_cast<const float4*>(sc + f4 * 4);
+                    shv = *reinterpret_cast<const float4*>(sh + f4 * 4);
+                }
+                float acc[4][4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f;
+                const float* tp = tile + c4 * 4;
+                const float* xp = xt + f4 * 4;
+#pragma unroll 2
+                for (int r = g; r < trc; r += NG) {
+                    const float4 tv = *reinterpret_cast<const float4*>(tp + r * Tp);
+                    float4 xv = *reinterpret_cast<const float4*>(xp + r * Xp);
+                    xv.x = fmaf(xv.x, scv.x, shv.x); xv.y = fmaf(xv.y, scv.y, shv.y);
+                    xv.z = fmaf(xv.z, scv.z, shv.z); xv.w = fmaf(xv.w, scv.w, shv.w);
+                    const float tt[4] = {tv.x, tv.y, tv.z, tv.w};
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        acc[i][0] = fmaf(tt[i], xv.x, acc[i][0]);
+                        acc[i][1] = fmaf(tt[i], xv.y, acc[i][1]);
+                        acc[i][2] = fmaf(tt[i], xv.z, acc[i][2]);
+                        acc[i][3] = fmaf(tt[i], xv.w, acc[i][3]);
+                    }
+                }
+                float* d = dacc + (size_t)g * PD + (c4 * 4) * Fx + f4 * 4;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    float4 o = *reinterpret_cast<float4*>(d + i * Fx);
+                    o.x += acc[i][0]; o.y += acc[i][1]; o.z += acc[i][2]; o.w += acc[i][3];
+                    *reinterpret_cast<float4*>(d + i * Fx) = o;
+                }
+            }
+            if (is_self) {
+                for (int sidx = tid; sidx < NG * Fg; sidx += ENG_THREADS) {
+                    const int g = sidx / Fg, o = sidx - g * Fg;
+                    float acc = 0.f;
+                    for (int r = g; r < trc; r += NG) acc += tile[r * Tp + nT + o];
+                    dacc[(size_t)g * PD + P + o] += acc;
+                }
+            }
+        } else if (want_dw) {
             for (int sidx = tid; sidx < NG * PS; sidx += ENG_THREADS) {
                 const int g = sidx / PS, q = sidx - g * PS;
                 const int c = q / NQ, g4 = q - c * NQ;
@@ -748,8 +902,8 @@ __device__ __forceinline__ void bwd_part(const BwdArgs& a, const BwdPart& p, boo
     }
 }
 
-template <int VEC, int VS, int VC>
-__global__ void __launch_bounds__(ENG_THREADS, 4)
+template <int VEC, int VS, int VC, bool WIDE>
+__global__ void __launch_bounds__(ENG_THREADS, WIDE ? 2 : 4)
 bwd_kernel(const BwdArgs a) {
     extern __shared__ __align__(16) float smem[];
     __shared__ double dscratch[ENG_THREADS];
@@ -788,9 +942,9 @@ bwd_kernel(const BwdArgs a) {
     // CTAs [0, ns) work on the self rows, the rest on the cross rows (both persistent over tiles)
     const int ns = a.self.R > 0 ? (a.cross.R > 0 ? max(1, (int)(((long long)gridDim.x * ts) / (ts + a.cross.tiles))) : gridDim.x) : 0;
     if ((int)blockIdx.x < ns) {
-        bwd_part<VEC, VS>(a, a.self, true, blockIdx.x, ns, smem, dscratch, dtot, &dl, wpart, c0, c1, c2, has_bn);
+        bwd_part<VEC, VS, WIDE>(a, a.self, true, blockIdx.x, ns, smem, dscratch, dtot, &dl, wpart, c0, c1, c2, has_bn);
     } else {
-        bwd_part<VEC, VC>(a, a.cross, false, blockIdx.x - ns, gridDim.x - ns, smem, dscratch, dtot, &dl, wpart,
+        bwd_part<VEC, VC, WIDE>(a, a.cross, false, blockIdx.x - ns, gridDim.x - ns, smem, dscratch, dtot, &dl, wpart,
                           c0, c1, c2, has_bn);
     }
 }
@@ -941,7 +1095,8 @@ extern "C" int hgnn_lg_side_fwd(const hgnn_side_t* side, const hgnn_bn_ref_t* bn
     a.Cin_pad = eng_pad(a.Cin, vec4 ? 4 : 1);
     const int rows_per_pass = ENG_THREADS / (vout4 ? a.Fout / 4 : a.Fout);
     const int items_per_row = (a.Fs + a.Fc) / (vec4 ? 4 : 1);
-    int TR = min(rows_per_pass, max(32, ENG_THREADS / max(1, items_per_row)));
+    const bool wide = vec4 && vout4 && a.Fout >= 16 && items_per_row >= 8;
+    int TR = wide ? 4 * rows_per_pass : min(rows_per_pass, max(32, ENG_THREADS / max(1, items_per_row)));
     size_t fixed = ((size_t)a.Cin * a.Fout + ((a.Fout + 3) & ~3) + 2 * ((a.Fs + 3) & ~3) + 2 * ((a.Fc + 3) & ~3)) * sizeof(float);
     while (TR > 1 && fixed + (size_t)TR * a.Cin_pad * sizeof(float) > ENG_MAX_SMEM) TR >>= 1;
     size_t smem = fixed + (size_t)TR * a.Cin_pad * sizeof(float);
@@ -952,31 +1107,38 @@ extern "C" int hgnn_lg_side_fwd(const hgnn_side_t* side, const hgnn_bn_ref_t* bn
     a.TR = TR;
     const int ntiles = ceil_div(a.R, TR);
     cudaStream_t s = to_stream(stream);
-    if (vec4 && vout4) {
-        int grid = balanced_grid(ntiles, eng_resident(eng::fwd_kernel<4, 4>, smem));
-        eng::fwd_kernel<4, 4><<<grid, ENG_THREADS, smem, s>>>(a);
+    if (wide) {
+        int grid = balanced_grid(ntiles, eng_resident(eng::fwd_kernel<4, 4, true>, smem));
+        eng::fwd_kernel<4, 4, true><<<grid, ENG_THREADS, smem, s>>>(a);
+    } else if (vec4 && vout4) {
+        int grid = balanced_grid(ntiles, eng_resident(eng::fwd_kernel<4, 4, false>, smem));
+        eng::fwd_kernel<4, 4, false><<<grid, ENG_THREADS, smem, s>>>(a);
     } else if (vec4) {
-        int grid = balanced_grid(ntiles, eng_resident(eng::fwd_kernel<4, 1>, smem));
-        eng::fwd_kernel<4, 1><<<grid, ENG_THREADS, smem, s>>>(a);
+        int grid = balanced_grid(ntiles, eng_resident(eng::fwd_kernel<4, 1, false>, smem));
+        eng::fwd_kernel<4, 1, false><<<grid, ENG_THREADS, smem, s>>>(a);
     } else {
-        int grid = balanced_grid(ntiles, eng_resident(eng::fwd_kernel<1, 1>, smem));
-        eng::fwd_kernel<1, 1><<<grid, ENG_THREADS, smem, s>>>(a);
+        int grid = balanced_grid(ntiles, eng_resident(eng::fwd_kernel<1, 1, false>, smem));
+        eng::fwd_kernel<1, 1, false><<<grid, ENG_THREADS, smem, s>>>(a);
     }
     return hgnn_check_launch("hgnn_lg_side_fwd");
 }
 
 // fill the derived fields of one backward part; returns false if it does not fit shared memory
-static bool eng_plan_part(eng::BwdPart& p, int Fg, bool vec4, bool& vout4, bool is_self) {
+static bool eng_part_vout4(const float* X, const float* gX, int Fx) {
+    return (Fx % 4 == 0) && eng_aligned16(X) && (!gX || eng_aligned16(gX));
+}
+
+static bool eng_plan_part(eng::BwdPart& p, int Fg, bool vec4, bool& vout4, bool is_self, bool wide) {
     p.nT = p.ops.n * Fg;
     p.P = p.nT * p.Fx;
-    vout4 = vec4 && (p.Fx % 4 == 0) && eng_aligned16(p.X) && (!p.gX || eng_aligned16(p.gX));
-    const int slots = p.nT * (vout4 ? p.Fx / 4 : p.Fx);
+    vout4 = vec4 && eng_part_vout4(p.X, p.gX, p.Fx);
+    const int slots = wide ? (p.nT / 4) * (p.Fx / 4) : p.nT * (vout4 ? p.Fx / 4 : p.Fx);
     p.NG = slots >= ENG_THREADS ? 1 : ENG_THREADS / slots;
     const int tw = is_self ? p.nT + Fg : p.nT;
     p.Tp = eng_pad(tw, vec4 ? 4 : 1);
     p.Xp = vout4 ? eng_pad(p.Fx, 4) : (p.Fx | 1);
     const int rows_per_pass = ENG_THREADS / (vout4 ? p.Fx / 4 : p.Fx);
-    int TR = min(rows_per_pass, max(32, ENG_THREADS / max(1, Fg / (vec4 ? 4 : 1))));
+    int TR = wide ? 4 * rows_per_pass : min(rows_per_pass, max(32, ENG_THREADS / max(1, Fg / (vec4 ? 4 : 1))));
     const int PD = is_self ? p.P + Fg : p.P;
     auto smem_for = [&](int tr) {
         return ((size_t)((p.nT * p.Fx + 3) & ~3) + 4 * (size_t)((p.Fx + 3) & ~3) + (size_t)tr * p.Tp +
@@ -1074,6 +1236,10 @@ extern "C" int hgnn_lg_side_bwd(const hgnn_side_bwd_t* d, hgnn_stream_t stream) 
     a.Wa = d->Wa; a.Ha = d->Ha; a.Wb = d->Wb; a.Hb = d->Hb; a.Cin = d->Cin;
     a.dW_bins = d->dW_bins; a.db_bins = d->db_bins;
     const bool vec4 = (d->Fg % 4 == 0) && eng_aligned16(d->gY) && (!d->Z || eng_aligned16(d->Z));
+    // wide states: register-tiled phases (both parts must take the float4 paths)
+    const bool wide = vec4 && d->Fg >= 16 &&
+        (d->R_self <= 0 || (d->Fs >= 16 && d->Xs && eng_part_vout4(d->Xs, d->gXs, d->Fs))) &&
+        (d->R_cross <= 0 || (d->Fc >= 16 && d->Xc && eng_part_vout4(d->Xc, d->gXc, d->Fc)));
     // self part
     a.self.R = d->R_self;
     bool vs4 = false, vc4 = false;
@@ -1083,7 +1249,7 @@ extern "C" int hgnn_lg_side_bwd(const hgnn_side_bwd_t* d, hgnn_stream_t stream) 
         a.self.X = d->Xs; a.self.Fx = d->Fs; a.self.bn = to_bnref(&d->bn_self);
         a.self.gX = d->gXs; a.self.accumulate = d->accumulate_self; a.self.acc_b = d->acc_b_self;
         a.self.col0 = 0;
-        if (!eng_plan_part(a.self, d->Fg, vec4, vs4, true)) {
+        if (!eng_plan_part(a.self, d->Fg, vec4, vs4, true, wide)) {
             hgnn_set_error("hgnn_lg_side_bwd: self block %d x %d does not fit shared memory", a.self.nT, d->Fs);
             return HGNN_ERR_ARG;
         }
@@ -1103,7 +1269,7 @@ extern "C" int hgnn_lg_side_bwd(const hgnn_side_bwd_t* d, hgnn_stream_t stream) 
         a.cross.X = d->Xc; a.cross.Fx = d->Fc; a.cross.bn = to_bnref(&d->bn_cross);
         a.cross.gX = d->gXc; a.cross.accumulate = d->accumulate_cross; a.cross.acc_b = d->acc_b_cross;
         a.cross.col0 = d->n_ops * d->Fs;
-        if (!eng_plan_part(a.cross, d->Fg, vec4, vc4, false)) {
+        if (!eng_plan_part(a.cross, d->Fg, vec4, vc4, false, wide)) {
             hgnn_set_error("hgnn_lg_side_bwd: cross block %d x %d does not fit shared memory", a.cross.nT, d->Fc);
             return HGNN_ERR_ARG;
         }
@@ -1114,19 +1280,21 @@ extern "C" int hgnn_lg_side_bwd(const hgnn_side_bwd_t* d, hgnn_stream_t stream) 
     if (total_tiles == 0) return HGNN_OK;
     const size_t smem = a.self.smem > a.cross.smem ? a.self.smem : a.cross.smem;
     cudaStream_t s = to_stream(stream);
-#define ENG_LAUNCH(VEC, VS, VC)                                                                   \
-    {                                                                                             \
-        int grid = balanced_grid(total_tiles, eng_resident(eng::bwd_kernel<VEC, VS, VC>, smem));  \
-        if (a.self.tiles > 0 && a.cross.tiles > 0 && grid < 2) grid = 2;                          \
-        eng::bwd_kernel<VEC, VS, VC><<<grid, ENG_THREADS, smem, s>>>(a);                          \
+#define ENG_LAUNCH(VEC, VS, VC, W)                                                                   \
+    {                                                                                                \
+        int grid = balanced_grid(total_tiles, eng_resident(eng::bwd_kernel<VEC, VS, VC, W>, smem));  \
+        if (a.self.tiles > 0 && a.cross.tiles > 0 && grid < 2) grid = 2;                             \
+        eng::bwd_kernel<VEC, VS, VC, W><<<grid, ENG_THREADS, smem, s>>>(a);                          \
     }
-    if (vec4) {
-        if (vs4 && vc4) ENG_LAUNCH(4, 4, 4)
-        else if (vs4) ENG_LAUNCH(4, 4, 1)
-        else if (vc4) ENG_LAUNCH(4, 1, 4)
-        else ENG_LAUNCH(4, 1, 1)
+    if (wide) {
+        ENG_LAUNCH(4, 4, 4, true)
+    } else if (vec4) {
+        if (vs4 && vc4) ENG_LAUNCH(4, 4, 4, false)
+        else if (vs4) ENG_LAUNCH(4, 4, 1, false)
+        else if (vc4) ENG_LAUNCH(4, 1, 4, false)
+        else ENG_LAUNCH(4, 1, 1, false)
     } else {
-        ENG_LAUNCH(1, 1, 1)
+        ENG_LAUNCH(1, 1, 1, false)
     }
 #undef ENG_LAUNCH
     return hgnn_check_launch("hgnn_lg_side_bwd");
@@ -1162,6 +1330,7 @@ extern "C" int hgnn_bins_reduce(const double* arena, const long long* off, const
 // running + run_off[k]:  r = (1-momentum)*batch + momentum*r   (batch_normalization.py:37-38)
 __global__ void bn_running_kernel(const double* __restrict__ arena, const long long* __restrict__ acc_off,
                                   const int* __restrict__ F, const int* __restrict__ n_rows,
+                                  const int* __restrict__ rows_kind, int Rn, int Rm,
                                   const long long* __restrict__ run_off, int n_bn, float momentum,
                                   float* __restrict__ running) {
     const int k = blockIdx.x;
@@ -1176,7 +1345,7 @@ __global__ void bn_running_kernel(const double* __restrict__ arena, const long l
             a += acc[(size_t)bin * 2 * Fk + f];
             b += acc[(size_t)bin * 2 * Fk + Fk + f];
         }
-        const double n = (double)n_rows[k];
+        const double n = (double)(n_rows ? n_rows[k] : (rows_kind[k] ? Rm : Rn));
         const double m = a / n;
         double var = b / n - m * m;
         if (var < 0.0) var = 0.0;
@@ -1191,8 +1360,19 @@ extern "C" int hgnn_bn_running_update(const double* arena, const long long* acc_
                                       float momentum, float* running, hgnn_stream_t stream) {
     HGNN_REQUIRE(arena && acc_off && F && n_rows && run_off && running && n_bn >= 0, "bad argument");
     if (n_bn == 0) return HGNN_OK;
-    bn_running_kernel<<<n_bn, 64, 0, to_stream(stream)>>>(arena, acc_off, F, n_rows, run_off, n_bn, momentum, running);
+    bn_running_kernel<<<n_bn, 64, 0, to_stream(stream)>>>(arena, acc_off, F, n_rows, nullptr, 0, 0, run_off, n_bn,
+                                                          momentum, running);
     return hgnn_check_launch("hgnn_bn_running_update");
+}
+
+extern "C" int hgnn_bn_running_update_k(const double* arena, const long long* acc_off, const int* F,
+                                        const int* rows_kind, int Rn, int Rm, const long long* run_off, int n_bn,
+                                        float momentum, float* running, hgnn_stream_t stream) {
+    HGNN_REQUIRE(arena && acc_off && F && rows_kind && run_off && running && n_bn >= 0, "bad argument");
+    if (n_bn == 0) return HGNN_OK;
+    bn_running_kernel<<<n_bn, 64, 0, to_stream(stream)>>>(arena, acc_off, F, nullptr, rows_kind, Rn, Rm, run_off, n_bn,
+                                                          momentum, running);
+    return hgnn_check_launch("hgnn_bn_running_update_k");
 }
 
 // readout backward prologue (layers_mnb.py:92,:386): G[r, o] = g[graph(r), o], and the bias gradient

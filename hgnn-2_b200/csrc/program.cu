@@ -1,0 +1,261 @@
+// program.cu -- the whole GNN_simple / GNN_lg layer stack as two host calls.
+//
+// The Python engine (hgnn-2_b200/engine.py) used to walk the sides of a model itself: ~90 ctypes
+// calls per training step, each with a freshly filled descriptor struct - 3 ms of host time against
+// 1.3 ms of device time at the headline configuration.  Here the walk is native: the model is
+// described once as a static `hgnn_program_t` (tensor table + side list, parameters by index), a
+// batch as `hgnn_batch_t`, and hgnn_program_fwd / hgnn_program_bwd issue the very same launches
+// (hgnn_lg_side_fwd / hgnn_lg_side_bwd / readout / step-end reductions) from C++.
+//
+// Reference semantics: models/gnns/model_mnb.py:58-66,124-129 (layer loop), layers_mnb.py:92,:386
+// (readout sum over the padded slots).  Host code only; no kernels live in this file.
+#include <atomic>
+#include <vector>
+#include "common.cuh"
+
+static std::atomic<long long> g_program_launches{0};
+
+extern "C" long long hgnn_program_launches(void) { return g_program_launches.load(); }
+
+namespace {
+
+// activation / gradient workspace: every non-input tensor, then the readout rows (Rn x Fout_readout)
+struct WorkLayout {
+    std::vector<long long> off;   // per tensor, floats; -1 for the inputs
+    long long readout_off = 0;
+    long long total = 0;
+};
+
+inline long long align32(long long n) { return (n + 31) & ~31ll; }
+
+bool plan_work(const hgnn_program_t* prog, int Rn, int Rm, WorkLayout* w) {
+    if (!prog || prog->n_tensors < 1 || prog->n_sides < 1 || !prog->tensors || !prog->sides) return false;
+    const int n_in = prog->dual ? 2 : 1;
+    w->off.assign(prog->n_tensors, -1);
+    long long cur = 0;
+    for (int t = n_in; t < prog->n_tensors; ++t) {
+        const hgnn_prog_tensor_t& T = prog->tensors[t];
+        w->off[t] = cur;
+        cur += align32((long long)(T.rows ? Rm : Rn) * T.F);
+    }
+    const hgnn_prog_side_t& last = prog->sides[prog->n_sides - 1];
+    w->readout_off = cur;
+    cur += align32((long long)Rn * (last.Ha + last.Hb));
+    w->total = cur;
+    return true;
+}
+
+inline const float* param(const long long* addr, int idx) {
+    return idx < 0 ? nullptr : reinterpret_cast<const float*>(static_cast<uintptr_t>(addr[idx]));
+}
+
+inline int rows_of(const hgnn_program_t* prog, const hgnn_batch_t* b, int t) {
+    return prog->tensors[t].rows ? b->Rm : b->Rn;
+}
+
+// how a consumer normalises tensor t on load (training: from the producer's binned sums)
+hgnn_bn_ref_t bn_ref(const hgnn_program_t* prog, const hgnn_batch_t* b, int t, const long long* addr,
+                     const double* arena) {
+    hgnn_bn_ref_t r;
+    const hgnn_prog_tensor_t& T = prog->tensors[t];
+    r.affine = nullptr;
+    if (T.bn_weight < 0) {
+        r.acc = nullptr;
+        r.weight = r.bias = nullptr;
+        r.n_rows = 0;
+    } else {
+        r.acc = arena + T.acc_f;
+        r.weight = param(addr, T.bn_weight);
+        r.bias = param(addr, T.bn_bias);
+        r.n_rows = rows_of(prog, b, t);
+    }
+    return r;
+}
+
+inline const float* tensor_ptr(const hgnn_program_t* prog, const WorkLayout& w, int t, const float* X,
+                               const float* XL, const float* work) {
+    if (t == 0) return X;
+    if (prog->dual && t == 1) return XL;
+    return work + w.off[t];
+}
+
+bool check_program(const hgnn_program_t* prog, const hgnn_batch_t* b) {
+    for (int i = 0; i < prog->n_sides; ++i) {
+        const hgnn_prog_side_t& s = prog->sides[i];
+        if (s.src_self < 0 || s.src_self >= prog->n_tensors || s.src_cross >= prog->n_tensors ||
+            s.out >= prog->n_tensors || s.Wa < 0 || s.ba < 0 || s.Ha < 1 || (s.Hb > 0 && (s.Wb < 0 || s.bb < 0)))
+            return false;
+        if ((s.out < 0) != (i == prog->n_sides - 1)) return false;      // exactly the last side is the readout
+        if (s.kind == 1 && !prog->dual) return false;
+        if (s.src_cross >= 0 && !prog->dual) return false;
+    }
+    if (prog->dual && (!b->edge_ops || !b->edge_ops_T || !b->p_rowptr || !b->pt_rowptr)) return false;
+    return b->node_ops && b->node_ops_T && b->node_off && b->pad_n;
+}
+
+}  // namespace
+
+extern "C" long long hgnn_program_work_floats(const hgnn_program_t* prog, int Rn, int Rm) {
+    WorkLayout w;
+    if (!plan_work(prog, Rn, Rm, &w)) return -1;
+    return w.total;
+}
+
+#define PROG_CALL(expr)                    \
+    do {                                   \
+        int rc_ = (expr);                  \
+        if (rc_ != HGNN_OK) return rc_;    \
+        g_program_launches.fetch_add(1);   \
+    } while (0)
+
+extern "C" int hgnn_program_fwd(const hgnn_program_t* prog, const hgnn_batch_t* b, const float* X, const float* XL,
+                                const long long* addr, float* work, double* arena, float* running, float* out,
+                                hgnn_stream_t stream) {
+    WorkLayout w;
+    HGNN_REQUIRE(prog && b && X && addr && work && arena && out, "null argument");
+    HGNN_REQUIRE(plan_work(prog, b->Rn, b->Rm, &w) && check_program(prog, b), "malformed program or batch");
+    HGNN_REQUIRE(!prog->dual || XL, "line-graph model without XL");
+    cudaStream_t s = to_stream(stream);
+    if (prog->arena_doubles > 0) {
+        cudaError_t e = cudaMemsetAsync(arena, 0, (size_t)prog->arena_doubles * sizeof(double), s);
+        if (e != cudaSuccess) {
+            hgnn_set_error("hgnn_program_fwd: cudaMemsetAsync: %s", cudaGetErrorString(e));
+            return HGNN_ERR_CUDA;
+        }
+        g_program_launches.fetch_add(1);
+    }
+    for (int i = 0; i < prog->n_sides; ++i) {
+        const hgnn_prog_side_t& sd = prog->sides[i];
+        const bool node = sd.kind == 0;
+        hgnn_side_t st;
+        st.R = node ? b->Rn : b->Rm;
+        st.ops = node ? b->node_ops : b->edge_ops;
+        st.n_ops = b->n_ops;
+        st.Xs = tensor_ptr(prog, w, sd.src_self, X, XL, work);
+        st.Fs = prog->tensors[sd.src_self].F;
+        hgnn_bn_ref_t bs_ = bn_ref(prog, b, sd.src_self, addr, arena), bc_;
+        const bool cross = sd.src_cross >= 0;
+        if (cross) {
+            st.p_rowptr = node ? b->p_rowptr : b->pt_rowptr;
+            st.p_col = node ? b->p_col : b->pt_col;
+            st.p_pm = node ? b->p_pm : b->pt_pm;
+            st.p_pd = node ? b->p_pd : b->pt_pd;
+            st.Xc = tensor_ptr(prog, w, sd.src_cross, X, XL, work);
+            st.Fc = prog->tensors[sd.src_cross].F;
+            bc_ = bn_ref(prog, b, sd.src_cross, addr, arena);
+        } else {
+            st.p_rowptr = st.p_col = nullptr;
+            st.p_pm = st.p_pd = st.Xc = nullptr;
+            st.Fc = 0;
+        }
+        const bool readout = sd.out < 0;
+        float* Z = work + (readout ? w.readout_off : w.off[sd.out]);
+        double* acc_out = readout ? nullptr : arena + prog->tensors[sd.out].acc_f;
+        PROG_CALL(hgnn_lg_side_fwd(&st, &bs_, cross ? &bc_ : nullptr, param(addr, sd.Wa), param(addr, sd.ba), sd.Ha,
+                                   param(addr, sd.Wb), param(addr, sd.bb), sd.Hb, sd.relu_from, Z, acc_out, nullptr,
+                                   stream));
+        if (readout)   // sum over all Nmax slots; padded slots add fc.bias (layers_mnb.py:92, :386)
+            PROG_CALL(hgnn_segment_sum(Z, b->bs, sd.Ha + sd.Hb, b->node_off, b->pad_n, param(addr, sd.ba), out, stream));
+    }
+    if (running && prog->n_bn > 0)
+        PROG_CALL(hgnn_bn_running_update_k(arena, prog->bn_acc_off, prog->bn_F, prog->bn_rows_kind, b->Rn, b->Rm,
+                                           prog->bn_run_off, prog->n_bn, prog->momentum, running, stream));
+    return HGNN_OK;
+}
+
+extern "C" int hgnn_program_bwd(const hgnn_program_t* prog, const hgnn_batch_t* b, const float* X, const float* XL,
+                                const long long* addr, const float* work, float* gwork, double* arena,
+                                const float* g_out, float* gX, float* gflat, hgnn_stream_t stream) {
+    WorkLayout w;
+    HGNN_REQUIRE(prog && b && X && addr && work && gwork && arena && g_out && gflat, "null argument");
+    HGNN_REQUIRE(plan_work(prog, b->Rn, b->Rm, &w) && check_program(prog, b), "malformed program or batch");
+    cudaStream_t s = to_stream(stream);
+    std::vector<char> started(prog->n_tensors, 0);
+    auto grad_ptr = [&](int t) -> float* { return t == 0 ? gX : gwork + w.off[t]; };
+    auto wants_grad = [&](int t) { return prog->tensors[t].bn_weight >= 0 || (t == 0 && gX != nullptr); };
+    for (int i = prog->n_sides - 1; i >= 0; --i) {
+        const hgnn_prog_side_t& sd = prog->sides[i];
+        const bool node = sd.kind == 0;
+        hgnn_side_bwd_t d;
+        const int Fout = sd.Ha + sd.Hb;
+        if (sd.out < 0) {   // readout: gPre = g_out broadcast over the rows of each graph
+            float* G = gwork + w.readout_off;
+            PROG_CALL(hgnn_readout_bwd_prep(g_out, b->bs, Fout, b->node_off, b->pad_n, G, arena + sd.db_off, stream));
+            d.gY = G;
+            d.Z = nullptr;
+            d.acc_f = d.acc_b = nullptr;
+            d.bn_weight = nullptr;
+            d.Rg = b->Rn;
+        } else {
+            const hgnn_prog_tensor_t& T = prog->tensors[sd.out];
+            const size_t n = (size_t)rows_of(prog, b, sd.out) * T.F;
+            if (!started[sd.out]) {   // output never used downstream: zero gradient
+                if (n && cudaMemsetAsync(gwork + w.off[sd.out], 0, n * sizeof(float), s) != cudaSuccess) {
+                    hgnn_set_error("hgnn_program_bwd: cudaMemsetAsync failed");
+                    return HGNN_ERR_CUDA;
+                }
+                g_program_launches.fetch_add(1);
+            }
+            d.gY = gwork + w.off[sd.out];
+            d.Z = work + w.off[sd.out];
+            d.acc_f = arena + T.acc_f;
+            d.acc_b = arena + T.acc_b;
+            d.bn_weight = param(addr, T.bn_weight);
+            d.Rg = rows_of(prog, b, sd.out);
+        }
+        d.Fg = Fout;
+        d.relu_from = sd.relu_from;
+        d.Wa = param(addr, sd.Wa);
+        d.Ha = sd.Ha;
+        d.Wb = param(addr, sd.Wb);
+        d.Hb = sd.Hb;
+        const int Fs = prog->tensors[sd.src_self].F;
+        const int Fc = sd.src_cross >= 0 ? prog->tensors[sd.src_cross].F : 0;
+        d.Cin = b->n_ops * Fs + 2 * Fc;
+        d.dW_bins = arena + sd.dW_off;
+        d.db_bins = arena + sd.db_off;
+        // self part
+        d.R_self = node ? b->Rn : b->Rm;
+        d.ops_T = node ? b->node_ops_T : b->edge_ops_T;
+        d.n_ops = b->n_ops;
+        d.Xs = tensor_ptr(prog, w, sd.src_self, X, XL, work);
+        d.Fs = Fs;
+        d.bn_self = bn_ref(prog, b, sd.src_self, addr, arena);
+        const bool need_self = wants_grad(sd.src_self);
+        d.gXs = need_self ? grad_ptr(sd.src_self) : nullptr;
+        d.accumulate_self = started[sd.src_self] ? 1 : 0;
+        d.acc_b_self = prog->tensors[sd.src_self].bn_weight >= 0 ? arena + prog->tensors[sd.src_self].acc_b : nullptr;
+        if (need_self) started[sd.src_self] = 1;
+        // cross part
+        d.R_cross = 0;
+        d.pt_rowptr = d.pt_col = nullptr;
+        d.pt_pm = d.pt_pd = d.Xc = nullptr;
+        d.Fc = 0;
+        d.gXc = nullptr;
+        d.accumulate_cross = 0;
+        d.acc_b_cross = nullptr;
+        d.bn_cross = bn_ref(prog, b, 0, addr, arena);   // tensor 0 is never normalised: an empty reference
+        if (sd.src_cross >= 0) {
+            d.R_cross = rows_of(prog, b, sd.src_cross);
+            // rows = the cross tensor's rows: the other side's incidence pattern
+            d.pt_rowptr = node ? b->pt_rowptr : b->p_rowptr;
+            d.pt_col = node ? b->pt_col : b->p_col;
+            d.pt_pm = node ? b->pt_pm : b->p_pm;
+            d.pt_pd = node ? b->pt_pd : b->p_pd;
+            d.Xc = tensor_ptr(prog, w, sd.src_cross, X, XL, work);
+            d.Fc = Fc;
+            d.bn_cross = bn_ref(prog, b, sd.src_cross, addr, arena);
+            const bool need_cross = wants_grad(sd.src_cross);
+            d.gXc = need_cross ? grad_ptr(sd.src_cross) : nullptr;
+            d.accumulate_cross = started[sd.src_cross] ? 1 : 0;
+            d.acc_b_cross =
+                prog->tensors[sd.src_cross].bn_weight >= 0 ? arena + prog->tensors[sd.src_cross].acc_b : nullptr;
+            if (need_cross) started[sd.src_cross] = 1;
+        }
+        d.skip_dw = 0;
+        PROG_CALL(hgnn_lg_side_bwd(&d, stream));
+    }
+    PROG_CALL(hgnn_bins_reduce(arena, prog->red_off, prog->red_nb, prog->red_stride, prog->red_cnt, prog->n_flat,
+                               gflat, stream));
+    return HGNN_OK;
+}

@@ -7,10 +7,20 @@ data-path collective - the only exchange is the gradient sum (SURVEY.md section 
 few thousand floats (LGNN L=20, h=2: ~3 k parameters), i.e. latency-bound: one collective per step,
 never per layer.  Batch-norm statistics stay per-rank (= the reference run on the local shard).
 """
+import weakref
+
 import torch
 import torch.distributed as dist
 
 from ._lib import call, fptr, stream
+
+_FLAT_OF = weakref.WeakKeyDictionary()      # model -> weakref(FlatParams)
+
+
+def flat_params_of(model):
+    """The live ``FlatParams`` that re-homed this model's parameters, or None."""
+    ref = _FLAT_OF.get(model)
+    return ref() if ref is not None else None
 
 
 def shard_range(n_items, rank, world):
@@ -25,7 +35,11 @@ class FlatParams(object):
     gathered into one flat gradient buffer (so a step needs one concat, one all-reduce, one optimizer
     launch).  Parameter names/shapes are untouched, so state_dicts still match the reference."""
 
-    def __init__(self, model):
+    def __init__(self, model, fused_grad=True):
+        """``fused_grad``: the model-level engine (engine.run_model) differentiates w.r.t. ONE leaf
+        tensor aliasing the flat buffer (``flat_leaf``), so a step produces a single flat gradient
+        instead of ~230 per-parameter views + AccumulateGrad nodes; per-parameter ``.grad`` views are
+        then made on demand by ``scatter_grads()``.  False: gradients arrive per parameter."""
         self.params = [p for p in model.parameters()]
         dev = self.params[0].device
         sizes = [p.numel() for p in self.params]
@@ -37,16 +51,50 @@ class FlatParams(object):
             self.flat[off:off + k].copy_(p.detach().reshape(-1))
             p.data = self.flat[off:off + k].view(p.shape)
             off += k
+        self.fused_grad = bool(fused_grad)
+        self.fused_used = False
+        self.flat_leaf = self.flat.detach().requires_grad_()     # same storage, its own autograd leaf
+        self._last_off = off - sizes[-1]
+        _FLAT_OF[model] = weakref.ref(self)
+
+    def matches(self, params):
+        """True while ``params`` are still the views this object created (cheap check on both ends)."""
+        return (len(params) == len(self.params) and params[0] is self.params[0] and params[-1] is self.params[-1]
+                and params[0].data_ptr() == self.flat.data_ptr()
+                and params[-1].data_ptr() == self.flat.data_ptr() + 4 * self._last_off)
 
     def zero_grad(self):
-        """Drop the per-parameter gradients: autograd then *moves* each fresh gradient into place
-        instead of launching one accumulate-add kernel per parameter (~230 per LGNN step)."""
+        """Drop the gradients: autograd then *moves* each fresh gradient into place instead of
+        launching one accumulate-add kernel per parameter (~230 per LGNN step)."""
+        self.flat_leaf.grad = None
+        if self.fused_used:
+            self.fused_used = False
+            if not self._scattered:
+                return
+        self._scattered = False
         for p in self.params:
             p.grad = None
+
+    _scattered = False
+
+    def scatter_grads(self):
+        """Per-parameter ``.grad`` views of the flat gradient (fused_grad mode leaves them unset)."""
+        g = self.flat_leaf.grad
+        if g is None:
+            return
+        off = 0
+        for p in self.params:
+            k = p.numel()
+            p.grad = g[off:off + k].view(p.shape)
+            off += k
+        self._scattered = True
 
     def _adopt_flat_grad(self):
         """The model-level engine returns every .grad as a view of ONE flat buffer laid out in
         parameter order: use it as is (no copy).  Returns False for any other layout."""
+        if self.flat_leaf.grad is not None:
+            self.grad = self.flat_leaf.grad
+            return True
         g0 = self.params[0].grad
         if g0 is None or g0.dtype != torch.float32 or g0.storage_offset() != 0:
             return False

@@ -19,12 +19,20 @@ models/layers/layers_mnb.py); the layer-level modules keep their own (per-module
 reference's layer API.
 """
 import ctypes
+import os
 
 import numpy as np
 import torch
 
 from . import _lib
-from ._lib import BnRefT, SideBwdT, SideT, call, fptr, iptr, make_ops, stream
+from ._lib import (BatchT, BnRefT, ProgramT, ProgSideT, ProgTensorT, SideBwdT, SideT, call, call_program, fptr, iptr,
+                   make_ops, stream)
+
+# Training steps run through the native program executor (csrc/program.cu: the side loop in C++, two
+# foreign calls per step).  False (or env HGNN_B200_PY_ENGINE=1): the per-side Python loop below, which
+# issues the same launches one ctypes call at a time - kept for eval mode, SPLIT_DW and bench.py's
+# per-entry-point profiling.
+USE_PROGRAM = os.environ.get("HGNN_B200_PY_ENGINE", "0") != "1"
 
 
 # Optional: split the weight gradients of width-4 sides off the backward gather chain (x1 rows saved
@@ -160,6 +168,74 @@ class _Plan(object):
         self.bn_list = [t for t in self.tensors.values() if t["bn"] is not None]
         self._device_tables = {}
         self._running = None
+        self._programs = {}
+        self.readout_width = self.sides[-1].Fout
+
+        # ---- the same plan as C structs for csrc/program.cu (parameters by index)
+        pidx = {id(p): i for i, p in enumerate(self.params)}
+        tidx = {name: i for i, name in enumerate(self.tensors)}
+        self.c_tensors = (ProgTensorT * len(self.tensors))()
+        for i, t in enumerate(self.tensors.values()):
+            ct = self.c_tensors[i]
+            ct.F, ct.rows = t["F"], 1 if t["rows"] == "m" else 0
+            if t["bn"] is None:
+                ct.bn_weight = ct.bn_bias = -1
+                ct.acc_f = ct.acc_b = 0
+            else:
+                ct.bn_weight, ct.bn_bias = pidx[id(t["bn"].weight)], pidx[id(t["bn"].bias)]
+                ct.acc_f, ct.acc_b = t["acc_f"], t["acc_b"]
+        self.c_sides = (ProgSideT * len(self.sides))()
+        for i, sd in enumerate(self.sides):
+            cs = self.c_sides[i]
+            cs.kind = 0 if sd.kind == "node" else 1
+            cs.src_self = tidx[sd.src_self]
+            cs.src_cross = tidx[sd.src_cross] if sd.src_cross else -1
+            cs.out = tidx[sd.out] if sd.out is not None else -1
+            cs.Wa, cs.ba, cs.Ha = pidx[id(sd.conv_a.weight)], pidx[id(sd.conv_a.bias)], sd.conv_a.weight.shape[0]
+            if sd.conv_b is not None:
+                cs.Wb, cs.bb, cs.Hb = pidx[id(sd.conv_b.weight)], pidx[id(sd.conv_b.bias)], sd.conv_b.weight.shape[0]
+            else:
+                cs.Wb, cs.bb, cs.Hb = -1, -1, 0
+            cs.relu_from, cs.dW_off, cs.db_off = sd.relu_from, sd.dW_off, sd.db_off
+
+    def program(self, device):
+        """``ProgramT`` for csrc/program.cu with this device's tables (rebuilt when the running
+        statistics were re-homed)."""
+        flat, tabs = self.running_flat(device)
+        key = str(device)
+        hit = self._programs.get(key)
+        if hit is not None and hit[1] is tabs:
+            return hit[0]
+        offs, nbs, strides, cnts = self.tables(device)
+        pr = ProgramT()
+        pr.n_tensors, pr.tensors = len(self.tensors), self.c_tensors
+        pr.n_sides, pr.sides = len(self.sides), self.c_sides
+        pr.dual, pr.arena_doubles = 1 if self.lg else 0, self.arena_size
+        pr.n_flat = self.n_flat
+        pr.red_off, pr.red_nb, pr.red_stride, pr.red_cnt = (offs.data_ptr(), nbs.data_ptr(), strides.data_ptr(),
+                                                            cnts.data_ptr())
+        keep = None
+        if tabs is not None:
+            acc_off, Fs, run_off = tabs
+            kinds = torch.tensor([1 if t["rows"] == "m" else 0 for t in self.bn_list], dtype=torch.int32,
+                                 device=device)
+            pr.n_bn = len(self.bn_list)
+            pr.bn_acc_off, pr.bn_F, pr.bn_rows_kind, pr.bn_run_off = (acc_off.data_ptr(), Fs.data_ptr(),
+                                                                      kinds.data_ptr(), run_off.data_ptr())
+            pr.momentum = float(self.bn_list[0]["bn"].momentum)
+            keep = kinds
+        else:
+            pr.n_bn = 0
+        self._programs[key] = (pr, tabs, keep)
+        return pr
+
+    def param_addresses(self):
+        """Device addresses of all parameters (numpy int64, model.parameters() order).  Layout and
+        dtype are validated on the first and last parameter per call, on all of them when the plan
+        is built (``_param_ptrs``)."""
+        fptr(self.params[0])
+        fptr(self.params[-1])
+        return np.fromiter((p.data_ptr() for p in self.params), dtype=np.int64, count=len(self.params))
 
     # ---- per-device tables ---------------------------------------------------------------------
     def tables(self, device):
@@ -232,6 +308,15 @@ def _pack_cache(pack):
             for k, p in (("p", pack.p), ("pt", pack.pt)):
                 c[k] = (iptr(p.rowptr), iptr(p.col), fptr(p.val), fptr(p.val2))
         c["node_off"], c["pad_n"] = iptr(pack.node_off), fptr(pack.pad_n)
+        b = BatchT()
+        b.bs, b.Rn, b.Rm, b.n_ops = pack.bs, pack.Rn, (pack.Rm if pack.dual else 0), pack.K
+        b.node_ops, b.node_ops_T = c["node"][0], c["nodeT"][0]
+        if pack.dual:
+            b.edge_ops, b.edge_ops_T = c["edge"][0], c["edgeT"][0]
+            b.p_rowptr, b.p_col, b.p_pm, b.p_pd = c["p"]
+            b.pt_rowptr, b.pt_col, b.pt_pm, b.pt_pd = c["pt"]
+        b.node_off, b.pad_n = c["node_off"], c["pad_n"]
+        c["batch"] = b
         pack.__dict__["_engine_cache"] = c
     return c
 
@@ -334,9 +419,27 @@ def _forward(plan, pack, Xp, XLp, training, arena, save_x1=False):
 class _ModelFunction(torch.autograd.Function):
 
     @staticmethod
-    def forward(ctx, model, pack, Xp, XLp, *params):
+    def forward(ctx, model, pack, Xp, XLp, flat_mode, *params):
         plan = get_plan(model)
         dev = Xp.device
+        ctx.flat_mode = flat_mode
+        ctx.program = USE_PROGRAM and not SPLIT_DW
+        if ctx.program:
+            prog = plan.program(dev)
+            batch = _pack_cache(pack)["batch"]
+            n_work = int(_lib.lib.hgnn_program_work_floats(ctypes.byref(prog), batch.Rn, batch.Rm))
+            work = torch.empty(max(n_work, 1), device=dev)
+            arena = torch.empty(max(plan.arena_size, 1), dtype=torch.float64, device=dev)
+            out = torch.empty(pack.bs, plan.readout_width, device=dev)
+            addr = plan.param_addresses()
+            run = plan.running_flat(dev)[0]
+            _lib.tag = "program"
+            call_program("hgnn_program_fwd", ctypes.byref(prog), ctypes.byref(batch), fptr(Xp),
+                         fptr(XLp) if XLp is not None else None, addr.ctypes.data, work.data_ptr(), arena.data_ptr(),
+                         run.data_ptr() if run is not None else None, out.data_ptr(), stream())
+            ctx.plan, ctx.pack, ctx.arena, ctx.work, ctx.inputs = plan, pack, arena, work, (Xp, XLp)
+            ctx.need_x = Xp.requires_grad
+            return out
         arena = torch.zeros(max(plan.arena_size, 1), dtype=torch.float64, device=dev)
         vals, out = _forward(plan, pack, Xp, XLp, True, arena, save_x1=SPLIT_DW and any(ctx.needs_input_grad))
         run = plan.running_flat(dev)
@@ -350,10 +453,30 @@ class _ModelFunction(torch.autograd.Function):
         return out
 
     @staticmethod
+    def _grads_out(ctx, plan, gX, gflat):
+        if ctx.flat_mode:
+            return (None, None, gX, None, None, gflat)
+        return (None, None, gX, None, None) + tuple(gflat[o:o + n].view(shape) for o, n, shape in plan.param_slices)
+
+    @staticmethod
     def backward(ctx, g_out):
-        plan, pack, vals, arena = ctx.plan, ctx.pack, ctx.vals, ctx.arena
+        plan, pack, arena = ctx.plan, ctx.pack, ctx.arena
         dev = g_out.device
         g_out = g_out.contiguous().float()
+        if ctx.program:
+            prog = plan.program(dev)
+            batch = _pack_cache(pack)["batch"]
+            Xp, XLp = ctx.inputs
+            gwork = torch.empty_like(ctx.work)
+            gflat = torch.empty(plan.n_flat, device=dev)
+            gX = torch.empty_like(Xp) if ctx.need_x else None
+            addr = plan.param_addresses()
+            call_program("hgnn_program_bwd", ctypes.byref(prog), ctypes.byref(batch), fptr(Xp),
+                         fptr(XLp) if XLp is not None else None, addr.ctypes.data, ctx.work.data_ptr(),
+                         gwork.data_ptr(), arena.data_ptr(), fptr(g_out), gX.data_ptr() if gX is not None else None,
+                         gflat.data_ptr(), stream())
+            return _ModelFunction._grads_out(ctx, plan, gX, gflat)
+        vals = ctx.vals
         grads, started = {}, set()
         base = arena.data_ptr()
         main, side_stream, forked = torch.cuda.current_stream(), None, False
@@ -440,9 +563,8 @@ class _ModelFunction(torch.autograd.Function):
         gflat = torch.empty(plan.n_flat, device=dev)
         call("hgnn_bins_reduce", arena.data_ptr(), offs.data_ptr(), iptr(nbs), iptr(strides), iptr(cnts),
              plan.n_flat, fptr(gflat), stream())
-        pgrads = tuple(gflat[o:o + n].view(shape) for o, n, shape in plan.param_slices)
         gX = grads.get("X") if ctx.need_x else None
-        return (None, None, gX, None) + pgrads
+        return _ModelFunction._grads_out(ctx, plan, gX, gflat)
 
 
 def supported(model):
@@ -454,9 +576,16 @@ def run_model(model, pack, Xp, XLp):
     """Forward of the whole layer stack on packed rows; returns (bs, dim_output)."""
     plan = get_plan(model)
     if model.training and torch.is_grad_enabled():
-        return _ModelFunction.apply(model, pack, Xp, XLp, *plan.params)
+        # dist.FlatParams (fused_grad): ONE leaf aliasing all parameters takes the flat gradient, instead
+        # of ~230 per-parameter views and AccumulateGrad nodes per step
+        from .dist import flat_params_of
+        fp = flat_params_of(model)
+        if fp is not None and fp.fused_grad and fp.matches(plan.params):
+            fp.fused_used = True
+            return _ModelFunction.apply(model, pack, Xp, XLp, True, fp.flat_leaf)
+        return _ModelFunction.apply(model, pack, Xp, XLp, False, *plan.params)
     if model.training:      # train mode without autograd: batch statistics, running stats updated
         with torch.no_grad():
-            return _ModelFunction.apply(model, pack, Xp, XLp, *plan.params)
+            return _ModelFunction.apply(model, pack, Xp, XLp, False, *plan.params)
     arena = torch.zeros(1, dtype=torch.float64, device=Xp.device)
     return _forward(plan, pack, Xp, XLp, False, arena)[1]

@@ -83,13 +83,12 @@ def prepare_batch(batch, task, J=1, sparse=None, device="cuda"):
     pin = torch.cuda.is_available()
     X = torch.zeros(bs, n_feat, Nmax, pin_memory=pin)
     XL = torch.zeros(bs, 1, Emax, pin_memory=pin)
-    T = torch.zeros(bs, 1)
+    T = torch.tensor([float(inst[2][task]) for inst in batch], dtype=torch.float32).view(bs, 1)
     Xn, XLn = X.numpy(), XL.numpy()
     for i, inst in enumerate(batch):
         g = graphs[i]
         Xn[i, :, :g.N] = inst[0].numpy().T
         XLn[i, 0, :g.M] = g.dl
-        T[i, 0] = float(inst[2][task])
     pack = BatchPack.from_graphs(graphs, J, dual=True, device=device)
     W, WL = OperatorHandle(pack, "W"), OperatorHandle(pack, "WL")
     Pm, Pd = OperatorHandle(pack, "Pm"), OperatorHandle(pack, "Pd")
@@ -98,3 +97,71 @@ def prepare_batch(batch, task, J=1, sparse=None, device="cuda"):
         W, WL, Pm, Pd = (h.to_dense().cpu() for h in (W, WL, Pm, Pd))
         mask, mask_lg = mask.to_dense().cpu(), mask_lg.to_dense().cpu()
     return X, W, T, XL, WL, Pm, Pd, mask, mask_lg, N_batch, E_batch
+
+
+class BatchLoader(object):
+    """Prepared batches with one batch of look-ahead: ``prepare_batch`` (host concat of the graph
+    blobs + the pinned host->device copy + the GPU offset fix-up) for batch k+1 runs on a background
+    thread and a dedicated copy stream while the caller trains on batch k.
+
+        for X, W, T, XL, WL, Pm, Pd, mask, mask_lg, N_batch, E_batch in BatchLoader(data, idx_lists, task, J):
+            ...   # exactly the body of the reference's loop (scripts/train_mnb.py:43-70)
+
+    ``index_lists`` is what ``get_batches`` returns.  Each yielded tuple is what
+    ``prepare_batch([data[i] for i in idx], task, J)`` returns; the consumer's current stream is made
+    to wait for the copy, and the pack buffer is registered with it (``record_stream``), so no
+    synchronisation is needed in user code."""
+
+    def __init__(self, data, index_lists, task, J=1, depth=2, device="cuda"):
+        self.data, self.index_lists, self.task, self.J = data, list(index_lists), task, J
+        self.depth, self.device = max(1, int(depth)), torch.device(device)
+        if self.device.type == "cuda" and self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
+
+    def __len__(self):
+        return len(self.index_lists)
+
+    def __iter__(self):
+        import queue
+        import threading
+        q = queue.Queue(maxsize=self.depth)
+        stop = threading.Event()
+        copy_stream = torch.cuda.Stream(device=self.device)
+
+        def produce():
+            try:
+                torch.cuda.set_device(self.device)
+                for idx in self.index_lists:
+                    if stop.is_set():
+                        return
+                    with torch.cuda.stream(copy_stream):
+                        batch = prepare_batch([self.data[i] for i in idx], self.task, self.J, device=self.device)
+                        ev = torch.cuda.Event()
+                        ev.record(copy_stream)
+                    q.put((batch, ev))
+                q.put(None)
+            except BaseException as e:      # surfaced in the consumer thread
+                q.put(e)
+
+        t = threading.Thread(target=produce, daemon=True)
+        t.start()
+        try:
+            while True:
+                item = q.get()
+                if item is None:
+                    break
+                if isinstance(item, BaseException):
+                    raise item
+                batch, ev = item
+                cur = torch.cuda.current_stream(self.device)
+                cur.wait_event(ev)
+                batch[1].pack._buffer.record_stream(cur)
+                yield batch
+        finally:
+            stop.set()
+            while t.is_alive():             # unblock a producer waiting on a full queue
+                try:
+                    q.get_nowait()
+                except queue.Empty:
+                    pass
+                t.join(timeout=0.01)

@@ -11,11 +11,16 @@ host->device copy from pinned memory), 16-byte aligned sub-arrays: int32 rowptr/
 block-diagonal with global row numbers.  At C2 (32 graphs, N=1000) that is ~10 MB instead of the
 reference's 9.6 GB of dense WL.
 """
+import ctypes
+import os
+import threading
+
 import numpy as np
 import torch
 
 from . import _lib
 from ._lib import call, fptr, iptr, stream
+from . import sparse_ops
 from .sparse_ops import GraphOps, concat_block_diagonal  # noqa: F401
 
 
@@ -43,9 +48,145 @@ def _pinned_alloc(holder):
     return alloc
 
 
+class _StagingRing(object):
+    """A few long-lived pinned staging buffers reused round-robin.  A fresh
+    ``torch.empty(17 MB, pin_memory=True)`` per batch costs 3-4 ms whenever the caching host allocator
+    cannot recycle a block (measured: profiles/README.md, prepare_probe) - ten times the copy itself.
+    A slot is handed out again only after the CUDA event recorded behind its last copy completed."""
+
+    def __init__(self, n_slots=4):
+        self.bufs, self.events, self.next = [None] * n_slots, [None] * n_slots, 0
+        self.lock = threading.Lock()
+
+    def acquire(self, nbytes):
+        with self.lock:
+            i = self.next
+            self.next = (i + 1) % len(self.bufs)
+            ev, self.events[i] = self.events[i], None
+        if ev is not None:
+            ev.synchronize()
+        buf = self.bufs[i]
+        if buf is None or buf.numel() < nbytes:
+            buf = torch.empty(int(nbytes * 1.25) + 4096, dtype=torch.uint8, pin_memory=True)
+            self.bufs[i] = buf
+        return i, buf
+
+    def copied(self, i):
+        """Call after enqueueing the copy out of slot i on the current stream."""
+        ev = torch.cuda.Event()
+        ev.record()
+        self.events[i] = ev
+
+
+_staging = _StagingRing()
+_meta_ring = _StagingRing(8)
+
+
+class _PinnedSlabs(object):
+    """Bump allocator over pinned slabs for the graph blobs of a dataset (sparse_ops.blob_alloc):
+    with the dataset in pinned memory, ``BatchPack.from_graphs`` needs no host-side concatenation
+    - every blob is DMA'd as it is and the GPU assembles the batch (csrc/hostpack.cu).  Slabs are
+    never recycled blob by blob; a slab is released when all graphs carved from it are gone.
+    Beyond ``HGNN_B200_PINNED_DATASET_MB`` (default 16384) blobs fall back to pageable memory
+    (the copies are then staged by the driver: slower, same result)."""
+    SLAB = 32 << 20
+
+    def __init__(self):
+        self.cur, self.pos, self.total = None, 0, 0
+        self.cap = int(os.environ.get("HGNN_B200_PINNED_DATASET_MB", "16384")) << 20
+        self.lock = threading.Lock()
+
+    def __call__(self, nbytes):
+        if not torch.cuda.is_available() or self.total + nbytes > self.cap:
+            return np.empty(nbytes, dtype=np.uint8)
+        need = (nbytes + 63) & ~63
+        with self.lock:
+            if self.cur is None or self.pos + need > self.cur.shape[0]:
+                size = max(self.SLAB, need)
+                self.cur = torch.empty(size, dtype=torch.uint8, pin_memory=True).numpy()
+                self.pos = 0
+            out = self.cur[self.pos:self.pos + nbytes]
+            self.pos += need
+            self.total += need
+        return out
+
+
+sparse_ops.blob_alloc = _PinnedSlabs()
+
+
+def device_pack(graphs, dual=True, skip_bt=False, device="cuda"):
+    """Block-diagonal batch assembled ON THE GPU: one host->device DMA per graph blob, then one
+    gather kernel that concatenates the fields and globalises the indices
+    (``hgnn_pack_device_upload``).  Returns ``(views {name: device tensor}, buffer, nbytes copied)``."""
+    global _HOST_KEYS
+    lib = _lib.lib
+    if _HOST_KEYS is None:
+        _HOST_KEYS = [lib.hgnn_host_pack_key(k).decode() for k in range(lib.hgnn_host_pack_n_keys())]
+    bs = len(graphs)
+    blobs = (ctypes.c_void_p * max(bs, 1))(*[g.blob_ptr() for g in graphs])
+    lay = (ctypes.c_longlong * (2 * len(_HOST_KEYS)))()
+    stage_b, meta_b = ctypes.c_longlong(), ctypes.c_longlong()
+    du, sk = 1 if dual else 0, 1 if skip_bt else 0
+    total = lib.hgnn_pack_device_plan(bs, blobs, du, sk, lay, ctypes.byref(stage_b), ctypes.byref(meta_b))
+    if total < 0:
+        raise RuntimeError("hgnn_pack_device_plan failed: %s" % lib.hgnn_last_error().decode())
+    buf = torch.empty(total, dtype=torch.uint8, device=device)
+    stage = torch.empty(stage_b.value, dtype=torch.uint8, device=device)
+    meta_dev = torch.empty(meta_b.value, dtype=torch.uint8, device=device)
+    slot, meta_host = _meta_ring.acquire(meta_b.value)
+    _lib.call("hgnn_pack_device_upload", bs, blobs, du, sk, buf.data_ptr(), stage.data_ptr(), meta_host.data_ptr(),
+              meta_dev.data_ptr(), stream())
+    _meta_ring.copied(slot)
+    views = {}
+    for k, name in enumerate(_HOST_KEYS):
+        n = lay[2 * k + 1]
+        if n >= 0:
+            o = lay[2 * k]
+            views[name] = buf[o:o + 4 * n].view(torch.float32 if name in _FLOAT_KEYS else torch.int32)
+    return views, buf, stage_b.value + meta_b.value
+
+
+_HOST_KEYS = None
+_FLOAT_KEYS = frozenset(["pad_n", "deg", "dl", "a_val", "at_val", "b_val", "bt_val", "bts_val", "bts_rng_val",
+                         "p_pm", "p_pd", "pt_pm", "pt_pd"])
+HOST_PACK_THREADS = max(1, min(8, (os.cpu_count() or 1) // 2))
+# True (env HGNN_B200_HOST_CONCAT=1): concatenate a batch on the host (host_pack) and copy it once,
+# instead of the default per-graph DMA + GPU gather (device_pack).  Same arrays either way.
+HOST_CONCAT = os.environ.get("HGNN_B200_HOST_CONCAT", "0") == "1"
+
+
+def host_pack(graphs, dual=True, skip_bt=False, alloc=None, n_threads=None):
+    """Block-diagonal batch of ``GraphOps`` through the native packer (csrc/hostpack.cu): every
+    graph's blob is concatenated field by field into ONE staging buffer by a small thread pool.
+    Same arrays and fix-up table as ``sparse_ops.concat_block_diagonal(defer_offsets=True)``
+    (functions/batching.py:77-185 is the reference's dense zero-padding).  Host code only - works
+    without a GPU.  Returns ``(buffer (numpy uint8), layout {name: (byte offset, dtype, length)})``."""
+    global _HOST_KEYS
+    lib = _lib.lib
+    if _HOST_KEYS is None:
+        _HOST_KEYS = [lib.hgnn_host_pack_key(k).decode() for k in range(lib.hgnn_host_pack_n_keys())]
+    bs = len(graphs)
+    blobs = (ctypes.c_void_p * max(bs, 1))(*[g.blob_ptr() for g in graphs])
+    lay = (ctypes.c_longlong * (2 * len(_HOST_KEYS)))()
+    total = lib.hgnn_host_pack_layout(bs, blobs, 1 if dual else 0, 1 if skip_bt else 0, lay)
+    if total < 0:
+        raise RuntimeError("hgnn_host_pack_layout failed: %s" % lib.hgnn_last_error().decode())
+    buf = alloc(total) if alloc is not None else np.empty(total, dtype=np.uint8)
+    rc = lib.hgnn_host_pack_fill(bs, blobs, 1 if dual else 0, 1 if skip_bt else 0, lay, buf.ctypes.data,
+                                 HOST_PACK_THREADS if n_threads is None else int(n_threads))
+    if rc != 0:
+        raise RuntimeError("hgnn_host_pack_fill failed: %s" % lib.hgnn_last_error().decode())
+    layout = {}
+    for k, name in enumerate(_HOST_KEYS):
+        if lay[2 * k + 1] >= 0:
+            layout[name] = (lay[2 * k], np.float32 if name in _FLOAT_KEYS else np.int32, lay[2 * k + 1])
+    return buf, layout
+
+
 def _device_views(host_tensor, layout, device):
     """One H2D copy of the staging buffer; the arrays become views of the device buffer."""
-    dev = host_tensor.to(device, non_blocking=True)
+    dev = torch.empty(host_tensor.numel(), dtype=torch.uint8, device=device)
+    dev.copy_(host_tensor, non_blocking=True)
     out = {}
     for k, (o, dt, length) in layout.items():
         tdt = torch.int32 if dt is np.int32 else torch.float32
@@ -137,22 +278,33 @@ class BatchPack(object):
         # The full transposed line-graph operator is only needed by the layer-level kernels and by
         # the powers; the engine uses its run-length split twin.  It is uploaded on first use.
         lazy_bt = dual and self.J == 1
-        holder = {}
-        # raw per-graph arrays -> pinned staging (one np.concatenate per field); the per-graph index
-        # offsets are added on the GPU after the copy (hgnn_fixup_offsets)
-        _, _, layout = concat_block_diagonal(graphs, dual=dual, skip=("bt",) if lazy_bt else (),
-                                             alloc=_pinned_alloc(holder), defer_offsets=True)
+        if HOST_CONCAT:
+            # raw per-graph arrays -> pinned staging slot (native multi-threaded concat of the graph
+            # blobs); the per-graph index offsets are added on the GPU after the copy
+            slot = {}
+
+            def staging(nbytes):
+                slot["i"], slot["buf"] = _staging.acquire(nbytes)
+                slot["n"] = nbytes
+                return slot["buf"].numpy()[:nbytes]
+
+            _, layout = host_pack(graphs, dual=dual, skip_bt=lazy_bt, alloc=staging)
         self.bs = len(graphs)
         self.n_nodes = np.array([g.N for g in graphs], dtype=np.int64)
         self.n_edges = np.array([g.M for g in graphs], dtype=np.int64)
         self.Nmax = int(self.n_nodes.max())
         self.Emax = int(self.n_edges.max()) if dual else 0
         self.Rn, self.Rm = int(self.n_nodes.sum()), int(self.n_edges.sum())
-        dev, self._buffer = _device_views(holder["host"], layout, device)
-        self.nbytes = holder["host"].numel()
-        call("hgnn_fixup_offsets", self._buffer.data_ptr(), iptr(dev["fixup"]), dev["fixup"].numel() // 4,
-             len(graphs), stream())
-        self._host_graphs = graphs if lazy_bt else None
+        if HOST_CONCAT:
+            dev, self._buffer = _device_views(slot["buf"][:slot["n"]], layout, device)
+            _staging.copied(slot["i"])
+            self.nbytes = slot["n"]
+            call("hgnn_fixup_offsets", self._buffer.data_ptr(), iptr(dev["fixup"]), dev["fixup"].numel() // 4,
+                 len(graphs), stream())
+        else:
+            # the product path: blobs DMA'd as they are, batch assembled by one gather kernel
+            dev, self._buffer, self.nbytes = device_pack(graphs, dual=dual, skip_bt=lazy_bt, device=device)
+        self._host_graphs = graphs       # keeps the blobs alive behind the asynchronous copies
         self.node_off, self.edge_off = dev["node_off"], dev["edge_off"]
         self.pad_n = dev["pad_n"]
         self.deg = dev["deg"]

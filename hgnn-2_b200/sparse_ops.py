@@ -75,6 +75,23 @@ def split_runs(n_rows, rowptr, col, val, min_run=64):
             uniq[:, 0].astype(I32), uniq[:, 1].astype(I32))
 
 
+def _numpy_blob_alloc(nbytes):
+    return np.empty(nbytes, dtype=np.uint8)
+
+
+# where graph blobs live: plain numpy memory by default; ``pack.py`` installs a pinned-slab allocator
+# when a CUDA device is present, so that a batch is copied host->device straight out of the dataset
+blob_alloc = _numpy_blob_alloc
+
+BLOB_MAGIC = 0x48474e4e424c4f42
+BLOB_FIELDS = ("deg", "a_rowptr", "a_col", "a_val", "at_rowptr", "at_col", "at_val",
+               "dl", "b_rowptr", "b_col", "b_val", "bt_rowptr", "bt_col", "bt_val",
+               "p_rowptr", "p_col", "p_pm", "p_pd", "pt_rowptr", "pt_col", "pt_pm", "pt_pd",
+               "bts_rowptr", "bts_col", "bts_val", "bts_rng_rowptr", "bts_rng_id", "bts_rng_val",
+               "bts_rng_lo", "bts_rng_hi")
+N_PRIMAL_FIELDS = 7
+
+
 class GraphOps(object):
     """Sparse twin of ``graph_operators([V, A], J, dual=True)`` for ONE graph (local indices).
 
@@ -88,7 +105,44 @@ class GraphOps(object):
                  "deg", "b_rowptr", "b_col", "b_val", "bt_rowptr", "bt_col", "bt_val", "dl",
                  "p_rowptr", "p_col", "p_pm", "p_pd", "pt_rowptr", "pt_col", "pt_pm", "pt_pd",
                  "bts_rowptr", "bts_col", "bts_val", "bts_rng_rowptr", "bts_rng_id", "bts_rng_val",
-                 "bts_rng_lo", "bts_rng_hi", "dual")
+                 "bts_rng_lo", "bts_rng_hi", "dual", "_blob", "_blob_ptr")
+
+    def blob_ptr(self):
+        """Address of this graph's contiguous host blob (built on first use): int64 header
+        ``[magic, N, M, E, n_fields, (byte offset, length) x n_fields]`` followed by the arrays of
+        ``BLOB_FIELDS`` (16-byte aligned).  The attribute arrays are re-pointed at the blob, so it is
+        the single copy of the graph.  ``hgnn_host_pack_fill`` (csrc/hostpack.cu) concatenates a
+        batch straight from these blobs."""
+        ptr = getattr(self, "_blob_ptr", None)
+        if ptr is not None:
+            return ptr
+        fields = BLOB_FIELDS if self.dual else BLOB_FIELDS[:N_PRIMAL_FIELDS]
+        arrs = [np.ascontiguousarray(getattr(self, f)) for f in fields]
+        for f, a in zip(fields, arrs):
+            if a.dtype.itemsize != 4:
+                raise TypeError("GraphOps.%s must be a 4-byte array, got %s" % (f, a.dtype))
+        head = 8 * (5 + 2 * len(fields))
+        pos = (head + 15) & ~15
+        table = []
+        for a in arrs:
+            table += [pos, a.shape[0]]
+            pos += (a.nbytes + 15) & ~15
+        blob = blob_alloc(pos)
+        blob[:head].view(np.int64)[:] = [BLOB_MAGIC, self.N, self.M, self.E, len(fields)] + table
+        for f, a, o in zip(fields, arrs, table[0::2]):
+            view = blob[o:o + a.nbytes].view(a.dtype)
+            view[:] = a
+            setattr(self, f, view)
+        self._blob = blob
+        self._blob_ptr = blob.ctypes.data
+        return self._blob_ptr
+
+    def __getstate__(self):       # pickled datasets (functions/data_generator.py) carry plain arrays
+        return {s: getattr(self, s) for s in self.__slots__ if not s.startswith("_blob") and hasattr(self, s)}
+
+    def __setstate__(self, state):
+        for k, v in state.items():
+            setattr(self, k, v)
 
     @classmethod
     def from_dense(cls, A, dual=True):

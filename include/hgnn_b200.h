@@ -292,6 +292,108 @@ int hgnn_adamax_step(float* param, const float* grad, float* exp_avg, float* exp
                      float lr, float beta1, float beta2, float eps, float grad_scale,
                      int* step /* device counter, incremented by the call */, hgnn_stream_t stream);
 
+/* ---- whole-model training step in two calls (csrc/program.cu) ---------------------------------
+ * The layer stack of GNN_simple / GNN_lg (models/gnns/model_mnb.py:58-66, 124-129) as a static
+ * "program": a table of tensors (0 = X, 1 = XL for the line-graph model, then one per layer side
+ * output) and a list of sides in forward order.  hgnn_program_fwd / _bwd walk that list on the host
+ * and issue the same launches as a per-side loop over hgnn_lg_side_fwd / hgnn_lg_side_bwd would,
+ * without ~90 foreign-function calls per step.  Parameters are addressed by INDEX into `param_addr`,
+ * a host array of device addresses in model.parameters() order. */
+typedef struct hgnn_prog_tensor_t {
+    int F;                  /* feature width */
+    int rows;               /* 0: node rows (Rn), 1: line-graph rows (Rm) */
+    int bn_weight, bn_bias; /* parameter indices of the scalar BN affine; -1: not normalised (inputs) */
+    long long acc_f, acc_b; /* arena offsets (doubles) of the (sum z, sum z^2) / (sum g, sum g xhat) bins */
+} hgnn_prog_tensor_t;
+
+typedef struct hgnn_prog_side_t {
+    int kind;               /* 0: node side, 1: edge (line-graph) side */
+    int src_self, src_cross /* -1: none */, out /* -1: readout */;
+    int Wa, ba, Ha, Wb, bb, Hb; /* parameter indices; Wb = bb = -1 when Hb == 0 */
+    int relu_from;
+    long long dW_off, db_off;   /* arena offsets (doubles) of the dW / dbias bins */
+} hgnn_prog_side_t;
+
+typedef struct hgnn_program_t {
+    int n_tensors; const hgnn_prog_tensor_t* tensors;
+    int n_sides; const hgnn_prog_side_t* sides;
+    int dual;
+    long long arena_doubles;
+    /* device tables: accumulators -> flat gradient (hgnn_bins_reduce) */
+    int n_flat; const long long* red_off; const int* red_nb; const int* red_stride; const int* red_cnt;
+    /* device tables: running statistics (hgnn_bn_running_update); bn_rows_kind[k] = 0 node / 1 line-graph rows */
+    int n_bn; const long long* bn_acc_off; const int* bn_F; const int* bn_rows_kind; const long long* bn_run_off;
+    float momentum;
+} hgnn_program_t;
+
+typedef struct hgnn_batch_t {
+    int bs, Rn, Rm, n_ops;
+    const hgnn_op_t* node_ops; const hgnn_op_t* node_ops_T;
+    const hgnn_op_t* edge_ops; const hgnn_op_t* edge_ops_T;          /* NULL when not dual */
+    const int* p_rowptr; const int* p_col; const float* p_pm; const float* p_pd;      /* rows = nodes */
+    const int* pt_rowptr; const int* pt_col; const float* pt_pm; const float* pt_pd;  /* rows = line-graph nodes */
+    const int* node_off; const float* pad_n;
+} hgnn_batch_t;
+
+/* floats of activation workspace for a batch with Rn node rows and Rm line-graph rows (every side
+ * output + the readout rows); the gradient workspace of hgnn_program_bwd has the same size. */
+long long hgnn_program_work_floats(const hgnn_program_t* prog, int Rn, int Rm);
+/* Training forward: zeroes `arena` (prog->arena_doubles doubles), runs every side (raw activations into
+ * `work`), the readout sum into out (bs, Fout_readout) and the running-statistics update (running != NULL). */
+int hgnn_program_fwd(const hgnn_program_t* prog, const hgnn_batch_t* batch, const float* X, const float* XL,
+                     const long long* param_addr, float* work, double* arena, float* running, float* out,
+                     hgnn_stream_t stream);
+/* Backward of the same step: g_out (bs, Fout_readout) -> gX (Rn, F_X; NULL = not needed) and the flat
+ * parameter gradient gflat (prog->n_flat).  gwork: scratch of hgnn_program_work_floats floats. */
+int hgnn_program_bwd(const hgnn_program_t* prog, const hgnn_batch_t* batch, const float* X, const float* XL,
+                     const long long* param_addr, const float* work, float* gwork, double* arena,
+                     const float* g_out, float* gX, float* gflat, hgnn_stream_t stream);
+/* kernels launched by hgnn_program_* calls so far (the host layer adds it to its own launch count) */
+long long hgnn_program_launches(void);
+/* hgnn_bn_running_update with the row counts given as (kind table, Rn, Rm) instead of a device vector */
+int hgnn_bn_running_update_k(const double* arena, const long long* acc_off, const int* F, const int* rows_kind,
+                             int Rn, int Rm, const long long* run_off, int n_bn, float momentum, float* running,
+                             hgnn_stream_t stream);
+
+/* ---- host side of the batch pack (csrc/hostpack.cu; plain CPU code, no CUDA calls) ---------------
+ * functions/batching.py:77-185 zero-pads and stacks dense per-graph operators; here every graph carries
+ * ONE contiguous host blob of its CSR arrays (sparse_ops.GraphOps.blob) and a batch is their
+ * block-diagonal concatenation into one (pinned) staging buffer, laid out exactly like
+ * sparse_ops.concat_block_diagonal(defer_offsets=True): raw per-field concatenation + segment tables
+ * + the fix-up table that hgnn_fixup_offsets applies on the GPU after the copy.
+ * Blob = int64 header [HGNN_BLOB_MAGIC, N, M, E, n_fields, (byte offset, length in 4-byte elements) x n_fields]
+ * followed by the arrays, each 16-byte aligned, in the field order of HGNN_BLOB_FIELDS (hostpack.cu). */
+#define HGNN_BLOB_MAGIC 0x48474e4e424c4f42ll
+/* Wall-clock split of the last hgnn_host_pack_fill call in ns: which = 0 task list, 1 copies (profiling aid). */
+long long hgnn_host_pack_last_ns(int which);
+/* Number of output arrays of a batch layout (`layout` below holds that many (offset, length) pairs). */
+int hgnn_host_pack_n_keys(void);
+/* Name of output array k (static string; the Python layer builds its view table from these). */
+const char* hgnn_host_pack_key(int k);
+/* Computes the batch layout: layout[2k] = byte offset, layout[2k+1] = length (4-byte elements) of array k
+ * (length -1: array absent, e.g. the line-graph arrays when dual == 0 or bt when skip_bt != 0).
+ * Returns the total number of bytes (16-byte aligned sub-arrays), < 0 on error. */
+long long hgnn_host_pack_layout(int bs, const void* const* blobs, int dual, int skip_bt, long long* layout);
+/* Fills `out` (total bytes from hgnn_host_pack_layout) using up to n_threads host threads. */
+int hgnn_host_pack_fill(int bs, const void* const* blobs, int dual, int skip_bt, const long long* layout,
+                        void* out, int n_threads);
+
+/* ---- device-side batch assembly (the product path of prepare_batch) ------------------------------
+ * Every graph blob goes host->device as it is (one cudaMemcpyAsync per graph, straight from the dataset's
+ * pinned memory), then one kernel gathers the fields into the block-diagonal arrays and adds the per-graph
+ * row / column / nnz offsets on the way: same arrays as hgnn_host_pack_fill + hgnn_fixup_offsets, without
+ * the host-side concatenation (functions/batching.py:77-185 is the reference's dense zero-padding).
+ * hgnn_pack_device_plan: layout[2k], layout[2k+1] = byte offset / length of output array k (keys of
+ * hgnn_host_pack_key; segment tables and the fix-up table are absent: length -1); returns the bytes of the
+ * output buffer, *stage_bytes = device staging for the raw blobs, *meta_bytes = size of the task table
+ * (needed twice: pinned host + device).  < 0 on error. */
+long long hgnn_pack_device_plan(int bs, const void* const* blobs, int dual, int skip_bt, long long* layout,
+                                long long* stage_bytes, long long* meta_bytes);
+/* Enqueues the copies and the gather kernel on `stream`.  meta_host must stay untouched, and the blobs alive,
+ * until the stream has passed this point. */
+int hgnn_pack_device_upload(int bs, const void* const* blobs, int dual, int skip_bt, void* out_dev,
+                            void* stage_dev, void* meta_host, void* meta_dev, hgnn_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -24,6 +24,33 @@ print('e2e ms', (time.perf_counter()-t)*100)
 t=time.perf_counter()
 for _ in range(10): b = prepare_batch(inst, 0, 1); torch.cuda.synchronize()
 print('prepare_batch ms', (time.perf_counter()-t)*100)
+t=time.perf_counter()
+for _ in range(10): b = prepare_batch(inst, 0, 1)
+print('prepare_batch host-only ms', (time.perf_counter()-t)*100); torch.cuda.synchronize()
+from hgnn_b200 import pack as _pk
+gs=[i[3].graph_ops for i in inst]
+hold={}
+t=time.perf_counter()
+for _ in range(10): _pk.host_pack(gs, True, True, alloc=_pk._pinned_alloc(hold))
+print('host_pack (pinned) ms', (time.perf_counter()-t)*100)
+def step_only(b):
+    X, W, T, XL, WL, Pm, Pd, mask, mask_lg, N_batch, E_batch = b
+    Xd, XLd, y = X.cuda(non_blocking=True), XL.cuda(non_blocking=True), T.squeeze(1).long().cuda(non_blocking=True)
+    fp.zero_grad()
+    out = model([Xd, XLd, W, WL, Pm, Pd], N_batch, mask, E_batch, mask_lg)
+    loss = torch.nn.functional.cross_entropy(out, y); loss.backward(); fp.all_reduce_grad(); opt.step()
+    return loss
+for _ in range(3): step_only(b)
+torch.cuda.synchronize(); t=time.perf_counter()
+for _ in range(10): step_only(b)
+th=time.perf_counter()-t; torch.cuda.synchronize()
+print('step host issue ms', th*100, ' step incl. device ms', (time.perf_counter()-t)*100)
+from hgnn_b200.functions.batching import BatchLoader
+t0=None
+for k, b in enumerate(BatchLoader(inst, [list(range(32))]*14, 0, 1)):
+    if k == 4: torch.cuda.synchronize(); t0=time.perf_counter()
+    step_only(b).item()
+torch.cuda.synchronize(); print('e2e loader ms', (time.perf_counter()-t0)*100)
 pr=cProfile.Profile(); pr.enable()
 for _ in range(10): step()
 pr.disable()

@@ -104,9 +104,61 @@ def test_engine_grads_are_one_flat_buffer():
     fp.zero_grad()
     out = model([X.cuda(), XL.cuda(), W, WL, Pm, Pd], N_batch, mask, E_batch, mask_lg)
     out.sum().backward()
+    # fused_grad (default): ONE gradient for the leaf that aliases the flat parameter buffer
+    assert model.layer0.cv1.weight.grad is None and fp.flat_leaf.grad is not None
     assert fp._adopt_flat_grad()
     assert fp.grad.numel() == fp.n and torch.isfinite(fp.grad).all()
+    fp.scatter_grads()
     assert torch.equal(fp.grad[:model.layer0.cv1.weight.numel()], model.layer0.cv1.weight.grad.reshape(-1))
+    fused = fp.grad.clone()
+    fp.zero_grad()
+    assert model.layer0.cv1.weight.grad is None and fp.flat_leaf.grad is None
+    # per-parameter gradients (fused_grad=False): views of one flat buffer, adopted without a copy
+    fp.fused_grad = False
+    out = model([X.cuda(), XL.cuda(), W, WL, Pm, Pd], N_batch, mask, E_batch, mask_lg)
+    out.sum().backward()
+    assert fp.flat_leaf.grad is None and fp._adopt_flat_grad()
+    assert torch.equal(fp.grad[:model.layer0.cv1.weight.numel()], model.layer0.cv1.weight.grad.reshape(-1))
+    assert rel_err(fp.grad.cpu(), fused.cpu()) < 1e-5
+
+
+@pytest.mark.parametrize("kind,order,h,J", [("lg", 1, 2, 1), ("lg", 2, 2, 1), ("lg", 3, 8, 2), ("simple", 0, 2, 1),
+                                            ("simple", 0, 4, 2)])
+def test_program_executor_matches_python_engine(kind, order, h, J):
+    """csrc/program.cu (the side loop in C++) must issue exactly what the per-side Python loop issues:
+    outputs, input gradient, every parameter gradient and the running statistics."""
+    import hgnn_b200  # noqa: F401
+    from hgnn_b200 import engine, synth
+    from hgnn_b200.functions.batching import prepare_batch
+    from hgnn_b200.models.gnns.model_mnb import GNN_lg, GNN_simple
+    torch.manual_seed(3)
+    model = (GNN_lg(0, h, 4, 5, 2, J, order) if kind == "lg" else GNN_simple(0, h, 4, 5, 2, J)).cuda().train()
+    X, W, T, XL, WL, Pm, Pd, mask, mask_lg, N_batch, E_batch = prepare_batch(synth.sbm_dataset(5, N=60, J=J), 0, J)
+    res = []
+    for use in (True, False):
+        engine.USE_PROGRAM = use
+        try:
+            for b in (m for m in model.modules() if hasattr(m, "running_mean")):
+                b.running_mean.zero_()
+                b.running_std.zero_()
+            for p_ in model.parameters():
+                p_.grad = None
+            Xc = X.cuda().requires_grad_()
+            if kind == "lg":
+                out = model([Xc, XL.cuda(), W, WL, Pm, Pd], N_batch, mask, E_batch, mask_lg)
+            else:
+                out = model([Xc, W], N_batch, mask)
+            (out * torch.arange(1, out.numel() + 1, device="cuda").view_as(out)).sum().backward()
+            g = {k: v.grad.detach().clone() for k, v in model.named_parameters()}
+            g["X"], g["out"] = Xc.grad.clone(), out.detach().clone()
+            for i, b in enumerate(m for m in model.modules() if hasattr(m, "running_mean")):
+                g["rm%d" % i], g["rs%d" % i] = b.running_mean.clone(), b.running_std.clone()
+            res.append(g)
+        finally:
+            engine.USE_PROGRAM = True
+    fl = 0.1 * max(float(v.abs().max()) for k, v in res[1].items() if k not in ("X", "out"))
+    for k in res[1]:
+        assert rel_err(res[0][k].cpu(), res[1][k].cpu(), fl if k not in ("X", "out") else 0.0) < 1e-5, k
 
 
 def test_generic_engine_kernels_at_width4():

@@ -1,0 +1,57 @@
+"""GPU: the device-side batch assembly (per-graph DMA + one gather kernel, csrc/hostpack.cu) must give
+exactly the arrays of the host-side block-diagonal concatenation (sparse_ops.concat_block_diagonal with
+the offsets applied) - bit-exact index bookkeeping, BASELINE.json north_star."""
+import numpy as np
+import pytest
+import torch
+
+from test_hostpack import _graphs
+
+pytestmark = pytest.mark.gpu
+
+
+def _check(graphs, dual, skip_bt):
+    from hgnn_b200 import pack
+    from hgnn_b200.sparse_ops import concat_block_diagonal
+    arrays, _, _ = concat_block_diagonal(graphs, dual=dual, skip=("bt",) if skip_bt else ())
+    views, buf, nbytes = pack.device_pack(graphs, dual=dual, skip_bt=skip_bt, device="cuda")
+    torch.cuda.synchronize()
+    want = {k for k in arrays if not k.startswith("_seg")}
+    assert set(views) == want, set(views) ^ want
+    for k in want:
+        got = views[k].cpu().numpy()
+        assert got.dtype == arrays[k].dtype and np.array_equal(got, arrays[k]), k
+    assert nbytes >= sum(g._blob.nbytes for g in graphs)
+
+
+@pytest.mark.parametrize("sizes", [[12, 7, 30], [5], [40, 40, 40, 40, 3, 25, 9], [300, 2, 150]])
+@pytest.mark.parametrize("skip_bt", [True, False])
+def test_device_pack_equals_host_concat(sizes, skip_bt):
+    _check(_graphs(sizes, seed=sum(sizes)), True, skip_bt)
+
+
+def test_device_pack_primal_only_and_edgeless_graph():
+    from hgnn_b200.sparse_ops import GraphOps
+    _check(_graphs([9, 14, 4], seed=5, dual=False), False, False)
+    empty = GraphOps.from_dense(np.zeros((6, 6), np.float32), dual=True)
+    _check([_graphs([8], seed=1)[0], empty, _graphs([10], seed=2)[0]], True, True)
+
+
+def test_device_and_host_concat_paths_give_the_same_pack():
+    from hgnn_b200 import pack, synth
+    graphs = [i[3].graph_ops for i in synth.sbm_dataset(4, N=200, J=1, sparse=True)]
+    a = pack.BatchPack.from_graphs(graphs, 1, True, "cuda")
+    pack.HOST_CONCAT = True
+    try:
+        b = pack.BatchPack.from_graphs(graphs, 1, True, "cuda")
+    finally:
+        pack.HOST_CONCAT = False
+    for name in ("node_off", "edge_off", "pad_n", "deg", "dl"):
+        assert torch.equal(getattr(a, name), getattr(b, name)), name
+    for ca, cb in ((a.a[0], b.a[0]), (a.at[0], b.at[0]), (a.b[0], b.b[0]), (a.p, b.p), (a.pt, b.pt), (a.bts, b.bts)):
+        assert torch.equal(ca.rowptr, cb.rowptr) and torch.equal(ca.col, cb.col) and torch.equal(ca.val, cb.val)
+        if ca.val2 is not None:
+            assert torch.equal(ca.val2, cb.val2)
+    for ra, rb in zip(a.bts_ranges, b.bts_ranges):
+        assert torch.equal(ra, rb)
+    assert graphs[0]._blob is not None and torch.from_numpy(graphs[0]._blob).is_pinned()
