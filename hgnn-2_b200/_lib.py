@@ -28,13 +28,13 @@ MAX_OPS = 8
 class OpT(ctypes.Structure):
     _fields_ = [("kind", c_int), ("diag", c_void), ("rowptr", c_void), ("col", c_void),
                 ("val", c_void), ("rng_rowptr", c_void), ("rng_id", c_void), ("rng_val", c_void),
-                ("rng_lo", c_void), ("rng_hi", c_void)]
+                ("rng_lo", c_void), ("rng_hi", c_void), ("nnz", c_ll)]
 
 
 class SideT(ctypes.Structure):
     _fields_ = [("R", c_int), ("ops", ctypes.POINTER(OpT)), ("n_ops", c_int), ("Xs", c_void),
                 ("Fs", c_int), ("p_rowptr", c_void), ("p_col", c_void), ("p_pm", c_void),
-                ("p_pd", c_void), ("Xc", c_void), ("Fc", c_int)]
+                ("p_pd", c_void), ("Xc", c_void), ("Fc", c_int), ("p_nnz", c_ll)]
 
 
 class BnRefT(ctypes.Structure):
@@ -51,7 +51,7 @@ class SideBwdT(ctypes.Structure):
                 ("acc_b_self", c_void),
                 ("R_cross", c_int), ("pt_rowptr", c_void), ("pt_col", c_void), ("pt_pm", c_void),
                 ("pt_pd", c_void), ("Xc", c_void), ("Fc", c_int), ("bn_cross", BnRefT), ("gXc", c_void),
-                ("accumulate_cross", c_int), ("acc_b_cross", c_void), ("skip_dw", c_int)]
+                ("accumulate_cross", c_int), ("acc_b_cross", c_void), ("skip_dw", c_int), ("pt_nnz", c_ll)]
 
 
 class ProgTensorT(ctypes.Structure):
@@ -81,7 +81,7 @@ class BatchT(ctypes.Structure):
                 ("edge_ops", ctypes.POINTER(OpT)), ("edge_ops_T", ctypes.POINTER(OpT)),
                 ("p_rowptr", c_void), ("p_col", c_void), ("p_pm", c_void), ("p_pd", c_void),
                 ("pt_rowptr", c_void), ("pt_col", c_void), ("pt_pm", c_void), ("pt_pd", c_void),
-                ("node_off", c_void), ("pad_n", c_void)]
+                ("node_off", c_void), ("pad_n", c_void), ("p_nnz", c_ll)]
 
 
 _P = c_void
@@ -259,6 +259,7 @@ def make_ops(descs):
         else:
             arr[i].kind = OP_CSR
             arr[i].rowptr, arr[i].col, arr[i].val = iptr(d[1]), iptr(d[2]), fptr(d[3])
+            arr[i].nnz = d[2].numel()
             if len(d) > 4 and d[4] is not None and d[4][1].numel() > 0:
                 r = d[4]
                 arr[i].rng_rowptr, arr[i].rng_id, arr[i].rng_val = iptr(r[0]), iptr(r[1]), fptr(r[2])

@@ -10,6 +10,11 @@
 
 void hgnn_set_error(const char* fmt, ...);
 int hgnn_check_launch(const char* what);
+// Programmatic dependent launch for the next width-4 engine kernels issued by this thread (set by the
+// step executor in program.cu around launches whose stream predecessor is another side kernel of the
+// same chain: such a predecessor writes activations / accumulators only, never parameters or graph
+// structure, which is all a PDL kernel touches before its griddepcontrol.wait).
+void hgnn_eng_set_pdl(bool on);
 
 #define HGNN_REQUIRE(cond, msg)                      \
     do {                                             \

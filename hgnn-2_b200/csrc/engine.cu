@@ -1012,6 +1012,33 @@ static eng::BnRef to_bnref(const hgnn_bn_ref_t* r) {
     return o;
 }
 
+// ---- programmatic dependent launch -----------------------------------------------------------------
+static thread_local bool g_pdl = false;
+void hgnn_eng_set_pdl(bool on) {
+    static int disabled = -1;
+    if (disabled < 0) { const char* e = getenv("HGNN_B200_NO_PDL"); disabled = (e && e[0] == '1') ? 1 : 0; }
+    g_pdl = on && !disabled;
+}
+
+template <typename Kernel, typename Args>
+static void eng_launch(Kernel kernel, int grid, int threads, size_t smem, cudaStream_t s, const Args& a) {
+    if (!g_pdl) {
+        kernel<<<grid, threads, smem, s>>>(a);
+        return;
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(threads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    cudaLaunchKernelEx(&cfg, kernel, a);
+}
+
 // ---- thread-per-row fast path for width-4 states (h = 2) ---------------------------------------
 static bool eng_row4_ops(const hgnn_op_t* ops, int n_ops) {
     if (n_ops < 3 || n_ops > 4) return false;
@@ -1051,15 +1078,30 @@ static bool eng_try_fwd_row4(const eng::FwdArgs& g, const hgnn_side_t* side, hgn
     a.p_rowptr = g.p_rowptr; a.p_col = g.p_col; a.p_pm = g.p_pm; a.p_pd = g.p_pd; a.Xc = g.Xc; a.bn_c = g.bn_c;
     a.Wa = g.Wa; a.ba = g.ba; a.Ha = g.Ha; a.Wb = g.Wb; a.bb = g.bb; a.Hb = g.Hb;
     a.relu_from = g.relu_from; a.Cin = g.Cin; a.Z = g.Z; a.acc_out = g.acc_out; a.X1 = g.X1;
+    static int ablate = -1;
+    if (ablate < 0) { const char* e = getenv("HGNN_B200_ABLATE"); ablate = e ? atoi(e) : 0; }
+    a.ablate = ablate;
     cudaStream_t s = to_stream(stream);
     const int want = ceil_div(a.R, R4_THREADS);
-#define R4_FWD(NCSR, CROSS)                                                                              \
+    // entries per gather batch from the average row length (nnz hints; unknown -> 4): a typical row
+    // should fit ONE batch so that its loads form three dependent rounds in total
+    const double avg_a = a.R > 0 ? (double)side->ops[2].nnz / a.R : 0.0;
+    const double avg_p = (cross && a.R > 0) ? (double)side->p_nnz / a.R : 0.0;
+    bool big_a = avg_a > 3.5, big_p = avg_p > 5.0;
+    static int force = -2;
+    if (force == -2) { const char* e = getenv("HGNN_B200_FWD_BATCH"); force = e ? atoi(e) : -1; }   // bit 0: big_a, bit 1: big_p
+    if (force >= 0) { big_a = force & 1; big_p = (force & 2) != 0; }
+#define R4_FWD(NCSR, CROSS, BA, BP)                                                                      \
     {                                                                                                    \
-        int grid = min(want, eng_resident_impl((const void*)eng::fwd_row4_kernel<NCSR, CROSS>, 0, R4_THREADS)); \
-        eng::fwd_row4_kernel<NCSR, CROSS><<<grid, R4_THREADS, 0, s>>>(a);                                \
+        int grid = min(want, eng_resident_impl((const void*)eng::fwd_row4_kernel<NCSR, CROSS, BA, BP>, 0, R4_THREADS)); \
+        eng_launch(eng::fwd_row4_kernel<NCSR, CROSS, BA, BP>, grid, R4_THREADS, 0, s, a);                \
     }
-    if (a.n_csr == 1) { if (cross) R4_FWD(1, true) else R4_FWD(1, false) }
-    else { if (cross) R4_FWD(2, true) else R4_FWD(2, false) }
+#define R4_FWD_B(NCSR)                                                                                   \
+    if (!cross) { if (big_a) R4_FWD(NCSR, false, 8, 4) else R4_FWD(NCSR, false, 4, 4) }                  \
+    else if (big_a) { if (big_p) R4_FWD(NCSR, true, 8, 16) else R4_FWD(NCSR, true, 8, 4) }               \
+    else { if (big_p) R4_FWD(NCSR, true, 4, 16) else R4_FWD(NCSR, true, 4, 4) }
+    if (a.n_csr == 1) { R4_FWD_B(1) } else { R4_FWD_B(2) }
+#undef R4_FWD_B
 #undef R4_FWD
     return true;
 }
@@ -1178,21 +1220,42 @@ static bool eng_try_bwd_row4(const hgnn_side_bwd_t* d, hgnn_stream_t stream) {
     a.pt_rowptr = d->pt_rowptr; a.pt_col = d->pt_col; a.pt_pm = d->pt_pm; a.pt_pd = d->pt_pd;
     a.Xc = d->Xc; a.bn_c = to_bnref(&d->bn_cross); a.gXc = d->gXc; a.acc_cross = d->accumulate_cross;
     a.acc_b_cross = d->acc_b_cross; a.col0_cross = d->n_ops * 4;
+    static int ablate = -1;
+    if (ablate < 0) { const char* e = getenv("HGNN_B200_ABLATE"); ablate = e ? atoi(e) : 0; }
+    a.ablate = ablate;
     cudaStream_t s = to_stream(stream);
     const long long rows = (long long)d->R_self + (d->R_cross > 0 ? d->R_cross : 0);
-#define R4_BWD(NCSR, DW)                                                                                  \
+    // The CTAs of one launch are split between the two parts in proportion to their estimated cost, not
+    // their row counts: a row costs about one unit plus a third of a unit per gathered entry (two row
+    // loads each).  At the C2 workload the edge side differentiates 160 k line-graph rows with 0.5
+    // entries each against 32 k node rows with 8 entries each - a split by rows left the node rows
+    // with 17 % of the CTAs and 3x the work per thread.
+    const double avg_s = (double)d->ops_T[2].nnz / d->R_self;
+    const double avg_c = d->R_cross > 0 ? (double)d->pt_nnz / d->R_cross : 0.0;
+    static double w_entry = -1.0;
+    if (w_entry < 0.0) { const char* e = getenv("HGNN_B200_BWD_ENTRY_COST"); w_entry = e ? atof(e) : 0.2; }
+    const double cost_s = (double)d->R_self * (1.0 + w_entry * avg_s);
+    const double cost_c = d->R_cross > 0 ? (double)d->R_cross * (1.0 + w_entry * avg_c) : 0.0;
+    bool big_s = false, big_c = false;      // measured: the small batches win in the backward (register pressure)
+    static int bforce = -2;
+    if (bforce == -2) { const char* e = getenv("HGNN_B200_BWD_BATCH"); bforce = e ? atoi(e) : -1; }  // 0: (2,4), 1: (8,4), 2: (2,8)
+    if (bforce >= 0) { big_s = bforce == 1; big_c = bforce == 2; }
+#define R4_BWD(NCSR, DW, GB, CB)                                                                          \
     {                                                                                                     \
-        const int cap = eng_resident_impl((const void*)eng::bwd_row4_kernel<NCSR, DW>, 0, R4_THREADS);    \
+        const int cap = eng_resident_impl((const void*)eng::bwd_row4_kernel<NCSR, DW, GB, CB>, 0, R4_THREADS); \
         int grid = (int)min((long long)cap, (rows + R4_THREADS - 1) / R4_THREADS);                        \
         if (d->R_cross > 0 && grid < 2) grid = 2;                                                         \
-        int cs = d->R_cross > 0 ? (int)(((long long)grid * d->R_self + rows / 2) / rows) : grid;          \
+        int cs = d->R_cross > 0 ? (int)(grid * cost_s / (cost_s + cost_c) + 0.5) : grid;                  \
         if (cs < 1) cs = 1;                                                                               \
         if (d->R_cross > 0 && cs > grid - 1) cs = grid - 1;                                               \
         a.ctas_self = cs;                                                                                 \
-        eng::bwd_row4_kernel<NCSR, DW><<<grid, R4_THREADS, 0, s>>>(a);                                    \
+        eng_launch(eng::bwd_row4_kernel<NCSR, DW, GB, CB>, grid, R4_THREADS, 0, s, a);                    \
     }
-    if (d->skip_dw) { if (a.n_csr == 1) R4_BWD(1, false) else R4_BWD(2, false) }
-    else { if (a.n_csr == 1) R4_BWD(1, true) else R4_BWD(2, true) }
+#define R4_BWD_B(NCSR, DW)                                                                                \
+    if (big_s) R4_BWD(NCSR, DW, 8, 4) else if (big_c) R4_BWD(NCSR, DW, 2, 8) else R4_BWD(NCSR, DW, 2, 4)
+    if (d->skip_dw) { if (a.n_csr == 1) { R4_BWD_B(1, false) } else { R4_BWD_B(2, false) } }
+    else { if (a.n_csr == 1) { R4_BWD_B(1, true) } else { R4_BWD_B(2, true) } }
+#undef R4_BWD_B
 #undef R4_BWD
     return true;
 }

@@ -123,9 +123,143 @@ struct Fwd4Args {
     float* Z;
     double* acc_out;
     float* X1;                       // optional: the concatenated x1 rows (R, Cin) for the dW pass
+    int ablate;                      // timing experiments only (HGNN_B200_ABLATE): 1 no gathers, 2 no BN, 4 no epilogue
 };
 
-template <int NCSR, bool CROSS>
+// One batch of a CSR gather, split in two so that the index loads of several operators can be in
+// flight together before any feature row is requested: `Batch::load_entries` (columns / values of
+// up to B entries, predicated), then `load_rows`, then `accumulate`.
+template <int B, bool TWO>
+struct GatherBatch {
+    int c[B];
+    float v[B], v2[TWO ? B : 1];
+    float4 x[B];
+    __device__ __forceinline__ void load_entries(const int* __restrict__ col, const float* __restrict__ val,
+                                                 const float* __restrict__ val2, int k, int k1) {
+#pragma unroll
+        for (int j = 0; j < B; ++j) {
+            const bool on = k + j < k1;
+            c[j] = on ? __ldg(col + k + j) : -1;
+            v[j] = on ? __ldg(val + k + j) : 0.f;
+            if (TWO) v2[j] = on ? __ldg(val2 + k + j) : 0.f;
+        }
+    }
+    __device__ __forceinline__ void load_rows(const float* __restrict__ X) {
+#pragma unroll
+        for (int j = 0; j < B; ++j) x[j] = c[j] >= 0 ? ld4(X + (size_t)c[j] * 4) : f4_zero();
+    }
+    __device__ __forceinline__ void accumulate(float4& acc, float& ws, float4& acc2, float& ws2) const {
+#pragma unroll
+        for (int j = 0; j < B; ++j) {
+            acc = f4_fma(v[j], x[j], acc);
+            ws += v[j];
+            if (TWO) {
+                acc2 = f4_fma(v2[j], x[j], acc2);
+                ws2 += v2[j];
+            }
+        }
+    }
+};
+
+// Programmatic dependent launch (PDL): a kernel launched with
+// cudaLaunchAttributeProgrammaticStreamSerialization may start while its producer is still running;
+// everything before pdl_wait() may only touch data the producer does not write (parameters, graph
+// structure).  Without the attribute both instructions are no-ops.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+// (sum, sum^2)-style totals of a width-4 tensor from its 32 binned doubles, given the lane's own load
+__device__ __forceinline__ void warp_totals8_from(double v, double tot[8]) {
+    v += __shfl_xor_sync(0xffffffffu, v, 8);
+    v += __shfl_xor_sync(0xffffffffu, v, 16);
+#pragma unroll
+    for (int c = 0; c < 8; ++c) tot[c] = __shfl_sync(0xffffffffu, v, c);
+}
+
+// batch-norm vectors from the totals; w, b already in registers; inv_n computed on the host
+__device__ __forceinline__ Bn4 bn4_from_totals(const double tot[8], float w, float b, double inv_n) {
+    Bn4 o;
+    o.on = true;
+    float sc[4], sh[4], mu[4], rs[4];
+#pragma unroll
+    for (int f = 0; f < 4; ++f) {
+        const double m = tot[f] * inv_n;
+        const double var = fma(-m, m, tot[4 + f] * inv_n);
+        const float r_ = 1.0f / sqrtf(fmaxf((float)var, 0.f) + (float)ENG_BN_EPS);
+        mu[f] = (float)m;
+        rs[f] = r_;
+        sc[f] = w * r_;
+        sh[f] = b - w * mu[f] * r_;
+    }
+    o.sc = make_float4(sc[0], sc[1], sc[2], sc[3]);
+    o.sh = make_float4(sh[0], sh[1], sh[2], sh[3]);
+    o.mu = make_float4(mu[0], mu[1], mu[2], mu[3]);
+    o.rs = make_float4(rs[0], rs[1], rs[2], rs[3]);
+    return o;
+}
+
+// Issue-then-resolve form of bn4_from_ref: `issue` puts the loads in flight (accumulators after
+// pdl_wait, the scalar affine before it), `resolve` does the arithmetic.
+struct Bn4Loader {
+    double v;
+    float w, b;
+    int mode;       // 0: identity, 1: precomputed affine, 2: batch statistics
+    __device__ __forceinline__ void issue_params(const BnRef& r) {
+        mode = r.affine ? 1 : (r.acc ? 2 : 0);
+        w = b = 0.f;
+        if (mode == 2) { w = __ldg(r.w); b = __ldg(r.b); }
+    }
+    __device__ __forceinline__ void issue_acc(const BnRef& r) {
+        v = 0.0;
+        if (mode == 2) v = __ldcg(r.acc + (threadIdx.x & 31));
+    }
+    __device__ __forceinline__ Bn4 resolve(const BnRef& r) const {
+        if (mode != 2) return bn4_from_ref(r);
+        double tot[8];
+        warp_totals8_from(v, tot);
+        return bn4_from_totals(tot, w, b, 1.0 / (double)r.n);
+    }
+};
+
+// Sum of NV per-lane values over the warp with a reduce-scatter butterfly: at every level a lane
+// keeps half of its values and ships the other half, so NV values cost ~NV shuffles instead of
+// 5 NV.  NV must be a multiple of 8 (and <= 64).  On return lane l holds in val[0 .. NV/8) (NV >= 8:
+// after three halvings) ... the caller reads the totals through `warp_reduce_scatter_index`.
+template <int NV>
+__device__ __forceinline__ void warp_reduce_scatter(float (&val)[NV]) {
+    const int lane = threadIdx.x & 31;
+    int n = NV;
+#pragma unroll
+    for (int bit = 0; bit < 5; ++bit) {
+        const int mask = 16 >> bit;            // partner distance 16, 8, 4, 2, 1
+        const bool upper = (lane & mask) != 0;
+        if (n > 1) {
+            const int half = n >> 1;
+#pragma unroll
+            for (int i = 0; i < NV / 2; ++i) {
+                if (i < half) {
+                    // lower lanes keep [0, half), upper lanes keep [half, n)
+                    const float send = upper ? val[i] : val[i + half];
+                    const float keep = upper ? val[i + half] : val[i];
+                    val[i] = keep + __shfl_xor_sync(0xffffffffu, send, mask);
+                }
+            }
+            n = half;
+        } else {
+            val[0] += __shfl_xor_sync(0xffffffffu, val[0], mask);
+        }
+    }
+}
+
+// BA / BP: entries per batch of the (first) self operator / of the incidence pair.  The host picks
+// them from the average row length, so that a typical row needs ONE batch: all its index loads go
+// out in one round and all its feature-row loads in the next (three dependent rounds per row in
+// total: row pointers -> entries -> rows), instead of two rounds per batch of four.
+//
+// Phases: (0) parameters and graph structure only - weights to shared memory, the row pointers and
+// the first batch of entries of the thread's first row; under PDL this overlaps the producer's tail.
+// (1) after pdl_wait: batch-norm accumulators and feature rows, all issued before the first use.
+template <int NCSR, bool CROSS, int BA, int BP>
 __global__ void __launch_bounds__(R4_THREADS)
 fwd_row4_kernel(const Fwd4Args a) {
     constexpr int NB = 2 + NCSR + (CROSS ? 2 : 0);     // float4 blocks of x1
@@ -133,39 +267,95 @@ fwd_row4_kernel(const Fwd4Args a) {
     __shared__ __align__(16) float bias[4];
     __shared__ double red[(R4_THREADS / 32) * 8];
     const int tid = threadIdx.x;
+    pdl_launch_dependents();
+    // ---- phase 0
     for (int i = tid; i < 4 * NB * 4; i += R4_THREADS) {
         const int o = i / (NB * 4), c = i - o * (NB * 4);
         W[i] = (o < a.Ha) ? a.Wa[(size_t)o * a.Cin + c] : a.Wb[(size_t)(o - a.Ha) * a.Cin + c];
     }
     if (tid < 4) bias[tid] = (tid < a.Ha) ? (a.ba ? a.ba[tid] : 0.f) : (a.bb ? a.bb[tid - a.Ha] : 0.f);
-    const Bn4 bs4 = bn4_from_ref(a.bn_s);
-    Bn4 bc4 = bs4;
-    if (CROSS) bc4 = bn4_from_ref(a.bn_c);
+    Bn4Loader ls, lc;
+    ls.issue_params(a.bn_s);
+    if (CROSS) lc.issue_params(a.bn_c);
+    const int stride = gridDim.x * R4_THREADS;
+    int row = blockIdx.x * R4_THREADS + tid;
+    float d = 0.f;
+    int k0[NCSR > 0 ? NCSR : 1], k1[NCSR > 0 ? NCSR : 1], p0 = 0, p1 = 0;
+    GatherBatch<BA, false> ga;
+    GatherBatch<BP, true> gb;
+    auto load_structure = [&](int r) {
+        d = __ldg(a.diag + r);
+#pragma unroll
+        for (int t = 0; t < NCSR; ++t) {
+            k0[t] = __ldg(a.rowptr[t] + r);
+            k1[t] = __ldg(a.rowptr[t] + r + 1);
+        }
+        if (CROSS) {
+            p0 = __ldg(a.p_rowptr + r);
+            p1 = __ldg(a.p_rowptr + r + 1);
+        }
+        if (a.ablate & 1) { k1[0] = k0[0]; p1 = p0; }
+        if (NCSR > 0) ga.load_entries(a.col[0], a.val[0], nullptr, k0[0], k1[0]);
+        if (CROSS) gb.load_entries(a.p_col, a.p_pm, a.p_pd, p0, p1);
+    };
+    if (row < a.R) load_structure(row);
+    // ---- phase 1: everything the producer wrote
+    pdl_wait();
+    ls.issue_acc(a.bn_s);
+    if (CROSS) lc.issue_acc(a.bn_c);
+    float4 xs_raw = f4_zero();
+    if (row < a.R) {
+        xs_raw = ld4(a.Xs + (size_t)row * 4);
+        if (NCSR > 0) ga.load_rows(a.Xs);
+        if (CROSS) gb.load_rows(a.Xc);
+    }
+    Bn4 bs4, bc4;
+    if (a.ablate & 2) {
+        bs4.sc = bs4.rs = make_float4(1.f, 1.f, 1.f, 1.f); bs4.sh = bs4.mu = f4_zero(); bc4 = bs4;
+    } else {
+        bs4 = ls.resolve(a.bn_s);
+        bc4 = bs4;
+        if (CROSS) bc4 = lc.resolve(a.bn_c);
+    }
     __syncthreads();                                   // weights in shared memory
     const float4 sc_s = bs4.sc, sh_s = bs4.sh, sc_c = bc4.sc, sh_c = bc4.sh;
     float s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
 
-    for (int row = blockIdx.x * R4_THREADS + tid; row < a.R; row += gridDim.x * R4_THREADS) {
+    for (bool first = true; row < a.R; row += stride, first = false) {
+        if (!first) {
+            load_structure(row);
+            xs_raw = ld4(a.Xs + (size_t)row * 4);
+            if (NCSR > 0) ga.load_rows(a.Xs);
+            if (CROSS) gb.load_rows(a.Xc);
+        }
         float4 x1[NB];
-        // round 1: everything addressed by the row itself
-        const float4 xs = f4_affine(ld4(a.Xs + (size_t)row * 4), sc_s, sh_s);
-        const float d = __ldg(a.diag + row);
-        int k0[NCSR > 0 ? NCSR : 1], k1[NCSR > 0 ? NCSR : 1];
-#pragma unroll
-        for (int t = 0; t < NCSR; ++t) {
-            k0[t] = __ldg(a.rowptr[t] + row);
-            k1[t] = __ldg(a.rowptr[t] + row + 1);
-        }
-        int p0 = 0, p1 = 0;
-        if (CROSS) {
-            p0 = __ldg(a.p_rowptr + row);
-            p1 = __ldg(a.p_rowptr + row + 1);
-        }
+        const float4 xs = f4_affine(xs_raw, sc_s, sh_s);
         x1[0] = xs;
         x1[1] = make_float4(d * xs.x, d * xs.y, d * xs.z, d * xs.w);
-        // rounds 2+3: entries, then feature rows.  sum val*(s*z+t) = s*(sum val*z) + t*(sum val)
+        // sum val*(s*z+t) = s*(sum val*z) + t*(sum val)
+        float4 acc0 = f4_zero(), am = f4_zero(), ad = f4_zero(), unused4 = f4_zero();
+        float ws0 = 0.f, wm = 0.f, wd = 0.f, unused = 0.f;
+        if (NCSR > 0) ga.accumulate(acc0, ws0, unused4, unused);
+        if (CROSS) gb.accumulate(am, wm, ad, wd);
+        if (NCSR > 0)       // long rows: the remaining entries, batch by batch
+            for (int k = k0[0] + BA; k < k1[0]; k += BA) {
+                GatherBatch<BA, false> g;
+                g.load_entries(a.col[0], a.val[0], nullptr, k, k1[0]);
+                g.load_rows(a.Xs);
+                g.accumulate(acc0, ws0, unused4, unused);
+            }
+        if (CROSS)
+            for (int k = p0 + BP; k < p1; k += BP) {
+                GatherBatch<BP, true> g;
+                g.load_entries(a.p_col, a.p_pm, a.p_pd, k, p1);
+                g.load_rows(a.Xc);
+                g.accumulate(am, wm, ad, wd);
+            }
+        if (NCSR > 0)
+            x1[2] = make_float4(fmaf(acc0.x, sc_s.x, ws0 * sh_s.x), fmaf(acc0.y, sc_s.y, ws0 * sh_s.y),
+                                fmaf(acc0.z, sc_s.z, ws0 * sh_s.z), fmaf(acc0.w, sc_s.w, ws0 * sh_s.w));
 #pragma unroll
-        for (int t = 0; t < NCSR; ++t) {
+        for (int t = 1; t < NCSR; ++t) {
             float4 acc = f4_zero();
             float ws = 0.f;
             csr_gather4(a.col[t], a.val[t], k0[t], k1[t], a.Xs, acc, ws);
@@ -173,29 +363,6 @@ fwd_row4_kernel(const Fwd4Args a) {
                                     fmaf(acc.z, sc_s.z, ws * sh_s.z), fmaf(acc.w, sc_s.w, ws * sh_s.w));
         }
         if (CROSS) {
-            float4 am = f4_zero(), ad = f4_zero();
-            float wm = 0.f, wd = 0.f;
-            for (int k = p0; k < p1; k += 4) {
-                int c[4];
-                float vm[4], vd[4];
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const bool on = k + j < p1;
-                    c[j] = __ldg(a.p_col + (on ? k + j : k));
-                    vm[j] = on ? __ldg(a.p_pm + k + j) : 0.f;
-                    vd[j] = on ? __ldg(a.p_pd + k + j) : 0.f;
-                }
-                float4 x[4];
-#pragma unroll
-                for (int j = 0; j < 4; ++j) x[j] = ld4(a.Xc + (size_t)c[j] * 4);
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    am = f4_fma(vm[j], x[j], am);
-                    ad = f4_fma(vd[j], x[j], ad);
-                    wm += vm[j];
-                    wd += vd[j];
-                }
-            }
             x1[2 + NCSR] = make_float4(fmaf(am.x, sc_c.x, wm * sh_c.x), fmaf(am.y, sc_c.y, wm * sh_c.y),
                                        fmaf(am.z, sc_c.z, wm * sh_c.z), fmaf(am.w, sc_c.w, wm * sh_c.w));
             x1[3 + NCSR] = make_float4(fmaf(ad.x, sc_c.x, wd * sh_c.x), fmaf(ad.y, sc_c.y, wd * sh_c.y),
@@ -220,7 +387,7 @@ fwd_row4_kernel(const Fwd4Args a) {
         }
         *reinterpret_cast<float4*>(a.Z + (size_t)row * 4) = make_float4(out[0], out[1], out[2], out[3]);
     }
-    if (a.acc_out) {       // warp shuffle tree -> one row per warp in shared memory -> 8 fp64 atomics per CTA
+    if (a.acc_out && !(a.ablate & 4)) {   // warp shuffle tree -> one row per warp in shared memory -> 8 fp64 atomics per CTA
         const int lane = tid & 31, warp = tid >> 5;
 #pragma unroll
         for (int o = 0; o < 4; ++o) {
@@ -257,6 +424,7 @@ struct Bwd4Args {
     const float* Xc; BnRef bn_c; float* gXc; int acc_cross; double* acc_b_cross;
     int col0_cross;
     int ctas_self;        // CTAs [0, ctas_self) work on the self rows
+    int ablate;           // timing experiments only (HGNN_B200_ABLATE): 1 no gathers, 2 no range phase, 4 no flush
 };
 
 struct Gpre4 {
@@ -279,17 +447,25 @@ struct Gpre4 {
     }
 };
 
-// sum_k val[k] * gpre(col[k]); batches of 2 (two loads per entry)
+// sum_k val[k] * gpre(col[k]); batches of GB entries (two row loads per entry), predicated
+template <int GB>
 __device__ __forceinline__ float4 gpre_gather(const Gpre4& gp, const int* __restrict__ col,
                                               const float* __restrict__ val, int k0, int k1) {
     float4 acc = f4_zero();
-    for (int k = k0; k < k1; k += 2) {
-        const bool on = k + 1 < k1;
-        const int c0 = __ldg(col + k), c1 = __ldg(col + (on ? k + 1 : k));
-        const float v0 = __ldg(val + k), v1 = on ? __ldg(val + k + 1) : 0.f;
-        const float4 g0 = gp(c0), g1 = gp(c1);
-        acc = f4_fma(v0, g0, acc);
-        acc = f4_fma(v1, g1, acc);
+    for (int k = k0; k < k1; k += GB) {
+        int c[GB];
+        float v[GB];
+#pragma unroll
+        for (int j = 0; j < GB; ++j) {
+            const bool on = k + j < k1;
+            c[j] = on ? __ldg(col + k + j) : -1;
+            v[j] = on ? __ldg(val + k + j) : 0.f;
+        }
+        float4 g[GB];
+#pragma unroll
+        for (int j = 0; j < GB; ++j) g[j] = c[j] >= 0 ? gp(c[j]) : f4_zero();
+#pragma unroll
+        for (int j = 0; j < GB; ++j) acc = f4_fma(v[j], g[j], acc);
     }
     return acc;
 }
@@ -298,7 +474,9 @@ __device__ __forceinline__ float4 gpre_gather(const Gpre4& gp, const int* __rest
 
 // DW = false: the gather-only variant (the weight gradients come from dw_row4_kernel, which streams
 // over the x1 rows saved by the forward on a parallel graph branch): ~48 fewer live registers.
-template <int NCSR, bool DW>
+// GB / CB: entries per gather batch of the self part (first transposed operator) / of the cross part,
+// picked by the host from the average row lengths so that a typical row needs one batch.
+template <int NCSR, bool DW, int GB, int CB>
 __global__ void __launch_bounds__(R4_THREADS)
 bwd_row4_kernel(const Bwd4Args a) {
     constexpr int NT = 2 + NCSR;                          // self blocks
@@ -311,6 +489,8 @@ bwd_row4_kernel(const Bwd4Args a) {
     __shared__ int rsum_id;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const bool is_self = (int)blockIdx.x < a.ctas_self;
+    pdl_launch_dependents();
+    // ---- phase 0 (parameters only; under PDL this overlaps the producer's tail)
     if (tid == 0) { n_flagged = 0; rsum_id = -1; }
     for (int i = tid; i < NT * 16; i += R4_THREADS) {
         const int t = i >> 4, o = (i >> 2) & 3, f = i & 3;
@@ -323,6 +503,7 @@ bwd_row4_kernel(const Bwd4Args a) {
             const float* wrow = (o < a.Ha) ? a.Wa + (size_t)o * a.Cin : a.Wb + (size_t)(o - a.Ha) * a.Cin;
             Wc[i] = wrow[a.col0_cross + t * 4 + f];
         }
+    pdl_wait();
     // ---- coefficients of this side's BN + ReLU backward, and the input's BN vectors: warp-level
     Gpre4 gp;
     gp.relu_from = a.relu_from; gp.bn = a.has_bn != 0; gp.need_z = a.has_bn != 0 || a.relu_from < 4;
@@ -373,9 +554,12 @@ bwd_row4_kernel(const Bwd4Args a) {
             const float d = __ldg(a.diag + row);
             T[1] = make_float4(d * T[0].x, d * T[0].y, d * T[0].z, d * T[0].w);
 #pragma unroll
-            for (int t = 0; t < NCSR; ++t)
-                T[2 + t] = gpre_gather(gp, a.col[t], a.val[t], __ldg(a.rowptr[t] + row), __ldg(a.rowptr[t] + row + 1));
-            if (NCSR > 0 && a.rng_rowptr && __ldg(a.rng_rowptr + row + 1) > __ldg(a.rng_rowptr + row)) {
+            for (int t = 0; t < NCSR; ++t) {
+                const int k0 = __ldg(a.rowptr[t] + row), k1 = (a.ablate & 1) ? k0 : __ldg(a.rowptr[t] + row + 1);
+                T[2 + t] = t == 0 ? gpre_gather<GB>(gp, a.col[t], a.val[t], k0, k1)
+                                  : gpre_gather<2>(gp, a.col[t], a.val[t], k0, k1);
+            }
+            if (NCSR > 0 && a.rng_rowptr && !(a.ablate & 2) && __ldg(a.rng_rowptr + row + 1) > __ldg(a.rng_rowptr + row)) {
                 const int slot = atomicAdd(&n_flagged, 1);
                 if (slot < R4_MAX_FLAGGED) {
                     flagged[slot] = row;
@@ -485,22 +669,22 @@ bwd_row4_kernel(const Bwd4Args a) {
         const int ncta = gridDim.x - a.ctas_self;
         for (int row = (blockIdx.x - a.ctas_self) * R4_THREADS + tid; row < a.R_cross; row += ncta * R4_THREADS) {
             float4 Tm = f4_zero(), Td = f4_zero();
-            const int k0 = __ldg(a.pt_rowptr + row), k1 = __ldg(a.pt_rowptr + row + 1);
-            for (int k = k0; k < k1; k += 4) {          // 4 entries (8 row loads) in flight
-                int c[4];
-                float vm[4], vd[4];
+            const int k0 = __ldg(a.pt_rowptr + row), k1 = (a.ablate & 1) ? k0 : __ldg(a.pt_rowptr + row + 1);
+            for (int k = k0; k < k1; k += CB) {         // CB entries (2 CB row loads) in flight
+                int c[CB];
+                float vm[CB], vd[CB];
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
+                for (int j = 0; j < CB; ++j) {
                     const bool on = k + j < k1;
-                    c[j] = __ldg(a.pt_col + (on ? k + j : k));
+                    c[j] = on ? __ldg(a.pt_col + k + j) : -1;
                     vm[j] = on ? __ldg(a.pt_pm + k + j) : 0.f;
                     vd[j] = on ? __ldg(a.pt_pd + k + j) : 0.f;
                 }
-                float4 gv[4];
+                float4 gv[CB];
 #pragma unroll
-                for (int j = 0; j < 4; ++j) gv[j] = gp(c[j]);
+                for (int j = 0; j < CB; ++j) gv[j] = c[j] >= 0 ? gp(c[j]) : f4_zero();
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
+                for (int j = 0; j < CB; ++j) {
                     Tm = f4_fma(vm[j], gv[j], Tm);
                     Td = f4_fma(vd[j], gv[j], Td);
                 }
@@ -545,6 +729,7 @@ bwd_row4_kernel(const Bwd4Args a) {
     const int nbw = hgnn_ws_bins(4 * a.Cin);
     const int col_base = is_self ? 0 : a.col0_cross;
     __syncthreads();
+    if (a.ablate & 4) return;
     if (DW) {
 #pragma unroll
         for (int i = 0; i < NT * 16; ++i) {

@@ -142,18 +142,23 @@ extern "C" int hgnn_program_fwd(const hgnn_program_t* prog, const hgnn_batch_t* 
             st.p_pd = node ? b->p_pd : b->pt_pd;
             st.Xc = tensor_ptr(prog, w, sd.src_cross, X, XL, work);
             st.Fc = prog->tensors[sd.src_cross].F;
+            st.p_nnz = b->p_nnz;
             bc_ = bn_ref(prog, b, sd.src_cross, addr, arena);
         } else {
             st.p_rowptr = st.p_col = nullptr;
             st.p_pm = st.p_pd = st.Xc = nullptr;
             st.Fc = 0;
+            st.p_nnz = 0;
         }
         const bool readout = sd.out < 0;
         float* Z = work + (readout ? w.readout_off : w.off[sd.out]);
         double* acc_out = readout ? nullptr : arena + prog->tensors[sd.out].acc_f;
-        PROG_CALL(hgnn_lg_side_fwd(&st, &bs_, cross ? &bc_ : nullptr, param(addr, sd.Wa), param(addr, sd.ba), sd.Ha,
-                                   param(addr, sd.Wb), param(addr, sd.bb), sd.Hb, sd.relu_from, Z, acc_out, nullptr,
-                                   stream));
+        hgnn_eng_set_pdl(i >= 1);      // the stream predecessor is the previous side's forward kernel
+        const int rc_fwd = hgnn_lg_side_fwd(&st, &bs_, cross ? &bc_ : nullptr, param(addr, sd.Wa), param(addr, sd.ba),
+                                            sd.Ha, param(addr, sd.Wb), param(addr, sd.bb), sd.Hb, sd.relu_from, Z,
+                                            acc_out, nullptr, stream);
+        hgnn_eng_set_pdl(false);
+        PROG_CALL(rc_fwd);
         if (readout)   // sum over all Nmax slots; padded slots add fc.bias (layers_mnb.py:92, :386)
             PROG_CALL(hgnn_segment_sum(Z, b->bs, sd.Ha + sd.Hb, b->node_off, b->pad_n, param(addr, sd.ba), out, stream));
     }
@@ -234,6 +239,7 @@ extern "C" int hgnn_program_bwd(const hgnn_program_t* prog, const hgnn_batch_t* 
         d.gXc = nullptr;
         d.accumulate_cross = 0;
         d.acc_b_cross = nullptr;
+        d.pt_nnz = 0;
         d.bn_cross = bn_ref(prog, b, 0, addr, arena);   // tensor 0 is never normalised: an empty reference
         if (sd.src_cross >= 0) {
             d.R_cross = rows_of(prog, b, sd.src_cross);
@@ -244,6 +250,7 @@ extern "C" int hgnn_program_bwd(const hgnn_program_t* prog, const hgnn_batch_t* 
             d.pt_pd = node ? b->pt_pd : b->p_pd;
             d.Xc = tensor_ptr(prog, w, sd.src_cross, X, XL, work);
             d.Fc = Fc;
+            d.pt_nnz = b->p_nnz;
             d.bn_cross = bn_ref(prog, b, sd.src_cross, addr, arena);
             const bool need_cross = wants_grad(sd.src_cross);
             d.gXc = need_cross ? grad_ptr(sd.src_cross) : nullptr;
@@ -253,7 +260,10 @@ extern "C" int hgnn_program_bwd(const hgnn_program_t* prog, const hgnn_batch_t* 
             if (need_cross) started[sd.src_cross] = 1;
         }
         d.skip_dw = 0;
-        PROG_CALL(hgnn_lg_side_bwd(&d, stream));
+        hgnn_eng_set_pdl(i < prog->n_sides - 1);   // the stream predecessor is the backward kernel of side i + 1
+        const int rc_bwd = hgnn_lg_side_bwd(&d, stream);
+        hgnn_eng_set_pdl(false);
+        PROG_CALL(rc_bwd);
     }
     PROG_CALL(hgnn_bins_reduce(arena, prog->red_off, prog->red_nb, prog->red_stride, prog->red_cnt, prog->n_flat,
                                gflat, stream));

@@ -307,6 +307,7 @@ def _pack_cache(pack):
             c["edgeT"] = make_ops(pack.edge_ops_T(split=True))
             for k, p in (("p", pack.p), ("pt", pack.pt)):
                 c[k] = (iptr(p.rowptr), iptr(p.col), fptr(p.val), fptr(p.val2))
+            c["p_nnz"] = pack.p.nnz
         c["node_off"], c["pad_n"] = iptr(pack.node_off), fptr(pack.pad_n)
         b = BatchT()
         b.bs, b.Rn, b.Rm, b.n_ops = pack.bs, pack.Rn, (pack.Rm if pack.dual else 0), pack.K
@@ -315,6 +316,7 @@ def _pack_cache(pack):
             b.edge_ops, b.edge_ops_T = c["edge"][0], c["edgeT"][0]
             b.p_rowptr, b.p_col, b.p_pm, b.p_pd = c["p"]
             b.pt_rowptr, b.pt_col, b.pt_pm, b.pt_pd = c["pt"]
+            b.p_nnz = c["p_nnz"]
         b.node_off, b.pad_n = c["node_off"], c["pad_n"]
         c["batch"] = b
         pack.__dict__["_engine_cache"] = c
@@ -331,6 +333,7 @@ def _side_struct(pack, side, Xs, Xc):
     if Xc is not None:
         s.p_rowptr, s.p_col, s.p_pm, s.p_pd = pc["p" if node else "pt"]
         s.Xc, s.Fc = Xc.data_ptr(), Xc.shape[1]
+        s.p_nnz = pc["p_nnz"]
     else:
         s.p_rowptr = s.p_col = s.p_pm = s.p_pd = s.Xc = None
         s.Fc = 0
@@ -532,6 +535,7 @@ class _ModelFunction(torch.autograd.Function):
                 d.R_cross = _rows_of(pack, plan, s.src_cross)
                 d.pt_rowptr, d.pt_col, d.pt_pm, d.pt_pd = pc["pt" if node else "p"]   # rows = the cross tensor's rows
                 d.Xc, d.Fc = vals[s.src_cross].data_ptr(), s.Fc
+                d.pt_nnz = pc["p_nnz"]
                 d.bn_cross = _bn_ref(plan, s.src_cross, arena, d.R_cross, None, pp)
                 need_cross = tc["bn"] is not None or (s.src_cross == "X" and ctx.need_x)
                 d.gXc = grad_buf(s.src_cross).data_ptr() if need_cross else None

@@ -51,6 +51,7 @@ typedef struct hgnn_op_t {
     const float* rng_val;
     const int* rng_lo;
     const int* rng_hi;
+    long long nnz;       /* CSR: number of stored entries, 0 = unknown (a scheduling hint only) */
 } hgnn_op_t;
 
 const char* hgnn_last_error(void);
@@ -161,6 +162,7 @@ typedef struct hgnn_side_t {
     const float* p_pd;
     const float* Xc;        /* (Rc, Fc) */
     int Fc;
+    long long p_nnz;        /* entries of the incidence pattern, 0 = unknown (scheduling hint) */
 } hgnn_side_t;
 
 int hgnn_side_fwd(const hgnn_side_t* side, const float* Wa, const float* ba, int Ha,
@@ -231,6 +233,7 @@ typedef struct hgnn_side_bwd_t {
     int R_cross; const int* pt_rowptr; const int* pt_col; const float* pt_pm; const float* pt_pd;
     const float* Xc; int Fc; hgnn_bn_ref_t bn_cross; float* gXc; int accumulate_cross; double* acc_b_cross;
     int skip_dw; /* 1: leave dW / dbias to hgnn_lg_side_dw (width-4 fast path only) */
+    long long pt_nnz; /* entries of the pt_* pattern, 0 = unknown (scheduling hint) */
 } hgnn_side_bwd_t;
 int hgnn_lg_side_bwd(const hgnn_side_bwd_t* desc, hgnn_stream_t stream);
 
@@ -333,6 +336,7 @@ typedef struct hgnn_batch_t {
     const int* p_rowptr; const int* p_col; const float* p_pm; const float* p_pd;      /* rows = nodes */
     const int* pt_rowptr; const int* pt_col; const float* pt_pm; const float* pt_pd;  /* rows = line-graph nodes */
     const int* node_off; const float* pad_n;
+    long long p_nnz;      /* entries of the incidence pattern (p and pt hold the same entries) */
 } hgnn_batch_t;
 
 /* floats of activation workspace for a batch with Rn node rows and Rm line-graph rows (every side

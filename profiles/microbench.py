@@ -45,6 +45,8 @@ model = GNN_lg(0, 2, 20, 5, 2, 1, 1).cuda().train()
 Xd, XLd, y = X.cuda(), XL.cuda(), T.squeeze(1).long().cuda()
 calls = []
 orig = _lib.call
+hgnn_b200.engine.USE_PROGRAM = False     # the per-side Python loop: one visible C-ABI call per launch
+only_sides = os.environ.get("MICROBENCH_ONLY_SIDES") == "1"
 
 
 def rec(name, *args):
@@ -71,7 +73,7 @@ for name, tag, args in calls:
     if tag.startswith("L0."):
         kind = "L0." + kind
     key = (name, kind if name.startswith("hgnn_lg_side") else "")
-    if key in seen:
+    if key in seen or (only_sides and (not name.startswith("hgnn_lg_side") or kind.startswith("L0") or kind == "readout")):
         continue
     fn = getattr(_lib.lib, name)
     seen[key] = timed(lambda: fn(*args), 40)
