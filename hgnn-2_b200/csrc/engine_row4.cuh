@@ -223,10 +223,10 @@ struct Bn4Loader {
 
 // Sum of NV per-lane values over the warp with a reduce-scatter butterfly: at every level a lane
 // keeps half of its values and ships the other half, so NV values cost ~NV shuffles instead of
-// 5 NV.  NV must be a multiple of 8 (and <= 64).  On return lane l holds in val[0 .. NV/8) (NV >= 8:
-// after three halvings) ... the caller reads the totals through `warp_reduce_scatter_index`.
-template <int NV>
-__device__ __forceinline__ void warp_reduce_scatter(float (&val)[NV]) {
+// 5 NV.  NV is a power of two.  Afterwards lane l holds the warp totals of the original indices
+//   NV = 64: 2l, 2l+1 in val[0], val[1];  NV = 32: l in val[0];  NV = 16: l >> 1;  NV = 8: l >> 2.
+template <typename T, int NV>
+__device__ __forceinline__ void warp_reduce_scatter(T (&val)[NV]) {
     const int lane = threadIdx.x & 31;
     int n = NV;
 #pragma unroll
@@ -239,8 +239,8 @@ __device__ __forceinline__ void warp_reduce_scatter(float (&val)[NV]) {
             for (int i = 0; i < NV / 2; ++i) {
                 if (i < half) {
                     // lower lanes keep [0, half), upper lanes keep [half, n)
-                    const float send = upper ? val[i] : val[i + half];
-                    const float keep = upper ? val[i + half] : val[i];
+                    const T send = upper ? val[i] : val[i + half];
+                    const T keep = upper ? val[i + half] : val[i];
                     val[i] = keep + __shfl_xor_sync(0xffffffffu, send, mask);
                 }
             }
@@ -389,11 +389,11 @@ fwd_row4_kernel(const Fwd4Args a) {
     }
     if (a.acc_out && !(a.ablate & 4)) {   // warp shuffle tree -> one row per warp in shared memory -> 8 fp64 atomics per CTA
         const int lane = tid & 31, warp = tid >> 5;
+        double st[8];
 #pragma unroll
-        for (int o = 0; o < 4; ++o) {
-            const double x = warp_sum_d((double)s1[o]), y = warp_sum_d((double)s2[o]);
-            if (lane == 0) { red[warp * 8 + o] = x; red[warp * 8 + 4 + o] = y; }
-        }
+        for (int o = 0; o < 4; ++o) { st[o] = (double)s1[o]; st[4 + o] = (double)s2[o]; }
+        warp_reduce_scatter<double, 8>(st);              // lane l: total of value l >> 2
+        if ((lane & 3) == 0) red[warp * 8 + (lane >> 2)] = st[0];
         __syncthreads();
         if (tid < 8) {
             double v = 0.0;
@@ -471,6 +471,7 @@ __device__ __forceinline__ float4 gpre_gather(const Gpre4& gp, const int* __rest
 }
 
 #define R4_MAX_FLAGGED 64
+#define R4_MAX_IDS 8
 
 // DW = false: the gather-only variant (the weight gradients come from dw_row4_kernel, which streams
 // over the x1 rows saved by the forward on a parallel graph branch): ~48 fewer live registers.
@@ -485,13 +486,13 @@ bwd_row4_kernel(const Bwd4Args a) {
     __shared__ float red[(R4_THREADS / 32) * 64];
     __shared__ int flagged[R4_MAX_FLAGGED];
     __shared__ int n_flagged;
-    __shared__ float rsum[4];
-    __shared__ int rsum_id;
+    __shared__ int rng_ids[R4_MAX_IDS];
+    __shared__ float rng_sum[R4_MAX_IDS * 4];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const bool is_self = (int)blockIdx.x < a.ctas_self;
     pdl_launch_dependents();
     // ---- phase 0 (parameters only; under PDL this overlaps the producer's tail)
-    if (tid == 0) { n_flagged = 0; rsum_id = -1; }
+    if (tid == 0) n_flagged = 0;
     for (int i = tid; i < NT * 16; i += R4_THREADS) {
         const int t = i >> 4, o = (i >> 2) & 3, f = i & 3;
         const float* wrow = (o < a.Ha) ? a.Wa + (size_t)o * a.Cin : a.Wb + (size_t)(o - a.Ha) * a.Cin;
@@ -605,60 +606,90 @@ bwd_row4_kernel(const Bwd4Args a) {
                 }
             }
         }
-        // ---- run-length parts of the flagged rows: range sum once per CTA (cached), then the delta
-        //      of everything that is linear in T[2]
+        // ---- run-length parts of the flagged rows.  (1) the distinct range ids they refer to (a CTA's
+        //      rows lie in one or two graphs, so one or two ids), (2) each range sum once per CTA,
+        //      cooperatively, (3) every flagged row finished by its own thread, in parallel: the delta of
+        //      everything that is linear in T[2].
         __syncthreads();
         const int nf = min(n_flagged, R4_MAX_FLAGGED);
-        for (int it = 0; it < nf; ++it) {
-            const int row = flagged[it];
-            for (int e = __ldg(a.rng_rowptr + row); e < __ldg(a.rng_rowptr + row + 1); ++e) {
-                const int id = __ldg(a.rng_id + e);
-                if (id != rsum_id) {               // uniform
-                    const int lo = __ldg(a.rng_lo + id), hi = __ldg(a.rng_hi + id);
-                    float4 acc = f4_zero();
-                    for (int rr = lo + tid; rr < hi; rr += R4_THREADS) {
-                        const float4 gv = gp(rr);
-                        acc.x += gv.x; acc.y += gv.y; acc.z += gv.z; acc.w += gv.w;
+        if (nf > 0) {
+            if (tid < R4_MAX_IDS) rng_ids[tid] = -1;
+            __syncthreads();
+            int my_row = -1, e0 = 0, e1 = 0;
+            if (tid < nf) {
+                my_row = flagged[tid];
+                e0 = __ldg(a.rng_rowptr + my_row);
+                e1 = __ldg(a.rng_rowptr + my_row + 1);
+                for (int e = e0; e < e1; ++e) {
+                    const int id = __ldg(a.rng_id + e);
+                    for (int j = 0; j < R4_MAX_IDS; ++j) {
+                        const int old = atomicCAS(&rng_ids[j], -1, id);
+                        if (old == -1 || old == id) break;
                     }
-                    acc.x = warp_sum(acc.x); acc.y = warp_sum(acc.y); acc.z = warp_sum(acc.z); acc.w = warp_sum(acc.w);
-                    __syncthreads();
-                    if (lane == 0) { red[warp * 4] = acc.x; red[warp * 4 + 1] = acc.y; red[warp * 4 + 2] = acc.z; red[warp * 4 + 3] = acc.w; }
-                    __syncthreads();
-                    if (tid < 4) {
-                        float v = 0.f;
-                        for (int w = 0; w < R4_THREADS / 32; ++w) v += red[w * 4 + tid];
-                        rsum[tid] = v;
-                    }
-                    if (tid == 0) rsum_id = id;
-                    __syncthreads();
                 }
-                if (tid == 0) {                    // one thread finishes the row
+            }
+            __syncthreads();
+            for (int j = 0; j < R4_MAX_IDS; ++j) {
+                const int id = rng_ids[j];
+                if (id < 0) break;                     // uniform
+                const int lo = __ldg(a.rng_lo + id), hi = __ldg(a.rng_hi + id);
+                float4 acc = f4_zero();
+                for (int rr = lo + tid; rr < hi; rr += R4_THREADS) {
+                    const float4 gv = gp(rr);
+                    acc.x += gv.x; acc.y += gv.y; acc.z += gv.z; acc.w += gv.w;
+                }
+                acc.x = warp_sum(acc.x); acc.y = warp_sum(acc.y); acc.z = warp_sum(acc.z); acc.w = warp_sum(acc.w);
+                if (lane == 0) { red[warp * 4] = acc.x; red[warp * 4 + 1] = acc.y; red[warp * 4 + 2] = acc.z; red[warp * 4 + 3] = acc.w; }
+                __syncthreads();
+                if (tid < 4) {
+                    float v = 0.f;
+                    for (int w = 0; w < R4_THREADS / 32; ++w) v += red[w * 4 + tid];
+                    rng_sum[j * 4 + tid] = v;
+                }
+                __syncthreads();
+            }
+            if (tid < nf) {
+                const int row = my_row;
+                float dT[4] = {0.f, 0.f, 0.f, 0.f};
+                for (int e = e0; e < e1; ++e) {
+                    const int id = __ldg(a.rng_id + e);
                     const float v = __ldg(a.rng_val + e);
-                    const float dT[4] = {v * rsum[0], v * rsum[1], v * rsum[2], v * rsum[3]};
-                    const float4 xr = ld4(a.Xs + (size_t)row * 4);
-                    const float4 xn = f4_affine(xr, sc, sh);
-                    float g[4] = {0.f, 0.f, 0.f, 0.f};
+                    int j = 0;
+                    while (j < R4_MAX_IDS && rng_ids[j] != id) ++j;
+                    if (j < R4_MAX_IDS) {
 #pragma unroll
-                    for (int o = 0; o < 4; ++o) {
-                        const float4 w = *reinterpret_cast<const float4*>(Ws + (2 * 4 + o) * 4);
-                        g[0] = fmaf(dT[o], w.x, g[0]); g[1] = fmaf(dT[o], w.y, g[1]);
-                        g[2] = fmaf(dT[o], w.z, g[2]); g[3] = fmaf(dT[o], w.w, g[3]);
-                        if (DW) {
-                            dw[(2 * 4 + o) * 4 + 0] = fmaf(dT[o], xn.x, dw[(2 * 4 + o) * 4 + 0]);
-                            dw[(2 * 4 + o) * 4 + 1] = fmaf(dT[o], xn.y, dw[(2 * 4 + o) * 4 + 1]);
-                            dw[(2 * 4 + o) * 4 + 2] = fmaf(dT[o], xn.z, dw[(2 * 4 + o) * 4 + 2]);
-                            dw[(2 * 4 + o) * 4 + 3] = fmaf(dT[o], xn.w, dw[(2 * 4 + o) * 4 + 3]);
+                        for (int f = 0; f < 4; ++f) dT[f] = fmaf(v, rng_sum[j * 4 + f], dT[f]);
+                    } else {        // more distinct ranges than table slots: serial sum (correct, slow, rare)
+                        for (int rr = __ldg(a.rng_lo + id); rr < __ldg(a.rng_hi + id); ++rr) {
+                            const float4 gv = gp(rr);
+                            dT[0] = fmaf(v, gv.x, dT[0]); dT[1] = fmaf(v, gv.y, dT[1]);
+                            dT[2] = fmaf(v, gv.z, dT[2]); dT[3] = fmaf(v, gv.w, dT[3]);
                         }
                     }
-                    if (gX) {
-                        float4 old = __ldcg(reinterpret_cast<const float4*>(gX + (size_t)row * 4));
-                        old.x += g[0]; old.y += g[1]; old.z += g[2]; old.w += g[3];
-                        *reinterpret_cast<float4*>(gX + (size_t)row * 4) = old;
-                        if (stats) {
-                            const float xh[4] = {(xr.x - mu.x) * rs.x, (xr.y - mu.y) * rs.y, (xr.z - mu.z) * rs.z, (xr.w - mu.w) * rs.w};
+                }
+                const float4 xr = ld4(a.Xs + (size_t)row * 4);
+                const float4 xn = f4_affine(xr, sc, sh);
+                float g[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-                            for (int f = 0; f < 4; ++f) { sg[f] += g[f]; sgx[f] = fmaf(g[f], xh[f], sgx[f]); }
-                        }
+                for (int o = 0; o < 4; ++o) {
+                    const float4 w = *reinterpret_cast<const float4*>(Ws + (2 * 4 + o) * 4);
+                    g[0] = fmaf(dT[o], w.x, g[0]); g[1] = fmaf(dT[o], w.y, g[1]);
+                    g[2] = fmaf(dT[o], w.z, g[2]); g[3] = fmaf(dT[o], w.w, g[3]);
+                    if (DW) {
+                        dw[(2 * 4 + o) * 4 + 0] = fmaf(dT[o], xn.x, dw[(2 * 4 + o) * 4 + 0]);
+                        dw[(2 * 4 + o) * 4 + 1] = fmaf(dT[o], xn.y, dw[(2 * 4 + o) * 4 + 1]);
+                        dw[(2 * 4 + o) * 4 + 2] = fmaf(dT[o], xn.z, dw[(2 * 4 + o) * 4 + 2]);
+                        dw[(2 * 4 + o) * 4 + 3] = fmaf(dT[o], xn.w, dw[(2 * 4 + o) * 4 + 3]);
+                    }
+                }
+                if (gX) {
+                    float4 old = __ldcg(reinterpret_cast<const float4*>(gX + (size_t)row * 4));
+                    old.x += g[0]; old.y += g[1]; old.z += g[2]; old.w += g[3];
+                    *reinterpret_cast<float4*>(gX + (size_t)row * 4) = old;
+                    if (stats) {
+                        const float xh[4] = {(xr.x - mu.x) * rs.x, (xr.y - mu.y) * rs.y, (xr.z - mu.z) * rs.z, (xr.w - mu.w) * rs.w};
+#pragma unroll
+                        for (int f = 0; f < 4; ++f) { sg[f] += g[f]; sgx[f] = fmaf(g[f], xh[f], sgx[f]); }
                     }
                 }
             }
@@ -731,13 +762,12 @@ bwd_row4_kernel(const Bwd4Args a) {
     __syncthreads();
     if (a.ablate & 4) return;
     if (DW) {
+        float pad[64];                                   // NT * 16 <= 64 values, zero padded
 #pragma unroll
-        for (int i = 0; i < NT * 16; ++i) {
-            if (i < nvals) {
-                const float v = warp_sum(dw[i]);
-                if (lane == 0) red[warp * 64 + i] = v;
-            }
-        }
+        for (int i = 0; i < 64; ++i) pad[i] = i < NT * 16 ? dw[i] : 0.f;
+        warp_reduce_scatter<float, 64>(pad);             // lane l: totals of values 2l, 2l + 1
+        red[warp * 64 + 2 * lane] = pad[0];
+        red[warp * 64 + 2 * lane + 1] = pad[1];
     }
     __syncthreads();
     if (DW && a.dW_bins)
@@ -749,14 +779,11 @@ bwd_row4_kernel(const Bwd4Args a) {
         }
     __syncthreads();
     // dbias (self only) and the BN sums of the produced gradient
-    float extra[12];
+    float extra[16];
 #pragma unroll
-    for (int f = 0; f < 4; ++f) { extra[f] = db[f]; extra[4 + f] = sg[f]; extra[8 + f] = sgx[f]; }
-#pragma unroll
-    for (int i = 0; i < 12; ++i) {
-        const float v = warp_sum(extra[i]);
-        if (lane == 0) red[warp * 64 + i] = v;
-    }
+    for (int f = 0; f < 4; ++f) { extra[f] = db[f]; extra[4 + f] = sg[f]; extra[8 + f] = sgx[f]; extra[12 + f] = 0.f; }
+    warp_reduce_scatter<float, 16>(extra);               // lane l: total of value l >> 1
+    if ((lane & 1) == 0) red[warp * 64 + (lane >> 1)] = extra[0];
     __syncthreads();
     if (tid < 12) {
         double v = 0.0;
