@@ -1088,12 +1088,14 @@ static bool eng_try_fwd_row4(const eng::FwdArgs& g, const hgnn_side_t* side, hgn
     const double avg_a = a.R > 0 ? (double)side->ops[2].nnz / a.R : 0.0;
     const double avg_p = (cross && a.R > 0) ? (double)side->p_nnz / a.R : 0.0;
     bool big_a = avg_a > 3.5, big_p = avg_p > 5.0;
+    static int full_grid = -1;
+    if (full_grid < 0) { const char* e = getenv("HGNN_B200_FWD_FULLGRID"); full_grid = (e && e[0] == '1') ? 1 : 0; }
     static int force = -2;
     if (force == -2) { const char* e = getenv("HGNN_B200_FWD_BATCH"); force = e ? atoi(e) : -1; }   // bit 0: big_a, bit 1: big_p
     if (force >= 0) { big_a = force & 1; big_p = (force & 2) != 0; }
 #define R4_FWD(NCSR, CROSS, BA, BP)                                                                      \
     {                                                                                                    \
-        int grid = min(want, eng_resident_impl((const void*)eng::fwd_row4_kernel<NCSR, CROSS, BA, BP>, 0, R4_THREADS)); \
+        int grid = full_grid ? want : min(want, eng_resident_impl((const void*)eng::fwd_row4_kernel<NCSR, CROSS, BA, BP>, 0, R4_THREADS)); \
         eng_launch(eng::fwd_row4_kernel<NCSR, CROSS, BA, BP>, grid, R4_THREADS, 0, s, a);                \
     }
 #define R4_FWD_B(NCSR)                                                                                   \

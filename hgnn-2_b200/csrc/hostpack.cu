@@ -24,9 +24,11 @@ namespace {
 // ---- blob fields (order = sparse_ops.BLOB_FIELDS) ----------------------------------------------
 enum Field {
     F_DEG = 0, F_A_RP, F_A_COL, F_A_VAL, F_AT_RP, F_AT_COL, F_AT_VAL, N_PRIMAL_FIELDS,
-    F_DL = N_PRIMAL_FIELDS, F_B_RP, F_B_COL, F_B_VAL, F_BT_RP, F_BT_COL, F_BT_VAL,
+    F_DL = N_PRIMAL_FIELDS, F_B_RP, F_B_COL, F_B_VAL,
     F_P_RP, F_P_COL, F_P_PM, F_P_PD, F_PT_RP, F_PT_COL, F_PT_PM, F_PT_PD,
-    F_BTS_RP, F_BTS_COL, F_BTS_VAL, F_RNG_RP, F_RNG_ID, F_RNG_VAL, F_RNG_LO, F_RNG_HI, N_FIELDS
+    F_BTS_RP, F_BTS_COL, F_BTS_VAL, F_RNG_RP, F_RNG_ID, F_RNG_VAL, F_RNG_LO, F_RNG_HI,
+    F_BT_RP, F_BT_COL, F_BT_VAL,      // last: a batch that skips the full transposed operator copies a prefix
+    N_FIELDS
 };
 
 struct Blob {
@@ -401,7 +403,8 @@ __global__ void __launch_bounds__(256) pack_gather_kernel(const PackTask* __rest
     }
 }
 
-inline long long blob_bytes(const Blob& b) {
+inline long long blob_bytes(const Blob& b, int skip_bt = 0) {
+    if (skip_bt && b.n_fields() == N_FIELDS) return b.h[5 + 2 * F_BT_RP];
     const int last = b.n_fields() - 1;
     return b.h[5 + 2 * last] + ((4 * b.len(last) + 15) & ~15ll);
 }
@@ -451,7 +454,7 @@ DevicePlan plan_device(const std::vector<Blob>& B, int dual, int skip_bt, long l
         }
     }
     if (p.out_bytes < 16) p.out_bytes = 16;
-    for (const Blob& b : B) p.stage_bytes += blob_bytes(b);
+    for (const Blob& b : B) p.stage_bytes += blob_bytes(b, skip_bt);
     if (p.stage_bytes < 16) p.stage_bytes = 16;
     p.small_off = ((long long)p.n_tasks * sizeof(PackTask) + 15) & ~15ll;
     p.meta_bytes = p.small_off + 4ll * p.n_small + 16;
@@ -487,10 +490,10 @@ extern "C" int hgnn_pack_device_upload(int bs, const void* const* blobs, int dua
     cudaStream_t s = to_stream(stream);
     // ---- graph blobs -> device staging, one DMA each
     std::vector<long long> blob_off(bs + 1, 0);
-    for (int g = 0; g < bs; ++g) blob_off[g + 1] = blob_off[g] + blob_bytes(B[g]);
+    for (int g = 0; g < bs; ++g) blob_off[g + 1] = blob_off[g] + blob_bytes(B[g], skip_bt);
     char* stage = static_cast<char*>(stage_dev);
     for (int g = 0; g < bs; ++g) {
-        cudaError_t e = cudaMemcpyAsync(stage + blob_off[g], B[g].base, (size_t)blob_bytes(B[g]), cudaMemcpyHostToDevice, s);
+        cudaError_t e = cudaMemcpyAsync(stage + blob_off[g], B[g].base, (size_t)blob_bytes(B[g], skip_bt), cudaMemcpyHostToDevice, s);
         if (e != cudaSuccess) {
             hgnn_set_error("hgnn_pack_device_upload: cudaMemcpyAsync(blob %d): %s", g, cudaGetErrorString(e));
             return HGNN_ERR_CUDA;

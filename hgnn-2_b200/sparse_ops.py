@@ -85,10 +85,11 @@ blob_alloc = _numpy_blob_alloc
 
 BLOB_MAGIC = 0x48474e4e424c4f42
 BLOB_FIELDS = ("deg", "a_rowptr", "a_col", "a_val", "at_rowptr", "at_col", "at_val",
-               "dl", "b_rowptr", "b_col", "b_val", "bt_rowptr", "bt_col", "bt_val",
+               "dl", "b_rowptr", "b_col", "b_val",
                "p_rowptr", "p_col", "p_pm", "p_pd", "pt_rowptr", "pt_col", "pt_pm", "pt_pd",
                "bts_rowptr", "bts_col", "bts_val", "bts_rng_rowptr", "bts_rng_id", "bts_rng_val",
-               "bts_rng_lo", "bts_rng_hi")
+               "bts_rng_lo", "bts_rng_hi",
+               "bt_rowptr", "bt_col", "bt_val")     # last: batches that skip the full bt copy a prefix
 N_PRIMAL_FIELDS = 7
 
 
