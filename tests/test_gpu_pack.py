@@ -56,3 +56,47 @@ def test_device_and_host_concat_paths_give_the_same_pack():
     for ra, rb in zip(a.bts_ranges, b.bts_ranges):
         assert torch.equal(ra, rb)
     assert graphs[0]._blob is not None and torch.from_numpy(graphs[0]._blob).is_pinned()
+
+
+def test_batch_loader_yields_what_prepare_batch_returns():
+    """functions.batching.BatchLoader = prepare_batch one batch ahead on a background thread / copy stream:
+    same tuples in the same order, usable on the consumer's stream without any explicit synchronisation."""
+    from hgnn_b200 import synth
+    from hgnn_b200.functions.batching import BatchLoader, get_batches, prepare_batch
+    from hgnn_b200.models.gnns.model_mnb import GNN_lg
+    data = synth.sbm_dataset(10, N=80, J=1, sparse=True)
+    idx = get_batches(len(data), 4, data)
+    assert [len(i) for i in idx] == [4, 4, 2]
+    torch.manual_seed(1)
+    model = GNN_lg(0, 2, 3, 5, 2, 1, 1).cuda().train()
+    loader = BatchLoader(data, idx, 0, 1)
+    assert len(loader) == 3
+    n = 0
+    for k, got in enumerate(loader):
+        ref = prepare_batch([data[i] for i in idx[k]], 0, 1)
+        for pos in (0, 2, 3, 9, 10):                      # X, T, XL, N_batch, E_batch
+            assert torch.equal(got[pos], ref[pos]), pos
+        pa, pb = got[1].pack, ref[1].pack
+        for name in ("node_off", "edge_off", "deg", "dl"):
+            assert torch.equal(getattr(pa, name), getattr(pb, name)), name
+        for ca, cb in ((pa.a[0], pb.a[0]), (pa.b[0], pb.b[0]), (pa.p, pb.p), (pa.pt, pb.pt), (pa.bts, pb.bts)):
+            assert torch.equal(ca.rowptr, cb.rowptr) and torch.equal(ca.col, cb.col) and torch.equal(ca.val, cb.val)
+        outs = []
+        for b in (got, ref):
+            X, W, T, XL, WL, Pm, Pd, mask, mask_lg, N_batch, E_batch = b
+            outs.append(model([X.cuda(), XL.cuda(), W, WL, Pm, Pd], N_batch, mask, E_batch, mask_lg).detach())
+        assert torch.equal(outs[0], outs[1]) or float((outs[0] - outs[1]).abs().max()) < 1e-6
+        n += 1
+    assert n == 3
+
+
+def test_batch_loader_propagates_errors_and_stops_early():
+    from hgnn_b200 import synth
+    from hgnn_b200.functions.batching import BatchLoader
+    data = synth.sbm_dataset(6, N=40, J=1, sparse=True)
+    it = iter(BatchLoader(data, [[0, 1], [2, 3], [4, 5]], 0, 1))
+    next(it)
+    it.close()                                               # consumer leaves early: the producer thread must end
+    with pytest.raises(IndexError):
+        for _ in BatchLoader(data, [[0, 1], [99]], 0, 1):
+            pass
