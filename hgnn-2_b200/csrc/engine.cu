@@ -950,6 +950,7 @@ bwd_kernel(const BwdArgs a) {
 }
 
 #include "engine_row4.cuh"
+#include "engine_rowg.cuh"
 
 }  // namespace eng
 
@@ -1108,6 +1109,56 @@ static bool eng_try_fwd_row4(const eng::FwdArgs& g, const hgnn_side_t* side, hgn
     return true;
 }
 
+// thread-per-row kernels for the odd small widths of layer 0 and the readout (engine_rowg.cuh)
+static bool eng_try_fwd_rowg(const eng::FwdArgs& g, const hgnn_side_t* side, hgnn_stream_t stream) {
+    if (eng_row4_disabled() || g.X1) return false;
+    const bool cross = g.p_rowptr != nullptr;
+    const int Fs = g.Fs, Fc = cross ? g.Fc : 0, Fo = g.Fout;
+    if (!side->ops || !eng_row4_ops(side->ops, side->n_ops)) return false;
+    for (int i = 2; i < side->n_ops; ++i) if (side->ops[i].rng_rowptr) return false;
+    if (Fo < 1 || Fo > 4 || (g.acc_out && Fo != 4)) return false;
+    if ((g.bn_s.acc || g.bn_s.affine) && Fs != 4) return false;
+    if (cross && (g.bn_c.acc || g.bn_c.affine) && Fc != 4) return false;
+    if ((Fs == 4 && !eng_aligned16(g.Xs)) || (Fc == 4 && !eng_aligned16(g.Xc)) || (Fo == 4 && !eng_aligned16(g.Z))) return false;
+    eng::Fwd4Args a;
+    a.R = g.R; a.n_csr = side->n_ops - 2; a.diag = side->ops[1].diag;
+    for (int i = 0; i < 2; ++i) {
+        const bool on = i < a.n_csr;
+        a.rowptr[i] = on ? side->ops[2 + i].rowptr : nullptr;
+        a.col[i] = on ? side->ops[2 + i].col : nullptr;
+        a.val[i] = on ? side->ops[2 + i].val : nullptr;
+    }
+    a.Xs = g.Xs; a.bn_s = g.bn_s;
+    a.p_rowptr = g.p_rowptr; a.p_col = g.p_col; a.p_pm = g.p_pm; a.p_pd = g.p_pd; a.Xc = g.Xc; a.bn_c = g.bn_c;
+    a.Wa = g.Wa; a.ba = g.ba; a.Ha = g.Ha; a.Wb = g.Wb; a.bb = g.bb; a.Hb = g.Hb;
+    a.relu_from = g.relu_from; a.Cin = g.Cin; a.Z = g.Z; a.acc_out = g.acc_out; a.X1 = nullptr; a.ablate = 0;
+    cudaStream_t s = to_stream(stream);
+    const int want = ceil_div(a.R, R4_THREADS);
+    const double avg_a = a.R > 0 ? (double)side->ops[2].nnz / a.R : 0.0;
+    const double avg_p = (cross && a.R > 0) ? (double)side->p_nnz / a.R : 0.0;
+    const bool big = avg_a > 3.5 || avg_p > 5.0;       // node-like rows: batches of 8 / 16, else 4 / 4
+    bool done = false;
+#define RG_FWD(NCSR, CROSS, FS, FC, FO)                                                                             \
+    if (!done && a.n_csr == NCSR && cross == CROSS && Fs == FS && Fc == (CROSS ? FC : 0) && Fo == FO) {             \
+        if (big) {                                                                                                  \
+            int grid = min(want, eng_resident_impl((const void*)eng::fwd_rowg_kernel<NCSR, CROSS, 8, 16, FS, FC, FO>, 0, R4_THREADS)); \
+            eng_launch(eng::fwd_rowg_kernel<NCSR, CROSS, 8, 16, FS, FC, FO>, grid, R4_THREADS, 0, s, a);            \
+        } else {                                                                                                    \
+            int grid = min(want, eng_resident_impl((const void*)eng::fwd_rowg_kernel<NCSR, CROSS, 4, 4, FS, FC, FO>, 0, R4_THREADS)); \
+            eng_launch(eng::fwd_rowg_kernel<NCSR, CROSS, 4, 4, FS, FC, FO>, grid, R4_THREADS, 0, s, a);             \
+        }                                                                                                           \
+        done = true;                                                                                                \
+    }
+    // LGNN (models/gnns/model_mnb.py:98-100): layer 0 node side [5 | 1 -> 4], edge side [1 | 4 -> 4], readout [4 | 4 -> 1, 2]
+    RG_FWD(1, true, 5, 1, 4) RG_FWD(1, true, 1, 4, 4) RG_FWD(1, true, 4, 4, 2) RG_FWD(1, true, 4, 4, 1)
+    RG_FWD(2, true, 5, 1, 4) RG_FWD(2, true, 1, 4, 4) RG_FWD(2, true, 4, 4, 2) RG_FWD(2, true, 4, 4, 1)
+    // power GNN (:48-50): layer 0 [5 -> 4], readout [4 -> 1, 2]
+    RG_FWD(1, false, 5, 0, 4) RG_FWD(1, false, 4, 0, 2) RG_FWD(1, false, 4, 0, 1)
+    RG_FWD(2, false, 5, 0, 4) RG_FWD(2, false, 4, 0, 2) RG_FWD(2, false, 4, 0, 1)
+#undef RG_FWD
+    return done;
+}
+
 extern "C" int hgnn_lg_side_fwd(const hgnn_side_t* side, const hgnn_bn_ref_t* bn_self,
                                 const hgnn_bn_ref_t* bn_cross, const float* Wa, const float* ba, int Ha,
                                 const float* Wb, const float* bb, int Hb, int relu_from, float* Z,
@@ -1133,6 +1184,7 @@ extern "C" int hgnn_lg_side_fwd(const hgnn_side_t* side, const hgnn_bn_ref_t* bn
     a.Fout = Ha + Hb;
     a.Cin = side->n_ops * a.Fs + 2 * a.Fc;
     if (eng_try_fwd_row4(a, side, stream)) return hgnn_check_launch("hgnn_lg_side_fwd(row4)");
+    if (eng_try_fwd_rowg(a, side, stream)) return hgnn_check_launch("hgnn_lg_side_fwd(rowg)");
     HGNN_REQUIRE(!X1, "x1 rows can only be saved by the width-4 fast path (check hgnn_lg_row4_eligible)");
     const bool vec4 = (a.Fs % 4 == 0) && (a.Fc % 4 == 0) && eng_aligned16(a.Xs) && (a.Fc == 0 || eng_aligned16(a.Xc));
     const bool vout4 = vec4 && (a.Fout % 4 == 0) && eng_aligned16(Z);
