@@ -1314,6 +1314,64 @@ static bool eng_try_bwd_row4(const hgnn_side_bwd_t* d, hgnn_stream_t stream) {
     return true;
 }
 
+// thread-per-row backward for the odd small widths of layer 0 and the readout (engine_rowg.cuh)
+static bool eng_try_bwd_rowg(const hgnn_side_bwd_t* d, hgnn_stream_t stream) {
+    if (eng_row4_disabled() || d->skip_dw) return false;
+    const int Fg = d->Fg, Fs = d->Fs, Fc = d->R_cross > 0 ? d->Fc : 0;
+    if (d->R_self <= 0 || !d->ops_T || !eng_row4_ops(d->ops_T, d->n_ops)) return false;
+    for (int i = 3; i < d->n_ops; ++i) if (d->ops_T[i].rng_rowptr) return false;   // ranges only on the first CSR op
+    const bool has_bn = d->acc_b != nullptr;
+    if (Fg < 4 && (has_bn || d->relu_from < Fg)) return false;
+    if ((d->bn_self.acc || d->bn_self.affine) && Fs != 4) return false;
+    if (d->R_cross > 0 && (d->bn_cross.acc || d->bn_cross.affine) && Fc != 4) return false;
+    if (Fg == 4 && (!eng_aligned16(d->gY) || (d->Z && !eng_aligned16(d->Z)))) return false;
+    if ((Fs == 4 && !eng_aligned16(d->Xs)) || (Fc == 4 && !eng_aligned16(d->Xc))) return false;
+    eng::Bwd4Args a;
+    a.gY = d->gY; a.Z = d->Z; a.relu_from = d->relu_from; a.Rg = d->Rg; a.has_bn = has_bn;
+    a.acc_f = d->acc_f; a.acc_b = d->acc_b; a.bn_w = d->bn_weight;
+    a.Wa = d->Wa; a.Ha = d->Ha; a.Wb = d->Wb; a.Hb = d->Hb; a.Cin = d->Cin;
+    a.dW_bins = d->dW_bins; a.db_bins = d->db_bins;
+    a.R_self = d->R_self; a.n_csr = d->n_ops - 2; a.diag = d->ops_T[1].diag;
+    for (int i = 0; i < 2; ++i) {
+        const bool on = i < a.n_csr;
+        a.rowptr[i] = on ? d->ops_T[2 + i].rowptr : nullptr;
+        a.col[i] = on ? d->ops_T[2 + i].col : nullptr;
+        a.val[i] = on ? d->ops_T[2 + i].val : nullptr;
+    }
+    const hgnn_op_t& o2 = d->ops_T[2];
+    a.rng_rowptr = o2.rng_rowptr; a.rng_id = o2.rng_id; a.rng_val = o2.rng_val; a.rng_lo = o2.rng_lo; a.rng_hi = o2.rng_hi;
+    a.Xs = d->Xs; a.bn_s = to_bnref(&d->bn_self); a.gXs = d->gXs; a.acc_self = d->accumulate_self; a.acc_b_self = d->acc_b_self;
+    a.R_cross = d->R_cross > 0 ? d->R_cross : 0;
+    a.pt_rowptr = d->pt_rowptr; a.pt_col = d->pt_col; a.pt_pm = d->pt_pm; a.pt_pd = d->pt_pd;
+    a.Xc = d->Xc; a.bn_c = to_bnref(&d->bn_cross); a.gXc = d->gXc; a.acc_cross = d->accumulate_cross;
+    a.acc_b_cross = d->acc_b_cross; a.col0_cross = d->n_ops * Fs; a.ablate = 0;
+    cudaStream_t s = to_stream(stream);
+    const long long rows = (long long)d->R_self + a.R_cross;
+    const double avg_s = (double)d->ops_T[2].nnz / d->R_self;
+    const double avg_c = a.R_cross > 0 ? (double)d->pt_nnz / a.R_cross : 0.0;
+    const double cost_s = (double)d->R_self * (1.0 + 0.2 * avg_s);
+    const double cost_c = a.R_cross > 0 ? (double)a.R_cross * (1.0 + 0.2 * avg_c) : 0.0;
+    bool done = false;
+#define RG_BWD(NCSR, FG, FS, FC)                                                                           \
+    if (!done && a.n_csr == NCSR && Fg == FG && Fs == FS && Fc == FC) {                                    \
+        const int cap = eng_resident_impl((const void*)eng::bwd_rowg_kernel<NCSR, FG, FS, FC>, 0, R4_THREADS); \
+        int grid = (int)min((long long)cap, (rows + R4_THREADS - 1) / R4_THREADS);                         \
+        if (a.R_cross > 0 && grid < 2) grid = 2;                                                           \
+        int cs = a.R_cross > 0 ? (int)(grid * cost_s / (cost_s + cost_c) + 0.5) : grid;                    \
+        if (cs < 1) cs = 1;                                                                                \
+        if (a.R_cross > 0 && cs > grid - 1) cs = grid - 1;                                                 \
+        a.ctas_self = cs;                                                                                  \
+        eng_launch(eng::bwd_rowg_kernel<NCSR, FG, FS, FC>, grid, R4_THREADS, 0, s, a);                     \
+        done = true;                                                                                       \
+    }
+    // LGNN: layer 0 node side, layer 0 edge side, readout (dim_output 2 / 1); power GNN: layer 0, readout
+    RG_BWD(1, 4, 5, 1) RG_BWD(1, 4, 1, 4) RG_BWD(1, 2, 4, 4) RG_BWD(1, 1, 4, 4) RG_BWD(1, 4, 5, 0) RG_BWD(1, 2, 4, 0) RG_BWD(1, 1, 4, 0)
+    // J = 2: the layer-0 node side would need 80 dW accumulators per thread (> 64): generic tile kernels
+    RG_BWD(2, 4, 1, 4) RG_BWD(2, 2, 4, 4) RG_BWD(2, 1, 4, 4) RG_BWD(2, 2, 4, 0) RG_BWD(2, 1, 4, 0)
+#undef RG_BWD
+    return done;
+}
+
 extern "C" int hgnn_lg_side_dw(const float* gY, const float* Z, int R, int relu_from, const double* acc_f,
                                const double* acc_b, const float* bn_weight, const float* X1, int Cin,
                                double* dW_bins, double* db_bins, hgnn_stream_t stream) {
@@ -1346,6 +1404,7 @@ extern "C" int hgnn_lg_side_bwd(const hgnn_side_bwd_t* d, hgnn_stream_t stream) 
     HGNN_REQUIRE(!d->acc_b || (d->acc_f && d->bn_weight && d->Z), "batch-norm backward needs acc_f, bn_weight and Z");
     HGNN_REQUIRE(d->relu_from >= d->Fg || d->Z, "ReLU backward needs Z");
     if (eng_try_bwd_row4(d, stream)) return hgnn_check_launch("hgnn_lg_side_bwd(row4)");
+    if (eng_try_bwd_rowg(d, stream)) return hgnn_check_launch("hgnn_lg_side_bwd(rowg)");
     HGNN_REQUIRE(!d->skip_dw, "skip_dw needs the width-4 fast path (check hgnn_lg_row4_eligible)");
     eng::BwdArgs a;
     a.gY = d->gY; a.Z = d->Z; a.Fg = d->Fg; a.relu_from = d->relu_from; a.Rg = d->Rg;

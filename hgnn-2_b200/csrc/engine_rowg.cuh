@@ -248,3 +248,360 @@ fwd_rowg_kernel(const Fwd4Args a) {
         }
     }
 }
+
+// ---------------------------------------------------------------------------------------------
+// backward for the odd widths: gY is FG wide (4 with batch-norm + ReLU backward on the fly, or 1 / 2 for
+// the readout: plain), the self input FS wide, the cross input FC wide (ignored when R_cross == 0).
+// Same structure as bwd_row4_kernel (engine_row4.cuh), which stays the tuned path for 4 / 4 / 4.
+// ---------------------------------------------------------------------------------------------
+template <int FG>
+struct GpreG {
+    Gpre4 g4;                 // FG == 4
+    const float* G;           // FG < 4: plain rows (no batch-norm, no ReLU: checked by the host)
+    __device__ __forceinline__ RowV<FG> operator()(int row) const {
+        RowV<FG> r;
+        if constexpr (FG == 4) {
+            const float4 t = g4(row);
+            r.v[0] = t.x; r.v[1] = t.y; r.v[2] = t.z; r.v[3] = t.w;
+        } else {
+#pragma unroll
+            for (int o = 0; o < FG; ++o) r.v[o] = __ldg(G + (size_t)row * FG + o);
+        }
+        return r;
+    }
+};
+
+template <int NCSR, int FG, int FS, int FC>
+__global__ void __launch_bounds__(R4_THREADS)
+bwd_rowg_kernel(const Bwd4Args a) {
+    constexpr int NT = 2 + NCSR;                               // self blocks
+    constexpr int FCC = FC > 0 ? FC : 1;
+    constexpr int NDS = NT * FG * FS, NDC = 2 * FG * FCC;      // dW accumulators of a self / cross thread
+    constexpr int NDW = NDS > NDC ? NDS : NDC;
+    static_assert(NDW <= 64, "dW accumulators must fit the 64-value flush");
+    __shared__ float Ws[NT * FG * FS];                         // [t][o][f] = W[o][t*FS+f]
+    __shared__ float Wc[2 * FG * FCC];                         // [t][o][f] = W[o][col0 + t*FC + f]
+    __shared__ float red[(R4_THREADS / 32) * 64];
+    __shared__ int flagged[R4_MAX_FLAGGED];
+    __shared__ int n_flagged;
+    __shared__ int rng_ids[R4_MAX_IDS];
+    __shared__ float rng_sum[R4_MAX_IDS * FG];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const bool is_self = (int)blockIdx.x < a.ctas_self;
+    pdl_launch_dependents();
+    // ---- phase 0 (parameters only)
+    if (tid == 0) n_flagged = 0;
+    for (int i = tid; i < NT * FG * FS; i += R4_THREADS) {
+        const int t = i / (FG * FS), o = (i / FS) % FG, f = i % FS;
+        const float* wrow = (o < a.Ha) ? a.Wa + (size_t)o * a.Cin : a.Wb + (size_t)(o - a.Ha) * a.Cin;
+        Ws[i] = wrow[t * FS + f];
+    }
+    if (FC > 0 && a.R_cross > 0)
+        for (int i = tid; i < 2 * FG * FCC; i += R4_THREADS) {
+            const int t = i / (FG * FCC), o = (i / FCC) % FG, f = i % FCC;
+            const float* wrow = (o < a.Ha) ? a.Wa + (size_t)o * a.Cin : a.Wb + (size_t)(o - a.Ha) * a.Cin;
+            Wc[i] = wrow[a.col0_cross + t * FCC + f];
+        }
+    pdl_wait();
+    // ---- coefficients of this side's BN + ReLU backward (FG == 4 only), the input's BN vectors (width 4 only)
+    GpreG<FG> gp;
+    gp.G = a.gY;
+    if constexpr (FG == 4) {
+        Gpre4& g4 = gp.g4;
+        g4.relu_from = a.relu_from; g4.bn = a.has_bn != 0; g4.need_z = a.has_bn != 0 || a.relu_from < 4;
+        g4.G = a.gY; g4.Z = a.Z;
+        if (a.has_bn) {
+            double tf[8], tb[8];
+            warp_totals8(a.acc_f, tf);
+            warp_totals8(a.acc_b, tb);
+            const float w = a.bn_w[0];
+            const double inv_n = 1.0 / (double)a.Rg;
+            float c0[4], c1[4], c2[4];
+#pragma unroll
+            for (int f = 0; f < 4; ++f) {
+                const double m = tf[f] * inv_n;
+                const double var = fma(-m, m, tf[4 + f] * inv_n);
+                const float r_ = 1.0f / sqrtf(fmaxf((float)var, 0.f) + (float)ENG_BN_EPS);
+                const float k0 = w * r_;
+                const float k2 = -k0 * (float)(tb[4 + f] * inv_n) * r_;
+                c0[f] = k0;
+                c2[f] = k2;
+                c1[f] = -k0 * (float)(tb[f] * inv_n) - k2 * (float)m;
+            }
+            g4.c0 = make_float4(c0[0], c0[1], c0[2], c0[3]);
+            g4.c1 = make_float4(c1[0], c1[1], c1[2], c1[3]);
+            g4.c2 = make_float4(c2[0], c2[1], c2[2], c2[3]);
+        } else {
+            g4.c0 = make_float4(1.f, 1.f, 1.f, 1.f);
+            g4.c1 = f4_zero();
+            g4.c2 = f4_zero();
+        }
+    }
+    BnV<FS> bxs;
+    BnV<FCC> bxc;
+    bxs.identity();
+    bxc.identity();
+    if (is_self) {
+        if (FS == 4 && (a.bn_s.acc || a.bn_s.affine)) bxs.from4(bn4_from_ref(a.bn_s));
+    } else {
+        if (FC == 4 && (a.bn_c.acc || a.bn_c.affine)) bxc.from4(bn4_from_ref(a.bn_c));
+    }
+    __syncthreads();                                           // weights in shared memory
+
+    float dw[64];
+#pragma unroll
+    for (int i = 0; i < 64; ++i) dw[i] = 0.f;
+    float db[4] = {0.f, 0.f, 0.f, 0.f};
+    float sg[4] = {0.f, 0.f, 0.f, 0.f}, sgx[4] = {0.f, 0.f, 0.f, 0.f};
+
+    if (is_self) {
+        float* const gX = a.gXs;
+        const bool stats = FS == 4 && a.acc_b_self != nullptr && gX != nullptr;
+        // finishes one row from its T blocks: gX (+)= W^T T, dW += T (x) xn, statistics of the produced gradient
+        auto finish = [&](int row, const float (&T)[NT][FG], bool add_to_existing, bool first_visit) {
+            const RowV<FS> xr = ldrow<FS>(a.Xs, row);
+            float xn[FS], g[FS];
+#pragma unroll
+            for (int f = 0; f < FS; ++f) { xn[f] = fmaf(xr.v[f], bxs.sc[f], bxs.sh[f]); g[f] = 0.f; }
+#pragma unroll
+            for (int t = 0; t < NT; ++t)
+#pragma unroll
+                for (int o = 0; o < FG; ++o)
+#pragma unroll
+                    for (int f = 0; f < FS; ++f) {
+                        g[f] = fmaf(T[t][o], Ws[(t * FG + o) * FS + f], g[f]);
+                        dw[(t * FG + o) * FS + f] = fmaf(T[t][o], xn[f], dw[(t * FG + o) * FS + f]);
+                    }
+            if (first_visit) {
+#pragma unroll
+                for (int o = 0; o < FG; ++o) db[o] += T[0][o];
+            }
+            if (gX) {
+#pragma unroll
+                for (int f = 0; f < FS; ++f) {
+                    float v = g[f];
+                    if (add_to_existing) v += __ldcg(gX + (size_t)row * FS + f);
+                    gX[(size_t)row * FS + f] = v;
+                }
+                if (stats) {
+#pragma unroll
+                    for (int f = 0; f < FS; ++f) {
+                        sg[f & 3] += g[f];
+                        sgx[f & 3] = fmaf(g[f], (xr.v[f] - bxs.mu[f]) * bxs.rs[f], sgx[f & 3]);
+                    }
+                }
+            }
+        };
+        for (int row = blockIdx.x * R4_THREADS + tid; row < a.R_self; row += a.ctas_self * R4_THREADS) {
+            float T[NT][FG];
+            const RowV<FG> t0 = gp(row);
+            const float d = __ldg(a.diag + row);
+#pragma unroll
+            for (int o = 0; o < FG; ++o) { T[0][o] = t0.v[o]; T[1][o] = d * t0.v[o]; }
+#pragma unroll
+            for (int t = 0; t < NCSR; ++t) {
+#pragma unroll
+                for (int o = 0; o < FG; ++o) T[2 + t][o] = 0.f;
+                const int k0 = __ldg(a.rowptr[t] + row), k1 = __ldg(a.rowptr[t] + row + 1);
+                for (int k = k0; k < k1; k += 2) {
+                    const bool on = k + 1 < k1;
+                    const int c0 = __ldg(a.col[t] + k), c1 = on ? __ldg(a.col[t] + k + 1) : c0;
+                    const float v0 = __ldg(a.val[t] + k), v1 = on ? __ldg(a.val[t] + k + 1) : 0.f;
+                    const RowV<FG> g0 = gp(c0), g1 = gp(c1);
+#pragma unroll
+                    for (int o = 0; o < FG; ++o) T[2 + t][o] = fmaf(v1, g1.v[o], fmaf(v0, g0.v[o], T[2 + t][o]));
+                }
+            }
+            if (a.rng_rowptr && __ldg(a.rng_rowptr + row + 1) > __ldg(a.rng_rowptr + row)) {
+                const int slot = atomicAdd(&n_flagged, 1);
+                if (slot < R4_MAX_FLAGGED) {
+                    flagged[slot] = row;
+                } else {            // list full: add the run-length part serially (correct, slow, rare)
+                    for (int e = __ldg(a.rng_rowptr + row); e < __ldg(a.rng_rowptr + row + 1); ++e) {
+                        const int id = __ldg(a.rng_id + e);
+                        const float v = __ldg(a.rng_val + e);
+                        for (int rr = __ldg(a.rng_lo + id); rr < __ldg(a.rng_hi + id); ++rr) {
+                            const RowV<FG> gv = gp(rr);
+#pragma unroll
+                            for (int o = 0; o < FG; ++o) T[2][o] = fmaf(v, gv.v[o], T[2][o]);
+                        }
+                    }
+                }
+            }
+            finish(row, T, a.acc_self != 0, true);
+        }
+        // ---- run-length parts of the flagged rows (as in bwd_row4_kernel): distinct range ids -> range sums,
+        //      cooperatively -> every flagged row finished by its own thread
+        __syncthreads();
+        const int nf = min(n_flagged, R4_MAX_FLAGGED);
+        if (nf > 0) {
+            if (tid < R4_MAX_IDS) rng_ids[tid] = -1;
+            __syncthreads();
+            int my_row = -1, e0 = 0, e1 = 0;
+            if (tid < nf) {
+                my_row = flagged[tid];
+                e0 = __ldg(a.rng_rowptr + my_row);
+                e1 = __ldg(a.rng_rowptr + my_row + 1);
+                for (int e = e0; e < e1; ++e) {
+                    const int id = __ldg(a.rng_id + e);
+                    for (int j = 0; j < R4_MAX_IDS; ++j) {
+                        const int old = atomicCAS(&rng_ids[j], -1, id);
+                        if (old == -1 || old == id) break;
+                    }
+                }
+            }
+            __syncthreads();
+            for (int j = 0; j < R4_MAX_IDS; ++j) {
+                const int id = rng_ids[j];
+                if (id < 0) break;                             // uniform
+                const int lo = __ldg(a.rng_lo + id), hi = __ldg(a.rng_hi + id);
+                float acc[FG];
+#pragma unroll
+                for (int o = 0; o < FG; ++o) acc[o] = 0.f;
+                for (int rr = lo + tid; rr < hi; rr += R4_THREADS) {
+                    const RowV<FG> gv = gp(rr);
+#pragma unroll
+                    for (int o = 0; o < FG; ++o) acc[o] += gv.v[o];
+                }
+#pragma unroll
+                for (int o = 0; o < FG; ++o) {
+                    acc[o] = warp_sum(acc[o]);
+                    if (lane == 0) red[warp * FG + o] = acc[o];
+                }
+                __syncthreads();
+                if (tid < FG) {
+                    float v = 0.f;
+                    for (int w = 0; w < R4_THREADS / 32; ++w) v += red[w * FG + tid];
+                    rng_sum[j * FG + tid] = v;
+                }
+                __syncthreads();
+            }
+            if (tid < nf) {
+                float T[NT][FG];
+#pragma unroll
+                for (int t = 0; t < NT; ++t)
+#pragma unroll
+                    for (int o = 0; o < FG; ++o) T[t][o] = 0.f;
+                for (int e = e0; e < e1; ++e) {
+                    const int id = __ldg(a.rng_id + e);
+                    const float v = __ldg(a.rng_val + e);
+                    int j = 0;
+                    while (j < R4_MAX_IDS && rng_ids[j] != id) ++j;
+                    if (j < R4_MAX_IDS) {
+#pragma unroll
+                        for (int o = 0; o < FG; ++o) T[2][o] = fmaf(v, rng_sum[j * FG + o], T[2][o]);
+                    } else {        // more distinct ranges than table slots: serial sum (correct, slow, rare)
+                        for (int rr = __ldg(a.rng_lo + id); rr < __ldg(a.rng_hi + id); ++rr) {
+                            const RowV<FG> gv = gp(rr);
+#pragma unroll
+                            for (int o = 0; o < FG; ++o) T[2][o] = fmaf(v, gv.v[o], T[2][o]);
+                        }
+                    }
+                }
+                finish(my_row, T, true, false);                // the delta of everything that is linear in T[2]
+            }
+        }
+    } else if (FC > 0) {
+        float* const gX = a.gXc;
+        const bool stats = FC == 4 && a.acc_b_cross != nullptr && gX != nullptr;
+        const int ncta = gridDim.x - a.ctas_self;
+        for (int row = (blockIdx.x - a.ctas_self) * R4_THREADS + tid; row < a.R_cross; row += ncta * R4_THREADS) {
+            float T[2][FG];
+#pragma unroll
+            for (int o = 0; o < FG; ++o) { T[0][o] = 0.f; T[1][o] = 0.f; }
+            const int k0 = __ldg(a.pt_rowptr + row), k1 = __ldg(a.pt_rowptr + row + 1);
+            for (int k = k0; k < k1; k += 4) {
+                int c[4];
+                float vm[4], vd[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const bool on = k + j < k1;
+                    c[j] = on ? __ldg(a.pt_col + k + j) : -1;
+                    vm[j] = on ? __ldg(a.pt_pm + k + j) : 0.f;
+                    vd[j] = on ? __ldg(a.pt_pd + k + j) : 0.f;
+                }
+                RowV<FG> gv[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    if (c[j] >= 0) {
+                        gv[j] = gp(c[j]);
+                    } else {
+#pragma unroll
+                        for (int o = 0; o < FG; ++o) gv[j].v[o] = 0.f;
+                    }
+                }
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+#pragma unroll
+                    for (int o = 0; o < FG; ++o) {
+                        T[0][o] = fmaf(vm[j], gv[j].v[o], T[0][o]);
+                        T[1][o] = fmaf(vd[j], gv[j].v[o], T[1][o]);
+                    }
+            }
+            const RowV<FCC> xr = ldrow<FCC>(a.Xc, row);
+            float xn[FCC], g[FCC];
+#pragma unroll
+            for (int f = 0; f < FCC; ++f) { xn[f] = fmaf(xr.v[f], bxc.sc[f], bxc.sh[f]); g[f] = 0.f; }
+#pragma unroll
+            for (int t = 0; t < 2; ++t)
+#pragma unroll
+                for (int o = 0; o < FG; ++o)
+#pragma unroll
+                    for (int f = 0; f < FCC; ++f) {
+                        g[f] = fmaf(T[t][o], Wc[(t * FG + o) * FCC + f], g[f]);
+                        dw[(t * FG + o) * FCC + f] = fmaf(T[t][o], xn[f], dw[(t * FG + o) * FCC + f]);
+                    }
+            if (gX) {
+#pragma unroll
+                for (int f = 0; f < FCC; ++f) {
+                    float v = g[f];
+                    if (a.acc_cross) v += gX[(size_t)row * FCC + f];
+                    gX[(size_t)row * FCC + f] = v;
+                }
+                if (stats) {
+#pragma unroll
+                    for (int f = 0; f < FCC; ++f) {
+                        sg[f & 3] += g[f];
+                        sgx[f & 3] = fmaf(g[f], (xr.v[f] - bxc.mu[f]) * bxc.rs[f], sgx[f & 3]);
+                    }
+                }
+            }
+        }
+    }
+    // ---- flush: reduce-scatter butterflies -> per-warp rows in shared memory -> one fp64 atomic per value
+    const int nvals = is_self ? NDS : NDC;
+    const int fx = is_self ? FS : FCC;
+    const int nbw = hgnn_ws_bins(FG * a.Cin);
+    const int col_base = is_self ? 0 : a.col0_cross;
+    __syncthreads();
+    warp_reduce_scatter<float, 64>(dw);                        // lane l: totals of values 2l, 2l + 1
+    red[warp * 64 + 2 * lane] = dw[0];
+    red[warp * 64 + 2 * lane + 1] = dw[1];
+    __syncthreads();
+    if (a.dW_bins)
+        for (int i = tid; i < nvals; i += R4_THREADS) {
+            float v = 0.f;
+            for (int w = 0; w < R4_THREADS / 32; ++w) v += red[w * 64 + i];
+            const int t = i / (FG * fx), o = (i / fx) % FG, f = i % fx;
+            accum_add(a.dW_bins, FG * a.Cin, nbw, o * a.Cin + col_base + t * fx + f, (double)v);
+        }
+    __syncthreads();
+    float extra[16];
+#pragma unroll
+    for (int f = 0; f < 4; ++f) { extra[f] = db[f]; extra[4 + f] = sg[f]; extra[8 + f] = sgx[f]; extra[12 + f] = 0.f; }
+    warp_reduce_scatter<float, 16>(extra);                     // lane l: total of value l >> 1
+    if ((lane & 1) == 0) red[warp * 64 + (lane >> 1)] = extra[0];
+    __syncthreads();
+    if (tid < 12) {
+        double v = 0.0;
+        for (int w = 0; w < R4_THREADS / 32; ++w) v += (double)red[w * 64 + tid];
+        if (tid < 4) {
+            if (tid < FG && is_self && a.db_bins) accum_add(a.db_bins, FG, hgnn_ws_bins(FG), tid, v);
+        } else {
+            double* accb = is_self ? a.acc_b_self : a.acc_b_cross;
+            float* gXp = is_self ? a.gXs : a.gXc;
+            const bool wide4 = is_self ? FS == 4 : FC == 4;
+            if (wide4 && accb && gXp) accum_add(accb, 8, hgnn_ws_bins(8), tid - 4, v);
+        }
+    }
+}
