@@ -477,8 +477,11 @@ __device__ __forceinline__ float4 gpre_gather(const Gpre4& gp, const int* __rest
 // over the x1 rows saved by the forward on a parallel graph branch): ~48 fewer live registers.
 // GB / CB: entries per gather batch of the self part (first transposed operator) / of the cross part,
 // picked by the host from the average row lengths so that a typical row needs one batch.
+#ifndef R4_BWD_MIN_CTAS
+#define R4_BWD_MIN_CTAS 1
+#endif
 template <int NCSR, bool DW, int GB, int CB>
-__global__ void __launch_bounds__(R4_THREADS)
+__global__ void __launch_bounds__(R4_THREADS, R4_BWD_MIN_CTAS)
 bwd_row4_kernel(const Bwd4Args a) {
     constexpr int NT = 2 + NCSR;                          // self blocks
     __shared__ __align__(16) float Ws[NT * 4 * 4];        // [t][o][f] = W[o][t*4+f]
