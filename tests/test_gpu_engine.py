@@ -39,7 +39,10 @@ def _run(model, batch, use_engine, train=True):
 
 @pytest.mark.parametrize("kind,order,h,J,N", [("lg", 1, 2, 1, 300), ("lg", 2, 2, 1, 200), ("lg", 3, 4, 1, 200),
                                               ("lg", 1, 8, 2, 60), ("simple", 0, 2, 1, 300),
-                                              ("simple", 0, 16, 2, 100), ("lg", 1, 32, 1, 100)])
+                                              ("simple", 0, 16, 2, 100), ("lg", 1, 32, 1, 100),
+                                              # J = 2 at the script-default width: the two-CSR-operator variants of the
+                                              # thread-per-row kernels (engine_row4.cuh / engine_rowg.cuh)
+                                              ("lg", 1, 2, 2, 80), ("lg", 3, 2, 2, 80), ("simple", 0, 2, 2, 120)])
 def test_engine_matches_module_path(kind, order, h, J, N):
     import hgnn_b200  # noqa: F401
     from hgnn_b200 import synth
@@ -174,3 +177,36 @@ def test_generic_engine_kernels_at_width4():
                         "matches_module_path and (lg-1-2-1-300 or lg-2-2-1-200 or simple-0-2-1-300)"],
                        env=env, capture_output=True, text=True, cwd=root, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+@pytest.mark.parametrize("kind,order", [("lg", 1), ("lg", 2), ("simple", 0)])
+def test_engine_single_output_regression_head(kind, order):
+    """dim_output = 1 (the QM9 regression head, scripts/main_gnn_qm9.py): the width-1 readout variants of the
+    thread-per-row kernels against the per-module path, MSE loss."""
+    import hgnn_b200  # noqa: F401
+    from hgnn_b200 import engine, synth
+    from hgnn_b200.functions.batching import prepare_batch
+    from hgnn_b200.models.gnns.model_mnb import GNN_lg, GNN_simple
+    torch.manual_seed(11 + order)
+    batch = prepare_batch(synth.qm9_shaped_dataset(24), 0, 1)
+    X, W, T, XL, WL, Pm, Pd, mask, mask_lg, N_batch, E_batch = batch
+    model = (GNN_lg(0, 2, 4, 5, 1, 1, order) if kind == "lg" else GNN_simple(0, 2, 4, 5, 1, 1)).cuda().train()
+    twin = copy.deepcopy(model)
+    res = []
+    for m, use in ((model, True), (twin, False)):
+        old = engine.supported
+        engine.supported = (lambda _m: True) if use else (lambda _m: False)
+        try:
+            Xc = X.cuda().requires_grad_()
+            out = (m([Xc, XL.cuda(), W, WL, Pm, Pd], N_batch, mask, E_batch, mask_lg) if kind == "lg"
+                   else m([Xc, W], N_batch, mask))
+            torch.nn.functional.mse_loss(out, T.cuda()).backward()
+        finally:
+            engine.supported = old
+        g = {k: v.grad.detach().clone() for k, v in m.named_parameters()}
+        g["X"], g["out"] = Xc.grad.clone(), out.detach().clone()
+        res.append(g)
+    assert res[0]["out"].shape == (24, 1)
+    fl = 0.1 * max(float(v.abs().max()) for k, v in res[1].items() if k not in ("X", "out"))
+    for k in res[1]:
+        assert rel_err(res[0][k].cpu(), res[1][k].cpu(), fl if k not in ("X", "out") else 0.0) < 1e-4, k
