@@ -393,7 +393,7 @@ def run_ours(a):
     # ---- end to end through the public API: host instances -> prepare_batch -> step -> loss.item()
     e2e = None
     if not a.skip_e2e:
-        e2e_steps = max(3, min(a.steps, 20))
+        e2e_steps = 50 if a.steps >= 20 else max(3, a.steps)    # ~0.1 s per loop: one host hiccup must not dominate
         for k in range(6):      # warm-up: pinned slabs / staging slots / allocator pools reach steady state
             db, _ = to_device(prepare_batch(host_batches[k % n_host_batches], 0, a.J))
             train_step(db).item()
