@@ -22,6 +22,7 @@
 // Reference semantics are unchanged (models/layers/layers_mnb.py:52-69,189-225,256-290,322-358,
 // batch_normalization.py:34-43,65-93); parity is tested against the same golden vectors.
 #include <stdlib.h>
+#include <string.h>
 #include "common.cuh"
 
 #define ENG_THREADS 256
@@ -1286,10 +1287,14 @@ static bool eng_try_bwd_row4(const hgnn_side_bwd_t* d, hgnn_stream_t stream) {
     // with 17 % of the CTAs and 3x the work per thread.
     const double avg_s = (double)d->ops_T[2].nnz / d->R_self;
     const double avg_c = d->R_cross > 0 ? (double)d->pt_nnz / d->R_cross : 0.0;
-    static double w_entry = -1.0;
-    if (w_entry < 0.0) { const char* e = getenv("HGNN_B200_BWD_ENTRY_COST"); w_entry = e ? atof(e) : 0.2; }
-    const double cost_s = (double)d->R_self * (1.0 + w_entry * avg_s);
-    const double cost_c = d->R_cross > 0 ? (double)d->R_cross * (1.0 + w_entry * avg_c) : 0.0;
+    static double w_self = -1.0, w_cross = -1.0;
+    if (w_self < 0.0) {
+        w_self = 0.2; w_cross = 0.2;      // measured optimum of the uniform weight (profiles/README.md)
+        const char* e = getenv("HGNN_B200_BWD_ENTRY_COST");      // "w_self,w_cross" (tuning aid)
+        if (e) { w_self = atof(e); const char* c = strchr(e, ','); w_cross = c ? atof(c + 1) : w_self; }
+    }
+    const double cost_s = (double)d->R_self * (1.0 + w_self * avg_s);
+    const double cost_c = d->R_cross > 0 ? (double)d->R_cross * (1.0 + w_cross * avg_c) : 0.0;
     bool big_s = false, big_c = false;      // measured: the small batches win in the backward (register pressure)
     static int bforce = -2;
     if (bforce == -2) { const char* e = getenv("HGNN_B200_BWD_BATCH"); bforce = e ? atoi(e) : -1; }  // 0: (2,4), 1: (8,4), 2: (2,8)
