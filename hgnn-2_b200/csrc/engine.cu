@@ -1377,6 +1377,14 @@ static bool eng_try_bwd_rowg(const hgnn_side_bwd_t* d, hgnn_stream_t stream) {
     return done;
 }
 
+// profiling aid: copies (start ns, end ns, is_self) of the first n CTAs of the last width-4 backward launch
+extern "C" int hgnn_debug_cta_times(unsigned long long* out, int n) {
+    HGNN_REQUIRE(out && n > 0 && n <= 2048, "bad argument");
+    cudaError_t e = cudaMemcpyFromSymbol(out, eng::g_cta_times, (size_t)n * 3 * sizeof(unsigned long long));
+    if (e != cudaSuccess) { hgnn_set_error("hgnn_debug_cta_times: %s", cudaGetErrorString(e)); return HGNN_ERR_CUDA; }
+    return HGNN_OK;
+}
+
 extern "C" int hgnn_lg_side_dw(const float* gY, const float* Z, int R, int relu_from, const double* acc_f,
                                const double* acc_b, const float* bn_weight, const float* X1, int Cin,
                                double* dW_bins, double* db_bins, hgnn_stream_t stream) {

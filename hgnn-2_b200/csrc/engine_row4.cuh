@@ -424,7 +424,7 @@ struct Bwd4Args {
     const float* Xc; BnRef bn_c; float* gXc; int acc_cross; double* acc_b_cross;
     int col0_cross;
     int ctas_self;        // CTAs [0, ctas_self) work on the self rows
-    int ablate;           // timing experiments only (HGNN_B200_ABLATE): 1 no gathers, 2 no range phase, 4 no flush
+    int ablate;           // timing experiments only (HGNN_B200_ABLATE): 1 no gathers, 2 no range phase, 4 no flush, 8 CTA times
 };
 
 struct Gpre4 {
@@ -475,10 +475,18 @@ __device__ __forceinline__ float4 gpre_gather(const Gpre4& gp, const int* __rest
 
 // DW = false: the gather-only variant (the weight gradients come from dw_row4_kernel, which streams
 // over the x1 rows saved by the forward on a parallel graph branch): ~48 fewer live registers.
+// profiling aid (HGNN_B200_ABLATE bit 8): per-CTA start / end / role of the last backward launch
+__device__ unsigned long long g_cta_times[2048 * 3];
+__device__ __forceinline__ unsigned long long global_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+
 // GB / CB: entries per gather batch of the self part (first transposed operator) / of the cross part,
 // picked by the host from the average row lengths so that a typical row needs one batch.
 #ifndef R4_BWD_MIN_CTAS
-#define R4_BWD_MIN_CTAS 1
+#define R4_BWD_MIN_CTAS 4     // <= 128 registers = 4 CTAs per SM; without the bound ptxas takes 153 (3 CTAs per SM: 1.01 instead of 0.96 ms per step)
 #endif
 template <int NCSR, bool DW, int GB, int CB>
 __global__ void __launch_bounds__(R4_THREADS, R4_BWD_MIN_CTAS)
@@ -494,6 +502,10 @@ bwd_row4_kernel(const Bwd4Args a) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const bool is_self = (int)blockIdx.x < a.ctas_self;
     pdl_launch_dependents();
+    if ((a.ablate & 8) && tid == 0 && blockIdx.x < 2048) {
+        g_cta_times[blockIdx.x * 3] = global_ns();
+        g_cta_times[blockIdx.x * 3 + 2] = is_self ? 1 : 0;
+    }
     // ---- phase 0 (parameters only; under PDL this overlaps the producer's tail)
     if (tid == 0) n_flagged = 0;
     for (int i = tid; i < NT * 16; i += R4_THREADS) {
@@ -799,6 +811,7 @@ bwd_row4_kernel(const Bwd4Args a) {
             if (accb && gXp) accum_add(accb, 8, hgnn_ws_bins(8), tid - 4, v);
         }
     }
+    if ((a.ablate & 8) && tid == 0 && blockIdx.x < 2048) g_cta_times[blockIdx.x * 3 + 1] = global_ns();
 }
 
 // ---------------------------------------------------------------------------------------------
