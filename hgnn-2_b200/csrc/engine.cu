@@ -1248,6 +1248,28 @@ static bool eng_plan_part(eng::BwdPart& p, int Fg, bool vec4, bool& vout4, bool 
     return p.smem <= ENG_MAX_SMEM;
 }
 
+// CTAs of a backward launch that work on the self rows.  Every thread walks WHOLE rows one after the other, so
+// what matters is the integer number of rows of the slowest thread of each part: the split minimises
+// max(ceil(rows_self / threads_self) * row cost_self, ceil(rows_cross / threads_cross) * row cost_cross); ties go to the
+// split closest to the cost-proportional one.  (A proportional split left e.g. 1.3 rows per thread on the heavy
+// part - a third of its threads did two rows and set the kernel time: profiles/logs/cta_times_*.log.)
+static int eng_split_ctas(int grid, long long R_self, long long R_cross, double cost_s, double cost_c) {
+    if (R_cross <= 0) return grid;
+    if (grid < 2) return 1;
+    const double row_s = cost_s / (double)R_self, row_c = cost_c / (double)R_cross;
+    const double prop = grid * cost_s / (cost_s + cost_c);
+    int best = 1;
+    double best_t = 1e300, best_d = 1e300;
+    for (int cs = 1; cs <= grid - 1; ++cs) {
+        const long long ts = (long long)cs * R4_THREADS, tc = (long long)(grid - cs) * R4_THREADS;
+        const double t_s = (double)((R_self + ts - 1) / ts) * row_s, t_c = (double)((R_cross + tc - 1) / tc) * row_c;
+        const double t = t_s > t_c ? t_s : t_c;
+        const double dist = cs > prop ? cs - prop : prop - cs;
+        if (t < best_t - 1e-12 || (t < best_t + 1e-12 && dist < best_d)) { best_t = t; best_d = dist; best = cs; }
+    }
+    return best;
+}
+
 static bool eng_try_bwd_row4(const hgnn_side_bwd_t* d, hgnn_stream_t stream) {
     if (eng_row4_disabled()) return false;
     if (d->Fg != 4 || d->R_self <= 0 || d->Fs != 4 || !eng_row4_ops(d->ops_T, d->n_ops)) return false;
@@ -1289,7 +1311,7 @@ static bool eng_try_bwd_row4(const hgnn_side_bwd_t* d, hgnn_stream_t stream) {
     const double avg_c = d->R_cross > 0 ? (double)d->pt_nnz / d->R_cross : 0.0;
     static double w_self = -1.0, w_cross = -1.0;
     if (w_self < 0.0) {
-        w_self = 0.2; w_cross = 0.2;      // measured optimum of the uniform weight (profiles/README.md)
+        w_self = 0.6; w_cross = 0.3;      // per-row cost ratios measured with profiles/cta_times.py
         const char* e = getenv("HGNN_B200_BWD_ENTRY_COST");      // "w_self,w_cross" (tuning aid)
         if (e) { w_self = atof(e); const char* c = strchr(e, ','); w_cross = c ? atof(c + 1) : w_self; }
     }
@@ -1297,21 +1319,19 @@ static bool eng_try_bwd_row4(const hgnn_side_bwd_t* d, hgnn_stream_t stream) {
     const double cost_c = d->R_cross > 0 ? (double)d->R_cross * (1.0 + w_cross * avg_c) : 0.0;
     bool big_s = false, big_c = false;      // measured: the small batches win in the backward (register pressure)
     static int bforce = -2;
-    if (bforce == -2) { const char* e = getenv("HGNN_B200_BWD_BATCH"); bforce = e ? atoi(e) : -1; }  // 0: (2,4), 1: (8,4), 2: (2,8)
-    if (bforce >= 0) { big_s = bforce == 1; big_c = bforce == 2; }
+    if (bforce == -2) { const char* e = getenv("HGNN_B200_BWD_BATCH"); bforce = e ? atoi(e) : -1; }  // 0: (2,4), 1: (8,4), 2: (2,8), 3: (4,4)
+    bool mid_s = false;
+    if (bforce >= 0) { big_s = bforce == 1; big_c = bforce == 2; mid_s = bforce == 3; }
 #define R4_BWD(NCSR, DW, GB, CB)                                                                          \
     {                                                                                                     \
         const int cap = eng_resident_impl((const void*)eng::bwd_row4_kernel<NCSR, DW, GB, CB>, 0, R4_THREADS); \
         int grid = (int)min((long long)cap, (rows + R4_THREADS - 1) / R4_THREADS);                        \
         if (d->R_cross > 0 && grid < 2) grid = 2;                                                         \
-        int cs = d->R_cross > 0 ? (int)(grid * cost_s / (cost_s + cost_c) + 0.5) : grid;                  \
-        if (cs < 1) cs = 1;                                                                               \
-        if (d->R_cross > 0 && cs > grid - 1) cs = grid - 1;                                               \
-        a.ctas_self = cs;                                                                                 \
+        a.ctas_self = eng_split_ctas(grid, d->R_self, d->R_cross > 0 ? d->R_cross : 0, cost_s, cost_c);   \
         eng_launch(eng::bwd_row4_kernel<NCSR, DW, GB, CB>, grid, R4_THREADS, 0, s, a);                    \
     }
 #define R4_BWD_B(NCSR, DW)                                                                                \
-    if (big_s) R4_BWD(NCSR, DW, 8, 4) else if (big_c) R4_BWD(NCSR, DW, 2, 8) else R4_BWD(NCSR, DW, 2, 4)
+    if (big_s) R4_BWD(NCSR, DW, 8, 4) else if (big_c) R4_BWD(NCSR, DW, 2, 8) else if (mid_s) R4_BWD(NCSR, DW, 4, 4) else R4_BWD(NCSR, DW, 2, 4)
     if (d->skip_dw) { if (a.n_csr == 1) { R4_BWD_B(1, false) } else { R4_BWD_B(2, false) } }
     else { if (a.n_csr == 1) { R4_BWD_B(1, true) } else { R4_BWD_B(2, true) } }
 #undef R4_BWD_B
@@ -1354,18 +1374,15 @@ static bool eng_try_bwd_rowg(const hgnn_side_bwd_t* d, hgnn_stream_t stream) {
     const long long rows = (long long)d->R_self + a.R_cross;
     const double avg_s = (double)d->ops_T[2].nnz / d->R_self;
     const double avg_c = a.R_cross > 0 ? (double)d->pt_nnz / a.R_cross : 0.0;
-    const double cost_s = (double)d->R_self * (1.0 + 0.2 * avg_s);
-    const double cost_c = a.R_cross > 0 ? (double)a.R_cross * (1.0 + 0.2 * avg_c) : 0.0;
+    const double cost_s = (double)d->R_self * (1.0 + 0.6 * avg_s);
+    const double cost_c = a.R_cross > 0 ? (double)a.R_cross * (1.0 + 0.3 * avg_c) : 0.0;
     bool done = false;
 #define RG_BWD(NCSR, FG, FS, FC)                                                                           \
     if (!done && a.n_csr == NCSR && Fg == FG && Fs == FS && Fc == FC) {                                    \
         const int cap = eng_resident_impl((const void*)eng::bwd_rowg_kernel<NCSR, FG, FS, FC>, 0, R4_THREADS); \
         int grid = (int)min((long long)cap, (rows + R4_THREADS - 1) / R4_THREADS);                         \
         if (a.R_cross > 0 && grid < 2) grid = 2;                                                           \
-        int cs = a.R_cross > 0 ? (int)(grid * cost_s / (cost_s + cost_c) + 0.5) : grid;                    \
-        if (cs < 1) cs = 1;                                                                                \
-        if (a.R_cross > 0 && cs > grid - 1) cs = grid - 1;                                                 \
-        a.ctas_self = cs;                                                                                  \
+        a.ctas_self = eng_split_ctas(grid, d->R_self, a.R_cross, cost_s, cost_c);                          \
         eng_launch(eng::bwd_rowg_kernel<NCSR, FG, FS, FC>, grid, R4_THREADS, 0, s, a);                     \
         done = true;                                                                                       \
     }
@@ -1382,6 +1399,14 @@ extern "C" int hgnn_debug_cta_times(unsigned long long* out, int n) {
     HGNN_REQUIRE(out && n > 0 && n <= 2048, "bad argument");
     cudaError_t e = cudaMemcpyFromSymbol(out, eng::g_cta_times, (size_t)n * 3 * sizeof(unsigned long long));
     if (e != cudaSuccess) { hgnn_set_error("hgnn_debug_cta_times: %s", cudaGetErrorString(e)); return HGNN_ERR_CUDA; }
+    return HGNN_OK;
+}
+
+// (end of the row loop ns, end of the range phase ns, flagged rows) of the self CTAs of the same launch
+extern "C" int hgnn_debug_cta_phases(unsigned long long* out, int n) {
+    HGNN_REQUIRE(out && n > 0 && n <= 2048, "bad argument");
+    cudaError_t e = cudaMemcpyFromSymbol(out, eng::g_cta_phase, (size_t)n * 3 * sizeof(unsigned long long));
+    if (e != cudaSuccess) { hgnn_set_error("hgnn_debug_cta_phases: %s", cudaGetErrorString(e)); return HGNN_ERR_CUDA; }
     return HGNN_OK;
 }
 

@@ -477,6 +477,7 @@ __device__ __forceinline__ float4 gpre_gather(const Gpre4& gp, const int* __rest
 // over the x1 rows saved by the forward on a parallel graph branch): ~48 fewer live registers.
 // profiling aid (HGNN_B200_ABLATE bit 8): per-CTA start / end / role of the last backward launch
 __device__ unsigned long long g_cta_times[2048 * 3];
+__device__ unsigned long long g_cta_phase[2048 * 3];   // end of row loop, end of range phase, number of flagged rows
 __device__ __forceinline__ unsigned long long global_ns() {
     unsigned long long t;
     asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
@@ -621,6 +622,7 @@ bwd_row4_kernel(const Bwd4Args a) {
                 }
             }
         }
+        if ((a.ablate & 8) && tid == 0 && blockIdx.x < 2048) g_cta_phase[blockIdx.x * 3] = global_ns();
         // ---- run-length parts of the flagged rows.  (1) the distinct range ids they refer to (a CTA's
         //      rows lie in one or two graphs, so one or two ids), (2) each range sum once per CTA,
         //      cooperatively, (3) every flagged row finished by its own thread, in parallel: the delta of
@@ -649,9 +651,12 @@ bwd_row4_kernel(const Bwd4Args a) {
                 if (id < 0) break;                     // uniform
                 const int lo = __ldg(a.rng_lo + id), hi = __ldg(a.rng_hi + id);
                 float4 acc = f4_zero();
-                for (int rr = lo + tid; rr < hi; rr += R4_THREADS) {
-                    const float4 gv = gp(rr);
-                    acc.x += gv.x; acc.y += gv.y; acc.z += gv.z; acc.w += gv.w;
+                for (int rr = lo + tid; rr < hi; rr += 4 * R4_THREADS) {      // 4 rows (8 loads) in flight per thread
+                    float4 gv[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) gv[u] = rr + u * R4_THREADS < hi ? gp(rr + u * R4_THREADS) : f4_zero();
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) { acc.x += gv[u].x; acc.y += gv[u].y; acc.z += gv[u].z; acc.w += gv[u].w; }
                 }
                 acc.x = warp_sum(acc.x); acc.y = warp_sum(acc.y); acc.z = warp_sum(acc.z); acc.w = warp_sum(acc.w);
                 if (lane == 0) { red[warp * 4] = acc.x; red[warp * 4 + 1] = acc.y; red[warp * 4 + 2] = acc.z; red[warp * 4 + 3] = acc.w; }
@@ -708,6 +713,10 @@ bwd_row4_kernel(const Bwd4Args a) {
                     }
                 }
             }
+        }
+        if ((a.ablate & 8) && tid == 0 && blockIdx.x < 2048) {
+            g_cta_phase[blockIdx.x * 3 + 1] = global_ns();
+            g_cta_phase[blockIdx.x * 3 + 2] = (unsigned long long)n_flagged;
         }
     } else {
         float* const gX = a.gXc;

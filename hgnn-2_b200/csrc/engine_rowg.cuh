@@ -458,10 +458,21 @@ bwd_rowg_kernel(const Bwd4Args a) {
                 float acc[FG];
 #pragma unroll
                 for (int o = 0; o < FG; ++o) acc[o] = 0.f;
-                for (int rr = lo + tid; rr < hi; rr += R4_THREADS) {
-                    const RowV<FG> gv = gp(rr);
+                for (int rr = lo + tid; rr < hi; rr += 4 * R4_THREADS) {      // 4 rows in flight per thread
+                    RowV<FG> gv[4];
 #pragma unroll
-                    for (int o = 0; o < FG; ++o) acc[o] += gv.v[o];
+                    for (int u = 0; u < 4; ++u) {
+                        if (rr + u * R4_THREADS < hi) {
+                            gv[u] = gp(rr + u * R4_THREADS);
+                        } else {
+#pragma unroll
+                            for (int o = 0; o < FG; ++o) gv[u].v[o] = 0.f;
+                        }
+                    }
+#pragma unroll
+                    for (int u = 0; u < 4; ++u)
+#pragma unroll
+                        for (int o = 0; o < FG; ++o) acc[o] += gv[u].v[o];
                 }
 #pragma unroll
                 for (int o = 0; o < FG; ++o) {

@@ -31,7 +31,10 @@ def rec(name, *args):
         if kind not in seen or seen[kind][0] < 2:          # keep the third launch of each kind (warm)
             buf = (ctypes.c_ulonglong * (3 * 592))()
             orig("hgnn_debug_cta_times", buf, 592)
-            seen[kind] = (seen.get(kind, (0, None))[0] + 1, np.array(buf, dtype=np.int64).reshape(-1, 3))
+            ph = (ctypes.c_ulonglong * (3 * 592))()
+            orig("hgnn_debug_cta_phases", ph, 592)
+            seen[kind] = (seen.get(kind, (0, None))[0] + 1, np.array(buf, dtype=np.int64).reshape(-1, 3),
+                          np.array(ph, dtype=np.int64).reshape(-1, 3))
     return rc
 
 
@@ -42,7 +45,7 @@ for _ in range(2):
     out = model([Xd, XLd, W, WL, Pm, Pd], N_batch, mask, E_batch, mask_lg)
     torch.nn.functional.cross_entropy(out, y).backward()
 torch.cuda.synchronize()
-for kind, (_, t) in seen.items():
+for kind, (_, t, ph) in seen.items():
     t0 = t[:, 0].min()
     start, end, role = (t[:, 0] - t0) / 1e3, (t[:, 1] - t0) / 1e3, t[:, 2]
     dur = end - start
@@ -52,5 +55,16 @@ for kind, (_, t) in seen.items():
         if m.any():
             print("   %-5s CTAs %3d: duration min %.1f  median %.1f  p90 %.1f  max %.1f us; last end %.1f us"
                   % (name, m.sum(), dur[m].min(), np.median(dur[m]), np.percentile(dur[m], 90), dur[m].max(), end[m].max()))
+    selfs = np.nonzero(role == 1)[0]
+    loop_end, rng_end, nfl = (ph[:, 0] - t0) / 1e3, (ph[:, 1] - t0) / 1e3, ph[:, 2]
+    fl = selfs[nfl[selfs] > 0]
+    nofl = selfs[nfl[selfs] == 0]
+    if fl.size:
+        print("   self CTAs with flagged rows %d: row loop ends median %.1f, range phase takes median %.1f max %.1f us, "
+              "kernel end median %.1f; without flagged rows %d: row loop ends median %.1f max %.1f, end median %.1f max %.1f"
+              % (fl.size, np.median(loop_end[fl]), np.median(rng_end[fl] - loop_end[fl]), (rng_end[fl] - loop_end[fl]).max(),
+                 np.median(end[fl]), nofl.size, np.median(loop_end[nofl]), loop_end[nofl].max(), np.median(end[nofl]), end[nofl].max()))
     slow = np.argsort(-end)[:8]
+    print("   slowest: (index, flagged rows, row loop end, range phase end, end):",
+          [(int(i), int(nfl[i]), round(float(loop_end[i]), 1), round(float(rng_end[i]), 1), round(float(end[i]), 1)) for i in slow if role[i] == 1])
     print("   slowest CTAs (index, role, start, end):", [(int(i), "self" if role[i] else "cross", round(float(start[i]), 1), round(float(end[i]), 1)) for i in slow])
