@@ -28,7 +28,7 @@ MAX_OPS = 8
 class OpT(ctypes.Structure):
     _fields_ = [("kind", c_int), ("diag", c_void), ("rowptr", c_void), ("col", c_void),
                 ("val", c_void), ("rng_rowptr", c_void), ("rng_id", c_void), ("rng_val", c_void),
-                ("rng_lo", c_void), ("rng_hi", c_void), ("nnz", c_ll)]
+                ("rng_lo", c_void), ("rng_hi", c_void), ("nnz", c_ll), ("rng_n", c_int)]
 
 
 class SideT(ctypes.Structure):
@@ -51,7 +51,8 @@ class SideBwdT(ctypes.Structure):
                 ("acc_b_self", c_void),
                 ("R_cross", c_int), ("pt_rowptr", c_void), ("pt_col", c_void), ("pt_pm", c_void),
                 ("pt_pd", c_void), ("Xc", c_void), ("Fc", c_int), ("bn_cross", BnRefT), ("gXc", c_void),
-                ("accumulate_cross", c_int), ("acc_b_cross", c_void), ("skip_dw", c_int), ("pt_nnz", c_ll)]
+                ("accumulate_cross", c_int), ("acc_b_cross", c_void), ("skip_dw", c_int), ("pt_nnz", c_ll),
+                ("rng_scratch", c_void)]
 
 
 class ProgTensorT(ctypes.Structure):
@@ -87,7 +88,7 @@ class BatchT(ctypes.Structure):
 _P = c_void
 _SIGS = {
     "hgnn_program_fwd": [ctypes.POINTER(ProgramT), ctypes.POINTER(BatchT), _P, _P, _P, _P, _P, _P, _P, _P],
-    "hgnn_program_bwd": [ctypes.POINTER(ProgramT), ctypes.POINTER(BatchT), _P, _P, _P, _P, _P, _P, _P, _P, _P, _P],
+    "hgnn_program_bwd": [ctypes.POINTER(ProgramT), ctypes.POINTER(BatchT), _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, c_ll, _P],
     "hgnn_bn_running_update_k": [_P, _P, _P, _P, c_int, c_int, _P, c_int, c_float, _P, _P],
     "hgnn_host_pack_fill": [c_int, _P, c_int, c_int, _P, _P, c_int],
     "hgnn_pack_device_upload": [c_int, _P, c_int, c_int, _P, _P, _P, _P, _P],
@@ -136,7 +137,7 @@ _SIGS = {
 EXPORTS = sorted(list(_SIGS) + ["hgnn_last_error", "hgnn_version", "hgnn_workspace_bytes", "hgnn_bins_for",
                                 "hgnn_program_work_floats", "hgnn_program_launches", "hgnn_host_pack_n_keys",
                                 "hgnn_host_pack_key", "hgnn_host_pack_layout", "hgnn_host_pack_last_ns",
-                                "hgnn_pack_device_plan"])
+                                "hgnn_pack_device_plan", "hgnn_lg_rng_scratch_bytes", "hgnn_program_rng_scratch_bytes"])
 
 for _name, _args in _SIGS.items():
     _fn = getattr(lib, _name)
@@ -155,6 +156,10 @@ lib.hgnn_program_launches.restype = c_ll
 lib.hgnn_program_launches.argtypes = []
 lib.hgnn_host_pack_last_ns.restype = c_ll
 lib.hgnn_host_pack_last_ns.argtypes = [c_int]
+lib.hgnn_lg_rng_scratch_bytes.restype = c_ll
+lib.hgnn_lg_rng_scratch_bytes.argtypes = [c_int]
+lib.hgnn_program_rng_scratch_bytes.restype = c_ll
+lib.hgnn_program_rng_scratch_bytes.argtypes = [ctypes.POINTER(ProgramT), ctypes.POINTER(BatchT)]
 lib.hgnn_pack_device_plan.restype = c_ll
 lib.hgnn_pack_device_plan.argtypes = [c_int, _P, c_int, c_int, _P, _P, _P]
 lib.hgnn_host_pack_n_keys.restype = c_int
@@ -266,4 +271,5 @@ def make_ops(descs):
                 r = d[4]
                 arr[i].rng_rowptr, arr[i].rng_id, arr[i].rng_val = iptr(r[0]), iptr(r[1]), fptr(r[2])
                 arr[i].rng_lo, arr[i].rng_hi = iptr(r[3]), iptr(r[4])
+                arr[i].rng_n = r[3].numel()
     return arr, n

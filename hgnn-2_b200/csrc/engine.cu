@@ -1270,6 +1270,18 @@ static int eng_split_ctas(int grid, long long R_self, long long R_cross, double 
     return best;
 }
 
+static bool eng_no_range_ctas() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("HGNN_B200_NO_RANGE_CTAS"); v = (e && e[0] == '1') ? 1 : 0; }
+    return v == 1;
+}
+
+// scratch of the dedicated range-sum CTAs: rng_n ready flags (ints, 16-byte padded) + 4 floats per range
+extern "C" long long hgnn_lg_rng_scratch_bytes(int rng_n) {
+    if (rng_n <= 0) return 0;
+    return (((long long)rng_n * 4 + 15) & ~15ll) + (long long)rng_n * 16;
+}
+
 static bool eng_try_bwd_row4(const hgnn_side_bwd_t* d, hgnn_stream_t stream) {
     if (eng_row4_disabled()) return false;
     if (d->Fg != 4 || d->R_self <= 0 || d->Fs != 4 || !eng_row4_ops(d->ops_T, d->n_ops)) return false;
@@ -1297,6 +1309,14 @@ static bool eng_try_bwd_row4(const hgnn_side_bwd_t* d, hgnn_stream_t stream) {
     a.pt_rowptr = d->pt_rowptr; a.pt_col = d->pt_col; a.pt_pm = d->pt_pm; a.pt_pd = d->pt_pd;
     a.Xc = d->Xc; a.bn_c = to_bnref(&d->bn_cross); a.gXc = d->gXc; a.acc_cross = d->accumulate_cross;
     a.acc_b_cross = d->acc_b_cross; a.col0_cross = d->n_ops * 4;
+    // dedicated range-sum CTAs when the caller provided the (zeroed) scratch: [flags: rng_n ints | sums: 4 floats each]
+    a.rng_n = 0; a.range_ctas = 0; a.rng_sum_g = nullptr; a.rng_flag_g = nullptr;
+    if (d->rng_scratch && o2.rng_rowptr && o2.rng_n > 0 && !eng_no_range_ctas()) {
+        a.rng_n = o2.rng_n;
+        a.range_ctas = o2.rng_n < 32 ? o2.rng_n : 32;
+        a.rng_flag_g = static_cast<int*>(d->rng_scratch);
+        a.rng_sum_g = reinterpret_cast<float*>(static_cast<char*>(d->rng_scratch) + (((size_t)o2.rng_n * 4 + 15) & ~(size_t)15));
+    }
     static int ablate = -1;
     if (ablate < 0) { const char* e = getenv("HGNN_B200_ABLATE"); ablate = e ? atoi(e) : 0; }
     a.ablate = ablate;
@@ -1327,8 +1347,10 @@ static bool eng_try_bwd_row4(const hgnn_side_bwd_t* d, hgnn_stream_t stream) {
         const int cap = eng_resident_impl((const void*)eng::bwd_row4_kernel<NCSR, DW, GB, CB>, 0, R4_THREADS); \
         int grid = (int)min((long long)cap, (rows + R4_THREADS - 1) / R4_THREADS);                        \
         if (d->R_cross > 0 && grid < 2) grid = 2;                                                         \
-        a.ctas_self = eng_split_ctas(grid, d->R_self, d->R_cross > 0 ? d->R_cross : 0, cost_s, cost_c);   \
-        eng_launch(eng::bwd_row4_kernel<NCSR, DW, GB, CB>, grid, R4_THREADS, 0, s, a);                    \
+        int row_grid = grid;                            /* the range CTAs come out of the resident budget */ \
+        if (a.range_ctas > 0 && grid + a.range_ctas > cap) row_grid = max(2, cap - a.range_ctas);         \
+        a.ctas_self = eng_split_ctas(row_grid, d->R_self, d->R_cross > 0 ? d->R_cross : 0, cost_s, cost_c); \
+        eng_launch(eng::bwd_row4_kernel<NCSR, DW, GB, CB>, row_grid + a.range_ctas, R4_THREADS, 0, s, a); \
     }
 #define R4_BWD_B(NCSR, DW)                                                                                \
     if (big_s) R4_BWD(NCSR, DW, 8, 4) else if (big_c) R4_BWD(NCSR, DW, 2, 8) else if (mid_s) R4_BWD(NCSR, DW, 4, 4) else R4_BWD(NCSR, DW, 2, 4)
@@ -1370,6 +1392,7 @@ static bool eng_try_bwd_rowg(const hgnn_side_bwd_t* d, hgnn_stream_t stream) {
     a.pt_rowptr = d->pt_rowptr; a.pt_col = d->pt_col; a.pt_pm = d->pt_pm; a.pt_pd = d->pt_pd;
     a.Xc = d->Xc; a.bn_c = to_bnref(&d->bn_cross); a.gXc = d->gXc; a.acc_cross = d->accumulate_cross;
     a.acc_b_cross = d->acc_b_cross; a.col0_cross = d->n_ops * Fs; a.ablate = 0;
+    a.rng_n = 0; a.range_ctas = 0; a.rng_sum_g = nullptr; a.rng_flag_g = nullptr;
     cudaStream_t s = to_stream(stream);
     const long long rows = (long long)d->R_self + a.R_cross;
     const double avg_s = (double)d->ops_T[2].nnz / d->R_self;

@@ -424,6 +424,9 @@ struct Bwd4Args {
     const float* Xc; BnRef bn_c; float* gXc; int acc_cross; double* acc_b_cross;
     int col0_cross;
     int ctas_self;        // CTAs [0, ctas_self) work on the self rows
+    // dedicated range-sum CTAs (optional): the last `range_ctas` CTAs of the grid publish the sums of the rng_n ranges
+    // into rng_sum_g (4 floats each) and set rng_flag_g[r]; both zero on entry
+    int rng_n, range_ctas; float* rng_sum_g; int* rng_flag_g;
     int ablate;           // timing experiments only (HGNN_B200_ABLATE): 1 no gathers, 2 no range phase, 4 no flush, 8 CTA times
 };
 
@@ -502,6 +505,8 @@ bwd_row4_kernel(const Bwd4Args a) {
     __shared__ float rng_sum[R4_MAX_IDS * 4];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const bool is_self = (int)blockIdx.x < a.ctas_self;
+    const int row_ctas = gridDim.x - a.range_ctas;          // CTAs [row_ctas, gridDim.x) only compute range sums
+    const bool is_range = (int)blockIdx.x >= row_ctas;
     pdl_launch_dependents();
     if ((a.ablate & 8) && tid == 0 && blockIdx.x < 2048) {
         g_cta_times[blockIdx.x * 3] = global_ns();
@@ -555,6 +560,35 @@ bwd_row4_kernel(const Bwd4Args a) {
     __syncthreads();                                   // weights in shared memory
     const float4 sc = bx.sc, sh = bx.sh, mu = bx.mu, rs = bx.rs;
 
+    if (is_range) {
+        // ---- a range CTA: sum gPre over each of its ranges (4 rows = 8 loads in flight per thread), publish the
+        //      sum, then the flag.  The row CTAs read them after their row loops, microseconds later.
+        for (int r = blockIdx.x - row_ctas; r < a.rng_n; r += a.range_ctas) {
+            const int lo = __ldg(a.rng_lo + r), hi = __ldg(a.rng_hi + r);
+            float4 acc = f4_zero();
+            for (int rr = lo + tid; rr < hi; rr += 4 * R4_THREADS) {
+                float4 gv[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) gv[u] = rr + u * R4_THREADS < hi ? gp(rr + u * R4_THREADS) : f4_zero();
+#pragma unroll
+                for (int u = 0; u < 4; ++u) { acc.x += gv[u].x; acc.y += gv[u].y; acc.z += gv[u].z; acc.w += gv[u].w; }
+            }
+            acc.x = warp_sum(acc.x); acc.y = warp_sum(acc.y); acc.z = warp_sum(acc.z); acc.w = warp_sum(acc.w);
+            if (lane == 0) { red[warp * 4] = acc.x; red[warp * 4 + 1] = acc.y; red[warp * 4 + 2] = acc.z; red[warp * 4 + 3] = acc.w; }
+            __syncthreads();
+            if (tid < 4) {
+                float v = 0.f;
+                for (int w = 0; w < R4_THREADS / 32; ++w) v += red[w * 4 + tid];
+                a.rng_sum_g[(size_t)r * 4 + tid] = v;
+            }
+            __threadfence();
+            __syncthreads();
+            if (tid == 0) atomicExch(a.rng_flag_g + r, 1);
+        }
+        if ((a.ablate & 8) && tid == 0 && blockIdx.x < 2048) g_cta_times[blockIdx.x * 3 + 1] = global_ns();
+        return;
+    }
+
     // per-thread accumulators: dW (NT or 2 blocks of 4x4), dbias (4), (sum g, sum g*xhat) (8)
     float dw[NT * 16];
 #pragma unroll
@@ -565,6 +599,34 @@ bwd_row4_kernel(const Bwd4Args a) {
     if (is_self) {
         float* const gX = a.gXs;
         const bool stats = a.acc_b_self != nullptr && gX != nullptr;
+        // finishes a row that owns range entries: the delta of everything that is linear in T[2]
+        auto range_fixup = [&](int row, const float (&dT)[4]) {
+            const float4 xr = ld4(a.Xs + (size_t)row * 4);
+            const float4 xn = f4_affine(xr, sc, sh);
+            float g[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+            for (int o = 0; o < 4; ++o) {
+                const float4 w = *reinterpret_cast<const float4*>(Ws + (2 * 4 + o) * 4);
+                g[0] = fmaf(dT[o], w.x, g[0]); g[1] = fmaf(dT[o], w.y, g[1]);
+                g[2] = fmaf(dT[o], w.z, g[2]); g[3] = fmaf(dT[o], w.w, g[3]);
+                if (DW) {
+                    dw[(2 * 4 + o) * 4 + 0] = fmaf(dT[o], xn.x, dw[(2 * 4 + o) * 4 + 0]);
+                    dw[(2 * 4 + o) * 4 + 1] = fmaf(dT[o], xn.y, dw[(2 * 4 + o) * 4 + 1]);
+                    dw[(2 * 4 + o) * 4 + 2] = fmaf(dT[o], xn.z, dw[(2 * 4 + o) * 4 + 2]);
+                    dw[(2 * 4 + o) * 4 + 3] = fmaf(dT[o], xn.w, dw[(2 * 4 + o) * 4 + 3]);
+                }
+            }
+            if (gX) {
+                float4 old = __ldcg(reinterpret_cast<const float4*>(gX + (size_t)row * 4));
+                old.x += g[0]; old.y += g[1]; old.z += g[2]; old.w += g[3];
+                *reinterpret_cast<float4*>(gX + (size_t)row * 4) = old;
+                if (stats) {
+                    const float xh[4] = {(xr.x - mu.x) * rs.x, (xr.y - mu.y) * rs.y, (xr.z - mu.z) * rs.z, (xr.w - mu.w) * rs.w};
+#pragma unroll
+                    for (int f = 0; f < 4; ++f) { sg[f] += g[f]; sgx[f] = fmaf(g[f], xh[f], sgx[f]); }
+                }
+            }
+        };
         for (int row = blockIdx.x * R4_THREADS + tid; row < a.R_self; row += a.ctas_self * R4_THREADS) {
             float4 T[NT];
             T[0] = gp(row);
@@ -629,7 +691,33 @@ bwd_row4_kernel(const Bwd4Args a) {
         //      everything that is linear in T[2].
         __syncthreads();
         const int nf = min(n_flagged, R4_MAX_FLAGGED);
-        if (nf > 0) {
+        if (nf > 0 && a.rng_flag_g) {
+            // the sums come from the range CTAs of this launch: wait (bounded) for the flag, else sum the range here
+            if (tid < nf) {
+                const int row = flagged[tid];
+                float dT[4] = {0.f, 0.f, 0.f, 0.f};
+                for (int e = __ldg(a.rng_rowptr + row); e < __ldg(a.rng_rowptr + row + 1); ++e) {
+                    const int id = __ldg(a.rng_id + e);
+                    const float v = __ldg(a.rng_val + e);
+                    volatile int* flag = a.rng_flag_g + id;
+                    int spins = 0;
+                    while (*flag == 0 && spins < 100000) ++spins;
+                    if (*flag != 0) {
+                        __threadfence();
+                        const float4 sum = __ldcg(reinterpret_cast<const float4*>(a.rng_sum_g + (size_t)id * 4));
+                        dT[0] = fmaf(v, sum.x, dT[0]); dT[1] = fmaf(v, sum.y, dT[1]);
+                        dT[2] = fmaf(v, sum.z, dT[2]); dT[3] = fmaf(v, sum.w, dT[3]);
+                    } else {        // never seen in practice: the range CTAs are resident from the start of the launch
+                        for (int rr = __ldg(a.rng_lo + id); rr < __ldg(a.rng_hi + id); ++rr) {
+                            const float4 gv = gp(rr);
+                            dT[0] = fmaf(v, gv.x, dT[0]); dT[1] = fmaf(v, gv.y, dT[1]);
+                            dT[2] = fmaf(v, gv.z, dT[2]); dT[3] = fmaf(v, gv.w, dT[3]);
+                        }
+                    }
+                }
+                range_fixup(row, dT);
+            }
+        } else if (nf > 0) {
             if (tid < R4_MAX_IDS) rng_ids[tid] = -1;
             __syncthreads();
             int my_row = -1, e0 = 0, e1 = 0;
@@ -687,31 +775,7 @@ bwd_row4_kernel(const Bwd4Args a) {
                         }
                     }
                 }
-                const float4 xr = ld4(a.Xs + (size_t)row * 4);
-                const float4 xn = f4_affine(xr, sc, sh);
-                float g[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-                for (int o = 0; o < 4; ++o) {
-                    const float4 w = *reinterpret_cast<const float4*>(Ws + (2 * 4 + o) * 4);
-                    g[0] = fmaf(dT[o], w.x, g[0]); g[1] = fmaf(dT[o], w.y, g[1]);
-                    g[2] = fmaf(dT[o], w.z, g[2]); g[3] = fmaf(dT[o], w.w, g[3]);
-                    if (DW) {
-                        dw[(2 * 4 + o) * 4 + 0] = fmaf(dT[o], xn.x, dw[(2 * 4 + o) * 4 + 0]);
-                        dw[(2 * 4 + o) * 4 + 1] = fmaf(dT[o], xn.y, dw[(2 * 4 + o) * 4 + 1]);
-                        dw[(2 * 4 + o) * 4 + 2] = fmaf(dT[o], xn.z, dw[(2 * 4 + o) * 4 + 2]);
-                        dw[(2 * 4 + o) * 4 + 3] = fmaf(dT[o], xn.w, dw[(2 * 4 + o) * 4 + 3]);
-                    }
-                }
-                if (gX) {
-                    float4 old = __ldcg(reinterpret_cast<const float4*>(gX + (size_t)row * 4));
-                    old.x += g[0]; old.y += g[1]; old.z += g[2]; old.w += g[3];
-                    *reinterpret_cast<float4*>(gX + (size_t)row * 4) = old;
-                    if (stats) {
-                        const float xh[4] = {(xr.x - mu.x) * rs.x, (xr.y - mu.y) * rs.y, (xr.z - mu.z) * rs.z, (xr.w - mu.w) * rs.w};
-#pragma unroll
-                        for (int f = 0; f < 4; ++f) { sg[f] += g[f]; sgx[f] = fmaf(g[f], xh[f], sgx[f]); }
-                    }
-                }
+                range_fixup(row, dT);
             }
         }
         if ((a.ablate & 8) && tid == 0 && blockIdx.x < 2048) {
@@ -721,7 +785,7 @@ bwd_row4_kernel(const Bwd4Args a) {
     } else {
         float* const gX = a.gXc;
         const bool stats = a.acc_b_cross != nullptr && gX != nullptr;
-        const int ncta = gridDim.x - a.ctas_self;
+        const int ncta = row_ctas - a.ctas_self;
         for (int row = (blockIdx.x - a.ctas_self) * R4_THREADS + tid; row < a.R_cross; row += ncta * R4_THREADS) {
             float4 Tm = f4_zero(), Td = f4_zero();
             const int k0 = __ldg(a.pt_rowptr + row), k1 = (a.ablate & 1) ? k0 : __ldg(a.pt_rowptr + row + 1);

@@ -168,14 +168,41 @@ extern "C" int hgnn_program_fwd(const hgnn_program_t* prog, const hgnn_batch_t* 
     return HGNN_OK;
 }
 
+// one scratch region per edge side whose transposed operator has a run-length part
+static long long side_rng_bytes(const hgnn_program_t* prog, const hgnn_batch_t* b) {
+    if (!prog->dual || !b->edge_ops_T || b->n_ops < 3) return 0;
+    const hgnn_op_t& o = b->edge_ops_T[2];
+    if (o.kind != HGNN_OP_CSR || !o.rng_rowptr) return 0;
+    return hgnn_lg_rng_scratch_bytes(o.rng_n);
+}
+
+extern "C" long long hgnn_program_rng_scratch_bytes(const hgnn_program_t* prog, const hgnn_batch_t* b) {
+    if (!prog || !b || !prog->sides) return 0;
+    long long n = 0;
+    for (int i = 0; i < prog->n_sides; ++i) n += prog->sides[i].kind == 1 ? 1 : 0;
+    return side_rng_bytes(prog, b) * n;
+}
+
 extern "C" int hgnn_program_bwd(const hgnn_program_t* prog, const hgnn_batch_t* b, const float* X, const float* XL,
                                 const long long* addr, const float* work, float* gwork, double* arena,
-                                const float* g_out, float* gX, float* gflat, hgnn_stream_t stream) {
+                                const float* g_out, float* gX, float* gflat, void* rng_scratch,
+                                long long rng_scratch_bytes, hgnn_stream_t stream) {
     WorkLayout w;
     HGNN_REQUIRE(prog && b && X && addr && work && gwork && arena && g_out && gflat, "null argument");
     HGNN_REQUIRE(plan_work(prog, b->Rn, b->Rm, &w) && check_program(prog, b), "malformed program or batch");
     cudaStream_t s = to_stream(stream);
     std::vector<char> started(prog->n_tensors, 0);
+    const long long rng_per_side = side_rng_bytes(prog, b), rng_total = hgnn_program_rng_scratch_bytes(prog, b);
+    long long rng_used = 0;
+    if (rng_scratch && rng_per_side > 0 && rng_scratch_bytes >= rng_total) {
+        if (cudaMemsetAsync(rng_scratch, 0, (size_t)rng_total, s) != cudaSuccess) {
+            hgnn_set_error("hgnn_program_bwd: cudaMemsetAsync(rng_scratch) failed");
+            return HGNN_ERR_CUDA;
+        }
+        g_program_launches.fetch_add(1);
+    } else {
+        rng_scratch = nullptr;
+    }
     auto grad_ptr = [&](int t) -> float* { return t == 0 ? gX : gwork + w.off[t]; };
     auto wants_grad = [&](int t) { return prog->tensors[t].bn_weight >= 0 || (t == 0 && gX != nullptr); };
     for (int i = prog->n_sides - 1; i >= 0; --i) {
@@ -260,6 +287,11 @@ extern "C" int hgnn_program_bwd(const hgnn_program_t* prog, const hgnn_batch_t* 
             if (need_cross) started[sd.src_cross] = 1;
         }
         d.skip_dw = 0;
+        d.rng_scratch = nullptr;
+        if (rng_scratch && !node) {
+            d.rng_scratch = static_cast<char*>(rng_scratch) + rng_used;
+            rng_used += rng_per_side;
+        }
         hgnn_eng_set_pdl(i < prog->n_sides - 1);   // the stream predecessor is the backward kernel of side i + 1
         const int rc_bwd = hgnn_lg_side_bwd(&d, stream);
         hgnn_eng_set_pdl(false);

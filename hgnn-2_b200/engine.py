@@ -472,12 +472,14 @@ class _ModelFunction(torch.autograd.Function):
             Xp, XLp = ctx.inputs
             gwork = torch.empty_like(ctx.work)
             gflat = torch.empty(plan.n_flat, device=dev)
+            n_scr = int(_lib.lib.hgnn_program_rng_scratch_bytes(ctypes.byref(prog), ctypes.byref(batch)))
+            scratch = torch.empty(n_scr, dtype=torch.uint8, device=dev) if n_scr > 0 else None
             gX = torch.empty_like(Xp) if ctx.need_x else None
             addr = plan.param_addresses()
             call_program("hgnn_program_bwd", ctypes.byref(prog), ctypes.byref(batch), fptr(Xp),
                          fptr(XLp) if XLp is not None else None, addr.ctypes.data, ctx.work.data_ptr(),
                          gwork.data_ptr(), arena.data_ptr(), fptr(g_out), gX.data_ptr() if gX is not None else None,
-                         gflat.data_ptr(), stream())
+                         gflat.data_ptr(), scratch.data_ptr() if scratch is not None else None, n_scr, stream())
             return _ModelFunction._grads_out(ctx, plan, gX, gflat)
         vals = ctx.vals
         grads, started = {}, set()
@@ -492,9 +494,17 @@ class _ModelFunction(torch.autograd.Function):
                 grads[name] = torch.empty_like(vals[name])
             return grads[name]
 
-        for s in reversed(plan.sides):
+        # zeroed scratch for the dedicated range-sum CTAs of the width-4 edge-side backward (one region per side)
+        rng_bytes, rng_scratch = 0, None
+        if pack.dual and not pack.generic and getattr(pack, "bts", None) is not None:
+            rng_bytes = int(_lib.lib.hgnn_lg_rng_scratch_bytes(int(pack.bts_ranges[3].numel())))
+            if rng_bytes:
+                rng_scratch = torch.zeros(rng_bytes * len(plan.sides), dtype=torch.uint8, device=dev)
+        for si, s in reversed(list(enumerate(plan.sides))):
             node = s.kind == "node"
             d = SideBwdT()
+            if rng_scratch is not None and not node:
+                d.rng_scratch = rng_scratch.data_ptr() + si * rng_bytes
             Ha = s.conv_a.weight.shape[0]
             Hb = s.conv_b.weight.shape[0] if s.conv_b is not None else 0
             if s.out is None:       # readout: gPre = g_out broadcast over the rows of each graph

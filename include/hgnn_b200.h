@@ -52,6 +52,7 @@ typedef struct hgnn_op_t {
     const int* rng_lo;
     const int* rng_hi;
     long long nnz;       /* CSR: number of stored entries, 0 = unknown (a scheduling hint only) */
+    int rng_n;           /* number of distinct ranges (length of rng_lo / rng_hi), 0 = unknown */
 } hgnn_op_t;
 
 const char* hgnn_last_error(void);
@@ -234,7 +235,13 @@ typedef struct hgnn_side_bwd_t {
     const float* Xc; int Fc; hgnn_bn_ref_t bn_cross; float* gXc; int accumulate_cross; double* acc_b_cross;
     int skip_dw; /* 1: leave dW / dbias to hgnn_lg_side_dw (width-4 fast path only) */
     long long pt_nnz; /* entries of the pt_* pattern, 0 = unknown (scheduling hint) */
+    /* optional: ZEROED scratch of hgnn_lg_rng_scratch_bytes(ops_T[2].rng_n) bytes.  With it the width-4 backward
+     * dedicates a few CTAs of the launch to the range sums of the run-length part (they publish each sum + a ready
+     * flag here) and the rows that own range entries just read them - instead of every CTA with such a row summing
+     * the range itself after its row loop, a 7 us tail on 31 of 342 CTAs (profiles/logs/cta_times_phases.log). */
+    void* rng_scratch;
 } hgnn_side_bwd_t;
+long long hgnn_lg_rng_scratch_bytes(int rng_n);
 int hgnn_lg_side_bwd(const hgnn_side_bwd_t* desc, hgnn_stream_t stream);
 /* profiling aid (HGNN_B200_ABLATE bit 8): (start ns, end ns, is_self) of the first n <= 2048 CTAs of the last
  * width-4 backward launch, copied to the HOST array out (3 n values); synchronises the device */
@@ -356,7 +363,10 @@ int hgnn_program_fwd(const hgnn_program_t* prog, const hgnn_batch_t* batch, cons
  * parameter gradient gflat (prog->n_flat).  gwork: scratch of hgnn_program_work_floats floats. */
 int hgnn_program_bwd(const hgnn_program_t* prog, const hgnn_batch_t* batch, const float* X, const float* XL,
                      const long long* param_addr, const float* work, float* gwork, double* arena,
-                     const float* g_out, float* gX, float* gflat, hgnn_stream_t stream);
+                     const float* g_out, float* gX, float* gflat, void* rng_scratch, long long rng_scratch_bytes,
+                     hgnn_stream_t stream);
+/* bytes of rng_scratch for hgnn_program_bwd (0: none needed); the call zeroes it itself; NULL / too small: without */
+long long hgnn_program_rng_scratch_bytes(const hgnn_program_t* prog, const hgnn_batch_t* batch);
 /* kernels launched by hgnn_program_* calls so far (the host layer adds it to its own launch count) */
 long long hgnn_program_launches(void);
 /* hgnn_bn_running_update with the row counts given as (kind table, Rn, Rm) instead of a device vector */
