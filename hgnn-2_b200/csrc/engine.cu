@@ -1337,6 +1337,8 @@ static bool eng_try_bwd_row4(const hgnn_side_bwd_t* d, hgnn_stream_t stream) {
     }
     const double cost_s = (double)d->R_self * (1.0 + w_self * avg_s);
     const double cost_c = d->R_cross > 0 ? (double)d->R_cross * (1.0 + w_cross * avg_c) : 0.0;
+    static int debug_split = -1;
+    if (debug_split < 0) debug_split = getenv("HGNN_B200_DEBUG_SPLIT") ? 1 : 0;
     bool big_s = false, big_c = false;      // measured: the small batches win in the backward (register pressure)
     static int bforce = -2;
     if (bforce == -2) { const char* e = getenv("HGNN_B200_BWD_BATCH"); bforce = e ? atoi(e) : -1; }  // 0: (2,4), 1: (8,4), 2: (2,8), 3: (4,4)
@@ -1350,6 +1352,9 @@ static bool eng_try_bwd_row4(const hgnn_side_bwd_t* d, hgnn_stream_t stream) {
         int row_grid = grid;                            /* the range CTAs come out of the resident budget */ \
         if (a.range_ctas > 0 && grid + a.range_ctas > cap) row_grid = max(2, cap - a.range_ctas);         \
         a.ctas_self = eng_split_ctas(row_grid, d->R_self, d->R_cross > 0 ? d->R_cross : 0, cost_s, cost_c); \
+        if (debug_split)                                                                                  \
+            fprintf(stderr, "bwd_row4 split: cap %d grid %d row_grid %d range_ctas %d R_self %d R_cross %d avg_s %.3f avg_c %.3f -> ctas_self %d\n", \
+                    cap, grid, row_grid, a.range_ctas, d->R_self, d->R_cross, avg_s, avg_c, a.ctas_self); \
         eng_launch(eng::bwd_row4_kernel<NCSR, DW, GB, CB>, row_grid + a.range_ctas, R4_THREADS, 0, s, a); \
     }
 #define R4_BWD_B(NCSR, DW)                                                                                \
