@@ -422,13 +422,13 @@ def run_ours(a):
         from hgnn_b200.functions.batching import BatchLoader
         data = [inst for hb in host_batches for inst in hb]
         idx_lists = [list(range((k % n_host_batches) * a.bs, (k % n_host_batches + 1) * a.bs))
-                     for k in range(e2e_steps + 4)]
+                     for k in range(e2e_steps + 10)]
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
         t0 = None
         for k, batch in enumerate(BatchLoader(data, idx_lists, 0, a.J, device=dev)):
-            if k == 4:
+            if k == 10:     # pinned pools of the producer thread, copy-stream allocator pool: steady state
                 torch.cuda.synchronize()
                 t0 = time.perf_counter()
             db, _ = to_device(batch)
