@@ -371,7 +371,7 @@ struct FwdArgs {
     int TR, Cin, Cin_pad, Fout;
 };
 
-// WIDE (states of 16+ features, VEC = VOUT = 4): a warp's lanes walk the feature chunks of ONE row in the
+// WIDE (states of 32+ features, VEC = VOUT = 4): a warp's lanes walk the feature chunks of ONE row in the
 // gather (coalesced 16 B x 32 lanes, CSR entries broadcast), and the linear is register-tiled 4 rows x 4
 // outputs per thread (8 FMA per shared-memory load instead of 3.2).
 template <int VEC, int VOUT, bool WIDE>
@@ -1192,7 +1192,9 @@ extern "C" int hgnn_lg_side_fwd(const hgnn_side_t* side, const hgnn_bn_ref_t* bn
     a.Cin_pad = eng_pad(a.Cin, vec4 ? 4 : 1);
     const int rows_per_pass = ENG_THREADS / (vout4 ? a.Fout / 4 : a.Fout);
     const int items_per_row = (a.Fs + a.Fc) / (vec4 ? 4 : 1);
-    const bool wide = vec4 && vout4 && a.Fout >= 16 && items_per_row >= 8;
+    // register-tiled variant from 32 outputs up: measured at h = 8 (16 outputs) it is slower (10.3 vs 7.6 ms per step),
+    // at h = 32 faster (48.9 vs 84.6 ms)
+    const bool wide = vec4 && vout4 && a.Fout >= 32 && items_per_row >= 8;
     int TR = wide ? 4 * rows_per_pass : min(rows_per_pass, max(32, ENG_THREADS / max(1, items_per_row)));
     size_t fixed = ((size_t)a.Cin * a.Fout + ((a.Fout + 3) & ~3) + 2 * ((a.Fs + 3) & ~3) + 2 * ((a.Fc + 3) & ~3)) * sizeof(float);
     while (TR > 1 && fixed + (size_t)TR * a.Cin_pad * sizeof(float) > ENG_MAX_SMEM) TR >>= 1;
@@ -1479,7 +1481,7 @@ extern "C" int hgnn_lg_side_bwd(const hgnn_side_bwd_t* d, hgnn_stream_t stream) 
     a.dW_bins = d->dW_bins; a.db_bins = d->db_bins;
     const bool vec4 = (d->Fg % 4 == 0) && eng_aligned16(d->gY) && (!d->Z || eng_aligned16(d->Z));
     // wide states: register-tiled phases (both parts must take the float4 paths)
-    const bool wide = vec4 && d->Fg >= 16 &&
+    const bool wide = vec4 && d->Fg >= 32 &&
         (d->R_self <= 0 || (d->Fs >= 16 && d->Xs && eng_part_vout4(d->Xs, d->gXs, d->Fs))) &&
         (d->R_cross <= 0 || (d->Fc >= 16 && d->Xc && eng_part_vout4(d->Xc, d->gXc, d->Fc)));
     // self part
