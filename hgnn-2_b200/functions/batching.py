@@ -75,6 +75,8 @@ def prepare_batch(batch, task, J=1, sparse=None, device="cuda"):
         sparse = os.environ.get("HGNN_B200_DENSE_BATCH", "0") != "1"
     bs = len(batch)
     graphs = [_instance_ops(inst) for inst in batch]
+    # the operator pack first: its host->device DMAs (one per graph blob) then run while the rest is assembled
+    pack = BatchPack.from_graphs(graphs, J, dual=True, device=device)
     n_feat = batch[0][0].shape[1]
     N_batch = torch.tensor([g.N for g in graphs], dtype=torch.int64)
     E_batch = torch.tensor([g.M for g in graphs], dtype=torch.int64)
@@ -89,7 +91,6 @@ def prepare_batch(batch, task, J=1, sparse=None, device="cuda"):
         g = graphs[i]
         Xn[i, :, :g.N] = inst[0].numpy().T
         XLn[i, 0, :g.M] = g.dl
-    pack = BatchPack.from_graphs(graphs, J, dual=True, device=device)
     W, WL = OperatorHandle(pack, "W"), OperatorHandle(pack, "WL")
     Pm, Pd = OperatorHandle(pack, "Pm"), OperatorHandle(pack, "Pd")
     mask, mask_lg = MaskHandle(pack, False), MaskHandle(pack, True)

@@ -138,11 +138,12 @@ def device_pack(graphs, dual=True, skip_bt=False, device="cuda"):
               meta_dev.data_ptr(), stream())
     _meta_ring.copied(slot)
     views = {}
+    base_i, base_f = buf.view(torch.int32), buf.view(torch.float32)      # one slicing op per array below
     for k, name in enumerate(_HOST_KEYS):
         n = lay[2 * k + 1]
         if n >= 0:
-            o = lay[2 * k]
-            views[name] = buf[o:o + 4 * n].view(torch.float32 if name in _FLOAT_KEYS else torch.int32)
+            o = lay[2 * k] >> 2
+            views[name] = (base_f if name in _FLOAT_KEYS else base_i)[o:o + n]
     return views, buf, stage_b.value + meta_b.value
 
 
