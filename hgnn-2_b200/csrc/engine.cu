@@ -89,6 +89,15 @@ struct AffineLoader {
         if (on) x.affine(V<VEC>::loads(sc + xo), V<VEC>::loads(sh + xo));
         return x;
     }
+    // the loader is affine, so a weighted sum of loaded rows can be taken over the RAW rows and fixed up once:
+    // sum_k v_k (x_k * sc + sh) = (sum_k v_k x_k) * sc + (sum_k v_k) * sh      (engine_wide.cuh)
+    __device__ __forceinline__ V<VEC> raw(int row, int xo) const { return V<VEC>::load(X + (size_t)row * ld + xo); }
+    __device__ __forceinline__ void finish(V<VEC>& acc, float vsum, int xo) const {
+        if (!on) return;
+        V<VEC> t = V<VEC>::loads(sh + xo);
+        t.scale(vsum);
+        acc.affine(V<VEC>::loads(sc + xo), t);
+    }
 };
 
 // backward: gPre = (c0*g + c1 + c2*z) masked by the ReLU of the conv branch (z > 0 where f >= relu_from)
@@ -116,6 +125,9 @@ struct GpreLoader {
             if (xo + j >= relu_from && !(z.get(j) > 0.f)) g.set(j, 0.f);
         return g;
     }
+    // not linear in the stored rows (ReLU mask): the weighted sums are taken over the finished values
+    __device__ __forceinline__ V<VEC> raw(int row, int xo) const { return (*this)(row, xo); }
+    __device__ __forceinline__ void finish(V<VEC>&, float, int) const {}
 };
 
 // ---- gathers -----------------------------------------------------------------------------------
@@ -952,6 +964,7 @@ bwd_kernel(const BwdArgs a) {
 
 #include "engine_row4.cuh"
 #include "engine_rowg.cuh"
+#include "engine_wide.cuh"
 
 }  // namespace eng
 
@@ -1160,6 +1173,66 @@ static bool eng_try_fwd_rowg(const eng::FwdArgs& g, const hgnn_side_t* side, hgn
     return done;
 }
 
+static bool eng_part_vout4(const float* X, const float* gX, int Fx) {
+    return (Fx % 4 == 0) && eng_aligned16(X) && (!gX || eng_aligned16(gX));
+}
+
+// ---- tensor-core tile kernels for wide states (engine_wide.cuh) -----------------------------------
+#define WD_MAX_SMEM (212 * 1024)     // dynamic; the kernels hold <= 13 KB of static shared memory on top
+static bool eng_wide_disabled() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("HGNN_B200_NO_WIDE_MMA"); v = (e && e[0] == '1') ? 1 : 0; }
+    return v == 1;
+}
+// smallest output width that takes the tensor-core kernels (HGNN_B200_WIDE_MIN overrides; a multiple of 16)
+static int eng_wide_min() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("HGNN_B200_WIDE_MIN"); v = e ? atoi(e) : 32; if (v < 16) v = 16; }
+    return v;
+}
+
+static bool eng_try_fwd_wide(eng::FwdArgs& a, hgnn_stream_t stream) {
+    if (eng_wide_disabled()) return false;
+    if (a.Fout % 16 || a.Fout < eng_wide_min() || a.Fout > 128) return false;
+    if (a.Fs % 4 || a.Fc % 4 || a.Cin % 8) return false;
+    if (!eng_aligned16(a.Xs) || (a.Fc && !eng_aligned16(a.Xc)) || !eng_aligned16(a.Z)) return false;
+    const int Cp = eng_pad(a.Cin, 4);
+    int TR = WD_TR;
+    size_t smem = 0;
+    for (; TR >= 16; TR >>= 1) {
+        smem = (size_t)eng::wide_fwd_layout(a.Cin, Cp, a.Fout, a.Fs, a.Fc, TR).total * sizeof(float);
+        if (smem <= WD_MAX_SMEM) break;
+    }
+    if (TR < 16) return false;
+    a.Cin_pad = Cp;
+    a.TR = TR;
+    const int ntiles = ceil_div(a.R, TR);
+    const int grid = balanced_grid(ntiles, eng_resident_impl(reinterpret_cast<const void*>(eng::fwd_wide_kernel), smem, WD_THREADS));
+    eng::fwd_wide_kernel<<<grid, WD_THREADS, smem, to_stream(stream)>>>(a);
+    return true;
+}
+
+// derived fields of one backward part for bwd_wide_kernel; false if it does not qualify / fit
+static bool eng_plan_part_wide(eng::BwdPart& p, int Fg, bool is_self) {
+    if (p.Fx % 16 || p.Fx > 128 || !eng_part_vout4(p.X, p.gX, p.Fx)) return false;
+    p.nT = p.ops.n * Fg;
+    p.P = p.nT * p.Fx;
+    if ((p.nT / 16) * (p.Fx / 16) > WD_MAXDW * WD_WARPS) return false;
+    p.NG = 1;
+    p.Tp = eng_pad(is_self ? p.nT + Fg : p.nT, 4);
+    p.Xp = p.Fx + 8;
+    for (int TR = WD_TR; TR >= 16; TR >>= 1) {
+        const size_t smem = (size_t)eng::wide_bwd_layout(p.nT, p.Fx, p.Tp, p.Xp, TR).total * sizeof(float);
+        if (smem <= WD_MAX_SMEM) {
+            p.TR = TR;
+            p.smem = smem;
+            p.tiles = ceil_div(p.R, TR);
+            return true;
+        }
+    }
+    return false;
+}
+
 extern "C" int hgnn_lg_side_fwd(const hgnn_side_t* side, const hgnn_bn_ref_t* bn_self,
                                 const hgnn_bn_ref_t* bn_cross, const float* Wa, const float* ba, int Ha,
                                 const float* Wb, const float* bb, int Hb, int relu_from, float* Z,
@@ -1187,6 +1260,7 @@ extern "C" int hgnn_lg_side_fwd(const hgnn_side_t* side, const hgnn_bn_ref_t* bn
     if (eng_try_fwd_row4(a, side, stream)) return hgnn_check_launch("hgnn_lg_side_fwd(row4)");
     if (eng_try_fwd_rowg(a, side, stream)) return hgnn_check_launch("hgnn_lg_side_fwd(rowg)");
     HGNN_REQUIRE(!X1, "x1 rows can only be saved by the width-4 fast path (check hgnn_lg_row4_eligible)");
+    if (eng_try_fwd_wide(a, stream)) return hgnn_check_launch("hgnn_lg_side_fwd(wide)");
     const bool vec4 = (a.Fs % 4 == 0) && (a.Fc % 4 == 0) && eng_aligned16(a.Xs) && (a.Fc == 0 || eng_aligned16(a.Xc));
     const bool vout4 = vec4 && (a.Fout % 4 == 0) && eng_aligned16(Z);
     a.Cin_pad = eng_pad(a.Cin, vec4 ? 4 : 1);
@@ -1223,9 +1297,6 @@ extern "C" int hgnn_lg_side_fwd(const hgnn_side_t* side, const hgnn_bn_ref_t* bn
 }
 
 // fill the derived fields of one backward part; returns false if it does not fit shared memory
-static bool eng_part_vout4(const float* X, const float* gX, int Fx) {
-    return (Fx % 4 == 0) && eng_aligned16(X) && (!gX || eng_aligned16(gX));
-}
 
 static bool eng_plan_part(eng::BwdPart& p, int Fg, bool vec4, bool& vout4, bool is_self, bool wide) {
     p.nT = p.ops.n * Fg;
@@ -1484,6 +1555,8 @@ extern "C" int hgnn_lg_side_bwd(const hgnn_side_bwd_t* d, hgnn_stream_t stream) 
     const bool wide = vec4 && d->Fg >= 32 &&
         (d->R_self <= 0 || (d->Fs >= 16 && d->Xs && eng_part_vout4(d->Xs, d->gXs, d->Fs))) &&
         (d->R_cross <= 0 || (d->Fc >= 16 && d->Xc && eng_part_vout4(d->Xc, d->gXc, d->Fc)));
+    // tensor-core tile kernel (engine_wide.cuh) when both parts qualify
+    bool mma = !eng_wide_disabled() && vec4 && d->Fg % 16 == 0 && d->Fg >= eng_wide_min() && d->Fg <= 128;
     // self part
     a.self.R = d->R_self;
     bool vs4 = false, vc4 = false;
@@ -1493,7 +1566,8 @@ extern "C" int hgnn_lg_side_bwd(const hgnn_side_bwd_t* d, hgnn_stream_t stream) 
         a.self.X = d->Xs; a.self.Fx = d->Fs; a.self.bn = to_bnref(&d->bn_self);
         a.self.gX = d->gXs; a.self.accumulate = d->accumulate_self; a.self.acc_b = d->acc_b_self;
         a.self.col0 = 0;
-        if (!eng_plan_part(a.self, d->Fg, vec4, vs4, true, wide)) {
+        if (mma) mma = eng_plan_part_wide(a.self, d->Fg, true);
+        if (!mma && !eng_plan_part(a.self, d->Fg, vec4, vs4, true, wide)) {
             hgnn_set_error("hgnn_lg_side_bwd: self block %d x %d does not fit shared memory", a.self.nT, d->Fs);
             return HGNN_ERR_ARG;
         }
@@ -1513,7 +1587,15 @@ extern "C" int hgnn_lg_side_bwd(const hgnn_side_bwd_t* d, hgnn_stream_t stream) 
         a.cross.X = d->Xc; a.cross.Fx = d->Fc; a.cross.bn = to_bnref(&d->bn_cross);
         a.cross.gX = d->gXc; a.cross.accumulate = d->accumulate_cross; a.cross.acc_b = d->acc_b_cross;
         a.cross.col0 = d->n_ops * d->Fs;
-        if (!eng_plan_part(a.cross, d->Fg, vec4, vc4, false, wide)) {
+        if (mma && !eng_plan_part_wide(a.cross, d->Fg, false)) {
+            // the cross part does not qualify: plan both parts for the generic kernel
+            mma = false;
+            if (d->R_self > 0 && !eng_plan_part(a.self, d->Fg, vec4, vs4, true, wide)) {
+                hgnn_set_error("hgnn_lg_side_bwd: self block %d x %d does not fit shared memory", a.self.nT, d->Fs);
+                return HGNN_ERR_ARG;
+            }
+        }
+        if (!mma && !eng_plan_part(a.cross, d->Fg, vec4, vc4, false, wide)) {
             hgnn_set_error("hgnn_lg_side_bwd: cross block %d x %d does not fit shared memory", a.cross.nT, d->Fc);
             return HGNN_ERR_ARG;
         }
@@ -1524,6 +1606,12 @@ extern "C" int hgnn_lg_side_bwd(const hgnn_side_bwd_t* d, hgnn_stream_t stream) 
     if (total_tiles == 0) return HGNN_OK;
     const size_t smem = a.self.smem > a.cross.smem ? a.self.smem : a.cross.smem;
     cudaStream_t s = to_stream(stream);
+    if (mma) {
+        int grid = balanced_grid(total_tiles, eng_resident_impl(reinterpret_cast<const void*>(eng::bwd_wide_kernel), smem, WD_THREADS));
+        if (a.self.tiles > 0 && a.cross.tiles > 0 && grid < 2) grid = 2;
+        eng::bwd_wide_kernel<<<grid, WD_THREADS, smem, s>>>(a);
+        return hgnn_check_launch("hgnn_lg_side_bwd(wide)");
+    }
 #define ENG_LAUNCH(VEC, VS, VC, W)                                                                   \
     {                                                                                                \
         int grid = balanced_grid(total_tiles, eng_resident(eng::bwd_kernel<VEC, VS, VC, W>, smem));  \

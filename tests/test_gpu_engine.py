@@ -40,6 +40,9 @@ def _run(model, batch, use_engine, train=True):
 @pytest.mark.parametrize("kind,order,h,J,N", [("lg", 1, 2, 1, 300), ("lg", 2, 2, 1, 200), ("lg", 3, 4, 1, 200),
                                               ("lg", 1, 8, 2, 60), ("simple", 0, 2, 1, 300),
                                               ("simple", 0, 16, 2, 100), ("lg", 1, 32, 1, 100),
+                                              # wide states on the tensor-core tile kernels (engine_wide.cuh): two CSR
+                                              # operators (J = 2), orders 2 / 3, no cross part (GNN_simple), h = 16
+                                              ("lg", 2, 32, 2, 70), ("lg", 3, 16, 1, 120), ("simple", 0, 32, 1, 150),
                                               # J = 2 at the script-default width: the two-CSR-operator variants of the
                                               # thread-per-row kernels (engine_row4.cuh / engine_rowg.cuh)
                                               ("lg", 1, 2, 2, 80), ("lg", 3, 2, 2, 80), ("simple", 0, 2, 2, 120)])
