@@ -1217,7 +1217,8 @@ static bool eng_plan_part_wide(eng::BwdPart& p, int Fg, bool is_self) {
     if (p.Fx % 16 || p.Fx > 128 || !eng_part_vout4(p.X, p.gX, p.Fx)) return false;
     p.nT = p.ops.n * Fg;
     p.P = p.nT * p.Fx;
-    if ((p.nT / 16) * (p.Fx / 16) > WD_MAXDW * WD_WARPS) return false;
+    const int njx = p.Fx / 16;               // dW: a warp owns one 16-column block and <= WD_MAXDW row blocks
+    if (WD_WARPS % njx || p.nT / 16 > WD_MAXDW * (WD_WARPS / njx)) return false;
     p.NG = 1;
     p.Tp = eng_pad(is_self ? p.nT + Fg : p.nT, 4);
     p.Xp = p.Fx + 8;
@@ -1607,8 +1608,9 @@ extern "C" int hgnn_lg_side_bwd(const hgnn_side_bwd_t* d, hgnn_stream_t stream) 
     const size_t smem = a.self.smem > a.cross.smem ? a.self.smem : a.cross.smem;
     cudaStream_t s = to_stream(stream);
     if (mma) {
-        int grid = balanced_grid(total_tiles, eng_resident_impl(reinterpret_cast<const void*>(eng::bwd_wide_kernel), smem, WD_THREADS));
-        if (a.self.tiles > 0 && a.cross.tiles > 0 && grid < 2) grid = 2;
+        // every CTA works on both parts (see bwd_wide_kernel)
+        const int most = a.self.tiles > a.cross.tiles ? a.self.tiles : a.cross.tiles;
+        const int grid = balanced_grid(most, eng_resident_impl(reinterpret_cast<const void*>(eng::bwd_wide_kernel), smem, WD_THREADS));
         eng::bwd_wide_kernel<<<grid, WD_THREADS, smem, s>>>(a);
         return hgnn_check_launch("hgnn_lg_side_bwd(wide)");
     }

@@ -28,12 +28,13 @@
 #define WD_SLOTS 2         // staged CSR operators of the self part (forward: plus the Pm/Pd pattern)
 #define WD_MAXDW 4         // 16x16 dW blocks per warp
 
-// x = hi + lo with hi on the TF32 grid (round-to-nearest by integer add + mask: 2 instructions; cvt.rna.tf32.f32 is
-// a 4-instruction sequence with Inf / NaN handling on sm_100a and dominated the first version of these kernels,
-// profiles/README.md) and lo = x - hi exact in fp32; the tensor core reads the top 19 bits of lo.
+// x = hi + lo for the 3xTF32 products.  The tensor core reads only the top 19 bits of a .tf32 operand (the low 13
+// mantissa bits are ignored), so x itself serves as hi = trunc_tf32(x) and lo = x - trunc_tf32(x) is exact in fp32:
+// two instructions per element (LOP3 + FADD).  cvt.rna.tf32.f32 is a 4-instruction sequence with Inf / NaN
+// handling on sm_100a; with it the splits were 40 % of all executed instructions (profiles/README.md).
 __device__ __forceinline__ void tf32_split(float x, uint32_t& hi, uint32_t& lo) {
-    hi = (__float_as_uint(x) + 0x1000u) & 0xffffe000u;
-    lo = __float_as_uint(x - __uint_as_float(hi));
+    hi = __float_as_uint(x);
+    lo = __float_as_uint(x - __uint_as_float(hi & 0xffffe000u));
 }
 // c (16x8, fp32) += a (16x8, row) * b (8x8, col); fragment layouts of PTX mma.m16n8k8.tf32:
 //   a0 (g, t)  a1 (g+8, t)  a2 (g, t+4)  a3 (g+8, t+4);  b0 (k=t, n=g)  b1 (k=t+4, n=g);
@@ -49,19 +50,55 @@ __device__ __forceinline__ void mma_tf32_zero(float (&d)[4], const uint32_t (&a)
                  : "=f"(d[0]), "=f"(d[1]), "=f"(d[2]), "=f"(d[3])
                  : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1), "f"(0.f));
 }
-// 3xTF32 step.  The tensor core adds into its fp32 accumulator with truncation, which biases a long chain of
-// accumulations (measured: 5e-4 relative on a bias gradient after 120 chained mma); so the large term hi*hi of
-// every k-step starts from a zero accumulator and is added to `acc` by an ordinary round-to-nearest FADD, and the
-// two small terms (2^-11 of the large one) chain in their own accumulator `sm`, added once at the end.
+// 3xTF32 steps.  The tensor core adds into its fp32 accumulator with truncation, which biases a long chain of
+// accumulations (measured: 5e-4 relative on a bias gradient after 120 chained mma); so the large terms hi*hi start
+// from a zero accumulator, at most two k-steps are chained, and the result is added to `acc` by an ordinary
+// round-to-nearest FADD; the small terms (2^-11 of the large ones) chain in their own accumulator `sm`, added once
+// at the end.
+struct SplitB { uint32_t h0, l0, h1, l1; };
+__device__ __forceinline__ SplitB split_b(float b0, float b1) {
+    SplitB r;
+    tf32_split(b0, r.h0, r.l0);
+    tf32_split(b1, r.h1, r.l1);
+    return r;
+}
+// one k-step
 __device__ __forceinline__ void mma_3xtf32(float (&acc)[4], float (&sm)[4], const uint32_t (&ah)[4],
-                                           const uint32_t (&al)[4], float b0, float b1) {
-    uint32_t bh0, bl0, bh1, bl1;
-    tf32_split(b0, bh0, bl0);
-    tf32_split(b1, bh1, bl1);
-    mma_tf32(sm, al, bh0, bh1);
-    mma_tf32(sm, ah, bl0, bl1);
+                                           const uint32_t (&al)[4], const SplitB& b) {
+    mma_tf32(sm, al, b.h0, b.h1);
+    mma_tf32(sm, ah, b.l0, b.l1);
     float t[4];
-    mma_tf32_zero(t, ah, bh0, bh1);
+    mma_tf32_zero(t, ah, b.h0, b.h1);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) acc[e] += t[e];
+}
+// two k-steps (a / b and a2 / b2)
+__device__ __forceinline__ void mma_3xtf32_pair(float (&acc)[4], float (&sm)[4], const uint32_t (&ah)[4],
+                                                const uint32_t (&al)[4], const SplitB& b, const uint32_t (&ah2)[4],
+                                                const uint32_t (&al2)[4], const SplitB& b2) {
+    mma_tf32(sm, al, b.h0, b.h1);
+    mma_tf32(sm, ah, b.l0, b.l1);
+    mma_tf32(sm, al2, b2.h0, b2.h1);
+    mma_tf32(sm, ah2, b2.l0, b2.l1);
+    float t[4];
+    mma_tf32_zero(t, ah, b.h0, b.h1);
+    mma_tf32(t, ah2, b2.h0, b2.h1);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) acc[e] += t[e];
+}
+
+// two k-steps into a fresh accumulator (small terms first), then one FADD per element: no separate small-term
+// accumulator (used where the accumulators of many blocks stay live, dW)
+__device__ __forceinline__ void mma_3xtf32_fresh_pair(float (&acc)[4], const uint32_t (&ah)[4], const uint32_t (&al)[4],
+                                                      const SplitB& b, const uint32_t (&ah2)[4],
+                                                      const uint32_t (&al2)[4], const SplitB& b2) {
+    float t[4];
+    mma_tf32_zero(t, al, b.h0, b.h1);
+    mma_tf32(t, ah, b.l0, b.l1);
+    mma_tf32(t, al2, b2.h0, b2.h1);
+    mma_tf32(t, ah2, b2.l0, b2.l1);
+    mma_tf32(t, ah, b.h0, b.h1);
+    mma_tf32(t, ah2, b2.h0, b2.h1);
 #pragma unroll
     for (int e = 0; e < 4; ++e) acc[e] += t[e];
 }
@@ -71,28 +108,65 @@ __device__ __forceinline__ void mma_3xtf32(float (&acc)[4], float (&sm)[4], cons
 __device__ __forceinline__ void wide_mma_rows(float (&acc)[2][4], const float* __restrict__ A, int lda,
                                               const float* __restrict__ B, int ldb, int Kd) {
     const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
-    const float* Ap = A + g * lda + t;
-    const float* Bp = B + t * ldb + g;
+    const float* A0 = A + g * lda + t;         // rows g / g + 8 of the block
+    const float* A1 = A0 + 8 * lda;
+    const float* B0 = B + t * ldb + g;         // k rows t / t + 4 of the k-step
+    const float* B1 = B0 + 4 * ldb;
+    const int bstep = 8 * ldb;
     float sm[2][4];
 #pragma unroll
     for (int j = 0; j < 2; ++j)
 #pragma unroll
         for (int e = 0; e < 4; ++e) acc[j][e] = sm[j][e] = 0.f;
-#pragma unroll 2
-    for (int k0 = 0; k0 < Kd; k0 += 8) {
-        uint32_t ah[4], al[4];
-        tf32_split(Ap[k0], ah[0], al[0]);
-        tf32_split(Ap[8 * lda + k0], ah[1], al[1]);
-        tf32_split(Ap[k0 + 4], ah[2], al[2]);
-        tf32_split(Ap[8 * lda + k0 + 4], ah[3], al[3]);
+    int k0 = 0;
+    for (; k0 + 16 <= Kd; k0 += 16) {
+        uint32_t ah[4], al[4], ah2[4], al2[4];
+        tf32_split(A0[k0], ah[0], al[0]);
+        tf32_split(A1[k0], ah[1], al[1]);
+        tf32_split(A0[k0 + 4], ah[2], al[2]);
+        tf32_split(A1[k0 + 4], ah[3], al[3]);
+        tf32_split(A0[k0 + 8], ah2[0], al2[0]);
+        tf32_split(A1[k0 + 8], ah2[1], al2[1]);
+        tf32_split(A0[k0 + 12], ah2[2], al2[2]);
+        tf32_split(A1[k0 + 12], ah2[3], al2[3]);
 #pragma unroll
         for (int j = 0; j < 2; ++j)
-            mma_3xtf32(acc[j], sm[j], ah, al, Bp[k0 * ldb + j * 8], Bp[(k0 + 4) * ldb + j * 8]);
+            mma_3xtf32_pair(acc[j], sm[j], ah, al, split_b(B0[j * 8], B1[j * 8]), ah2, al2,
+                            split_b(B0[bstep + j * 8], B1[bstep + j * 8]));
+        B0 += 2 * bstep;
+        B1 += 2 * bstep;
+    }
+    if (k0 < Kd) {                             // Kd = 8 mod 16
+        uint32_t ah[4], al[4];
+        tf32_split(A0[k0], ah[0], al[0]);
+        tf32_split(A1[k0], ah[1], al[1]);
+        tf32_split(A0[k0 + 4], ah[2], al[2]);
+        tf32_split(A1[k0 + 4], ah[3], al[3]);
+#pragma unroll
+        for (int j = 0; j < 2; ++j) mma_3xtf32(acc[j], sm[j], ah, al, split_b(B0[j * 8], B1[j * 8]));
     }
 #pragma unroll
     for (int j = 0; j < 2; ++j)
 #pragma unroll
         for (int e = 0; e < 4; ++e) acc[j][e] += sm[j][e];
+}
+
+// column sums of a 16 x 8 accumulator block: the lanes that share t = lane % 4 hold the same two columns; their
+// partial sums (s: plain, q: second statistic) go to the CTA's fp64 totals stat[col], stat[F + col]
+__device__ __forceinline__ void wide_stat_flush(double* stat, int F, int col, float s0, float s1, float q0, float q1) {
+#pragma unroll
+    for (int o = 4; o < 32; o <<= 1) {
+        s0 += __shfl_xor_sync(0xffffffffu, s0, o);
+        s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+        q0 += __shfl_xor_sync(0xffffffffu, q0, o);
+        q1 += __shfl_xor_sync(0xffffffffu, q1, o);
+    }
+    if ((threadIdx.x & 31) < 4) {
+        atomicAdd(stat + col, (double)s0);
+        atomicAdd(stat + col + 1, (double)s1);
+        atomicAdd(stat + F + col, (double)q0);
+        atomicAdd(stat + F + col + 1, (double)q1);
+    }
 }
 
 // ---- staged CSR structure of one tile ---------------------------------------------------------------
@@ -399,6 +473,10 @@ fwd_wide_kernel(const FwdArgs a) {
     const int Qc = Fc >> 2;
     const int MB = TR >> 4, NJ = Fout >> 4;
     const int ntiles = (a.R + TR - 1) / TR;
+    const bool one_block = MB * NJ == WD_WARPS;
+    float rst[2][4];
+#pragma unroll
+    for (int j = 0; j < 2; ++j) rst[j][0] = rst[j][1] = rst[j][2] = rst[j][3] = 0.f;
 
     for (int tile_id = blockIdx.x; tile_id < ntiles; tile_id += gridDim.x) {
         const int row0 = tile_id * TR;
@@ -450,24 +528,21 @@ fwd_wide_kernel(const FwdArgs a) {
                 if (rB < trc) *reinterpret_cast<float2*>(a.Z + (size_t)(row0 + rB) * Fout + col) = make_float2(v2, v3);
                 else v2 = v3 = 0.f;
                 if (a.acc_out) {
-                    float s0 = v0 + v2, s1 = v1 + v3;
-                    float q0 = fmaf(v0, v0, v2 * v2), q1 = fmaf(v1, v1, v3 * v3);
-#pragma unroll
-                    for (int o = 4; o < 32; o <<= 1) {
-                        s0 += __shfl_xor_sync(0xffffffffu, s0, o);
-                        s1 += __shfl_xor_sync(0xffffffffu, s1, o);
-                        q0 += __shfl_xor_sync(0xffffffffu, q0, o);
-                        q1 += __shfl_xor_sync(0xffffffffu, q1, o);
-                    }
-                    if (g == 0) {
-                        atomicAdd(sstat + col, (double)s0);
-                        atomicAdd(sstat + col + 1, (double)s1);
-                        atomicAdd(sstat + Fout + col, (double)q0);
-                        atomicAdd(sstat + Fout + col + 1, (double)q1);
+                    const float s0 = v0 + v2, s1 = v1 + v3;
+                    const float q0 = fmaf(v0, v0, v2 * v2), q1 = fmaf(v1, v1, v3 * v3);
+                    if (one_block) {           // this warp's columns never change: keep the partial sums in registers
+                        rst[j][0] += s0; rst[j][1] += s1; rst[j][2] += q0; rst[j][3] += q1;
+                    } else {
+                        wide_stat_flush(sstat, Fout, col, s0, s1, q0, q1);
                     }
                 }
             }
         }
+    }
+    if (a.acc_out && one_block) {
+#pragma unroll
+        for (int j = 0; j < 2; ++j)
+            wide_stat_flush(sstat, Fout, ((warp / MB) << 4) + (j << 3) + (t4 << 1), rst[j][0], rst[j][1], rst[j][2], rst[j][3]);
     }
     if (a.acc_out) {
         __syncthreads();
@@ -516,6 +591,8 @@ __device__ __forceinline__ void bwd_wide_part(const BwdArgs& a, const BwdPart& p
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, t4 = lane & 3;
     const bool want_dw = a.dW_bins != nullptr;
 
+    __syncthreads();                           // a previous part of this CTA is done with shared memory
+    if (tid == 0) dl->rsum_id = -1;
     for (int i = tid; i < nT * Fx; i += WD_THREADS) {
         const int c = i / Fx, f = i - c * Fx;
         const int t = c / Fg, o = c - t * Fg;
@@ -535,13 +612,19 @@ __device__ __forceinline__ void bwd_wide_part(const BwdArgs& a, const BwdPart& p
     for (int i = tid; i < 2 * Fx + Fg; i += WD_THREADS) dtot[i] = 0.0;
 
     const int MBr = TR >> 4, NJx = Fx >> 4;    // gX blocks
-    const int MBc = nT >> 4;                   // dW blocks: MBc x NJx
-    const int ndw = MBc * NJx;
+    // dW = MBc x NJx blocks of 16 x 16: warp w owns column block nj = w % NJx and the row blocks
+    // mi = w / NJx + i * (WD_WARPS / NJx), i < WD_MAXDW, so that its blocks share one B fragment per k-step
+    const int MBc = nT >> 4;
+    const int dw_nj = warp % NJx, dw_m0 = warp / NJx, dw_ms = WD_WARPS / NJx;
     float dw[WD_MAXDW][2][4];
 #pragma unroll
     for (int i = 0; i < WD_MAXDW; ++i)
 #pragma unroll
         for (int j = 0; j < 2; ++j) dw[i][j][0] = dw[i][j][1] = dw[i][j][2] = dw[i][j][3] = 0.f;
+    const bool one_block = MBr * NJx == WD_WARPS;
+    float rst[2][4];
+#pragma unroll
+    for (int j = 0; j < 2; ++j) rst[j][0] = rst[j][1] = rst[j][2] = rst[j][3] = 0.f;
     const int db_groups = WD_THREADS / Fg;
     const int db_o = tid % Fg, db_g = tid / Fg;
     float dbacc = 0.f;
@@ -587,21 +670,13 @@ __device__ __forceinline__ void bwd_wide_part(const BwdArgs& a, const BwdPart& p
                         const float m0 = mu[f], m1 = mu[f + 1], r0 = rs[f], r1 = rs[f + 1];
                         const float2 xa = *reinterpret_cast<const float2*>(xt + rA * Xp + f);
                         const float2 xb = *reinterpret_cast<const float2*>(xt + rB * Xp + f);
-                        float s0 = v0 + v2, s1 = v1 + v3;
-                        float q0 = fmaf(v0, (xa.x - m0) * r0, v2 * ((xb.x - m0) * r0));
-                        float q1 = fmaf(v1, (xa.y - m1) * r1, v3 * ((xb.y - m1) * r1));
-#pragma unroll
-                        for (int o = 4; o < 32; o <<= 1) {
-                            s0 += __shfl_xor_sync(0xffffffffu, s0, o);
-                            s1 += __shfl_xor_sync(0xffffffffu, s1, o);
-                            q0 += __shfl_xor_sync(0xffffffffu, q0, o);
-                            q1 += __shfl_xor_sync(0xffffffffu, q1, o);
-                        }
-                        if (g == 0) {
-                            atomicAdd(sstat + f, (double)s0);
-                            atomicAdd(sstat + f + 1, (double)s1);
-                            atomicAdd(sstat + Fx + f, (double)q0);
-                            atomicAdd(sstat + Fx + f + 1, (double)q1);
+                        const float s0 = v0 + v2, s1 = v1 + v3;
+                        const float q0 = fmaf(v0, (xa.x - m0) * r0, v2 * ((xb.x - m0) * r0));
+                        const float q1 = fmaf(v1, (xa.y - m1) * r1, v3 * ((xb.y - m1) * r1));
+                        if (one_block) {
+                            rst[j][0] += s0; rst[j][1] += s1; rst[j][2] += q0; rst[j][3] += q1;
+                        } else {
+                            wide_stat_flush(sstat, Fx, f, s0, s1, q0, q1);
                         }
                     }
                     if (rA < trc) {
@@ -621,34 +696,33 @@ __device__ __forceinline__ void bwd_wide_part(const BwdArgs& a, const BwdPart& p
         }
         // ---- dW[c][f] += sum_r T[r][c] * xnorm[r][f]  (A = T^T from the tile, B = normalised input rows)
         if (want_dw) {
+            const float* Bp = xt + t4 * Xp + (dw_nj << 4) + g;
+            const float s0 = sc[(dw_nj << 4) + g], h0 = sh[(dw_nj << 4) + g];
+            const float s1 = sc[(dw_nj << 4) + 8 + g], h1 = sh[(dw_nj << 4) + 8 + g];
+            const float* Ap = tile + t4 * Tp + g;
+            for (int k0 = 0; k0 < TR; k0 += 16) {
+                const float* b = Bp + k0 * Xp;
+                const SplitB b00 = split_b(fmaf(b[0], s0, h0), fmaf(b[4 * Xp], s0, h0));
+                const SplitB b01 = split_b(fmaf(b[8], s1, h1), fmaf(b[4 * Xp + 8], s1, h1));
+                const SplitB b10 = split_b(fmaf(b[8 * Xp], s0, h0), fmaf(b[12 * Xp], s0, h0));
+                const SplitB b11 = split_b(fmaf(b[8 * Xp + 8], s1, h1), fmaf(b[12 * Xp + 8], s1, h1));
 #pragma unroll
-            for (int i = 0; i < WD_MAXDW; ++i) {
-                const int b = warp + i * WD_WARPS;
-                if (b < ndw) {
-                    const int mi = b % MBc, nj = b / MBc;
-                    const float* Ap = tile + t4 * Tp + (mi << 4) + g;
-                    const float* Bp = xt + t4 * Xp + (nj << 4) + g;
-                    const float s0 = sc[(nj << 4) + g], h0 = sh[(nj << 4) + g];
-                    const float s1 = sc[(nj << 4) + 8 + g], h1 = sh[(nj << 4) + 8 + g];
-                    float tm[2][4], ts[2][4];       // this tile's contribution (large / small terms)
-#pragma unroll
-                    for (int j = 0; j < 2; ++j)
-#pragma unroll
-                        for (int e = 0; e < 4; ++e) tm[j][e] = ts[j][e] = 0.f;
-#pragma unroll 2
-                    for (int k0 = 0; k0 < TR; k0 += 8) {
-                        uint32_t ah[4], al[4];
-                        tf32_split(Ap[k0 * Tp], ah[0], al[0]);
-                        tf32_split(Ap[k0 * Tp + 8], ah[1], al[1]);
-                        tf32_split(Ap[(k0 + 4) * Tp], ah[2], al[2]);
-                        tf32_split(Ap[(k0 + 4) * Tp + 8], ah[3], al[3]);
-                        mma_3xtf32(tm[0], ts[0], ah, al, fmaf(Bp[k0 * Xp], s0, h0), fmaf(Bp[(k0 + 4) * Xp], s0, h0));
-                        mma_3xtf32(tm[1], ts[1], ah, al, fmaf(Bp[k0 * Xp + 8], s1, h1), fmaf(Bp[(k0 + 4) * Xp + 8], s1, h1));
+                for (int i = 0; i < WD_MAXDW; ++i) {
+                    const int mi = dw_m0 + i * dw_ms;
+                    if (mi < MBc) {
+                        const float* a = Ap + k0 * Tp + (mi << 4);
+                        uint32_t ah[4], al[4], ah2[4], al2[4];
+                        tf32_split(a[0], ah[0], al[0]);
+                        tf32_split(a[8], ah[1], al[1]);
+                        tf32_split(a[4 * Tp], ah[2], al[2]);
+                        tf32_split(a[4 * Tp + 8], ah[3], al[3]);
+                        tf32_split(a[8 * Tp], ah2[0], al2[0]);
+                        tf32_split(a[8 * Tp + 8], ah2[1], al2[1]);
+                        tf32_split(a[12 * Tp], ah2[2], al2[2]);
+                        tf32_split(a[12 * Tp + 8], ah2[3], al2[3]);
+                        mma_3xtf32_fresh_pair(dw[i][0], ah, al, b00, ah2, al2, b10);
+                        mma_3xtf32_fresh_pair(dw[i][1], ah, al, b01, ah2, al2, b11);
                     }
-#pragma unroll
-                    for (int j = 0; j < 2; ++j)
-#pragma unroll
-                        for (int e = 0; e < 4; ++e) dw[i][j][e] += tm[j][e] + ts[j][e];
                 }
             }
             if (is_self && db_g < db_groups) {
@@ -661,9 +735,8 @@ __device__ __forceinline__ void bwd_wide_part(const BwdArgs& a, const BwdPart& p
         const int nbw = hgnn_ws_bins(Fg * a.Cin);
 #pragma unroll
         for (int i = 0; i < WD_MAXDW; ++i) {
-            const int b = warp + i * WD_WARPS;
-            if (b < ndw) {
-                const int mi = b % MBc, nj = b / MBc;
+            const int mi = dw_m0 + i * dw_ms, nj = dw_nj;
+            if (mi < MBc) {
 #pragma unroll
                 for (int j = 0; j < 2; ++j)
 #pragma unroll
@@ -683,6 +756,11 @@ __device__ __forceinline__ void bwd_wide_part(const BwdArgs& a, const BwdPart& p
         }
     }
     if (p.acc_b && p.gX) {
+        if (one_block) {
+#pragma unroll
+            for (int j = 0; j < 2; ++j)
+                wide_stat_flush(sstat, Fx, ((warp / MBr) << 4) + (j << 3) + (t4 << 1), rst[j][0], rst[j][1], rst[j][2], rst[j][3]);
+        }
         __syncthreads();
         const int nb = hgnn_ws_bins(2 * Fx);
         for (int i = tid; i < 2 * Fx; i += WD_THREADS) accum_add(p.acc_b, 2 * Fx, nb, i, sstat[i]);
@@ -724,11 +802,13 @@ bwd_wide_kernel(const BwdArgs a) {
         }
         __syncthreads();
     }
-    const int ts = a.self.R > 0 ? a.self.tiles : 0;
-    const int ns = a.self.R > 0 ? (a.cross.R > 0 ? max(1, (int)(((long long)gridDim.x * ts) / (ts + a.cross.tiles))) : gridDim.x) : 0;
-    if ((int)blockIdx.x < ns)
-        bwd_wide_part(a, a.self, true, blockIdx.x, ns, smem, dscratch, dtot, &dl, wpart, c0, c1, c2, has_bn);
-    else
-        bwd_wide_part(a, a.cross, false, blockIdx.x - ns, gridDim.x - ns, smem, dscratch, dtot, &dl, wpart, c0, c1, c2,
-                      has_bn);
+    // Every CTA takes its share of BOTH parts, one after the other (self tiles dealt from CTA 0 up, cross tiles
+    // from the last CTA down, so the remainders land on different CTAs): the two kinds of tile cost different
+    // amounts, and a split of the CTAs by tile count left the cross CTAs of the edge side running 25 % longer than
+    // the self CTAs (ncu sampling, profiles/README.md).  Costs one more prologue and dW flush per CTA.
+    if (a.self.R > 0)
+        bwd_wide_part(a, a.self, true, blockIdx.x, gridDim.x, smem, dscratch, dtot, &dl, wpart, c0, c1, c2, has_bn);
+    if (a.cross.R > 0)
+        bwd_wide_part(a, a.cross, false, gridDim.x - 1 - blockIdx.x, gridDim.x, smem, dscratch, dtot, &dl, wpart, c0, c1,
+                      c2, has_bn);
 }
