@@ -482,9 +482,18 @@ def run_ours(a):
     achieved = dom_bytes / t_cold / 1e9
     traffic = None
     try:
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get("%s[%s]" % dom)
+        tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        # the captures are per state width (h = 2: thread-per-row kernels, h = 32: tensor-core tile kernels)
+        traffic = (tj if a.h == 2 else tj.get("h%d" % a.h, {})).get("%s[%s]" % dom)
     except Exception:
         pass
+    if a.h < 16:
+        note = ("h=%d: <= %d MB per launch; each launch is a chain of ~5 dependent memory rounds, so the fraction "
+                "is bounded by latency, not by HBM bandwidth" % (a.h, dom_bytes // 1000000))
+    else:
+        note = ("h=%d: tensor-core tile kernels (csrc/engine_wide.cuh): staged CSR structure + 3xTF32 mma.sync "
+                "contractions; instruction-issue bound (the on-the-fly fp32 -> 2 x tf32 operand splits), "
+                "profiles/README.md" % a.h)
     roofline = {"bound": "hbm",
                 "kernel": "%s [%s side of a middle layer] = fused multi-operator + Pm/Pd gather, conv, ReLU, BN "
                           "(its transposed-gather backward for _bwd)" % dom,
@@ -498,8 +507,7 @@ def run_ours(a):
                        "flush-only graph subtracted); algorithmic bytes per SURVEY.md 8(d), backward = forward",
                 "per_kernel": {"columns": ["entry point [side]", "launches/step", "warm us", "cold us", "% of step"],
                                "rows": breakdown[:10]},
-                "note": "h=2: <= %d MB per launch; each launch is a chain of ~5 dependent memory rounds, so the "
-                        "fraction is bounded by latency, not by HBM bandwidth" % (dom_bytes // 1000000)}
+                "note": note}
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps,
             "warmup": a.warmup, "ms_per_step": elapsed * 1e3 / a.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",

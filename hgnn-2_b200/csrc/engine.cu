@@ -1194,7 +1194,7 @@ static int eng_wide_min() {
 static bool eng_try_fwd_wide(eng::FwdArgs& a, hgnn_stream_t stream) {
     if (eng_wide_disabled()) return false;
     if (a.Fout % 16 || a.Fout < eng_wide_min() || a.Fout > 128) return false;
-    if (a.Fs % 4 || a.Fc % 4 || a.Cin % 8) return false;
+    if (a.Fs % 8 || a.Fc % 8) return false;          // two 16-byte chunks per gather item; Cin is then 0 mod 8
     if (!eng_aligned16(a.Xs) || (a.Fc && !eng_aligned16(a.Xc)) || !eng_aligned16(a.Z)) return false;
     const int Cp = eng_pad(a.Cin, 4);
     int TR = WD_TR;

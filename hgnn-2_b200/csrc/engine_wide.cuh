@@ -190,16 +190,19 @@ __device__ __forceinline__ int wr_col(const WideRow& w, int k) { return w.smem ?
 __device__ __forceinline__ float wr_val(const WideRow& w, int k) { return w.smem ? w.val[k] : __ldg(w.val + k); }
 __device__ __forceinline__ float wr_val2(const WideRow& w, int k) { return w.smem ? w.val2[k] : __ldg(w.val2 + k); }
 
-// acc = sum_k val[k] * ld(col[k], xo): BATCH independent feature loads in flight (raw rows; the loader's fix-up
-// of the weighted sum is applied once at the end)
-template <int BATCH, typename L>
-__device__ __forceinline__ V<4> wide_gather(const WideRow& w, const L& ld_, int xo) {
-    V<4> acc = V<4>::zero();
+// acc[h] = sum_k val[k] * ld(col[k], xo + h * xs), h < NCH: BATCH * NCH independent 16-byte feature loads in flight
+// (raw rows; the loader's fix-up of the weighted sum is applied once at the end).  An item of the tile gathers covers
+// NCH = 2 chunks of its row, half a row apart, so the index work (row pointers, entries, predicates) is paid once
+// per 32 bytes of every gathered row and a tile is one item per thread.
+template <int BATCH, int NCH, typename L>
+__device__ __forceinline__ void wide_gather(const WideRow& w, const L& ld_, int xo, int xs, V<4> (&acc)[NCH]) {
+#pragma unroll
+    for (int h = 0; h < NCH; ++h) acc[h] = V<4>::zero();
     float vsum = 0.f;
     for (int k = w.k0; k < w.k1; k += BATCH) {
         int c[BATCH];
         float v[BATCH];
-        V<4> x[BATCH];
+        V<4> x[BATCH][NCH];
 #pragma unroll
         for (int j = 0; j < BATCH; ++j) {
             const bool on = k + j < w.k1;
@@ -208,18 +211,21 @@ __device__ __forceinline__ V<4> wide_gather(const WideRow& w, const L& ld_, int 
             v[j] = on ? wr_val(w, kk) : 0.f;
         }
 #pragma unroll
-        for (int j = 0; j < BATCH; ++j) {
-            x[j] = V<4>::zero();
-            if (k + j < w.k1) x[j] = ld_.raw(c[j], xo);
-        }
+        for (int j = 0; j < BATCH; ++j)
+#pragma unroll
+            for (int h = 0; h < NCH; ++h) {
+                x[j][h] = V<4>::zero();
+                if (k + j < w.k1) x[j][h] = ld_.raw(c[j], xo + h * xs);
+            }
 #pragma unroll
         for (int j = 0; j < BATCH; ++j) {
-            acc.fma(v[j], x[j]);
+#pragma unroll
+            for (int h = 0; h < NCH; ++h) acc[h].fma(v[j], x[j][h]);
             vsum += v[j];
         }
     }
-    ld_.finish(acc, vsum, xo);
-    return acc;
+#pragma unroll
+    for (int h = 0; h < NCH; ++h) ld_.finish(acc[h], vsum, xo + h * xs);
 }
 
 // Stage the structure of rows [row0, row0 + trc) of the CSR operators in `slots` (all threads; two barriers inside,
@@ -316,15 +322,16 @@ __device__ __forceinline__ void wide_assign_slots(WideStage* st, const OpList& o
 }
 
 // Two value arrays on one pattern (Pm / Pd): am = sum_k val[k] x_k, ad = sum_k val2[k] x_k, every row loaded once
-template <int BATCH, typename L>
-__device__ __forceinline__ void wide_gather2(const WideRow& w, const L& ld_, int xo, V<4>& am, V<4>& ad) {
-    am = V<4>::zero();
-    ad = V<4>::zero();
+template <int BATCH, int NCH, typename L>
+__device__ __forceinline__ void wide_gather2(const WideRow& w, const L& ld_, int xo, int xs, V<4> (&am)[NCH],
+                                             V<4> (&ad)[NCH]) {
+#pragma unroll
+    for (int h = 0; h < NCH; ++h) { am[h] = V<4>::zero(); ad[h] = V<4>::zero(); }
     float sm_ = 0.f, sd_ = 0.f;
     for (int k = w.k0; k < w.k1; k += BATCH) {
         int c[BATCH];
         float vm[BATCH], vd[BATCH];
-        V<4> x[BATCH];
+        V<4> x[BATCH][NCH];
 #pragma unroll
         for (int j = 0; j < BATCH; ++j) {
             const bool on = k + j < w.k1;
@@ -334,71 +341,97 @@ __device__ __forceinline__ void wide_gather2(const WideRow& w, const L& ld_, int
             vd[j] = on ? wr_val2(w, kk) : 0.f;
         }
 #pragma unroll
-        for (int j = 0; j < BATCH; ++j) {
-            x[j] = V<4>::zero();
-            if (k + j < w.k1) x[j] = ld_.raw(c[j], xo);
-        }
+        for (int j = 0; j < BATCH; ++j)
+#pragma unroll
+            for (int h = 0; h < NCH; ++h) {
+                x[j][h] = V<4>::zero();
+                if (k + j < w.k1) x[j][h] = ld_.raw(c[j], xo + h * xs);
+            }
 #pragma unroll
         for (int j = 0; j < BATCH; ++j) {
-            am.fma(vm[j], x[j]);
-            ad.fma(vd[j], x[j]);
+#pragma unroll
+            for (int h = 0; h < NCH; ++h) {
+                am[h].fma(vm[j], x[j][h]);
+                ad[h].fma(vd[j], x[j][h]);
+            }
             sm_ += vm[j];
             sd_ += vd[j];
         }
     }
-    ld_.finish(am, sm_, xo);
-    ld_.finish(ad, sd_, xo);
+#pragma unroll
+    for (int h = 0; h < NCH; ++h) {
+        ld_.finish(am[h], sm_, xo + h * xs);
+        ld_.finish(ad[h], sd_, xo + h * xs);
+    }
 }
 
-// Self part of the tile gather: item (r, q) = feature chunk q of row r; writes tile[r][t * F + 4q ..] for every
-// operator t.  CSR operators first (their feature loads are issued together with the own-row load), identity /
-// diagonal blocks last.  `dual`: the list is two CSR operators on ONE pattern (Pm^T / Pd^T of the backward's cross
-// part): one pass over the entries, every gathered row loaded once.
+// Self part of the tile gather: item (r, q) = feature chunks q and q + F/8 of row r (F is a multiple of 8); writes
+// tile[r][t * F + ..] for every operator t.  CSR operators first (their feature loads are issued together with the
+// own-row load), identity / diagonal blocks last.  `dual`: the list is two CSR operators on ONE pattern (Pm^T / Pd^T
+// of the backward's cross part): one pass over the entries, every gathered row loaded once.
 template <int BATCH, typename L>
 __device__ __forceinline__ void wide_gather_self(const WideStage* st, const OpList& ops, const L& ld_, int F, int row0,
                                                  int trc, float* tile, int ldt, const int* scol, const float* sval,
                                                  DeferList* dl, bool own_block, int own_col, bool dual) {
-    const int Q = F >> 2, K = ops.n;
+    const int Qh = F >> 3, xs = F >> 1, K = ops.n;
     bool need_own = own_block;
     for (int t = 0; t < K; ++t) need_own = need_own || ops.kind[t] != HGNN_OP_CSR;
-    for (int i = threadIdx.x; i < Q * trc; i += WD_THREADS) {
-        const int r = i / Q, q = i - r * Q;
+    for (int i = threadIdx.x; i < Qh * trc; i += WD_THREADS) {
+        const int r = i / Qh, q = i - r * Qh;
         const int row = row0 + r, xo = q << 2;
         float* trow = tile + r * ldt;
         if (dual) {
             WideRow w = wide_row(st, ops, 0, row0, r, scol, sval);
             const WideRow w1 = wide_row(st, ops, 1, row0, r, scol, sval);
             w.val2 = w1.val;
-            V<4> am, ad;
-            wide_gather2<BATCH>(w, ld_, xo, am, ad);
-            am.store(trow + xo);
-            ad.store(trow + F + xo);
+            V<4> am[2], ad[2];
+            wide_gather2<BATCH, 2>(w, ld_, xo, xs, am, ad);
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                am[h].store(trow + xo + h * xs);
+                ad[h].store(trow + F + xo + h * xs);
+            }
             continue;
         }
-        V<4> own = V<4>::zero();
-        if (need_own) own = ld_(row, xo);
+        V<4> own[2];
+        own[0] = own[1] = V<4>::zero();
+        if (need_own) {
+            own[0] = ld_(row, xo);
+            own[1] = ld_(row, xo + xs);
+        }
         for (int t = 0; t < K; ++t) {
             if (ops.kind[t] != HGNN_OP_CSR) continue;
             const WideRow w = wide_row(st, ops, t, row0, r, scol, sval);
             if (w.k1 - w.k0 > ENG_LONG_ROW) {
-                const int slot = atomicAdd(&dl->cnt, 1);
-                if (slot < ENG_MAX_DEFER) {
+                const int slot = atomicAdd(&dl->cnt, 2);
+                if (slot + 1 < ENG_MAX_DEFER) {
                     dl->items[slot] = defer_code(t, q, r);
+                    dl->items[slot + 1] = defer_code(t, q + Qh, r);
                     continue;
                 }
             }
-            wide_gather<BATCH>(w, ld_, xo).store(trow + t * F + xo);
+            V<4> acc[2];
+            wide_gather<BATCH, 2>(w, ld_, xo, xs, acc);
+            acc[0].store(trow + t * F + xo);
+            acc[1].store(trow + t * F + xo + xs);
         }
         for (int t = 0; t < K; ++t) {
             if (ops.kind[t] == HGNN_OP_IDENT) {
-                own.store(trow + t * F + xo);
+                own[0].store(trow + t * F + xo);
+                own[1].store(trow + t * F + xo + xs);
             } else if (ops.kind[t] == HGNN_OP_DIAG) {
-                V<4> x = own;
-                x.scale(__ldg(ops.diag[t] + row));
-                x.store(trow + t * F + xo);
+                const float dg = __ldg(ops.diag[t] + row);
+                V<4> x0 = own[0], x1 = own[1];
+                x0.scale(dg);
+                x1.scale(dg);
+                x0.store(trow + t * F + xo);
+                x1.store(trow + t * F + xo + xs);
             }
         }
-        if (own_block) own.store(trow + own_col + xo);
+        if (own_block) {
+            own[0].store(trow + own_col + xo);
+            own[1].store(trow + own_col + xo + xs);
+        }
     }
 }
 
@@ -470,7 +503,7 @@ fwd_wide_kernel(const FwdArgs a) {
     for (int i = tid; i < 2 * Fout; i += WD_THREADS) sstat[i] = 0.0;
 
     const int xc0 = K * Fs;
-    const int Qc = Fc >> 2;
+    const int Qc = Fc >> 3;
     const int MB = TR >> 4, NJ = Fout >> 4;
     const int ntiles = (a.R + TR - 1) / TR;
     const bool one_block = MB * NJ == WD_WARPS;
@@ -488,9 +521,9 @@ fwd_wide_kernel(const FwdArgs a) {
         if (cross) {
             const bool sm = st->staged[WD_SLOTS] != 0;
             const int base = st->base[WD_SLOTS];
-            for (int i = tid; i < Qc * trc; i += WD_THREADS) {
+            for (int i = tid; i < Qc * trc; i += WD_THREADS) {      // Qc = Fc / 8: two chunks per item
                 const int r = i / Qc, q = i - r * Qc;
-                const int xo = q << 2;
+                const int xo = q << 2, xs = Fc >> 1;
                 WideRow w;
                 w.k0 = st->rp[WD_SLOTS][r];
                 w.k1 = st->rp[WD_SLOTS][r + 1];
@@ -498,11 +531,14 @@ fwd_wide_kernel(const FwdArgs a) {
                 w.col = sm ? pcol - base : a.p_col;
                 w.val = sm ? pv1 - base : a.p_pm;
                 w.val2 = sm ? pv2 - base : a.p_pd;
-                V<4> am, ad;
-                wide_gather2<4>(w, lc, xo, am, ad);
+                V<4> am[2], ad[2];
+                wide_gather2<4, 2>(w, lc, xo, xs, am, ad);
                 float* trow = tile + r * Cp;
-                am.store(trow + xc0 + xo);
-                ad.store(trow + xc0 + Fc + xo);
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    am[h].store(trow + xc0 + xo + h * xs);
+                    ad[h].store(trow + xc0 + Fc + xo + h * xs);
+                }
             }
         }
         __syncthreads();
@@ -635,7 +671,7 @@ __device__ __forceinline__ void bwd_wide_part(const BwdArgs& a, const BwdPart& p
         if (tid == 0) { dl->cnt = 0; dl->rng_cnt = 0; }
         __syncthreads();                       // previous tile's contractions are done with tile / xt
         wide_stage(st, p.ops, nullptr, nullptr, nullptr, nullptr, row0, trc, scol, sval, nullptr, nullptr, nullptr, dl);
-        wide_gather_self<4>(st, p.ops, lg, Fg, row0, trc, tile, Tp, scol, sval, dl, is_self, nT, dual);
+        wide_gather_self<3>(st, p.ops, lg, Fg, row0, trc, tile, Tp, scol, sval, dl, is_self, nT, dual);
         {
             const int NQ = Fx >> 2;
             for (int i = tid; i < trc * NQ; i += WD_THREADS) {

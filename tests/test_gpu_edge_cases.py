@@ -89,3 +89,28 @@ def test_node_zero_hub_overflows_nothing():
     A[0, 1:100] = 1.0
     A[1:100, 0] = 1.0
     _compare("lg", 1, 2, 1, [A, _adj(30, 0.2, gen)], seed=15)
+
+
+@pytest.mark.parametrize("kind,order", [("simple", 0), ("lg", 1), ("lg", 3)])
+def test_wide_states_degenerate_graphs(kind, order):
+    """h = 16 (32-wide states): the middle layers run on the tensor-core tile kernels (csrc/engine_wide.cuh);
+    same degenerate batch as above plus a ragged one, against the CPU oracle."""
+    gen = torch.Generator().manual_seed(5)
+    single = torch.zeros(3, 3)
+    single[1, 2] = single[2, 1] = 2.0
+    adjs = [_adj(9, 0.4, gen, True), torch.zeros(4, 4), single, _adj(6, 0.5, gen), _adj(40, 0.12, gen, True)]
+    _compare(kind, order, 16, 1, adjs, seed=16, L=4)
+    _compare(kind, order, 16, 1, [_adj(17, 0.3, gen, True)], seed=17, L=3)
+
+
+def test_wide_states_long_rows():
+    """32-wide states with rows longer than the in-line gather limit (deferred to warp-cooperative gathers), more
+    deferred items than the list holds, tiles whose CSR slice exceeds the staging buffers, and the run-length
+    ranges of a node-0 hub."""
+    gen = torch.Generator().manual_seed(6)
+    hub = _adj(120, 0.05, gen)
+    hub[0, 1:100] = 1.0
+    hub[1:100, 0] = 1.0
+    _compare("lg", 1, 16, 1, [hub, _adj(30, 0.2, gen)], seed=18)
+    _compare("lg", 1, 16, 1, [_adj(50, 0.7, gen), _adj(12, 0.3, gen, True)], seed=19)
+    _compare("simple", 0, 16, 2, [_adj(50, 0.7, gen), _adj(12, 0.3, gen, True)], seed=20, L=4)
