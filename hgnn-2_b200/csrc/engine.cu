@@ -1191,20 +1191,30 @@ static int eng_wide_min() {
     return v;
 }
 
-static bool eng_try_fwd_wide(eng::FwdArgs& a, hgnn_stream_t stream) {
+// width-only part of the forward dispatch: tile rows and dynamic shared memory, or false
+static bool eng_wide_fwd_fits(int n_ops, int Fs, int Fc, int Fout, int* TR_out, size_t* smem_out) {
     if (eng_wide_disabled()) return false;
-    if (a.Fout % 16 || a.Fout < eng_wide_min() || a.Fout > 128) return false;
-    if (a.Fs % 8 || a.Fc % 8) return false;          // two 16-byte chunks per gather item; Cin is then 0 mod 8
-    if (!eng_aligned16(a.Xs) || (a.Fc && !eng_aligned16(a.Xc)) || !eng_aligned16(a.Z)) return false;
-    const int Cp = eng_pad(a.Cin, 4);
-    int TR = WD_TR;
-    size_t smem = 0;
-    for (; TR >= 16; TR >>= 1) {
-        smem = (size_t)eng::wide_fwd_layout(a.Cin, Cp, a.Fout, a.Fs, a.Fc, TR).total * sizeof(float);
-        if (smem <= WD_MAX_SMEM) break;
+    if (Fout % 16 || Fout < eng_wide_min() || Fout > 128) return false;
+    if (Fs < 8 || Fs % 8 || Fc % 8 || Fs > 128 || Fc > 128) return false;   // two 16-byte chunks per gather item
+    const int Cin = n_ops * Fs + 2 * Fc;
+    const int Cp = eng_pad(Cin, 4);
+    for (int TR = WD_TR; TR >= 16; TR >>= 1) {
+        const size_t smem = (size_t)eng::wide_fwd_layout(Cin, Cp, Fout, Fs, Fc, TR).total * sizeof(float);
+        if (smem <= WD_MAX_SMEM) {
+            *TR_out = TR;
+            *smem_out = smem;
+            return true;
+        }
     }
-    if (TR < 16) return false;
-    a.Cin_pad = Cp;
+    return false;
+}
+
+static bool eng_try_fwd_wide(eng::FwdArgs& a, hgnn_stream_t stream) {
+    int TR = 0;
+    size_t smem = 0;
+    if (!eng_wide_fwd_fits(a.ops.n, a.Fs, a.Fc, a.Fout, &TR, &smem)) return false;
+    if (!eng_aligned16(a.Xs) || (a.Fc && !eng_aligned16(a.Xc)) || !eng_aligned16(a.Z)) return false;
+    a.Cin_pad = eng_pad(a.Cin, 4);
     a.TR = TR;
     const int ntiles = ceil_div(a.R, TR);
     const int grid = balanced_grid(ntiles, eng_resident_impl(reinterpret_cast<const void*>(eng::fwd_wide_kernel), smem, WD_THREADS));
@@ -1212,26 +1222,52 @@ static bool eng_try_fwd_wide(eng::FwdArgs& a, hgnn_stream_t stream) {
     return true;
 }
 
-// derived fields of one backward part for bwd_wide_kernel; false if it does not qualify / fit
-static bool eng_plan_part_wide(eng::BwdPart& p, int Fg, bool is_self) {
-    if (p.Fx % 16 || p.Fx > 128 || !eng_part_vout4(p.X, p.gX, p.Fx)) return false;
-    p.nT = p.ops.n * Fg;
-    p.P = p.nT * p.Fx;
-    const int njx = p.Fx / 16;               // dW: a warp owns one 16-column block and <= WD_MAXDW row blocks
-    if (WD_WARPS % njx || p.nT / 16 > WD_MAXDW * (WD_WARPS / njx)) return false;
-    p.NG = 1;
-    p.Tp = eng_pad(is_self ? p.nT + Fg : p.nT, 4);
-    p.Xp = p.Fx + 8;
+// width-only part of the backward dispatch for one part (n_ops operators gathered, gPre width Fg, input width Fx)
+static bool eng_wide_part_fits(int n_ops, int Fg, int Fx, bool is_self, int* TR_out, size_t* smem_out) {
+    if (Fx % 16 || Fx > 128) return false;
+    const int nT = n_ops * Fg;
+    const int njx = Fx / 16;                 // dW: a warp owns one 16-column block and <= WD_MAXDW row blocks
+    if (WD_WARPS % njx || nT / 16 > WD_MAXDW * (WD_WARPS / njx)) return false;
+    const int Tp = eng_pad(is_self ? nT + Fg : nT, 4);
     for (int TR = WD_TR; TR >= 16; TR >>= 1) {
-        const size_t smem = (size_t)eng::wide_bwd_layout(p.nT, p.Fx, p.Tp, p.Xp, TR).total * sizeof(float);
+        const size_t smem = (size_t)eng::wide_bwd_layout(nT, Fx, Tp, Fx + 8, TR).total * sizeof(float);
         if (smem <= WD_MAX_SMEM) {
-            p.TR = TR;
-            p.smem = smem;
-            p.tiles = ceil_div(p.R, TR);
+            *TR_out = TR;
+            *smem_out = smem;
             return true;
         }
     }
     return false;
+}
+static bool eng_wide_bwd_width(int Fg) {
+    return !eng_wide_disabled() && Fg % 16 == 0 && Fg >= eng_wide_min() && Fg <= 128;
+}
+
+// derived fields of one backward part for bwd_wide_kernel; false if it does not qualify / fit
+static bool eng_plan_part_wide(eng::BwdPart& p, int Fg, bool is_self) {
+    int TR = 0;
+    size_t smem = 0;
+    if (!eng_part_vout4(p.X, p.gX, p.Fx) || !eng_wide_part_fits(p.ops.n, Fg, p.Fx, is_self, &TR, &smem)) return false;
+    p.nT = p.ops.n * Fg;
+    p.P = p.nT * p.Fx;
+    p.NG = 1;
+    p.Tp = eng_pad(is_self ? p.nT + Fg : p.nT, 4);
+    p.Xp = p.Fx + 8;
+    p.TR = TR;
+    p.smem = smem;
+    p.tiles = ceil_div(p.R, TR);
+    return true;
+}
+
+extern "C" int hgnn_lg_wide_eligible(int n_ops, int Fs, int Fc, int Fout, int backward) {
+    int TR = 0;
+    size_t smem = 0;
+    if (n_ops < 1 || n_ops > HGNN_MAX_OPS || Fs < 1 || Fc < 0 || Fout < 1) return 0;
+    if (!backward) return eng_wide_fwd_fits(n_ops, Fs, Fc, Fout, &TR, &smem) ? 1 : 0;
+    if (!eng_wide_bwd_width(Fout)) return 0;
+    if (!eng_wide_part_fits(n_ops, Fout, Fs, true, &TR, &smem)) return 0;
+    if (Fc > 0 && !eng_wide_part_fits(2, Fout, Fc, false, &TR, &smem)) return 0;
+    return 1;
 }
 
 extern "C" int hgnn_lg_side_fwd(const hgnn_side_t* side, const hgnn_bn_ref_t* bn_self,
@@ -1557,7 +1593,7 @@ extern "C" int hgnn_lg_side_bwd(const hgnn_side_bwd_t* d, hgnn_stream_t stream) 
         (d->R_self <= 0 || (d->Fs >= 16 && d->Xs && eng_part_vout4(d->Xs, d->gXs, d->Fs))) &&
         (d->R_cross <= 0 || (d->Fc >= 16 && d->Xc && eng_part_vout4(d->Xc, d->gXc, d->Fc)));
     // tensor-core tile kernel (engine_wide.cuh) when both parts qualify
-    bool mma = !eng_wide_disabled() && vec4 && d->Fg % 16 == 0 && d->Fg >= eng_wide_min() && d->Fg <= 128;
+    bool mma = vec4 && eng_wide_bwd_width(d->Fg);
     // self part
     a.self.R = d->R_self;
     bool vs4 = false, vc4 = false;

@@ -209,6 +209,12 @@ int hgnn_lg_side_fwd(const hgnn_side_t* side, const hgnn_bn_ref_t* bn_self, cons
 /* 1 if the (ops, widths) combination runs on the thread-per-row width-4 kernels (engine_row4.cuh);
  * only then may X1 (the saved concatenated input rows, (R, Cin)) and skip_dw be used. */
 int hgnn_lg_row4_eligible(const hgnn_op_t* ops, int n_ops, int Fs, int Fc, int Fout);
+/* 1 if a side with n_ops operators, self / cross input widths Fs / Fc (Fc = 0: no cross part) and Fout outputs
+ * runs on the tensor-core tile kernels for wide states (engine_wide.cuh) - forward (backward = 0) or backward
+ * (backward = 1; Fout is then the width of the incoming gradient) - given 16-byte aligned tensors.  Widths only:
+ * host code and tests use it to know which code path a model takes (replaces nothing in the reference, whose
+ * layers_mnb.py:189-225 has a single dense path). */
+int hgnn_lg_wide_eligible(int n_ops, int Fs, int Fc, int Fout, int backward);
 /* Weight gradients of a width-4 side as a streaming pass over the saved x1 rows:
  * dW[o][c] += sum_r gPre[r][o] x1[r][c], dbias[o] += sum_r gPre[r][o] (gPre as in hgnn_lg_side_bwd).
  * Independent of hgnn_lg_side_bwd(skip_dw=1): the host layer runs it on a parallel stream. */

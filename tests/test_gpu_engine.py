@@ -51,6 +51,12 @@ def test_engine_matches_module_path(kind, order, h, J, N):
     from hgnn_b200 import synth
     from hgnn_b200.functions.batching import prepare_batch
     from hgnn_b200.models.gnns.model_mnb import GNN_lg, GNN_simple
+    if h >= 16:
+        # the middle layers of these cases must run on the tensor-core tile kernels, not on a fallback
+        from hgnn_b200 import _lib
+        Fc = 2 * h if kind == "lg" else 0
+        assert _lib.lib.hgnn_lg_wide_eligible(J + 2, 2 * h, Fc, 2 * h, 0) == 1
+        assert _lib.lib.hgnn_lg_wide_eligible(J + 2, 2 * h, Fc, 2 * h, 1) == 1
     torch.manual_seed(order * 10 + h)
     inst = synth.sbm_dataset(6, N=N, J=J)
     batch = prepare_batch(inst, 0, J)
