@@ -10,15 +10,18 @@
 // Here
 //   * a CTA has 16 warps and STAGES the CSR structure of its 64-row tile first: the row pointers of every CSR
 //     operator (one coalesced round), then the tile's contiguous slice of (col, val) (a second coalesced round)
-//     into shared memory.  The gather proper then issues nothing but independent 16-byte feature loads, 4-8 in
-//     flight per thread, own row and neighbour rows together;
+//     into shared memory.  The gather proper then issues nothing but independent 16-byte feature loads: one item
+//     per thread and tile = two chunks of a row, own row and 3-4 neighbour rows in flight together, raw rows
+//     summed and the producer's batch-norm applied once per sum;
 //   * the three contractions (forward Z = T W, backward gX = T W^T-block, dW += T^T Xn) run on the tensor
-//     cores as mma.sync m16n8k8 TF32 with the 3xTF32 error-compensated split (a = hi + lo: lo*hi + hi*lo + hi*hi,
-//     fp32 accumulate), which keeps the 1e-4 parity bound of fp32 with margin (measured ~1e-6); dW lives in the
-//     accumulator fragments across all tiles of the CTA and is flushed once.
+//     cores as mma.sync m16n8k8 TF32 with the 3xTF32 error-compensated split (a = hi + lo: lo*hi + hi*lo + hi*hi).
+//     The tensor core accumulates with truncation, so the large terms are summed outside it in round-to-nearest
+//     fp32 (see mma_3xtf32_pair); that keeps the 1e-4 parity bound of fp32 with margin (tests/test_wide_dispatch.py
+//     emulates the arithmetic).  dW lives in accumulator fragments across all tiles of the CTA and is flushed once;
+//   * in the backward every CTA works through its share of the self tiles and then of the cross tiles.
 // Long rows (> ENG_LONG_ROW entries) and the run-length ranges of the transposed line-graph operator keep using
 // gather_deferred of engine.cu.  Semantics are those of fwd_kernel / bwd_kernel (layers_mnb.py:189-225,
-// batch_normalization.py:34-43,65-77).
+// batch_normalization.py:34-43,65-77).  Measurements and the ncu evidence behind each choice: profiles/README.md.
 #pragma once
 
 #define WD_THREADS 512

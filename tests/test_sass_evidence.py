@@ -1,0 +1,66 @@
+"""CPU: static evidence from the built library (cuobjdump; nvcc cross-compiles without a GPU) that the wide-state
+kernels are what DESIGN.md says they are: tensor-core contractions (HMMA.1688.F32.TF32 = mma.sync.m16n8k8 tf32),
+within the 128-register budget of a 512-thread CTA without meaningful spills, and with the operand split that
+keeps the contraction loop at a handful of instructions per mma (the first version spent 7 instructions per
+split on the cvt.rna.tf32 emulation: profiles/README.md)."""
+import collections
+import re
+import shutil
+import subprocess
+
+import pytest
+
+KERNELS = {"fwd": "_ZN3eng15fwd_wide_kernelENS_7FwdArgsE", "bwd": "_ZN3eng15bwd_wide_kernelENS_7BwdArgsE"}
+
+pytestmark = pytest.mark.skipif(shutil.which("cuobjdump") is None, reason="needs the CUDA toolkit")
+
+
+def _lib_path():
+    import hgnn_b200  # noqa: F401
+    from hgnn_b200 import _lib
+    return _lib.LIB_PATH
+
+
+def _sass(fn):
+    out = subprocess.run(["cuobjdump", "-sass", "-fun", fn, _lib_path()], capture_output=True, text=True).stdout
+    ins = []
+    for line in out.splitlines():
+        m = re.search(r"/\*([0-9a-f]{4,})\*/\s+(.*?);", line)
+        if m:
+            ins.append((int(m.group(1), 16), re.sub(r"^@!?U?P\d+\s+", "", m.group(2).strip())))
+    return ins
+
+
+def test_wide_kernels_fit_the_register_file():
+    out = subprocess.run(["cuobjdump", "-res-usage", _lib_path()], capture_output=True, text=True).stdout
+    for fn in KERNELS.values():
+        m = re.search(re.escape(fn) + r":\s*\n\s*REG:(\d+) STACK:(\d+) SHARED:(\d+)", out)
+        assert m, "kernel %s not in the library" % fn
+        reg, stack, shared = map(int, m.groups())
+        assert reg <= 128            # 512 threads per CTA: 65536 / 512
+        assert stack <= 16           # no spills to speak of
+        assert shared <= 14 * 1024   # static part; the dispatch leaves 15 KB under the 227 KB limit for it
+
+
+@pytest.mark.parametrize("which", ["fwd", "bwd"])
+def test_wide_contractions_run_on_tensor_cores(which):
+    ins = _sass(KERNELS[which])
+    assert ins, "no SASS for %s" % KERNELS[which]
+    hmma = [t for _, t in ins if t.startswith("HMMA")]
+    assert len(hmma) >= 18 and all(t.startswith("HMMA.1688.F32.TF32") for t in hmma)
+    # innermost loops that contain mma: instructions per mma
+    best = None
+    for addr, t in ins:
+        m = re.match(r"BRA\s+(0x[0-9a-f]+)", t)
+        if not m or int(m.group(1), 16) >= addr:
+            continue
+        body = [x for a, x in ins if int(m.group(1), 16) <= a <= addr]
+        n = sum(x.startswith("HMMA") for x in body)
+        if n >= 6 and (best is None or len(body) < len(best)):
+            best = body
+    assert best is not None, "no loop with mma found"
+    n = sum(x.startswith("HMMA") for x in best)
+    ops = collections.Counter(x.split()[0].split(".")[0] for x in best)
+    assert len(best) / n <= 8.0, (len(best), n, ops.most_common(8))
+    # the cvt.rna.tf32 emulation (FSETP against +INF, SEL) must not be back in the loop
+    assert ops["FSETP"] == 0 and ops["SEL"] == 0, ops.most_common(8)
