@@ -10,7 +10,7 @@ seen, out, fname, hdr = set(), {}, None, None
 for r in rows:
     if not r:
         continue
-    if r[0] == "File Name":
+    if r[0] in ("File Name", "File Path"):
         fname = r[1]
         if fname in seen:           # second launch starts: stop
             break

@@ -9,6 +9,9 @@ import sys
 rows = list(csv.reader(open(sys.argv[1])))
 heads = [i for i, r in enumerate(rows) if r and r[0] == "Address"]      # one section per profiled launch
 sec = int(sys.argv[3]) if len(sys.argv) > 3 else 0
+if sec >= len(heads):
+    print("no such section (kernel not in the report?)")
+    sys.exit(0)
 hi = heads[sec]
 end = heads[sec + 1] if sec + 1 < len(heads) else len(rows)
 hdr = rows[hi]
