@@ -965,6 +965,7 @@ bwd_kernel(const BwdArgs a) {
 #include "engine_row4.cuh"
 #include "engine_rowg.cuh"
 #include "engine_wide.cuh"
+#include "engine_tc5.cuh"
 
 }  // namespace eng
 
@@ -1222,6 +1223,30 @@ static bool eng_try_fwd_wide(eng::FwdArgs& a, hgnn_stream_t stream) {
     return true;
 }
 
+// EXPERIMENTAL tcgen05 forward (engine_tc5.cuh): only with HGNN_B200_WIDE_TC5=1
+static bool eng_tc5_enabled() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("HGNN_B200_WIDE_TC5"); v = (e && e[0] == '1') ? 1 : 0; }
+    return v == 1;
+}
+static bool eng_try_fwd_tc5(eng::FwdArgs& a, hgnn_stream_t stream) {
+    if (!eng_tc5_enabled() || eng_wide_disabled()) return false;
+    const bool cross = a.p_rowptr != nullptr;
+    if (a.Fs != 32 && a.Fs != 64) return false;
+    if (cross && a.Fc != 32 && a.Fc != 64) return false;
+    if (a.Fout != 32 && a.Fout != 64) return false;
+    if ((a.ops.n + (cross ? 2 : 0) + 2) * a.Fout > 512) return false;        // TMEM columns
+    for (int t = 0; t < a.ops.n; ++t) if (a.ops.rng_rowptr[t]) return false;
+    if (!eng_aligned16(a.Xs) || (cross && !eng_aligned16(a.Xc)) || !eng_aligned16(a.Z)) return false;
+    const size_t smem = (size_t)eng::tc5_layout(a.Cin, a.Fout, a.Fs, a.Fc).total * sizeof(float);
+    if (smem > WD_MAX_SMEM) return false;
+    a.TR = 64;
+    const int ntiles = ceil_div(a.R, 64);
+    const int grid = balanced_grid(ntiles, eng_resident_impl(reinterpret_cast<const void*>(eng::fwd_tc5_kernel), smem, WD_THREADS));
+    eng::fwd_tc5_kernel<<<grid, WD_THREADS, smem, to_stream(stream)>>>(a);
+    return true;
+}
+
 // width-only part of the backward dispatch for one part (n_ops operators gathered, gPre width Fg, input width Fx)
 static bool eng_wide_part_fits(int n_ops, int Fg, int Fx, bool is_self, int* TR_out, size_t* smem_out) {
     if (Fx % 16 || Fx > 128) return false;
@@ -1297,6 +1322,7 @@ extern "C" int hgnn_lg_side_fwd(const hgnn_side_t* side, const hgnn_bn_ref_t* bn
     if (eng_try_fwd_row4(a, side, stream)) return hgnn_check_launch("hgnn_lg_side_fwd(row4)");
     if (eng_try_fwd_rowg(a, side, stream)) return hgnn_check_launch("hgnn_lg_side_fwd(rowg)");
     HGNN_REQUIRE(!X1, "x1 rows can only be saved by the width-4 fast path (check hgnn_lg_row4_eligible)");
+    if (eng_try_fwd_tc5(a, stream)) return hgnn_check_launch("hgnn_lg_side_fwd(tc5)");
     if (eng_try_fwd_wide(a, stream)) return hgnn_check_launch("hgnn_lg_side_fwd(wide)");
     const bool vec4 = (a.Fs % 4 == 0) && (a.Fc % 4 == 0) && eng_aligned16(a.Xs) && (a.Fc == 0 || eng_aligned16(a.Xc));
     const bool vout4 = vec4 && (a.Fout % 4 == 0) && eng_aligned16(Z);

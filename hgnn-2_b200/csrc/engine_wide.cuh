@@ -234,6 +234,7 @@ __device__ __forceinline__ void wide_gather(const WideRow& w, const L& ld_, int 
 // Stage the structure of rows [row0, row0 + trc) of the CSR operators in `slots` (all threads; two barriers inside,
 // ends synced).  slot s < WD_SLOTS: operator st->op_of[s] of `ops`; slot WD_SLOTS: the (rowptr, col, v1, v2) pattern
 // of the cross part when p_rowptr != NULL.  Also pushes the rows that own run-length entries to dl->rng_items.
+template <int CAP = WD_CAP>
 __device__ __forceinline__ void wide_stage(WideStage* st, const OpList& ops, const int* __restrict__ p_rowptr,
                                            const int* __restrict__ p_col, const float* __restrict__ p_v1,
                                            const float* __restrict__ p_v2, int row0, int trc, int* scol, float* sval,
@@ -262,7 +263,7 @@ __device__ __forceinline__ void wide_stage(WideStage* st, const OpList& ops, con
         const bool have = cross ? p_rowptr != nullptr : st->op_of[s] >= 0;
         if (!have) continue;
         const int b = st->rp[s][0], n = st->rp[s][trc] - b;
-        const bool fits = n <= WD_CAP;
+        const bool fits = n <= CAP;
         if (tid == 0) { st->base[s] = b; st->staged[s] = fits ? 1 : 0; }
         if (!fits) continue;
         if (cross) {
@@ -276,8 +277,8 @@ __device__ __forceinline__ void wide_stage(WideStage* st, const OpList& ops, con
             const int* __restrict__ gc = ops.col[t];
             const float* __restrict__ gv = ops.val[t];
             for (int i = tid; i < n; i += WD_THREADS) {
-                scol[s * WD_CAP + i] = __ldg(gc + b + i);
-                sval[s * WD_CAP + i] = __ldg(gv + b + i);
+                scol[s * CAP + i] = __ldg(gc + b + i);
+                sval[s * CAP + i] = __ldg(gv + b + i);
             }
         }
     }
@@ -285,6 +286,7 @@ __device__ __forceinline__ void wide_stage(WideStage* st, const OpList& ops, con
 }
 
 // (k0, k1, arrays) of row r of the tile for operator t
+template <int CAP = WD_CAP>
 __device__ __forceinline__ WideRow wide_row(const WideStage* st, const OpList& ops, int t, int row0, int r,
                                             const int* scol, const float* sval) {
     WideRow w;
@@ -295,8 +297,8 @@ __device__ __forceinline__ WideRow wide_row(const WideStage* st, const OpList& o
         w.k1 = st->rp[s][r + 1];
         if (st->staged[s]) {
             w.smem = true;
-            w.col = scol + s * WD_CAP - st->base[s];
-            w.val = sval + s * WD_CAP - st->base[s];
+            w.col = scol + s * CAP - st->base[s];
+            w.val = sval + s * CAP - st->base[s];
             return w;
         }
     } else {

@@ -219,3 +219,34 @@ def test_engine_single_output_regression_head(kind, order):
     fl = 0.1 * max(float(v.abs().max()) for k, v in res[1].items() if k not in ("X", "out"))
     for k in res[1]:
         assert rel_err(res[0][k].cpu(), res[1][k].cpu(), fl if k not in ("X", "out") else 0.0) < 1e-4, k
+
+
+@pytest.mark.skipif(__import__("os").environ.get("HGNN_B200_TEST_TC5") != "1",
+                    reason="experimental tcgen05 forward (csrc/engine_tc5.cuh): bring-up only, "
+                           "run with HGNN_B200_TEST_TC5=1 (DESIGN.md 3b)")
+def test_experimental_tc5_forward_in_a_subprocess():
+    """The tcgen05 forward kernel is opt-in (HGNN_B200_WIDE_TC5=1, read once per process), so the comparison with
+    the module path runs in a child process; a trap / fault there fails this test without touching the parent."""
+    import os
+    import subprocess
+    import sys
+    code = (
+        "import copy, sys, torch\n"
+        "sys.path.insert(0, %r); sys.path.insert(0, %r)\n"
+        "import test_gpu_engine as T\n"
+        "import hgnn_b200\n"
+        "from hgnn_b200 import synth\n"
+        "from hgnn_b200.functions.batching import prepare_batch\n"
+        "from hgnn_b200.models.gnns.model_mnb import GNN_lg\n"
+        "torch.manual_seed(3)\n"
+        "batch = prepare_batch(synth.sbm_dataset(6, N=150, J=1), 0, 1)\n"
+        "m = GNN_lg(0, 32, 4, 5, 2, 1, 1).cuda(); r = copy.deepcopy(m)\n"
+        "oe, ge = T._run(m, batch, True); om, gm = T._run(r, batch, False)\n"
+        "e = float((oe - om).abs().max() / om.abs().max()); print('rel err', e)\n"
+        "assert e < 1e-4\n"
+        "fl = 0.1 * max(float(v.abs().max()) for v in gm.values())\n"
+        "assert all(T.rel_err(ge[k].cpu(), gm[k].cpu(), fl) < 1e-4 for k in gm)\n"
+    ) % (os.path.dirname(os.path.abspath(__file__)), os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    env = dict(os.environ, HGNN_B200_WIDE_TC5="1")
+    out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=240)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
