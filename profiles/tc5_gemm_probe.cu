@@ -159,6 +159,77 @@ probe_kernel(const float* __restrict__ A, const float* __restrict__ B, int nchun
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 256;\n" ::"r"(tmem) : "memory");
 }
 
+// Second question for the backward: the SAME planes read MN-major.  E[f1][f2] = sum_r A[r][f1] B[r][f2]
+// over the 64 rows of chunk 0 (the dW contraction: M = feature of A, N = feature of B, K = row), a_major = b_major = 1,
+// k-groups of 8 rows 128 B apart (leading), m-groups of 4 features 1024 B apart (stride); mode bit 0 swaps the two.
+__global__ void __launch_bounds__(128, 1)
+probe_mn_kernel(const float* __restrict__ A, const float* __restrict__ B, int K, int mode, float* __restrict__ out,
+                int* __restrict__ status) {
+    extern __shared__ __align__(1024) float smem[];
+    __shared__ uint32_t tmem_base_s;
+    __shared__ __align__(8) uint64_t mbar_s;
+    float* a_hi = smem;
+    float* a_lo = a_hi + PLANE;
+    float* b_hi = a_lo + PLANE;
+    float* b_lo = b_hi + PLANE;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 64;\n" ::"r"(smem_u32(&tmem_base_s)) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
+    }
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" ::"r"(smem_u32(&mbar_s)) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    }
+    for (int i = tid; i < TM * KC; i += 128) {
+        const int r = i / KC, k = i - r * KC;
+        const float av = A[(size_t)r * K + k], bv = B[(size_t)r * K + k];
+        const int o = core_offset_floats(r, k, 1024, 128);
+        a_hi[o] = av;
+        a_lo[o] = av - __uint_as_float(__float_as_uint(av) & 0xffffe000u);
+        b_hi[o] = bv;
+        b_lo[o] = bv - __uint_as_float(__float_as_uint(bv) & 0xffffe000u);
+    }
+    asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+    asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+    const uint32_t tmem = tmem_base_s;
+    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) |
+                           ((uint32_t)(TN >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
+    if (tid == 0) {
+        const int lbo = 128, sbo = 1024, swap = mode & 1;
+        for (int ks = 0; ks < TM / 8; ++ks) {              // K = 8 rows per instruction: one k-group
+            const uint32_t koff = ks * 128;
+            const uint64_t dah = make_desc(smem_u32(a_hi) + koff, lbo, sbo, swap);
+            const uint64_t dal = make_desc(smem_u32(a_lo) + koff, lbo, sbo, swap);
+            const uint64_t dbh = make_desc(smem_u32(b_hi) + koff, lbo, sbo, swap);
+            const uint64_t dbl = make_desc(smem_u32(b_lo) + koff, lbo, sbo, swap);
+            mma_tf32(tmem, dal, dbh, idesc, ks == 0 ? 0u : 1u);
+            mma_tf32(tmem, dah, dbl, idesc, 1u);
+            mma_tf32(tmem, dah, dbh, idesc, 1u);
+        }
+        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(smem_u32(&mbar_s)) : "memory");
+    }
+    const bool ok = mbar_wait(smem_u32(&mbar_s), 0);
+    asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+    if (tid == 0) status[0] = ok ? 1 : -1;
+    if (ok) {
+        for (int c0 = 0; c0 < TN; c0 += 8) {
+            uint32_t v[8];
+            const uint32_t addr = tmem + ((uint32_t)(warp * 32) << 16) + c0;
+            asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];\n"
+                         : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+                         : "r"(addr) : "memory");
+            asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+            for (int j = 0; j < 8; ++j) out[(size_t)tid * TN + c0 + j] = __uint_as_float(v[j]);
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 64;\n" ::"r"(tmem) : "memory");
+}
+
 int main() {
     const int nchunk = 5, K = nchunk * KC;
     std::vector<float> A(TM * K), B(TN * K);
@@ -215,6 +286,32 @@ int main() {
         printf("  row -> TMEM lane:");
         for (int m = 0; m < TM; m += 8) printf(" %d:%d", m, lane_of[m]);
         printf("\n");
+    }
+    // ---- MN-major reading of the same planes (the dW contraction of the backward)
+    std::vector<double> eref(TM * TN), escale(TM * TN);
+    for (int f1 = 0; f1 < TM; ++f1)
+        for (int f2 = 0; f2 < TN; ++f2) {
+            double s2 = 0, a2 = 0;
+            for (int r = 0; r < TM; ++r) { s2 += (double)A[r * K + f1] * B[r * K + f2]; a2 += fabs((double)A[r * K + f1] * B[r * K + f2]); }
+            eref[f1 * TN + f2] = s2; escale[f1 * TN + f2] = a2;
+        }
+    cudaFuncSetAttribute(probe_mn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    for (int mode = 0; mode < 2; ++mode) {
+        cudaMemset(dOut, 0, out.size() * 4); cudaMemset(dStatus, 0, 4);
+        probe_mn_kernel<<<1, 128, smem>>>(dA, dB, K, mode, dOut, dStatus);
+        cudaError_t e = cudaDeviceSynchronize();
+        int status = 0;
+        cudaMemcpy(&status, dStatus, 4, cudaMemcpyDeviceToHost);
+        cudaMemcpy(out.data(), dOut, 128 * TN * 4, cudaMemcpyDeviceToHost);
+        printf("MN-major mode %d (swap offsets %d): %s, status %d\n", mode, mode & 1, cudaGetErrorString(e), status);
+        if (e != cudaSuccess) return 1;
+        if (status <= 0) continue;
+        double worst = 0;
+        for (int m = 0; m < TM; ++m) {
+            const int l = (m / 16) * 32 + m % 16;          // M = 64: half sub-partitions
+            for (int n = 0; n < TN; ++n) worst = fmax(worst, fabs(out[(size_t)l * TN + n] - eref[m * TN + n]) / escale[m * TN + n]);
+        }
+        printf("  max |err| / sum|a||b| = %.3e (rows taken from lanes 32 (m / 16) + m %% 16)\n", worst);
     }
     return 0;
 }
