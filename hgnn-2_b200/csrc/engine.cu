@@ -1229,6 +1229,11 @@ static bool eng_tc5_enabled() {
     if (v < 0) { const char* e = getenv("HGNN_B200_WIDE_TC5"); v = (e && e[0] == '1') ? 1 : 0; }
     return v == 1;
 }
+static bool eng_tc5_bwd_enabled() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("HGNN_B200_WIDE_TC5_BWD"); v = (e && e[0] == '1') ? 1 : 0; }
+    return v == 1;
+}
 static bool eng_try_fwd_tc5(eng::FwdArgs& a, hgnn_stream_t stream) {
     if (!eng_tc5_enabled() || eng_wide_disabled()) return false;
     const bool cross = a.p_rowptr != nullptr;
@@ -1669,6 +1674,27 @@ extern "C" int hgnn_lg_side_bwd(const hgnn_side_bwd_t* d, hgnn_stream_t stream) 
     if (total_tiles == 0) return HGNN_OK;
     const size_t smem = a.self.smem > a.cross.smem ? a.self.smem : a.cross.smem;
     cudaStream_t s = to_stream(stream);
+    // EXPERIMENTAL tcgen05 backward (engine_tc5.cuh): only with HGNN_B200_WIDE_TC5_BWD=1
+    if (eng_tc5_bwd_enabled() && !eng_wide_disabled() && vec4 && d->Fg == T5B_F) {
+        bool ok = true;
+        if (a.self.R > 0) {
+            ok = ok && a.self.Fx == T5B_F && a.self.ops.n <= 3 && eng_part_vout4(a.self.X, a.self.gX, a.self.Fx);
+            for (int t = 0; ok && t < a.self.ops.n; ++t) ok = !a.self.ops.rng_rowptr[t];
+        }
+        if (a.cross.R > 0) ok = ok && a.cross.Fx == T5B_F && eng_part_vout4(a.cross.X, a.cross.gX, a.cross.Fx);
+        if (ok) {
+            int nT = 0;
+            if (a.self.R > 0) { a.self.TR = 64; a.self.tiles = ceil_div(a.self.R, 64); nT = a.self.ops.n * T5B_F; }
+            if (a.cross.R > 0) { a.cross.TR = 64; a.cross.tiles = ceil_div(a.cross.R, 64); if (2 * T5B_F > nT) nT = 2 * T5B_F; }
+            const size_t sm5 = (size_t)eng::tc5_bwd_layout(nT).total * sizeof(float);
+            if (sm5 <= WD_MAX_SMEM) {
+                const int most = a.self.tiles > a.cross.tiles ? a.self.tiles : a.cross.tiles;
+                const int grid = balanced_grid(most, eng_resident_impl(reinterpret_cast<const void*>(eng::bwd_tc5_kernel), sm5, WD_THREADS));
+                eng::bwd_tc5_kernel<<<grid, WD_THREADS, sm5, s>>>(a);
+                return hgnn_check_launch("hgnn_lg_side_bwd(tc5)");
+            }
+        }
+    }
     if (mma) {
         // every CTA works on both parts (see bwd_wide_kernel)
         const int most = a.self.tiles > a.cross.tiles ? a.self.tiles : a.cross.tiles;

@@ -247,6 +247,9 @@ def test_experimental_tc5_forward_in_a_subprocess():
         "fl = 0.1 * max(float(v.abs().max()) for v in gm.values())\n"
         "assert all(T.rel_err(ge[k].cpu(), gm[k].cpu(), fl) < 1e-4 for k in gm)\n"
     ) % (os.path.dirname(os.path.abspath(__file__)), os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    # HGNN_B200_TEST_TC5_BWD=1 additionally sends the node-side / cross backward through bwd_tc5_kernel
     env = dict(os.environ, HGNN_B200_WIDE_TC5="1")
+    if os.environ.get("HGNN_B200_TEST_TC5_BWD") == "1":
+        env["HGNN_B200_WIDE_TC5_BWD"] = "1"
     out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=240)
     assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
