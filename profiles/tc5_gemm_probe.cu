@@ -163,7 +163,7 @@ probe_kernel(const float* __restrict__ A, const float* __restrict__ B, int nchun
 // over the 64 rows of chunk 0 (the dW contraction: M = feature of A, N = feature of B, K = row), a_major = b_major = 1,
 // k-groups of 8 rows 128 B apart (leading), m-groups of 4 features 1024 B apart (stride); mode bit 0 swaps the two.
 __global__ void __launch_bounds__(128, 1)
-probe_mn_kernel(const float* __restrict__ A, const float* __restrict__ B, int K, int mode, float* __restrict__ out,
+probe_mn_kernel(const float* __restrict__ A, const float* __restrict__ B, int K, int mode, int nx, float* __restrict__ out,
                 int* __restrict__ status) {
     extern __shared__ __align__(1024) float smem[];
     __shared__ uint32_t tmem_base_s;
@@ -171,10 +171,15 @@ probe_mn_kernel(const float* __restrict__ A, const float* __restrict__ B, int K,
     float* a_hi = smem;
     float* a_lo = a_hi + PLANE;
     float* b_hi = a_lo + PLANE;
-    float* b_lo = b_hi + PLANE;
+    float* b_lo = b_hi + TM * 72;              // room for nx = 72: 64 features + a column of ones + padding
     const int tid = threadIdx.x, warp = tid >> 5;
+    for (int i = tid; i < TM * 8; i += 128) {  // columns 64..71 of the B planes (only read when nx = 72)
+        const int r = i >> 3, f = 64 + (i & 7);
+        b_hi[core_offset_floats(r, f, 1024, 128)] = (i & 7) == 0 ? 1.f : 0.f;
+        b_lo[core_offset_floats(r, f, 1024, 128)] = 0.f;
+    }
     if (warp == 0) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 64;\n" ::"r"(smem_u32(&tmem_base_s)) : "memory");
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 128;\n" ::"r"(smem_u32(&tmem_base_s)) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
     }
     if (tid == 0) {
@@ -196,7 +201,7 @@ probe_mn_kernel(const float* __restrict__ A, const float* __restrict__ B, int K,
     asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
     const uint32_t tmem = tmem_base_s;
     const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) |
-                           ((uint32_t)(TN >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
+                           ((uint32_t)(nx >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
     if (tid == 0) {
         const int lbo = 128, sbo = 1024, swap = mode & 1;
         for (int ks = 0; ks < TM / 8; ++ks) {              // K = 8 rows per instruction: one k-group
@@ -215,19 +220,19 @@ probe_mn_kernel(const float* __restrict__ A, const float* __restrict__ B, int K,
     asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
     if (tid == 0) status[0] = ok ? 1 : -1;
     if (ok) {
-        for (int c0 = 0; c0 < TN; c0 += 8) {
+        for (int c0 = 0; c0 < nx; c0 += 8) {
             uint32_t v[8];
             const uint32_t addr = tmem + ((uint32_t)(warp * 32) << 16) + c0;
             asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];\n"
                          : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
                          : "r"(addr) : "memory");
             asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
-            for (int j = 0; j < 8; ++j) out[(size_t)tid * TN + c0 + j] = __uint_as_float(v[j]);
+            for (int j = 0; j < 8; ++j) out[(size_t)tid * 72 + c0 + j] = __uint_as_float(v[j]);
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
     __syncthreads();
-    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 64;\n" ::"r"(tmem) : "memory");
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 128;\n" ::"r"(tmem) : "memory");
 }
 
 int main() {
@@ -295,23 +300,35 @@ int main() {
             for (int r = 0; r < TM; ++r) { s2 += (double)A[r * K + f1] * B[r * K + f2]; a2 += fabs((double)A[r * K + f1] * B[r * K + f2]); }
             eref[f1 * TN + f2] = s2; escale[f1 * TN + f2] = a2;
         }
-    cudaFuncSetAttribute(probe_mn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    for (int mode = 0; mode < 2; ++mode) {
+    const size_t smem_mn = (2 * PLANE + 2 * TM * 72) * sizeof(float);
+    cudaFuncSetAttribute(probe_mn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_mn);
+    for (int mode = 0; mode < 4; ++mode) {         // bit 0: swap the offsets; bit 1: N = 72 (ones column: the dW operand)
+        const int nx = (mode & 2) ? 72 : 64;
         cudaMemset(dOut, 0, out.size() * 4); cudaMemset(dStatus, 0, 4);
-        probe_mn_kernel<<<1, 128, smem>>>(dA, dB, K, mode, dOut, dStatus);
+        probe_mn_kernel<<<1, 128, smem_mn>>>(dA, dB, K, mode, nx, dOut, dStatus);
         cudaError_t e = cudaDeviceSynchronize();
         int status = 0;
         cudaMemcpy(&status, dStatus, 4, cudaMemcpyDeviceToHost);
-        cudaMemcpy(out.data(), dOut, 128 * TN * 4, cudaMemcpyDeviceToHost);
-        printf("MN-major mode %d (swap offsets %d): %s, status %d\n", mode, mode & 1, cudaGetErrorString(e), status);
+        cudaMemcpy(out.data(), dOut, 128 * 72 * 4, cudaMemcpyDeviceToHost);
+        printf("MN-major mode %d (swap offsets %d, N = %d): %s, status %d\n", mode, mode & 1, nx, cudaGetErrorString(e), status);
         if (e != cudaSuccess) return 1;
         if (status <= 0) continue;
         double worst = 0;
         for (int m = 0; m < TM; ++m) {
             const int l = (m / 16) * 32 + m % 16;          // M = 64: half sub-partitions
-            for (int n = 0; n < TN; ++n) worst = fmax(worst, fabs(out[(size_t)l * TN + n] - eref[m * TN + n]) / escale[m * TN + n]);
+            for (int n = 0; n < TN; ++n) worst = fmax(worst, fabs(out[(size_t)l * 72 + n] - eref[m * TN + n]) / escale[m * TN + n]);
         }
         printf("  max |err| / sum|a||b| = %.3e (rows taken from lanes 32 (m / 16) + m %% 16)\n", worst);
+        if (nx == 72) {                            // column 64 = sum over the 64 rows of A[r][m]
+            double wc = 0;
+            for (int m = 0; m < TM; ++m) {
+                const int l = (m / 16) * 32 + m % 16;
+                double cs = 0, ca = 0;
+                for (int r = 0; r < TM; ++r) { cs += A[r * K + m]; ca += fabs(A[r * K + m]); }
+                wc = fmax(wc, fabs(out[(size_t)l * 72 + 64] - cs) / ca);
+            }
+            printf("  ones column: max |colsum err| / sum|a| = %.3e\n", wc);
+        }
     }
     return 0;
 }
