@@ -20,6 +20,7 @@ reference's layer API.
 """
 import ctypes
 import os
+import weakref
 
 import numpy as np
 import torch
@@ -276,14 +277,21 @@ class _Plan(object):
         return self._running
 
 
+# model -> _Plan.  Kept OUTSIDE the module's __dict__: a plan holds ctypes structs with raw device
+# pointers, which neither pickle (whole-module torch.save, functions/logs.py:99-111 of the reference)
+# nor copy.deepcopy can serialise; a reloaded / copied model simply gets a fresh plan on first use.
+_PLANS = weakref.WeakKeyDictionary()
+
+
 def get_plan(model):
     """The cached plan; rebuilt when the parameter objects were replaced (checked on two of them -
     walking all ~230 parameters costs more than a kernel launch)."""
-    plan = model.__dict__.get("_engine_plan")
+    plan = _PLANS.get(model)
     if (plan is None or plan.params[0] is not model.layer0.cv1.weight
             or plan.params[-1] is not model.layerlast.fc.bias):
+        model.__dict__.pop("_engine_plan", None)      # attribute written by older versions of this file
         plan = _Plan(model)
-        model.__dict__["_engine_plan"] = plan
+        _PLANS[model] = plan
     return plan
 
 
