@@ -96,6 +96,7 @@ _SIGS = {
                          _P, _P, c_int, c_int, _P, _P, _P, _P],
     "hgnn_lg_row4_eligible": [ctypes.POINTER(OpT), c_int, c_int, c_int, c_int],
     "hgnn_lg_wide_eligible": [c_int, c_int, c_int, c_int, c_int],
+    "hgnn_lg_side_fits": [c_int, c_int, c_int, c_int],
     "hgnn_lg_side_dw": [_P, _P, c_int, c_int, _P, _P, _P, _P, c_int, _P, _P, _P],
     "hgnn_lg_side_bwd": [ctypes.POINTER(SideBwdT), _P],
     "hgnn_debug_cta_times": [_P, c_int],

@@ -1389,6 +1389,41 @@ static bool eng_plan_part(eng::BwdPart& p, int Fg, bool vec4, bool& vout4, bool 
     return p.smem <= ENG_MAX_SMEM;
 }
 
+// Width-only eligibility of one side on the engine kernels (forward AND backward): the same shared-memory
+// arithmetic as hgnn_lg_side_fwd / hgnn_lg_side_bwd, assuming 16-byte aligned tensors (every torch allocation).
+// engine.supported() asks this per side, so that a model whose weight block does not fit (LGNN order 1 from
+// h ~ 48: Cin x Fout = 10h x 2h floats) runs on the per-layer kernels instead of failing inside a step.
+extern "C" int hgnn_lg_side_fits(int n_ops, int Fs, int Fc, int Fout) {
+    if (n_ops < 1 || n_ops > HGNN_MAX_OPS || Fs < 1 || Fs > 128 || Fc < 0 || Fc > 128 || Fout < 1 || Fout > 128) return 0;
+    int TRw = 0;
+    size_t smw = 0;
+    // ---- forward
+    bool fwd_ok = eng_wide_fwd_fits(n_ops, Fs, Fc, Fout, &TRw, &smw);
+    if (!fwd_ok) {
+        const bool vec4 = (Fs % 4 == 0) && (Fc % 4 == 0);
+        const int Cin = n_ops * Fs + 2 * Fc;
+        const size_t fixed = ((size_t)Cin * Fout + ((Fout + 3) & ~3) + 2 * ((Fs + 3) & ~3) + 2 * ((Fc + 3) & ~3)) * sizeof(float);
+        fwd_ok = fixed + (size_t)eng_pad(Cin, vec4 ? 4 : 1) * sizeof(float) <= ENG_MAX_SMEM;
+    }
+    if (!fwd_ok) return 0;
+    // ---- backward: both parts on the tensor-core tiles, or both on the generic tiles
+    if (eng_wide_bwd_width(Fout) && eng_wide_part_fits(n_ops, Fout, Fs, true, &TRw, &smw) &&
+        (Fc == 0 || eng_wide_part_fits(2, Fout, Fc, false, &TRw, &smw)))
+        return 1;
+    const bool vec4 = Fout % 4 == 0;
+    const bool wide = vec4 && Fout >= 32 && Fs >= 16 && Fs % 4 == 0 && (Fc == 0 || (Fc >= 16 && Fc % 4 == 0));
+    for (int part = 0; part < (Fc > 0 ? 2 : 1); ++part) {
+        eng::BwdPart p;
+        p.ops.n = part == 0 ? n_ops : 2;
+        p.Fx = part == 0 ? Fs : Fc;
+        p.R = 1;
+        p.X = nullptr; p.gX = nullptr;      // null pointers count as aligned
+        bool v4 = false;
+        if (!eng_plan_part(p, Fout, vec4, v4, part == 0, wide)) return 0;
+    }
+    return 1;
+}
+
 // CTAs of a backward launch that work on the self rows.  Every thread walks WHOLE rows one after the other, so
 // what matters is the integer number of rows of the slowest thread of each part: the split minimises
 // max(ceil(rows_self / threads_self) * row cost_self, ceil(rows_cross / threads_cross) * row cost_cross); ties go to the

@@ -170,6 +170,7 @@ class _Plan(object):
         self._device_tables = {}
         self._running = None
         self._programs = {}
+        self.fits = None          # filled by supported(): every side inside the kernels' shared-memory budgets
         self.readout_width = self.sides[-1].Fout
 
         # ---- the same plan as C structs for csrc/program.cu (parameters by index)
@@ -590,8 +591,16 @@ class _ModelFunction(torch.autograd.Function):
 
 
 def supported(model):
+    """True when every side of the model fits the engine kernels (widths <= 128, <= MAX_OPS operators, and
+    the resident weight block Cin x Fout inside the shared-memory budget of both directions:
+    ``hgnn_lg_side_fits``).  Otherwise the model runs layer by layer on the per-module kernels."""
     h2 = 2 * model.n_features
-    return h2 <= 128 and model.featuremap_in[0] <= 128 and model.J + 2 <= _lib.MAX_OPS
+    if not (h2 <= 128 and model.featuremap_in[0] <= 128 and model.J + 2 <= _lib.MAX_OPS):
+        return False
+    plan = get_plan(model)
+    if plan.fits is None:
+        plan.fits = all(_lib.lib.hgnn_lg_side_fits(plan.K, s.Fs, s.Fc, s.Fout) == 1 for s in plan.sides)
+    return plan.fits
 
 
 def run_model(model, pack, Xp, XLp):

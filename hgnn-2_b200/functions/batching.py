@@ -156,7 +156,10 @@ class BatchLoader(object):
                 batch, ev = item
                 cur = torch.cuda.current_stream(self.device)
                 cur.wait_event(ev)
-                batch[1].pack._buffer.record_stream(cur)
+                batch[1].pack.record_stream(cur)          # every allocation of the pack, incl. J > 1 powers
+                for t_ in batch:
+                    if torch.is_tensor(t_) and t_.is_cuda:
+                        t_.record_stream(cur)
                 yield batch
         finally:
             stop.set()

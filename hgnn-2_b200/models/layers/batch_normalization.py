@@ -31,6 +31,18 @@ class BN(nn.Module):
         self.register_buffer("running_std", torch.zeros(n_features), persistent=False)
         self.momentum = 0.1
 
+    def __setstate__(self, state):
+        """Whole-module pickles (functions/logs.py:99-123).  A module pickled by the REFERENCE keeps its
+        running statistics as plain attributes (batch_normalization.py:30-31) and has no ``n_features``:
+        re-home them as the non-persistent buffers this class uses, so they follow ``.cuda()``."""
+        super(BN, self).__setstate__(state)
+        for k in ("running_mean", "running_std"):
+            if k in self.__dict__:
+                v = self.__dict__.pop(k)
+                self.register_buffer(k, v.detach().float().contiguous(), persistent=False)
+        if "n_features" not in self.__dict__:
+            self.n_features = int(self.running_mean.numel())
+
     def forward_rows(self, Z):
         """Packed rows (R, F) -> (normalised rows, stats)."""
         return ops.BatchNormRows.apply(Z, self.weight, self.bias, self, self.training)

@@ -76,7 +76,7 @@ class layer_simple(nn.Module):
 
     def forward_packed(self, Xp, pack):
         node, _ = _side_cfgs(pack)
-        return ops.SideUpdate.apply(Xp, None, self.cv2.weight, self.cv2.bias, self.cv1.weight,
+        return ops.side_update(Xp, None, self.cv2.weight, self.cv2.bias, self.cv1.weight,
                                     self.cv1.bias, self.bn1.weight, self.bn1.bias, node, 0, self.bn1,
                                     self.training)
 
@@ -136,13 +136,13 @@ class _layer_with_lg(nn.Module):
 
     def _node(self, Xp, edge_state, cfg):
         # cat(cv2 branch [no ReLU], relu(cv1 branch)) -> bn1   (layers_mnb.py:206-212)
-        return ops.SideUpdate.apply(Xp, edge_state, self.cv2.weight, self.cv2.bias, self.cv1.weight,
+        return ops.side_update(Xp, edge_state, self.cv2.weight, self.cv2.bias, self.cv1.weight,
                                     self.cv1.bias, self.bn1.weight, self.bn1.bias, cfg,
                                     self.n_outputs, self.bn1, self.training)
 
     def _edge(self, XLp, node_state, cfg):
         # cat(cv4 branch [no ReLU], relu(cv3 branch)) -> bn2   (layers_mnb.py:217-223)
-        return ops.SideUpdate.apply(XLp, node_state, self.cv4.weight, self.cv4.bias, self.cv3.weight,
+        return ops.side_update(XLp, node_state, self.cv4.weight, self.cv4.bias, self.cv3.weight,
                                     self.cv3.bias, self.bn2.weight, self.bn2.bias, cfg,
                                     self.n_outputs, self.bn2, self.training)
 

@@ -260,6 +260,34 @@ class SideUpdate(torch.autograd.Function):
                 None, None, None, None)
 
 
+def side_fits_fused(cfg, Xs, Xc, Fout):
+    """Whether the fused side kernels (csrc/side.cu, csrc/engine.cu) can hold this side's resident weight
+    block ``Cin x Fout`` in shared memory (``hgnn_lg_side_fits``: same budget arithmetic)."""
+    from . import _lib
+    return _lib.lib.hgnn_lg_side_fits(len(cfg.ops), Xs.shape[1], Xc.shape[1] if Xc is not None else 0, Fout) == 1
+
+
+def side_update(Xs, Xc, Wa, ba, Wb, bb, bn_w, bn_b, cfg, relu_from, bn, training):
+    """One layer side (see ``SideUpdate``).  Sides whose weight block exceeds the fused kernels' shared-memory
+    budget (LGNN order 1 from h ~ 46: Cin x Fout = 10h x 2h floats) are composed instead from the
+    stand-alone kernels - multi-operator gather (``Gmul``), a dense linear (there a real GEMM: cuBLAS),
+    ReLU on the second branch, batch-norm on packed rows - with identical semantics
+    (layers_mnb.py:200-212, :214-223)."""
+    Ha, Hb = Wa.shape[0], Wb.shape[0]
+    if side_fits_fused(cfg, Xs, Xc, Ha + Hb):
+        return SideUpdate.apply(Xs, Xc, Wa, ba, Wb, bb, bn_w, bn_b, cfg, relu_from, bn, training)
+    blocks = [Gmul.apply(Xs, cfg.ops, cfg.ops_T, cfg.R)]
+    if Xc is not None and cfg.p is not None:
+        blocks.append(Gmul.apply(Xc, [cfg.p.desc(False), cfg.p.desc(True)],
+                                 [cfg.pt.desc(False), cfg.pt.desc(True)], cfg.R))
+    x1 = torch.cat(blocks, 1) if len(blocks) > 1 else blocks[0]
+    W = torch.cat([Wa.reshape(Ha, -1), Wb.reshape(Hb, -1)], 0)
+    z = torch.nn.functional.linear(x1, W, torch.cat([ba, bb], 0))
+    if relu_from < Ha + Hb:
+        z = torch.cat([z[:, :relu_from], torch.relu(z[:, relu_from:])], 1)
+    return BatchNormRows.apply(z, bn_w, bn_b, bn, training)
+
+
 class Readout(torch.autograd.Function):
     """layer_last / layer_last_lg (layers_mnb.py:88-95, 379-388): fc over the gathered blocks, then
     the sum over ALL Nmax slots - padded slots contribute fc.bias each (SURVEY.md parity item 8)."""

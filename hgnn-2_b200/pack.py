@@ -384,6 +384,32 @@ class BatchPack(object):
             self.n_edges, self.Emax, self.Rm = np.zeros(self.bs, np.int64), 0, 0
         return self
 
+    def record_stream(self, stream):
+        """Tie EVERY device allocation owned by this pack to ``stream`` (the consumer's), for packs built on
+        another stream (BatchLoader's copy stream): the main buffer, and the separately allocated SpGEMM
+        powers A^(2^j) / B^(2^j) and their transposes when J > 1.  Without it a dropped batch returns those
+        blocks to the producer stream's pool while consumer kernels may still be reading them."""
+        seen = set()
+
+        def visit(o, depth=0):
+            if torch.is_tensor(o):
+                if o.is_cuda and o.untyped_storage().data_ptr() not in seen:
+                    seen.add(o.untyped_storage().data_ptr())
+                    o.record_stream(stream)
+            elif isinstance(o, Csr):
+                for k in Csr.__slots__:
+                    visit(getattr(o, k, None), depth + 1)
+            elif isinstance(o, (list, tuple)) and depth < 4:
+                for v in o:
+                    visit(v, depth + 1)
+            elif isinstance(o, dict) and depth < 4:
+                for v in o.values():
+                    visit(v, depth + 1)
+
+        for key, v in self.__dict__.items():
+            if key != "_host_graphs":
+                visit(v)
+
     # ---- operator descriptor lists ------------------------------------------------------------
     def node_ops(self):
         if self.generic:

@@ -215,6 +215,11 @@ int hgnn_lg_row4_eligible(const hgnn_op_t* ops, int n_ops, int Fs, int Fc, int F
  * host code and tests use it to know which code path a model takes (replaces nothing in the reference, whose
  * layers_mnb.py:189-225 has a single dense path). */
 int hgnn_lg_wide_eligible(int n_ops, int Fs, int Fc, int Fout, int backward);
+/* 1 when BOTH directions of a side with these widths fit the engine kernels' shared-memory budgets
+ * (the weight block Cin x Fout stays resident; Cin = n_ops*Fs + 2*Fc).  Width-only; the host layer
+ * (engine.supported) uses it to route too-wide models to the per-layer kernels
+ * (reference: models/layers/layers_mnb.py:172-177 fixes Cin, Fout from the feature maps). */
+int hgnn_lg_side_fits(int n_ops, int Fs, int Fc, int Fout);
 /* Weight gradients of a width-4 side as a streaming pass over the saved x1 rows:
  * dW[o][c] += sum_r gPre[r][o] x1[r][c], dbias[o] += sum_r gPre[r][o] (gPre as in hgnn_lg_side_bwd).
  * Independent of hgnn_lg_side_bwd(skip_dw=1): the host layer runs it on a parallel stream. */

@@ -227,15 +227,64 @@ def gen_ccn(ref):
     np.savez_compressed(os.path.join(OUT, "ccn.npz"), **out)
 
 
+def gen_checkpoint(ref):
+    """What the reference's drivers write and read back (functions/logs.py:99-123: whole-module
+    ``torch.save(model)``; scripts/main_gnn.py:143-145: ``torch.load(args.model_path)``): a reference
+    GNN_lg pickled after one train-mode pass (running statistics set), its state_dict, and the eval-mode
+    output the reloaded model must reproduce."""
+    gen = torch.Generator().manual_seed(71)
+    torch.manual_seed(71)
+    inst = make_instances(ref, [6, 4, 7], 1, gen)
+    X, W, T, XL, WL, Pm, Pd, mask, mask_lg, N_batch, E_batch = ref.batching.prepare_batch(inst, 0, 1)
+    model = ref.model_mnb.GNN_lg(0, 2, 3, 5, 2, 1, 1)
+    model.train()
+    state = [X, XL, W, WL, Pm, Pd]
+    with torch.no_grad():
+        y_train = model(state, N_batch, mask, E_batch, mask_lg)
+    for mod in model.modules():        # the reference's running stats are graph-attached plain attributes
+        if hasattr(mod, "running_mean"):
+            mod.running_mean = mod.running_mean.detach()
+            mod.running_std = mod.running_std.detach()
+    model.eval()
+    with torch.no_grad():
+        y_eval = model(state, N_batch, mask, E_batch, mask_lg)
+    saved = {k: sys.modules.get(k) for k in ref.sys_modules}
+    sys.modules.update(ref.sys_modules)       # pickle looks the classes up as models.gnns.model_mnb.GNN_lg ...
+    try:
+        torch.save(model, os.path.join(OUT, "ref_gnn_lg_module.pt"))
+    finally:
+        for k, v in saved.items():
+            if v is None:
+                del sys.modules[k]
+            else:
+                sys.modules[k] = v
+    torch.save(model.state_dict(), os.path.join(OUT, "ref_gnn_lg_state.pt"))
+    out = {"n_inst": np.int64(len(inst)), "out_train": np_(y_train), "out_eval": np_(y_eval)}
+    for i, (x, A, t, *_rest) in enumerate(inst):
+        out["inst%d/x" % i] = np_(x)
+        out["inst%d/A" % i] = np_(A)
+    for name, mod in model.named_modules():
+        if hasattr(mod, "running_mean"):
+            out["running/%s.mean" % name] = np_(mod.running_mean)
+            out["running/%s.std" % name] = np_(mod.running_std)
+    np.savez_compressed(os.path.join(OUT, "checkpoint.npz"), **out)
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     ref = reference_shim.load()
     torch.set_num_threads(1)
+    only = set(sys.argv[1:])
+    if only:        # e.g. `python oracle/make_golden.py checkpoint`: regenerate only the named groups
+        for name in sorted(only):
+            globals()["gen_" + name](ref)
+        return
     gen_operators(ref)
     gen_batch(ref)
     gen_models(ref)
     gen_ops(ref)
     gen_ccn(ref)
+    gen_checkpoint(ref)
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))
 

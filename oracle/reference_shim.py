@@ -68,7 +68,7 @@ def load():
         raise RuntimeError("reference checkout not present at %s" % REFERENCE_ROOT)
     _stub_matplotlib()
     import torch
-    with _Isolated():
+    with _Isolated() as iso:
         import functions.operators as operators
         import functions.batching as batching
         import functions.utils as utils
@@ -95,5 +95,6 @@ def load():
         operators=operators, batching=batching, utils=utils, contraction=contraction,
         utils_ccn=utils_ccn, layers_mnb=layers_mnb, batch_normalization=batch_normalization,
         model_mnb=model_mnb, model_ccn=model_ccn)
+    ns.sys_modules = iso.modules       # {name: module} of the reference, for pickling by class path
     _CACHE["ns"] = ns
     return ns
