@@ -82,7 +82,10 @@ class BatchT(ctypes.Structure):
                 ("edge_ops", ctypes.POINTER(OpT)), ("edge_ops_T", ctypes.POINTER(OpT)),
                 ("p_rowptr", c_void), ("p_col", c_void), ("p_pm", c_void), ("p_pd", c_void),
                 ("pt_rowptr", c_void), ("pt_col", c_void), ("pt_pm", c_void), ("pt_pd", c_void),
-                ("node_off", c_void), ("pad_n", c_void), ("p_nnz", c_ll)]
+                ("node_off", c_void), ("pad_n", c_void), ("p_nnz", c_ll),
+                ("btc_rowptr", c_void), ("btc_col", c_void), ("btc_val", c_void),
+                ("erow", c_void), ("ew", c_void), ("n_act", c_int), ("collapse_ok", c_int),
+                ("mega_scratch", c_void)]
 
 
 _P = c_void

@@ -27,6 +27,7 @@ enum Field {
     F_DL = N_PRIMAL_FIELDS, F_B_RP, F_B_COL, F_B_VAL,
     F_P_RP, F_P_COL, F_P_PM, F_P_PD, F_PT_RP, F_PT_COL, F_PT_PM, F_PT_PD,
     F_BTS_RP, F_BTS_COL, F_BTS_VAL, F_RNG_RP, F_RNG_ID, F_RNG_VAL, F_RNG_LO, F_RNG_HI,
+    F_BTC_RP, F_BTC_COL, F_BTC_VAL, F_EW, F_EROW,     // collapsed line graph (sparse_ops.GraphOps._build_collapsed)
     F_BT_RP, F_BT_COL, F_BT_VAL,      // last: a batch that skips the full transposed operator copies a prefix
     N_FIELDS
 };
@@ -96,7 +97,14 @@ const KeyDesc KEYS[] = {
     {"bts_rowptr", T_RP, F_BTS_RP, G_DUAL},          // 39
     {"bts_col", T_RAW, F_BTS_COL, G_DUAL},           // 40
     {"bts_val", T_RAW, F_BTS_VAL, G_DUAL},           // 41
-    {"fixup", T_FIXUP, -1, G_PRIMAL},                // 42
+    {"_seg_nnz_btc", T_SEG, F_BTC_COL, G_DUAL},      // 42
+    {"btc_rowptr", T_RP, F_BTC_RP, G_DUAL},          // 43
+    {"btc_col", T_RAW, F_BTC_COL, G_DUAL},           // 44
+    {"btc_val", T_RAW, F_BTC_VAL, G_DUAL},           // 45
+    {"ew", T_RAW, F_EW, G_DUAL},                     // 46
+    {"_seg_erow", T_SEG, F_EROW, G_DUAL},            // 47
+    {"erow", T_RAW, F_EROW, G_DUAL},                 // 48
+    {"fixup", T_FIXUP, -1, G_PRIMAL},                // 49
 };
 constexpr int N_KEYS = sizeof(KEYS) / sizeof(KEYS[0]);
 enum { K_NODE_OFF = 0, K_EDGE_OFF = 1, K_FIXUP = N_KEYS - 1 };
@@ -113,6 +121,8 @@ const FixDesc FIXES[] = {
     {29, K_NODE_OFF, 28}, {30, 28, K_EDGE_OFF},          // p : rows n, cols m
     {34, K_EDGE_OFF, 33}, {35, 33, K_NODE_OFF},          // pt: rows m, cols n
     {39, K_EDGE_OFF, 38}, {40, 38, K_EDGE_OFF},          // bts
+    {43, K_EDGE_OFF, 42}, {44, 42, K_EDGE_OFF},          // btc
+    {48, 47, K_EDGE_OFF},                                // erow: active line-graph rows
 };
 // clang-format on
 constexpr int N_FIXES = sizeof(FIXES) / sizeof(FIXES[0]);

@@ -11,7 +11,9 @@
 // (readout sum over the padded slots).  Host code only; no kernels live in this file.
 #include <atomic>
 #include <vector>
+#include <cstdlib>
 #include "common.cuh"
+#include "mega.cuh"
 
 static std::atomic<long long> g_program_launches{0};
 
@@ -93,6 +95,156 @@ bool check_program(const hgnn_program_t* prog, const hgnn_batch_t* b) {
     return b->node_ops && b->node_ops_T && b->node_off && b->pad_n;
 }
 
+
+// ---- persistent ("mega") kernels: which sides they take, and their parameter block (mega.cuh) ----------
+bool mega_disabled() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("HGNN_B200_NO_MEGA"); v = (e && e[0] == '1') ? 1 : 0; }
+    return v == 1;
+}
+
+bool plain_ops(const hgnn_op_t* ops, int n) {      // [I, D, CSR] without a run-length part
+    return ops && n == 3 && ops[0].kind == HGNN_OP_IDENT && ops[1].kind == HGNN_OP_DIAG && ops[1].diag &&
+           ops[2].kind == HGNN_OP_CSR && ops[2].rowptr;
+}
+
+// sides [s0, s1) run inside the persistent kernels; s0 == s1: none.  Eligible: width-4 inputs and output with
+// batch-norm (every middle-layer side at h = 2), J = 1, and for line-graph models the collapsed structure of a
+// batch whose edge feature is the line-graph degree (hgnn_batch_t.collapse_ok).
+void mega_range(const hgnn_program_t* prog, const hgnn_batch_t* b, int* s0, int* s1) {
+    *s0 = *s1 = 0;
+    if (mega_disabled() || !b->mega_scratch || b->n_ops != 3 || prog->n_tensors > mk::MAX_TENSORS) return;
+    if (!plain_ops(b->node_ops, b->n_ops) || !plain_ops(b->node_ops_T, b->n_ops)) return;
+    if (prog->dual) {
+        if (!b->collapse_ok || !b->erow || !b->ew || !b->btc_rowptr || !b->btc_col || !b->btc_val) return;
+        if (!plain_ops(b->edge_ops, b->n_ops)) return;
+    }
+    auto ok = [&](int i) {
+        const hgnn_prog_side_t& sd = prog->sides[i];
+        if (sd.out < 0 || sd.Ha + sd.Hb != 4 || sd.Hb < 1) return false;
+        if (prog->tensors[sd.src_self].F != 4 || prog->tensors[sd.out].bn_weight < 0) return false;
+        if (sd.src_cross >= 0 && prog->tensors[sd.src_cross].F != 4) return false;
+        return true;
+    };
+    int best0 = 0, best1 = 0;
+    for (int i = 0; i < prog->n_sides;) {
+        if (!ok(i)) { ++i; continue; }
+        int j = i;
+        while (j < prog->n_sides && ok(j) && j - i < mk::MAX_SIDES) ++j;
+        if (j - i > best1 - best0) { best0 = i; best1 = j; }
+        i = j;
+    }
+    if (best1 - best0 < 2) return;
+    *s0 = best0;
+    *s1 = best1;
+}
+
+void mega_graph(const hgnn_batch_t* b, bool dual, mk::Graph* g) {
+    memset(g, 0, sizeof(*g));
+    g->Rn = b->Rn;
+    g->deg = b->node_ops[1].diag;
+    g->a_rp = b->node_ops[2].rowptr; g->a_col = b->node_ops[2].col; g->a_val = b->node_ops[2].val;
+    g->at_rp = b->node_ops_T[2].rowptr; g->at_col = b->node_ops_T[2].col; g->at_val = b->node_ops_T[2].val;
+    if (!dual) return;
+    g->Rm = b->Rm;
+    g->n_act = b->n_act;
+    g->dl = b->edge_ops[1].diag;
+    g->b_rp = b->edge_ops[2].rowptr; g->b_col = b->edge_ops[2].col; g->b_val = b->edge_ops[2].val;
+    g->btc_rp = b->btc_rowptr; g->btc_col = b->btc_col; g->btc_val = b->btc_val;
+    g->p_rp = b->p_rowptr; g->p_col = b->p_col; g->p_pm = b->p_pm; g->p_pd = b->p_pd;
+    g->pt_rp = b->pt_rowptr; g->pt_col = b->pt_col; g->pt_pm = b->pt_pm; g->pt_pd = b->pt_pd;
+    g->erow = b->erow;
+    g->ew = b->ew;
+}
+
+// tensor table + sides [s0, s1) of the program as a kernel parameter block
+void mega_params(const hgnn_program_t* prog, const hgnn_batch_t* b, const WorkLayout& w, const float* X, const float* XL,
+                 const long long* addr, const float* work, float* gwork, float* gX, double* arena, int s0, int s1,
+                 mk::Params* P) {
+    mega_graph(b, prog->dual != 0, &P->g);
+    P->n_tensors = prog->n_tensors;
+    P->n_sides = s1 - s0;
+    P->expand = -1;
+    P->pad = 0;
+    P->bar = static_cast<unsigned int*>(b->mega_scratch);
+    for (int t = 0; t < prog->n_tensors; ++t) {
+        const hgnn_prog_tensor_t& T = prog->tensors[t];
+        mk::Tensor& o = P->t[t];
+        o.data = const_cast<float*>(tensor_ptr(prog, w, t, X, XL, work));
+        o.grad = !gwork ? nullptr : (t == 0 ? gX : (w.off[t] >= 0 ? gwork + w.off[t] : nullptr));
+        const bool bn = T.bn_weight >= 0;
+        o.acc_f = bn ? arena + T.acc_f : nullptr;
+        o.acc_b = bn ? arena + T.acc_b : nullptr;
+        o.bn_w = bn ? param(addr, T.bn_weight) : nullptr;
+        o.bn_b = bn ? param(addr, T.bn_bias) : nullptr;
+        o.n_rows = T.rows ? b->Rm : b->Rn;
+        o.pad = 0;
+    }
+    for (int i = s0; i < s1; ++i) {
+        const hgnn_prog_side_t& sd = prog->sides[i];
+        mk::Side& o = P->s[i - s0];
+        o.kind = sd.kind; o.src_self = sd.src_self; o.src_cross = sd.src_cross; o.out = sd.out;
+        o.Wa = param(addr, sd.Wa); o.ba = param(addr, sd.ba); o.Wb = param(addr, sd.Wb); o.bb = param(addr, sd.bb);
+        o.Ha = sd.Ha; o.Hb = sd.Hb; o.relu_from = sd.relu_from;
+        o.Cin = b->n_ops * 4 + (sd.src_cross >= 0 ? 8 : 0);
+        o.dW_bins = arena + sd.dW_off;
+        o.db_bins = arena + sd.db_off;
+        o.need_self = o.need_cross = o.acc_self = o.acc_cross = 0;
+    }
+}
+
+// line-graph tensor produced inside [s0, s1) that a per-side kernel outside the range reads on ALL rows:
+// -1 none, -2 more than one (the persistent kernels expand a single tensor)
+int mega_expand_fwd(const hgnn_program_t* prog, int s0, int s1) {
+    int found = -1;
+    for (int i = s1; i < prog->n_sides; ++i) {
+        const int srcs[2] = {prog->sides[i].src_self, prog->sides[i].src_cross};
+        for (int t : srcs) {
+            if (t < 0 || !prog->tensors[t].rows) continue;
+            bool inside = false;
+            for (int k = s0; k < s1; ++k) inside = inside || prog->sides[k].out == t;
+            if (!inside || t == found) continue;
+            if (found >= 0) return -2;
+            found = t;
+        }
+    }
+    return found;
+}
+// line-graph tensor whose gradient is completed inside the range and consumed by the backward of a side before it
+int mega_expand_bwd(const hgnn_program_t* prog, int s0, int s1) {
+    int found = -1;
+    for (int i = 0; i < s0; ++i) {
+        const int t = prog->sides[i].out;
+        if (t < 0 || !prog->tensors[t].rows) continue;
+        bool inside = false;
+        for (int k = s0; k < s1; ++k) inside = inside || prog->sides[k].src_self == t || prog->sides[k].src_cross == t;
+        if (!inside || t == found) continue;
+        if (found >= 0) return -2;
+        found = t;
+    }
+    return found;
+}
+
+
+// The one decision both passes share (a forward on the persistent kernels leaves the skipped line-graph rows of
+// its activations unwritten, so the backward must take the same path): range, the tensors to expand, and every
+// output inside the range consumed by a later side (otherwise its gradient would need a zero fill).
+void mega_decide(const hgnn_program_t* prog, const hgnn_batch_t* b, int* m0, int* m1, int* fwd_expand, int* bwd_expand) {
+    mega_range(prog, b, m0, m1);
+    *fwd_expand = *bwd_expand = -1;
+    if (*m1 <= *m0) return;
+    *fwd_expand = mega_expand_fwd(prog, *m0, *m1);
+    *bwd_expand = mega_expand_bwd(prog, *m0, *m1);
+    bool ok = *fwd_expand != -2 && *bwd_expand != -2;
+    for (int i = *m0; ok && i < *m1; ++i) {
+        bool used = false;
+        for (int k = i + 1; k < prog->n_sides; ++k)
+            used = used || prog->sides[k].src_self == prog->sides[i].out || prog->sides[k].src_cross == prog->sides[i].out;
+        ok = used;
+    }
+    if (!ok) *m0 = *m1 = 0;
+}
+
 }  // namespace
 
 extern "C" long long hgnn_program_work_floats(const hgnn_program_t* prog, int Rn, int Rm) {
@@ -124,7 +276,17 @@ extern "C" int hgnn_program_fwd(const hgnn_program_t* prog, const hgnn_batch_t* 
         }
         g_program_launches.fetch_add(1);
     }
+    int m0 = 0, m1 = 0, fwd_expand = -1, bwd_expand_unused = -1;
+    mega_decide(prog, b, &m0, &m1, &fwd_expand, &bwd_expand_unused);
     for (int i = 0; i < prog->n_sides; ++i) {
+        if (m1 > m0 && i == m0) {      // sides [m0, m1): one persistent kernel (mega.cu)
+            mk::Params P;
+            mega_params(prog, b, w, X, XL, addr, work, nullptr, nullptr, arena, m0, m1, &P);
+            P.expand = fwd_expand;
+            PROG_CALL(hgnn_mega_launch_fwd(P, s));
+            i = m1 - 1;
+            continue;
+        }
         const hgnn_prog_side_t& sd = prog->sides[i];
         const bool node = sd.kind == 0;
         hgnn_side_t st;
@@ -153,7 +315,7 @@ extern "C" int hgnn_program_fwd(const hgnn_program_t* prog, const hgnn_batch_t* 
         const bool readout = sd.out < 0;
         float* Z = work + (readout ? w.readout_off : w.off[sd.out]);
         double* acc_out = readout ? nullptr : arena + prog->tensors[sd.out].acc_f;
-        hgnn_eng_set_pdl(i >= 1);      // the stream predecessor is the previous side's forward kernel
+        hgnn_eng_set_pdl(i >= 1 && i != m1);      // the stream predecessor is the previous side's forward kernel
         const int rc_fwd = hgnn_lg_side_fwd(&st, &bs_, cross ? &bc_ : nullptr, param(addr, sd.Wa), param(addr, sd.ba),
                                             sd.Ha, param(addr, sd.Wb), param(addr, sd.bb), sd.Hb, sd.relu_from, Z,
                                             acc_out, nullptr, stream);
@@ -205,7 +367,39 @@ extern "C" int hgnn_program_bwd(const hgnn_program_t* prog, const hgnn_batch_t* 
     }
     auto grad_ptr = [&](int t) -> float* { return t == 0 ? gX : gwork + w.off[t]; };
     auto wants_grad = [&](int t) { return prog->tensors[t].bn_weight >= 0 || (t == 0 && gX != nullptr); };
+    // ---- pre-pass in backward order: who writes which gradient first (the later writers accumulate)
+    struct Flags { char need_self, acc_self, need_cross, acc_cross, out_started; };
+    std::vector<Flags> fl(prog->n_sides);
     for (int i = prog->n_sides - 1; i >= 0; --i) {
+        const hgnn_prog_side_t& sd = prog->sides[i];
+        Flags& f = fl[i];
+        f.out_started = sd.out >= 0 ? started[sd.out] : 1;
+        f.need_self = wants_grad(sd.src_self) ? 1 : 0;
+        f.acc_self = started[sd.src_self];
+        if (f.need_self) started[sd.src_self] = 1;
+        f.need_cross = f.acc_cross = 0;
+        if (sd.src_cross >= 0) {
+            f.need_cross = wants_grad(sd.src_cross) ? 1 : 0;
+            f.acc_cross = started[sd.src_cross];
+            if (f.need_cross) started[sd.src_cross] = 1;
+        }
+    }
+    int m0 = 0, m1 = 0, fwd_expand_unused = -1, bwd_expand = -1;
+    mega_decide(prog, b, &m0, &m1, &fwd_expand_unused, &bwd_expand);     // the same decision as the forward
+    for (int i = prog->n_sides - 1; i >= 0; --i) {
+        if (m1 > m0 && i == m1 - 1) {     // sides [m0, m1) in reverse: one persistent kernel (mega.cu)
+            mk::Params P;
+            mega_params(prog, b, w, X, XL, addr, work, gwork, gX, arena, m0, m1, &P);
+            for (int k = m0; k < m1; ++k) {
+                mk::Side& o = P.s[k - m0];
+                o.need_self = fl[k].need_self; o.acc_self = fl[k].acc_self;
+                o.need_cross = fl[k].need_cross; o.acc_cross = fl[k].acc_cross;
+            }
+            P.expand = bwd_expand;
+            PROG_CALL(hgnn_mega_launch_bwd(P, s));
+            i = m0;
+            continue;
+        }
         const hgnn_prog_side_t& sd = prog->sides[i];
         const bool node = sd.kind == 0;
         hgnn_side_bwd_t d;
@@ -221,7 +415,7 @@ extern "C" int hgnn_program_bwd(const hgnn_program_t* prog, const hgnn_batch_t* 
         } else {
             const hgnn_prog_tensor_t& T = prog->tensors[sd.out];
             const size_t n = (size_t)rows_of(prog, b, sd.out) * T.F;
-            if (!started[sd.out]) {   // output never used downstream: zero gradient
+            if (!fl[i].out_started) {   // output never used downstream: zero gradient
                 if (n && cudaMemsetAsync(gwork + w.off[sd.out], 0, n * sizeof(float), s) != cudaSuccess) {
                     hgnn_set_error("hgnn_program_bwd: cudaMemsetAsync failed");
                     return HGNN_ERR_CUDA;
@@ -253,11 +447,9 @@ extern "C" int hgnn_program_bwd(const hgnn_program_t* prog, const hgnn_batch_t* 
         d.Xs = tensor_ptr(prog, w, sd.src_self, X, XL, work);
         d.Fs = Fs;
         d.bn_self = bn_ref(prog, b, sd.src_self, addr, arena);
-        const bool need_self = wants_grad(sd.src_self);
-        d.gXs = need_self ? grad_ptr(sd.src_self) : nullptr;
-        d.accumulate_self = started[sd.src_self] ? 1 : 0;
+        d.gXs = fl[i].need_self ? grad_ptr(sd.src_self) : nullptr;
+        d.accumulate_self = fl[i].acc_self;
         d.acc_b_self = prog->tensors[sd.src_self].bn_weight >= 0 ? arena + prog->tensors[sd.src_self].acc_b : nullptr;
-        if (need_self) started[sd.src_self] = 1;
         // cross part
         d.R_cross = 0;
         d.pt_rowptr = d.pt_col = nullptr;
@@ -279,12 +471,10 @@ extern "C" int hgnn_program_bwd(const hgnn_program_t* prog, const hgnn_batch_t* 
             d.Fc = Fc;
             d.pt_nnz = b->p_nnz;
             d.bn_cross = bn_ref(prog, b, sd.src_cross, addr, arena);
-            const bool need_cross = wants_grad(sd.src_cross);
-            d.gXc = need_cross ? grad_ptr(sd.src_cross) : nullptr;
-            d.accumulate_cross = started[sd.src_cross] ? 1 : 0;
+            d.gXc = fl[i].need_cross ? grad_ptr(sd.src_cross) : nullptr;
+            d.accumulate_cross = fl[i].acc_cross;
             d.acc_b_cross =
                 prog->tensors[sd.src_cross].bn_weight >= 0 ? arena + prog->tensors[sd.src_cross].acc_b : nullptr;
-            if (need_cross) started[sd.src_cross] = 1;
         }
         d.skip_dw = 0;
         d.rng_scratch = nullptr;
@@ -292,7 +482,7 @@ extern "C" int hgnn_program_bwd(const hgnn_program_t* prog, const hgnn_batch_t* 
             d.rng_scratch = static_cast<char*>(rng_scratch) + rng_used;
             rng_used += rng_per_side;
         }
-        hgnn_eng_set_pdl(i < prog->n_sides - 1);   // the stream predecessor is the backward kernel of side i + 1
+        hgnn_eng_set_pdl(i < prog->n_sides - 1 && i != m0 - 1);   // the stream predecessor is the backward kernel of side i + 1
         const int rc_bwd = hgnn_lg_side_bwd(&d, stream);
         hgnn_eng_set_pdl(false);
         PROG_CALL(rc_bwd);

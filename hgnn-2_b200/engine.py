@@ -52,6 +52,20 @@ def _side_stream(device):
     return _side_streams[key]
 
 
+_MEGA_SCRATCH = {}
+
+
+def _mega_scratch(device):
+    """256 zeroed bytes per (device, stream): the grid-barrier state of the persistent kernels (csrc/mega.cu)."""
+    device = torch.device(device)
+    idx = device.index if device.index is not None else torch.cuda.current_device()
+    key = (idx, torch.cuda.current_stream(idx).cuda_stream)
+    buf = _MEGA_SCRATCH.get(key)
+    if buf is None:
+        buf = _MEGA_SCRATCH[key] = torch.zeros(64, dtype=torch.int32, device=torch.device("cuda", idx))
+    return buf
+
+
 def _bins(width):
     return int(_lib.lib.hgnn_bins_for(int(width)))
 
@@ -327,6 +341,13 @@ def _pack_cache(pack):
             b.pt_rowptr, b.pt_col, b.pt_pm, b.pt_pd = c["pt"]
             b.p_nnz = c["p_nnz"]
         b.node_off, b.pad_n = c["node_off"], c["pad_n"]
+        # persistent-kernel path (csrc/mega.cu): collapsed line graph + grid-barrier scratch
+        b.collapse_ok = 0
+        b.mega_scratch = _mega_scratch(pack.device).data_ptr()
+        if pack.dual and not pack.generic and getattr(pack, "btc", None) is not None:
+            c["btc"] = (iptr(pack.btc.rowptr), iptr(pack.btc.col), fptr(pack.btc.val), iptr(pack.erow), fptr(pack.ew))
+            b.btc_rowptr, b.btc_col, b.btc_val, b.erow, b.ew = c["btc"]
+            b.n_act = int(pack.erow.numel())
         c["batch"] = b
         pack.__dict__["_engine_cache"] = c
     return c
@@ -431,10 +452,11 @@ def _forward(plan, pack, Xp, XLp, training, arena, save_x1=False):
 class _ModelFunction(torch.autograd.Function):
 
     @staticmethod
-    def forward(ctx, model, pack, Xp, XLp, flat_mode, *params):
+    def forward(ctx, model, pack, Xp, XLp, flat_mode, xl_is_degree, *params):
         plan = get_plan(model)
         dev = Xp.device
         ctx.flat_mode = flat_mode
+        ctx.xl_is_degree = 1 if xl_is_degree else 0
         ctx.program = USE_PROGRAM and not SPLIT_DW
         if ctx.program:
             prog = plan.program(dev)
@@ -446,6 +468,8 @@ class _ModelFunction(torch.autograd.Function):
             addr = plan.param_addresses()
             run = plan.running_flat(dev)[0]
             _lib.tag = "program"
+            batch.collapse_ok = ctx.xl_is_degree
+            batch.mega_scratch = _mega_scratch(dev).data_ptr()
             call_program("hgnn_program_fwd", ctypes.byref(prog), ctypes.byref(batch), fptr(Xp),
                          fptr(XLp) if XLp is not None else None, addr.ctypes.data, work.data_ptr(), arena.data_ptr(),
                          run.data_ptr() if run is not None else None, out.data_ptr(), stream())
@@ -467,8 +491,8 @@ class _ModelFunction(torch.autograd.Function):
     @staticmethod
     def _grads_out(ctx, plan, gX, gflat):
         if ctx.flat_mode:
-            return (None, None, gX, None, None, gflat)
-        return (None, None, gX, None, None) + tuple(gflat[o:o + n].view(shape) for o, n, shape in plan.param_slices)
+            return (None, None, gX, None, None, None, gflat)
+        return (None, None, gX, None, None, None) + tuple(gflat[o:o + n].view(shape) for o, n, shape in plan.param_slices)
 
     @staticmethod
     def backward(ctx, g_out):
@@ -485,6 +509,8 @@ class _ModelFunction(torch.autograd.Function):
             scratch = torch.empty(n_scr, dtype=torch.uint8, device=dev) if n_scr > 0 else None
             gX = torch.empty_like(Xp) if ctx.need_x else None
             addr = plan.param_addresses()
+            batch.collapse_ok = ctx.xl_is_degree
+            batch.mega_scratch = _mega_scratch(dev).data_ptr()
             call_program("hgnn_program_bwd", ctypes.byref(prog), ctypes.byref(batch), fptr(Xp),
                          fptr(XLp) if XLp is not None else None, addr.ctypes.data, ctx.work.data_ptr(),
                          gwork.data_ptr(), arena.data_ptr(), fptr(g_out), gX.data_ptr() if gX is not None else None,
@@ -603,8 +629,9 @@ def supported(model):
     return plan.fits
 
 
-def run_model(model, pack, Xp, XLp):
-    """Forward of the whole layer stack on packed rows; returns (bs, dim_output)."""
+def run_model(model, pack, Xp, XLp, xl_is_degree=False):
+    """Forward of the whole layer stack on packed rows; returns (bs, dim_output).  ``xl_is_degree``: XLp is the
+    pack's own line-graph degree (pack.PackTensor), so the persistent kernels may collapse phantom rows."""
     plan = get_plan(model)
     if model.training and torch.is_grad_enabled():
         # dist.FlatParams (fused_grad): ONE leaf aliasing all parameters takes the flat gradient, instead
@@ -613,10 +640,10 @@ def run_model(model, pack, Xp, XLp):
         fp = flat_params_of(model)
         if fp is not None and fp.fused_grad and fp.matches(plan.params):
             fp.fused_used = True
-            return _ModelFunction.apply(model, pack, Xp, XLp, True, fp.flat_leaf)
-        return _ModelFunction.apply(model, pack, Xp, XLp, False, *plan.params)
+            return _ModelFunction.apply(model, pack, Xp, XLp, True, xl_is_degree, fp.flat_leaf)
+        return _ModelFunction.apply(model, pack, Xp, XLp, False, xl_is_degree, *plan.params)
     if model.training:      # train mode without autograd: batch statistics, running stats updated
         with torch.no_grad():
-            return _ModelFunction.apply(model, pack, Xp, XLp, False, *plan.params)
+            return _ModelFunction.apply(model, pack, Xp, XLp, False, xl_is_degree, *plan.params)
     arena = torch.zeros(1, dtype=torch.float64, device=Xp.device)
     return _forward(plan, pack, Xp, XLp, False, arena)[1]

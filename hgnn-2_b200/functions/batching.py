@@ -15,7 +15,7 @@ from random import shuffle
 import numpy as np
 import torch
 
-from ..pack import BatchPack, GraphHandle, MaskHandle, OperatorHandle
+from ..pack import BatchPack, GraphHandle, MaskHandle, OperatorHandle, PackTensor
 from .operators import graph_ops_of
 
 
@@ -91,6 +91,7 @@ def prepare_batch(batch, task, J=1, sparse=None, device="cuda"):
         g = graphs[i]
         Xn[i, :, :g.N] = inst[0].numpy().T
         XLn[i, 0, :g.M] = g.dl
+    XL = PackTensor.wrap(XL, pack)      # remembers that it is this pack's line-graph degree (pack.PackTensor)
     W, WL = OperatorHandle(pack, "W"), OperatorHandle(pack, "WL")
     Pm, Pd = OperatorHandle(pack, "Pm"), OperatorHandle(pack, "Pd")
     mask, mask_lg = MaskHandle(pack, False), MaskHandle(pack, True)

@@ -9,7 +9,7 @@ import torch.nn as nn
 
 from ... import engine
 from ..._lib import require_cuda
-from ...pack import resolve_pack
+from ...pack import PackTensor, resolve_pack
 from ..layers import layers_mnb
 
 
@@ -70,9 +70,12 @@ class GNN_lg(nn.Module):
         X, XL, W, WL, Pm, Pd = state
         pack = resolve_pack(W, WL, Pm, Pd, N_batch, E_batch)
         Xp = layers_mnb._pack_nodes(pack, X)
-        XLp = layers_mnb._pack_edges(pack, XL)
+        # XL straight from prepare_batch IS the pack's line-graph degree (functions/batching.py:171): use the
+        # device copy the pack already holds, and let the engine collapse the identical phantom rows
+        degree = PackTensor.pack_of(XL) is pack and not pack.generic and not XL.requires_grad
+        XLp = pack.dl.view(-1, 1) if degree else layers_mnb._pack_edges(pack, XL)
         if engine.supported(self):       # whole stack on the model-level engine (csrc/engine.cu)
-            return engine.run_model(self, pack, Xp, XLp)
+            return engine.run_model(self, pack, Xp, XLp, xl_is_degree=degree)
         Xp, XLp, _, _ = self.layer0.forward_packed(Xp, XLp, pack)
         for i in range(self.n_layers - 2):
             Xp, XLp, _, _ = self._modules['layer{}'.format(i + 1)].forward_packed(Xp, XLp, pack)

@@ -148,7 +148,7 @@ def device_pack(graphs, dual=True, skip_bt=False, device="cuda"):
 
 
 _HOST_KEYS = None
-_FLOAT_KEYS = frozenset(["pad_n", "deg", "dl", "a_val", "at_val", "b_val", "bt_val", "bts_val", "bts_rng_val",
+_FLOAT_KEYS = frozenset(["pad_n", "deg", "dl", "a_val", "at_val", "b_val", "bt_val", "bts_val", "bts_rng_val", "btc_val", "ew",
                          "p_pm", "p_pd", "pt_pm", "pt_pd"])
 HOST_PACK_THREADS = max(1, min(8, (os.cpu_count() or 1) // 2))
 # True (env HGNN_B200_HOST_CONCAT=1): concatenate a batch on the host (host_pack) and copy it once,
@@ -321,6 +321,10 @@ class BatchPack(object):
             self.bts = Csr(dev["bts_rowptr"], dev["bts_col"], dev["bts_val"])
             self.bts_ranges = (dev["bts_rng_rowptr"], dev["bts_rng_id"], dev["bts_rng_val"],
                                dev["bts_rng_lo"], dev["bts_rng_hi"])
+            # collapsed line graph for the persistent engine kernels (sparse_ops.GraphOps._build_collapsed):
+            # transposed operator over the active rows, per-row weights, list of active rows
+            self.btc = Csr(dev["btc_rowptr"], dev["btc_col"], dev["btc_val"])
+            self.ew, self.erow = dev["ew"], dev["erow"]
         for _ in range(1, self.J):   # A^(2^j): repeated squaring on the GPU, unclipped by default
             self.a.append(spgemm(self.a[-1], self.a[-1], clip_powers))
             self.at.append(spgemm(self.at[-1], self.at[-1], clip_powers))
@@ -577,6 +581,48 @@ def is_handle(x):
 
 
 _DENSE_CACHE = {}
+
+
+class PackTensor(torch.Tensor):
+    """The edge feature ``XL`` as ``prepare_batch`` builds it (line-graph degree, functions/batching.py:171): an
+    ordinary tensor that remembers WHICH pack's degree it holds.  The tag survives the copies a train loop makes
+    (``.cuda()``, ``.to()``, ``.pin_memory()``, ``.contiguous()``, ``.detach()``, ``.clone()``; scripts/train_mnb.py:60)
+    and is dropped by every other operation and by in-place writes (version counter).  The model reads it to know,
+    without touching the data, that the reference's phantom line-graph rows carry identical features - the condition
+    under which the engine computes one representative per graph (sparse_ops.GraphOps._build_collapsed)."""
+    _KEEP = frozenset(["cuda", "to", "pin_memory", "contiguous", "detach", "clone", "float", "requires_grad_"])
+
+    @staticmethod
+    def wrap(t, pack):
+        r = t.as_subclass(PackTensor)
+        r._hgnn_pack, r._hgnn_version = pack, r._version
+        return r
+
+    @classmethod
+    def __torch_function__(cls, func, types, args=(), kwargs=None):
+        kwargs = kwargs or {}
+        with torch._C.DisableTorchFunctionSubclass():
+            out = func(*args, **kwargs)
+        src = args[0] if args else None
+        if (getattr(func, "__name__", "") in cls._KEEP and isinstance(src, PackTensor) and torch.is_tensor(out)
+                and out.dtype == torch.float32 and out.shape == src.shape and PackTensor.pack_of(src) is not None):
+            if out is src:
+                return out
+            out = out.as_subclass(PackTensor)
+            out._hgnn_pack, out._hgnn_version = src._hgnn_pack, out._version
+        elif isinstance(out, PackTensor):
+            out = out.as_subclass(torch.Tensor)
+        return out
+
+    @staticmethod
+    def pack_of(t):
+        """The pack whose line-graph degree ``t`` provably holds, else None."""
+        if not isinstance(t, PackTensor):
+            return None
+        pack = t.__dict__.get("_hgnn_pack")
+        if pack is None or t.__dict__.get("_hgnn_version") != t._version:
+            return None
+        return pack
 
 
 def resolve_pack(W, WL=None, Pm=None, Pd=None, N_batch=None, E_batch=None):

@@ -89,6 +89,7 @@ BLOB_FIELDS = ("deg", "a_rowptr", "a_col", "a_val", "at_rowptr", "at_col", "at_v
                "p_rowptr", "p_col", "p_pm", "p_pd", "pt_rowptr", "pt_col", "pt_pm", "pt_pd",
                "bts_rowptr", "bts_col", "bts_val", "bts_rng_rowptr", "bts_rng_id", "bts_rng_val",
                "bts_rng_lo", "bts_rng_hi",
+               "btc_rowptr", "btc_col", "btc_val", "ew", "erow",
                "bt_rowptr", "bt_col", "bt_val")     # last: batches that skip the full bt copy a prefix
 N_PRIMAL_FIELDS = 7
 
@@ -106,7 +107,8 @@ class GraphOps(object):
                  "deg", "b_rowptr", "b_col", "b_val", "bt_rowptr", "bt_col", "bt_val", "dl",
                  "p_rowptr", "p_col", "p_pm", "p_pd", "pt_rowptr", "pt_col", "pt_pm", "pt_pd",
                  "bts_rowptr", "bts_col", "bts_val", "bts_rng_rowptr", "bts_rng_id", "bts_rng_val",
-                 "bts_rng_lo", "bts_rng_hi", "dual", "_blob", "_blob_ptr")
+                 "bts_rng_lo", "bts_rng_hi", "btc_rowptr", "btc_col", "btc_val", "ew", "erow",
+                 "dual", "_blob", "_blob_ptr")
 
     def blob_ptr(self):
         """Address of this graph's contiguous host blob (built on first use): int64 header
@@ -144,6 +146,44 @@ class GraphOps(object):
     def __setstate__(self, state):
         for k, v in state.items():
             setattr(self, k, v)
+        if getattr(self, "dual", False) and "ew" not in state:     # pickled before the collapsed fields existed
+            self._build_collapsed()
+
+    def _build_collapsed(self):
+        """Duplicate-row compression of the line graph (used by the persistent engine kernels).
+
+        The reference's enumeration (operators.py:59) leaves line-graph rows E+1..M-1 as identical
+        phantom ``(0,0,0)`` entries: same row of ``AL`` (the edges leaving node 0, :68-71), empty
+        ``Pm``/``Pd`` columns, same degree - and no operator has an entry in their COLUMNS.  With the
+        degree as the edge feature (batching.py:171) they therefore carry identical values in every
+        layer, forward and backward, and influence the result only through sums over rows (batch-norm
+        statistics, weight gradients).  So one representative (row E+1) is computed with multiplicity
+        ``mu = M-E-1`` and the other phantom rows are skipped:
+
+        * ``erow``  - the active rows 0..E+1 (all rows when there is no phantom block);
+        * ``ew``    - per-row weight in every sum over rows: 1, ``mu`` for the representative; the skipped
+                      rows hold ``-(distance to their representative)`` (weight 0; the kernels use it to
+                      copy the representative's value where a full tensor is needed);
+        * ``btc_*`` - the transposed operator restricted to active source rows, the representative's
+                      entries scaled by ``mu``:  ``btc[r, k] = ew[k] * AL[k, r]``."""
+        M, E = self.M, self.E
+        n_ph = M - E - 1
+        ew = np.ones(M, dtype=F32)
+        if n_ph >= 2:
+            ew[E + 1] = n_ph
+            ew[E + 2:] = -np.arange(1, n_ph, dtype=F32)     # skipped copies: -(distance to the representative)
+            n_act = E + 2
+        else:
+            n_act = M
+        self.ew = ew
+        self.erow = np.arange(n_act, dtype=I32)
+        rp = np.asarray(self.b_rowptr, dtype=np.int64)
+        m1 = np.repeat(np.arange(M, dtype=np.int64), np.diff(rp))
+        keep = m1 < n_act
+        m1, m2 = m1[keep], np.asarray(self.b_col, dtype=np.int64)[keep]
+        v = (np.asarray(self.b_val, dtype=F32)[keep] * np.maximum(ew[m1], 0)).astype(F32)
+        t1, t2, tv = _sort_coo(m2, m1, v)
+        self.btc_rowptr, self.btc_col, self.btc_val = _csr_from_sorted_coo(M, t1, t2, tv)
 
     @classmethod
     def from_dense(cls, A, dual=True):
@@ -217,6 +257,7 @@ class GraphOps(object):
         dl = np.zeros(M, dtype=F32)
         np.add.at(dl, m1, bv)
         self.dl = dl
+        self._build_collapsed()
         # ---- Pm / Pd  (:52-66): column c gets edge c (+1 at i, -1 at j) written AFTER edge c-1
         #      (-1 at i, +1 at j); Pm is 1 on the union.
         c = np.arange(E, dtype=np.int64)
@@ -272,6 +313,7 @@ _FIELDS = {
     "p": ("p_rowptr", "n", "m", ("p_col", "p_pm", "p_pd")),
     "pt": ("pt_rowptr", "m", "n", ("pt_col", "pt_pm", "pt_pd")),
     "bts": ("bts_rowptr", "m", "m", ("bts_col", "bts_val")),
+    "btc": ("btc_rowptr", "m", "m", ("btc_col", "btc_val")),
 }
 
 
@@ -338,6 +380,12 @@ def concat_block_diagonal(graphs, dual=True, skip=(), alloc=None, defer_offsets=
         fix.append((arrs[0], seg_nnz, seg[cspace]))
         for a in arrs[1:]:
             spec[a] = (F32, [getattr(g, a) for g in graphs], False, None, None)
+    if dual:     # collapsed line graph: per-row weights and the list of active rows
+        spec["ew"] = (F32, [g.ew for g in graphs], False, None, None)
+        na_off = np.concatenate([[0], np.cumsum([g.erow.shape[0] for g in graphs])])
+        seg_table("_seg_erow", na_off)
+        spec["erow"] = (I32, [g.erow for g in graphs], False, edge_off[:-1], None)
+        fix.append(("erow", "_seg_erow", "edge_off"))
     # layout
     layout, total = {}, 0
     for key, (dt, parts, drop, add, tail) in spec.items():

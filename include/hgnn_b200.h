@@ -360,6 +360,17 @@ typedef struct hgnn_batch_t {
     const int* pt_rowptr; const int* pt_col; const float* pt_pm; const float* pt_pd;  /* rows = line-graph nodes */
     const int* node_off; const float* pad_n;
     long long p_nnz;      /* entries of the incidence pattern (p and pt hold the same entries) */
+    /* Persistent-kernel path (csrc/mega.cu); all NULL / 0: not available, every side gets its own launch.
+     * Collapsed line graph (sparse_ops.GraphOps._build_collapsed): the reference's phantom line-graph rows
+     * (functions/operators.py:59,68-71) are identical copies, so one representative per graph is computed with
+     * its multiplicity.  erow (n_act,) = the active rows; ew (Rm,) = row weight in sums over rows (1, the
+     * multiplicity, -(distance to the representative) for skipped copies); btc_* = AL^T over the active rows with
+     * the multiplicity folded in. */
+    const int* btc_rowptr; const int* btc_col; const float* btc_val;
+    const int* erow; const float* ew; int n_act;
+    int collapse_ok;      /* 1: the edge feature XL of this call is the line-graph degree built by prepare_batch
+                           * (functions/batching.py:171), i.e. identical on the copies of a phantom block */
+    void* mega_scratch;   /* >= 256 bytes, zeroed once, private to the stream: grid-barrier state */
 } hgnn_batch_t;
 
 /* floats of activation workspace for a batch with Rn node rows and Rm line-graph rows (every side

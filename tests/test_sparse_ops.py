@@ -112,3 +112,46 @@ def test_deferred_offsets_equal_host_offsets():
     apply_fixups(buf, layout, len(gs))
     for k, v in ref.items():
         assert np.array_equal(got[k], v), k
+
+
+def test_collapsed_line_graph_invariants():
+    """sparse_ops.GraphOps._build_collapsed: the phantom rows E+1..M-1 of the reference's line graph
+    (functions/operators.py:59,68-71) are identical copies that no operator reads from, so one representative with
+    weight M-E-1 stands for them.  Checked on the dense operators: identical rows, empty columns, weights summing
+    to M, and btc = (diag(ew+) AL restricted to the active rows)^T."""
+    import numpy as np
+    from hgnn_b200.sparse_ops import GraphOps
+    rng = np.random.default_rng(3)
+    for n, p, weighted in ((12, 0.3, False), (9, 0.5, True), (5, 0.9, False), (3, 1.0, False), (4, 0.0, False)):
+        up = np.triu((rng.random((n, n)) < p).astype(np.float32), 1)
+        if weighted:
+            up *= rng.choice([1.0, 1.5, 2.0, 3.0], size=(n, n)).astype(np.float32)
+        A = up + up.T
+        g = GraphOps.from_dense(A, dual=True)
+        M, E = g.M, g.E
+        if M == 0:
+            assert g.erow.shape[0] == 0 and g.ew.shape[0] == 0
+            continue
+        W, WL, Pm, Pd = g.dense()
+        AL = WL[:, :, 2]
+        wpos = np.maximum(g.ew, 0.0)
+        assert wpos.sum() == M
+        act = g.erow.astype(np.int64)
+        assert np.array_equal(act, np.arange(act.shape[0]))
+        skipped = np.nonzero(g.ew <= 0)[0]
+        if skipped.size:
+            rep = E + 1
+            assert g.ew[rep] == M - E - 1 and np.array_equal(skipped, np.arange(E + 2, M))
+            assert np.array_equal(skipped + g.ew[skipped].astype(np.int64), np.full(skipped.shape, rep))
+            for r in skipped:      # identical copies of the representative, read by nobody
+                assert np.array_equal(AL[r], AL[rep]) and g.dl[r] == g.dl[rep]
+                assert not AL[:, r].any() and not Pm[:, r].any() and not Pd[:, r].any()
+            assert not AL[:, rep].any() and not Pm[:, rep].any()
+        else:
+            assert (g.ew == 1).all() and act.shape[0] == M
+        btc = np.zeros((M, M), np.float32)
+        r = np.repeat(np.arange(M), np.diff(g.btc_rowptr))
+        btc[r, g.btc_col] = g.btc_val
+        want = (wpos[:, None] * AL).T
+        want[:, g.ew <= 0] = 0
+        assert np.array_equal(btc, want)
