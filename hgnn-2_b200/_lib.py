@@ -34,7 +34,7 @@ class OpT(ctypes.Structure):
 class SideT(ctypes.Structure):
     _fields_ = [("R", c_int), ("ops", ctypes.POINTER(OpT)), ("n_ops", c_int), ("Xs", c_void),
                 ("Fs", c_int), ("p_rowptr", c_void), ("p_col", c_void), ("p_pm", c_void),
-                ("p_pd", c_void), ("Xc", c_void), ("Fc", c_int), ("p_nnz", c_ll)]
+                ("p_pd", c_void), ("Xc", c_void), ("Fc", c_int), ("p_nnz", c_ll), ("roww", c_void)]
 
 
 class BnRefT(ctypes.Structure):
@@ -52,7 +52,8 @@ class SideBwdT(ctypes.Structure):
                 ("R_cross", c_int), ("pt_rowptr", c_void), ("pt_col", c_void), ("pt_pm", c_void),
                 ("pt_pd", c_void), ("Xc", c_void), ("Fc", c_int), ("bn_cross", BnRefT), ("gXc", c_void),
                 ("accumulate_cross", c_int), ("acc_b_cross", c_void), ("skip_dw", c_int), ("pt_nnz", c_ll),
-                ("rng_scratch", c_void)]
+                ("rng_scratch", c_void), ("roww_self", c_void), ("roww_cross", c_void),
+                ("active_self", c_int), ("active_cross", c_int)]
 
 
 class ProgTensorT(ctypes.Structure):
@@ -84,7 +85,7 @@ class BatchT(ctypes.Structure):
                 ("pt_rowptr", c_void), ("pt_col", c_void), ("pt_pm", c_void), ("pt_pd", c_void),
                 ("node_off", c_void), ("pad_n", c_void), ("p_nnz", c_ll),
                 ("btc_rowptr", c_void), ("btc_col", c_void), ("btc_val", c_void),
-                ("erow", c_void), ("ew", c_void), ("n_act", c_int), ("collapse_ok", c_int),
+                ("erow", c_void), ("ew", c_void), ("n_act", c_int), ("btc_nnz", c_ll), ("collapse_ok", c_int),
                 ("mega_scratch", c_void)]
 
 
@@ -100,6 +101,8 @@ _SIGS = {
     "hgnn_lg_row4_eligible": [ctypes.POINTER(OpT), c_int, c_int, c_int, c_int],
     "hgnn_lg_wide_eligible": [c_int, c_int, c_int, c_int, c_int],
     "hgnn_lg_side_fits": [c_int, c_int, c_int, c_int],
+    "hgnn_mega_set_trace": [_P],
+    "hgnn_mega_grid_for": [c_int, c_int],
     "hgnn_lg_side_dw": [_P, _P, c_int, c_int, _P, _P, _P, _P, c_int, _P, _P, _P],
     "hgnn_lg_side_bwd": [ctypes.POINTER(SideBwdT), _P],
     "hgnn_debug_cta_times": [_P, c_int],

@@ -1094,6 +1094,7 @@ static bool eng_try_fwd_row4(const eng::FwdArgs& g, const hgnn_side_t* side, hgn
     a.p_rowptr = g.p_rowptr; a.p_col = g.p_col; a.p_pm = g.p_pm; a.p_pd = g.p_pd; a.Xc = g.Xc; a.bn_c = g.bn_c;
     a.Wa = g.Wa; a.ba = g.ba; a.Ha = g.Ha; a.Wb = g.Wb; a.bb = g.bb; a.Hb = g.Hb;
     a.relu_from = g.relu_from; a.Cin = g.Cin; a.Z = g.Z; a.acc_out = g.acc_out; a.X1 = g.X1;
+    a.roww = side->roww;
     static int ablate = -1;
     if (ablate < 0) { const char* e = getenv("HGNN_B200_ABLATE"); ablate = e ? atoi(e) : 0; }
     a.ablate = ablate;
@@ -1147,6 +1148,7 @@ static bool eng_try_fwd_rowg(const eng::FwdArgs& g, const hgnn_side_t* side, hgn
     a.p_rowptr = g.p_rowptr; a.p_col = g.p_col; a.p_pm = g.p_pm; a.p_pd = g.p_pd; a.Xc = g.Xc; a.bn_c = g.bn_c;
     a.Wa = g.Wa; a.ba = g.ba; a.Ha = g.Ha; a.Wb = g.Wb; a.bb = g.bb; a.Hb = g.Hb;
     a.relu_from = g.relu_from; a.Cin = g.Cin; a.Z = g.Z; a.acc_out = g.acc_out; a.X1 = nullptr; a.ablate = 0;
+    a.roww = side->roww;
     cudaStream_t s = to_stream(stream);
     const int want = ceil_div(a.R, R4_THREADS);
     const double avg_a = a.R > 0 ? (double)side->ops[2].nnz / a.R : 0.0;
@@ -1327,6 +1329,7 @@ extern "C" int hgnn_lg_side_fwd(const hgnn_side_t* side, const hgnn_bn_ref_t* bn
     if (eng_try_fwd_row4(a, side, stream)) return hgnn_check_launch("hgnn_lg_side_fwd(row4)");
     if (eng_try_fwd_rowg(a, side, stream)) return hgnn_check_launch("hgnn_lg_side_fwd(rowg)");
     HGNN_REQUIRE(!X1, "x1 rows can only be saved by the width-4 fast path (check hgnn_lg_row4_eligible)");
+    HGNN_REQUIRE(!side->roww, "row weights need the thread-per-row kernels (widths of the h = 2 feature maps)");
     if (eng_try_fwd_tc5(a, stream)) return hgnn_check_launch("hgnn_lg_side_fwd(tc5)");
     if (eng_try_fwd_wide(a, stream)) return hgnn_check_launch("hgnn_lg_side_fwd(wide)");
     const bool vec4 = (a.Fs % 4 == 0) && (a.Fc % 4 == 0) && eng_aligned16(a.Xs) && (a.Fc == 0 || eng_aligned16(a.Xc));
@@ -1485,6 +1488,7 @@ static bool eng_try_bwd_row4(const hgnn_side_bwd_t* d, hgnn_stream_t stream) {
     a.pt_rowptr = d->pt_rowptr; a.pt_col = d->pt_col; a.pt_pm = d->pt_pm; a.pt_pd = d->pt_pd;
     a.Xc = d->Xc; a.bn_c = to_bnref(&d->bn_cross); a.gXc = d->gXc; a.acc_cross = d->accumulate_cross;
     a.acc_b_cross = d->acc_b_cross; a.col0_cross = d->n_ops * 4;
+    a.roww_s = d->roww_self; a.roww_c = d->roww_cross;
     // dedicated range-sum CTAs when the caller provided the (zeroed) scratch: [flags: rng_n ints | sums: 4 floats each]
     a.rng_n = 0; a.range_ctas = 0; a.rng_sum_g = nullptr; a.rng_flag_g = nullptr;
     if (d->rng_scratch && o2.rng_rowptr && o2.rng_n > 0 && !eng_no_range_ctas()) {
@@ -1511,8 +1515,11 @@ static bool eng_try_bwd_row4(const hgnn_side_bwd_t* d, hgnn_stream_t stream) {
         const char* e = getenv("HGNN_B200_BWD_ENTRY_COST");      // "w_self,w_cross" (tuning aid)
         if (e) { w_self = atof(e); const char* c = strchr(e, ','); w_cross = c ? atof(c + 1) : w_self; }
     }
-    const double cost_s = (double)d->R_self * (1.0 + w_self * avg_s);
-    const double cost_c = d->R_cross > 0 ? (double)d->R_cross * (1.0 + w_cross * avg_c) : 0.0;
+    // rows that are skipped (row weight <= 0, collapsed line graph) cost next to nothing
+    const double act_s = d->active_self > 0 ? (double)d->active_self : (double)d->R_self;
+    const double act_c = d->active_cross > 0 ? (double)d->active_cross : (double)d->R_cross;
+    const double cost_s = act_s * 1.0 + w_self * (double)d->ops_T[2].nnz;
+    const double cost_c = d->R_cross > 0 ? act_c * 1.0 + w_cross * (double)d->pt_nnz : 0.0;
     static int debug_split = -1;
     if (debug_split < 0) debug_split = getenv("HGNN_B200_DEBUG_SPLIT") ? 1 : 0;
     bool big_s = false, big_c = false;      // measured: the small batches win in the backward (register pressure)
@@ -1527,7 +1534,7 @@ static bool eng_try_bwd_row4(const hgnn_side_bwd_t* d, hgnn_stream_t stream) {
         if (d->R_cross > 0 && grid < 2) grid = 2;                                                         \
         int row_grid = grid;                            /* the range CTAs come out of the resident budget */ \
         if (a.range_ctas > 0 && grid + a.range_ctas > cap) row_grid = max(2, cap - a.range_ctas);         \
-        a.ctas_self = eng_split_ctas(row_grid, d->R_self, d->R_cross > 0 ? d->R_cross : 0, cost_s, cost_c); \
+        a.ctas_self = eng_split_ctas(row_grid, (long long)act_s, d->R_cross > 0 ? (long long)act_c : 0, cost_s, cost_c); \
         if (debug_split)                                                                                  \
             fprintf(stderr, "bwd_row4 split: cap %d grid %d row_grid %d range_ctas %d R_self %d R_cross %d avg_s %.3f avg_c %.3f -> ctas_self %d\n", \
                     cap, grid, row_grid, a.range_ctas, d->R_self, d->R_cross, avg_s, avg_c, a.ctas_self); \
@@ -1573,6 +1580,7 @@ static bool eng_try_bwd_rowg(const hgnn_side_bwd_t* d, hgnn_stream_t stream) {
     a.pt_rowptr = d->pt_rowptr; a.pt_col = d->pt_col; a.pt_pm = d->pt_pm; a.pt_pd = d->pt_pd;
     a.Xc = d->Xc; a.bn_c = to_bnref(&d->bn_cross); a.gXc = d->gXc; a.acc_cross = d->accumulate_cross;
     a.acc_b_cross = d->acc_b_cross; a.col0_cross = d->n_ops * Fs; a.ablate = 0;
+    a.roww_s = d->roww_self; a.roww_c = d->roww_cross;
     a.rng_n = 0; a.range_ctas = 0; a.rng_sum_g = nullptr; a.rng_flag_g = nullptr;
     cudaStream_t s = to_stream(stream);
     const long long rows = (long long)d->R_self + a.R_cross;
@@ -1648,6 +1656,7 @@ extern "C" int hgnn_lg_side_bwd(const hgnn_side_bwd_t* d, hgnn_stream_t stream) 
     if (eng_try_bwd_row4(d, stream)) return hgnn_check_launch("hgnn_lg_side_bwd(row4)");
     if (eng_try_bwd_rowg(d, stream)) return hgnn_check_launch("hgnn_lg_side_bwd(rowg)");
     HGNN_REQUIRE(!d->skip_dw, "skip_dw needs the width-4 fast path (check hgnn_lg_row4_eligible)");
+    HGNN_REQUIRE(!d->roww_self && !d->roww_cross, "row weights need the thread-per-row kernels (widths of the h = 2 feature maps)");
     eng::BwdArgs a;
     a.gY = d->gY; a.Z = d->Z; a.Fg = d->Fg; a.relu_from = d->relu_from; a.Rg = d->Rg;
     a.acc_f = d->acc_f; a.acc_b = d->acc_b; a.bn_w = d->bn_weight;

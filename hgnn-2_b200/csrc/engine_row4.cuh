@@ -123,6 +123,8 @@ struct Fwd4Args {
     float* Z;
     double* acc_out;
     float* X1;                       // optional: the concatenated x1 rows (R, Cin) for the dW pass
+    const float* roww;               // optional per-row weight (collapsed line graph): rows with weight <= 0 are skipped,
+                                     // the others enter the batch-norm sums weight times
     int ablate;                      // timing experiments only (HGNN_B200_ABLATE): 1 no gathers, 2 no BN, 4 no epilogue
 };
 
@@ -279,7 +281,7 @@ fwd_row4_kernel(const Fwd4Args a) {
     if (CROSS) lc.issue_params(a.bn_c);
     const int stride = gridDim.x * R4_THREADS;
     int row = blockIdx.x * R4_THREADS + tid;
-    float d = 0.f;
+    float d = 0.f, rw = 1.f;
     int k0[NCSR > 0 ? NCSR : 1], k1[NCSR > 0 ? NCSR : 1], p0 = 0, p1 = 0;
     GatherBatch<BA, false> ga;
     GatherBatch<BP, true> gb;
@@ -294,7 +296,8 @@ fwd_row4_kernel(const Fwd4Args a) {
             p0 = __ldg(a.p_rowptr + r);
             p1 = __ldg(a.p_rowptr + r + 1);
         }
-        if (a.ablate & 1) { k1[0] = k0[0]; p1 = p0; }
+        rw = a.roww ? __ldg(a.roww + r) : 1.f;
+        if ((a.ablate & 1) || rw <= 0.f) { k1[0] = k0[0]; p1 = p0; }
         if (NCSR > 0) ga.load_entries(a.col[0], a.val[0], nullptr, k0[0], k1[0]);
         if (CROSS) gb.load_entries(a.p_col, a.p_pm, a.p_pd, p0, p1);
     };
@@ -328,6 +331,7 @@ fwd_row4_kernel(const Fwd4Args a) {
             if (NCSR > 0) ga.load_rows(a.Xs);
             if (CROSS) gb.load_rows(a.Xc);
         }
+        if (rw <= 0.f) continue;                       // a skipped copy of a phantom line-graph row
         float4 x1[NB];
         const float4 xs = f4_affine(xs_raw, sc_s, sh_s);
         x1[0] = xs;
@@ -382,8 +386,8 @@ fwd_row4_kernel(const Fwd4Args a) {
                 acc += f4_dot(x1[b], *reinterpret_cast<const float4*>(W + (o * NB + b) * 4));
             if (o >= a.relu_from) acc = fmaxf(acc, 0.f);
             out[o] = acc;
-            s1[o] += acc;
-            s2[o] = fmaf(acc, acc, s2[o]);
+            s1[o] = fmaf(rw, acc, s1[o]);
+            s2[o] = fmaf(rw * acc, acc, s2[o]);
         }
         *reinterpret_cast<float4*>(a.Z + (size_t)row * 4) = make_float4(out[0], out[1], out[2], out[3]);
     }
@@ -423,6 +427,7 @@ struct Bwd4Args {
     const int* pt_rowptr; const int* pt_col; const float* pt_pm; const float* pt_pd;
     const float* Xc; BnRef bn_c; float* gXc; int acc_cross; double* acc_b_cross;
     int col0_cross;
+    const float* roww_s; const float* roww_c;   // optional row weights of the self / cross rows (see Fwd4Args::roww)
     int ctas_self;        // CTAs [0, ctas_self) work on the self rows
     // dedicated range-sum CTAs (optional): the last `range_ctas` CTAs of the grid publish the sums of the rng_n ranges
     // into rng_sum_g (4 floats each) and set rng_flag_g[r]; both zero on entry
@@ -628,6 +633,8 @@ bwd_row4_kernel(const Bwd4Args a) {
             }
         };
         for (int row = blockIdx.x * R4_THREADS + tid; row < a.R_self; row += a.ctas_self * R4_THREADS) {
+            const float rw = a.roww_s ? __ldg(a.roww_s + row) : 1.f;
+            if (rw <= 0.f) continue;                    // a skipped copy of a phantom line-graph row
             float4 T[NT];
             T[0] = gp(row);
             const float d = __ldg(a.diag + row);
@@ -651,7 +658,8 @@ bwd_row4_kernel(const Bwd4Args a) {
                 }
             }
             const float4 xr = ld4(a.Xs + (size_t)row * 4);
-            const float4 xn = f4_affine(xr, sc, sh);
+            const float4 xn1 = f4_affine(xr, sc, sh);
+            const float4 xn = make_float4(rw * xn1.x, rw * xn1.y, rw * xn1.z, rw * xn1.w);   // weight of the row in dW
             float g[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
             for (int t = 0; t < NT; ++t) {
@@ -669,7 +677,7 @@ bwd_row4_kernel(const Bwd4Args a) {
                     }
                 }
             }
-            if (DW) { db[0] += T[0].x; db[1] += T[0].y; db[2] += T[0].z; db[3] += T[0].w; }
+            if (DW) { db[0] = fmaf(rw, T[0].x, db[0]); db[1] = fmaf(rw, T[0].y, db[1]); db[2] = fmaf(rw, T[0].z, db[2]); db[3] = fmaf(rw, T[0].w, db[3]); }
             if (gX) {
                 float4 o4 = make_float4(g[0], g[1], g[2], g[3]);
                 if (a.acc_self) {
@@ -680,7 +688,7 @@ bwd_row4_kernel(const Bwd4Args a) {
                 if (stats) {
                     const float xh[4] = {(xr.x - mu.x) * rs.x, (xr.y - mu.y) * rs.y, (xr.z - mu.z) * rs.z, (xr.w - mu.w) * rs.w};
 #pragma unroll
-                    for (int f = 0; f < 4; ++f) { sg[f] += g[f]; sgx[f] = fmaf(g[f], xh[f], sgx[f]); }
+                    for (int f = 0; f < 4; ++f) { sg[f] = fmaf(rw, g[f], sg[f]); sgx[f] = fmaf(rw * g[f], xh[f], sgx[f]); }
                 }
             }
         }
@@ -787,6 +795,8 @@ bwd_row4_kernel(const Bwd4Args a) {
         const bool stats = a.acc_b_cross != nullptr && gX != nullptr;
         const int ncta = row_ctas - a.ctas_self;
         for (int row = (blockIdx.x - a.ctas_self) * R4_THREADS + tid; row < a.R_cross; row += ncta * R4_THREADS) {
+            const float rw = a.roww_c ? __ldg(a.roww_c + row) : 1.f;
+            if (rw <= 0.f) continue;
             float4 Tm = f4_zero(), Td = f4_zero();
             const int k0 = __ldg(a.pt_rowptr + row), k1 = (a.ablate & 1) ? k0 : __ldg(a.pt_rowptr + row + 1);
             for (int k = k0; k < k1; k += CB) {         // CB entries (2 CB row loads) in flight
@@ -809,7 +819,8 @@ bwd_row4_kernel(const Bwd4Args a) {
                 }
             }
             const float4 xr = ld4(a.Xc + (size_t)row * 4);
-            const float4 xn = f4_affine(xr, sc, sh);
+            const float4 xn1 = f4_affine(xr, sc, sh);
+            const float4 xn = make_float4(rw * xn1.x, rw * xn1.y, rw * xn1.z, rw * xn1.w);
             float g[4] = {0.f, 0.f, 0.f, 0.f};
             const float4 T[2] = {Tm, Td};
 #pragma unroll
@@ -838,7 +849,7 @@ bwd_row4_kernel(const Bwd4Args a) {
                 if (stats) {
                     const float xh[4] = {(xr.x - mu.x) * rs.x, (xr.y - mu.y) * rs.y, (xr.z - mu.z) * rs.z, (xr.w - mu.w) * rs.w};
 #pragma unroll
-                    for (int f = 0; f < 4; ++f) { sg[f] += g[f]; sgx[f] = fmaf(g[f], xh[f], sgx[f]); }
+                    for (int f = 0; f < 4; ++f) { sg[f] = fmaf(rw, g[f], sg[f]); sgx[f] = fmaf(rw * g[f], xh[f], sgx[f]); }
                 }
             }
         }

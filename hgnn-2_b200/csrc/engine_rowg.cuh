@@ -115,7 +115,7 @@ fwd_rowg_kernel(const Fwd4Args a) {
     if (CROSS) lc.issue_params(a.bn_c);
     const int stride = gridDim.x * R4_THREADS;
     int row = blockIdx.x * R4_THREADS + tid;
-    float d = 0.f;
+    float d = 0.f, rw = 1.f;
     int k0[NCSR], k1[NCSR], p0 = 0, p1 = 0;
     GatherBatchG<BA, false, FS> ga;
     GatherBatchG<BP, true, FCC> gb;
@@ -130,6 +130,8 @@ fwd_rowg_kernel(const Fwd4Args a) {
             p0 = __ldg(a.p_rowptr + r);
             p1 = __ldg(a.p_rowptr + r + 1);
         }
+        rw = a.roww ? __ldg(a.roww + r) : 1.f;
+        if (rw <= 0.f) { k1[0] = k0[0]; p1 = p0; }
         ga.load_entries(a.col[0], a.val[0], nullptr, k0[0], k1[0]);
         if (CROSS) gb.load_entries(a.p_col, a.p_pm, a.p_pd, p0, p1);
     };
@@ -162,6 +164,7 @@ fwd_rowg_kernel(const Fwd4Args a) {
             ga.load_rows(a.Xs);
             if (CROSS) gb.load_rows(a.Xc);
         }
+        if (rw <= 0.f) continue;                                // a skipped copy of a phantom line-graph row
         float x1[CIN];
 #pragma unroll
         for (int f = 0; f < FS; ++f) {
@@ -223,8 +226,8 @@ fwd_rowg_kernel(const Fwd4Args a) {
             for (int c = 0; c < CIN; ++c) acc = fmaf(x1[c], W[o * CIN + c], acc);
             if (o >= a.relu_from) acc = fmaxf(acc, 0.f);
             out[o] = acc;
-            s1[o] += acc;
-            s2[o] = fmaf(acc, acc, s2[o]);
+            s1[o] = fmaf(rw, acc, s1[o]);
+            s2[o] = fmaf(rw * acc, acc, s2[o]);
         }
         if constexpr (FO == 4) {
             *reinterpret_cast<float4*>(a.Z + (size_t)row * 4) = make_float4(out[0], out[1], out[2], out[3]);
@@ -360,9 +363,10 @@ bwd_rowg_kernel(const Bwd4Args a) {
         // finishes one row from its T blocks: gX (+)= W^T T, dW += T (x) xn, statistics of the produced gradient
         auto finish = [&](int row, const float (&T)[NT][FG], bool add_to_existing, bool first_visit) {
             const RowV<FS> xr = ldrow<FS>(a.Xs, row);
+            const float rw = a.roww_s ? __ldg(a.roww_s + row) : 1.f;      // weight of the row in every sum over rows
             float xn[FS], g[FS];
 #pragma unroll
-            for (int f = 0; f < FS; ++f) { xn[f] = fmaf(xr.v[f], bxs.sc[f], bxs.sh[f]); g[f] = 0.f; }
+            for (int f = 0; f < FS; ++f) { xn[f] = rw * fmaf(xr.v[f], bxs.sc[f], bxs.sh[f]); g[f] = 0.f; }
 #pragma unroll
             for (int t = 0; t < NT; ++t)
 #pragma unroll
@@ -374,7 +378,7 @@ bwd_rowg_kernel(const Bwd4Args a) {
                     }
             if (first_visit) {
 #pragma unroll
-                for (int o = 0; o < FG; ++o) db[o] += T[0][o];
+                for (int o = 0; o < FG; ++o) db[o] = fmaf(rw, T[0][o], db[o]);
             }
             if (gX) {
 #pragma unroll
@@ -386,13 +390,14 @@ bwd_rowg_kernel(const Bwd4Args a) {
                 if (stats) {
 #pragma unroll
                     for (int f = 0; f < FS; ++f) {
-                        sg[f & 3] += g[f];
-                        sgx[f & 3] = fmaf(g[f], (xr.v[f] - bxs.mu[f]) * bxs.rs[f], sgx[f & 3]);
+                        sg[f & 3] = fmaf(rw, g[f], sg[f & 3]);
+                        sgx[f & 3] = fmaf(rw * g[f], (xr.v[f] - bxs.mu[f]) * bxs.rs[f], sgx[f & 3]);
                     }
                 }
             }
         };
         for (int row = blockIdx.x * R4_THREADS + tid; row < a.R_self; row += a.ctas_self * R4_THREADS) {
+            if (a.roww_s && __ldg(a.roww_s + row) <= 0.f) continue;        // a skipped copy of a phantom line-graph row
             float T[NT][FG];
             const RowV<FG> t0 = gp(row);
             const float d = __ldg(a.diag + row);
@@ -517,6 +522,8 @@ bwd_rowg_kernel(const Bwd4Args a) {
         const bool stats = FC == 4 && a.acc_b_cross != nullptr && gX != nullptr;
         const int ncta = gridDim.x - a.ctas_self;
         for (int row = (blockIdx.x - a.ctas_self) * R4_THREADS + tid; row < a.R_cross; row += ncta * R4_THREADS) {
+            const float rw = a.roww_c ? __ldg(a.roww_c + row) : 1.f;
+            if (rw <= 0.f) continue;
             float T[2][FG];
 #pragma unroll
             for (int o = 0; o < FG; ++o) { T[0][o] = 0.f; T[1][o] = 0.f; }
@@ -552,7 +559,7 @@ bwd_rowg_kernel(const Bwd4Args a) {
             const RowV<FCC> xr = ldrow<FCC>(a.Xc, row);
             float xn[FCC], g[FCC];
 #pragma unroll
-            for (int f = 0; f < FCC; ++f) { xn[f] = fmaf(xr.v[f], bxc.sc[f], bxc.sh[f]); g[f] = 0.f; }
+            for (int f = 0; f < FCC; ++f) { xn[f] = rw * fmaf(xr.v[f], bxc.sc[f], bxc.sh[f]); g[f] = 0.f; }
 #pragma unroll
             for (int t = 0; t < 2; ++t)
 #pragma unroll
@@ -572,8 +579,8 @@ bwd_rowg_kernel(const Bwd4Args a) {
                 if (stats) {
 #pragma unroll
                     for (int f = 0; f < FCC; ++f) {
-                        sg[f & 3] += g[f];
-                        sgx[f & 3] = fmaf(g[f], (xr.v[f] - bxc.mu[f]) * bxc.rs[f], sgx[f & 3]);
+                        sg[f & 3] = fmaf(rw, g[f], sg[f & 3]);
+                        sgx[f & 3] = fmaf(rw * g[f], (xr.v[f] - bxc.mu[f]) * bxc.rs[f], sgx[f & 3]);
                     }
                 }
             }

@@ -41,28 +41,176 @@ __device__ __forceinline__ float4 f4_affine_sum(float4 acc, float ws, float4 s, 
     return make_float4(fmaf(acc.x, s.x, ws * t.x), fmaf(acc.y, s.y, ws * t.y), fmaf(acc.z, s.z, ws * t.z), fmaf(acc.w, s.w, ws * t.w));
 }
 
+__device__ __forceinline__ unsigned long long global_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+// profiling aid: time stamp k (0: phase entered, 1: barrier passed, 2: vectors ready, 3: rows + flush done)
+__device__ __forceinline__ void trace_mark(const Params& P, int phase, int k) {
+    if (P.trace && threadIdx.x == 0) P.trace[((size_t)phase * gridDim.x + blockIdx.x) * 4 + k] = global_ns();
+}
+
 __device__ __forceinline__ int slice_lo(int n, int b, int G) { return (int)(((long long)n * b) / G); }
 
-// ---- grid barrier: one arrival counter + a generation word; thread 0 of every CTA arrives and polls ----
+// ---- grid barrier: ONE monotonic arrival counter.  Thread 0 of every CTA arrives with a fire-and-forget
+// red.release (orders the CTA's earlier writes and atomics - bar.sync makes them cumulative) and polls the
+// counter with ld.acquire until all CTAs of the round are in.  The counter is 0 at launch: the CTA that
+// finishes the kernel last resets it (grid_exit).
 __device__ __forceinline__ unsigned ld_acquire(const unsigned* p) {
     unsigned v;
     asm volatile("ld.acquire.gpu.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
-__device__ __forceinline__ void grid_sync(unsigned* bar, unsigned& gen) {
+__device__ __forceinline__ void grid_sync(unsigned* bar, unsigned& target) {
     __syncthreads();
     if (threadIdx.x == 0) {
-        ++gen;
-        unsigned prev;
-        asm volatile("atom.add.acq_rel.gpu.u32 %0, [%1], 1;" : "=r"(prev) : "l"(bar) : "memory");
-        if (prev == gridDim.x - 1) {
-            asm volatile("st.relaxed.gpu.u32 [%0], %1;" ::"l"(bar), "r"(0u) : "memory");
-            asm volatile("st.release.gpu.u32 [%0], %1;" ::"l"(bar + 32), "r"(gen) : "memory");
-        } else {
-            while (ld_acquire(bar + 32) != gen) {}
-        }
+        target += gridDim.x;
+        asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(bar) : "memory");
+        while ((int)(ld_acquire(bar) - target) < 0) {}
     }
     __syncthreads();
+}
+__device__ __forceinline__ void grid_exit(unsigned* bar) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned prev;
+        asm volatile("atom.add.acq_rel.gpu.u32 %0, [%1], 1;" : "=r"(prev) : "l"(bar + 32) : "memory");
+        if (prev == gridDim.x - 1) {         // everybody is past its last poll
+            asm volatile("st.relaxed.gpu.u32 [%0], %1;" ::"l"(bar), "r"(0u) : "memory");
+            asm volatile("st.relaxed.gpu.u32 [%0], %1;" ::"l"(bar + 32), "r"(0u) : "memory");
+        }
+    }
+}
+
+// exclusive prefix sum of v over the CTA (thread order); total = sum over all threads.  scratch: THREADS/32 ints.
+__device__ __forceinline__ int block_excl_scan(int v, int* scratch, int& total) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(FULL, incl, o);
+        if (lane >= o) incl += t;
+    }
+    __syncthreads();
+    if (lane == 31) scratch[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+        int t = lane < THREADS / 32 ? scratch[lane] : 0;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int u = __shfl_up_sync(FULL, t, o);
+            if (lane >= o) t += u;
+        }
+        if (lane < THREADS / 32) scratch[lane] = t;
+    }
+    __syncthreads();
+    const int base = warp > 0 ? scratch[warp - 1] : 0;
+    total = scratch[THREADS / 32 - 1];
+    return base + incl - v;
+}
+
+// ---- thread-private structure cache in shared memory ---------------------------------------------------
+// A grid barrier ends in an acquire at gpu scope, which invalidates the SM's L1 (CCTL.IVALL): row pointers,
+// columns and values re-read through L1 after every barrier come from L2 again - four dependent round trips
+// per row and phase (profiles/logs/mega_trace_r2d.log: 4.4 us of row work per forward phase, 15-26 us per
+// backward phase).  Every thread owns the SAME rows in every phase, so at kernel start it copies the structure
+// of its rows into shared memory - header (row, weight, diagonal, counts, offset) + the entries of its two
+// operator sets - and from then on a row costs one shared-memory lookup plus ONE round of feature loads from L2.
+// Rows that do not fit the budget keep offset -1 and read their structure from global memory.
+struct StageSrc {
+    const float* diag;
+    const int* rp1; const int* col1; const float* val1;                      // CSR operator of this row space
+    const int* rp2; const int* col2; const float* pm2; const float* pd2;      // incidence rows (NULL: none)
+};
+template <int KIND>
+__device__ __forceinline__ StageSrc stage_src(const Graph& g, bool bwd) {
+    StageSrc s;
+    if (KIND == 0) {
+        s.diag = g.deg;
+        s.rp1 = bwd ? g.at_rp : g.a_rp; s.col1 = bwd ? g.at_col : g.a_col; s.val1 = bwd ? g.at_val : g.a_val;
+        s.rp2 = g.p_rp; s.col2 = g.p_col; s.pm2 = g.p_pm; s.pd2 = g.p_pd;
+    } else {
+        s.diag = g.dl;
+        s.rp1 = bwd ? g.btc_rp : g.b_rp; s.col1 = bwd ? g.btc_col : g.b_col; s.val1 = bwd ? g.btc_val : g.b_val;
+        s.rp2 = g.pt_rp; s.col2 = g.pt_col; s.pm2 = g.pt_pm; s.pd2 = g.pt_pd;
+    }
+    return s;
+}
+constexpr int HDR_N = 4;    // node row header:  d, off, n1, n2
+constexpr int HDR_E = 6;    // line-graph row header: row, w, d, off, n1, n2
+
+template <int KIND>
+__device__ __forceinline__ void stage_rows(const Graph& g, bool bwd, int* hdr, int* ent, int cap, int& used, int* scratch) {
+    const StageSrc src = stage_src<KIND>(g, bwd);
+    const int n = KIND == 0 ? g.Rn : g.n_act;
+    const int lo = slice_lo(n, blockIdx.x, gridDim.x), hi = slice_lo(n, blockIdx.x + 1, gridDim.x);
+    int words = 0;
+    for (int i = lo + (int)threadIdx.x; i < hi; i += THREADS) {
+        const int row = KIND == 0 ? i : __ldg(g.erow + i);
+        const int n1 = __ldg(src.rp1 + row + 1) - __ldg(src.rp1 + row);
+        const int n2 = src.rp2 ? __ldg(src.rp2 + row + 1) - __ldg(src.rp2 + row) : 0;
+        words += 2 * n1 + 3 * n2;
+    }
+    int total = 0;
+    int base = used + block_excl_scan(words, scratch, total);
+    for (int i = lo + (int)threadIdx.x; i < hi; i += THREADS) {
+        const int row = KIND == 0 ? i : __ldg(g.erow + i);
+        const int k1 = __ldg(src.rp1 + row), n1 = __ldg(src.rp1 + row + 1) - k1;
+        const int k2 = src.rp2 ? __ldg(src.rp2 + row) : 0, n2 = src.rp2 ? __ldg(src.rp2 + row + 1) - k2 : 0;
+        const int w_row = 2 * n1 + 3 * n2;
+        const int off = base + w_row <= cap ? base : -1;
+        base += w_row;
+        int* h = hdr + (size_t)(i - lo) * (KIND == 0 ? HDR_N : HDR_E);
+        if (KIND == 0) {
+            h[0] = __float_as_int(__ldg(src.diag + row)); h[1] = off; h[2] = n1; h[3] = n2;
+        } else {
+            h[0] = row; h[1] = __float_as_int(__ldg(g.ew + row)); h[2] = __float_as_int(__ldg(src.diag + row));
+            h[3] = off; h[4] = n1; h[5] = n2;
+        }
+        if (off >= 0) {
+            int* e = ent + off;
+            for (int k = 0; k < n1; ++k) { e[k] = __ldg(src.col1 + k1 + k); e[n1 + k] = __float_as_int(__ldg(src.val1 + k1 + k)); }
+            e += 2 * n1;
+            for (int k = 0; k < n2; ++k) {
+                e[k] = __ldg(src.col2 + k2 + k);
+                e[n2 + k] = __float_as_int(__ldg(src.pm2 + k2 + k));
+                e[2 * n2 + k] = __float_as_int(__ldg(src.pd2 + k2 + k));
+            }
+        }
+    }
+    used += total;
+}
+
+struct RowView {
+    int row, n1, n2;
+    float w, d;
+    const int* c1; const float* v1;
+    const int* c2; const float* m2; const float* d2;
+};
+template <int KIND>
+__device__ __forceinline__ RowView row_view(const Graph& g, bool bwd, const int* hdr, const int* ent, int li, int i) {
+    RowView r;
+    const int* h = hdr + (size_t)li * (KIND == 0 ? HDR_N : HDR_E);
+    int off;
+    if (KIND == 0) {
+        r.row = i; r.w = 1.f; r.d = __int_as_float(h[0]); off = h[1]; r.n1 = h[2]; r.n2 = h[3];
+    } else {
+        r.row = h[0]; r.w = __int_as_float(h[1]); r.d = __int_as_float(h[2]); off = h[3]; r.n1 = h[4]; r.n2 = h[5];
+    }
+    if (off >= 0) {
+        const int* e = ent + off;
+        r.c1 = e; r.v1 = reinterpret_cast<const float*>(e + r.n1);
+        e += 2 * r.n1;
+        r.c2 = e; r.m2 = reinterpret_cast<const float*>(e + r.n2); r.d2 = reinterpret_cast<const float*>(e + 2 * r.n2);
+    } else {
+        const StageSrc src = stage_src<KIND>(g, bwd);
+        const int k1 = __ldg(src.rp1 + r.row);
+        r.c1 = src.col1 + k1; r.v1 = src.val1 + k1;
+        const int k2 = src.rp2 ? __ldg(src.rp2 + r.row) : 0;
+        r.c2 = src.col2 + k2; r.m2 = src.pm2 + k2; r.d2 = src.pd2 + k2;
+    }
+    return r;
 }
 
 // Sum of NV per-lane values over the warp with a reduce-scatter butterfly (~NV shuffles instead of 5 NV).
@@ -108,7 +256,7 @@ __device__ __forceinline__ void bn_vectors(const Tensor& t, float* out) {
     const double sum = __shfl_sync(FULL, v, f), sq = __shfl_sync(FULL, v, 4 + f);
     if (lane < 4) {
         const float w = __ldg(t.bn_w), b = __ldg(t.bn_b);
-        const double inv_n = 1.0 / (double)t.n_rows;
+        const double inv_n = t.inv_n;
         const double m = sum * inv_n;
         const double var = fma(-m, m, sq * inv_n);
         const float r = 1.0f / sqrtf(fmaxf((float)var, 0.f) + BN_EPS);
@@ -134,7 +282,7 @@ __device__ __forceinline__ void gpre_vectors(const Tensor& t, float* out) {
     const double sg = __shfl_sync(FULL, vb, f), sgx = __shfl_sync(FULL, vb, 4 + f);
     if (lane < 4) {
         const float w = __ldg(t.bn_w);
-        const double inv_n = 1.0 / (double)t.n_rows;
+        const double inv_n = t.inv_n;
         const double m = sum * inv_n;
         const double var = fma(-m, m, sq * inv_n);
         const float r = 1.0f / sqrtf(fmaxf((float)var, 0.f) + BN_EPS);
@@ -152,14 +300,14 @@ struct GatherBatch {
     int c[B];
     float v[B], v2[TWO ? B : 1];
     float4 x[B];
-    __device__ __forceinline__ void load_entries(const int* __restrict__ col, const float* __restrict__ val,
-                                                 const float* __restrict__ val2, int k, int k1) {
+    // col / val point into the thread's shared-memory cache (or, for unstaged rows, into global memory)
+    __device__ __forceinline__ void load_entries(const int* col, const float* val, const float* val2, int k, int k1) {
 #pragma unroll
         for (int j = 0; j < B; ++j) {
             const bool on = k + j < k1;
-            c[j] = on ? __ldg(col + k + j) : -1;
-            v[j] = on ? __ldg(val + k + j) : 0.f;
-            if (TWO) v2[j] = on ? __ldg(val2 + k + j) : 0.f;
+            c[j] = on ? col[k + j] : -1;
+            v[j] = on ? val[k + j] : 0.f;
+            if (TWO) v2[j] = on ? val2[k + j] : 0.f;
         }
     }
     __device__ __forceinline__ void load_rows(const float* X) {
@@ -186,7 +334,8 @@ struct GatherBatch {
 // KIND 1: active line-graph rows (I, D = dl, AL; cross = Pm^T / Pd^T over the node tensor), weighted by ew
 template <int KIND, bool CROSS, int BA, int BP>
 __device__ __forceinline__ void fwd_side(const Params& P, const Side& sd, const float* W, const float* bias,
-                                         const float* bnv, float (&s1)[4], float (&s2)[4]) {
+                                         const float* bnv, const int* hdr, const int* ent,
+                                         float (&s1)[4], float (&s2)[4]) {
     constexpr int NB = 3 + (CROSS ? 2 : 0);
     const Graph& g = P.g;
     const float* Xs = P.t[sd.src_self].data;
@@ -194,47 +343,34 @@ __device__ __forceinline__ void fwd_side(const Params& P, const Side& sd, const 
     float* Z = P.t[sd.out].data;
     const int n = KIND == 0 ? g.Rn : g.n_act;
     const int lo = slice_lo(n, blockIdx.x, gridDim.x), hi = slice_lo(n, blockIdx.x + 1, gridDim.x);
-    const float* diag = KIND == 0 ? g.deg : g.dl;
-    const int* rp = KIND == 0 ? g.a_rp : g.b_rp;
-    const int* col = KIND == 0 ? g.a_col : g.b_col;
-    const float* val = KIND == 0 ? g.a_val : g.b_val;
-    const int* prp = KIND == 0 ? g.p_rp : g.pt_rp;
-    const int* pcol = KIND == 0 ? g.p_col : g.pt_col;
-    const float* ppm = KIND == 0 ? g.p_pm : g.pt_pm;
-    const float* ppd = KIND == 0 ? g.p_pd : g.pt_pd;
     const float4 sc_s = lds4(bnv), sh_s = lds4(bnv + 4), sc_c = lds4(bnv + 16), sh_c = lds4(bnv + 20);
     for (int i = lo + (int)threadIdx.x; i < hi; i += THREADS) {
-        const int row = KIND == 0 ? i : __ldg(g.erow + i);
-        const float w = KIND == 0 ? 1.f : __ldg(g.ew + row);
-        const float d = __ldg(diag + row);
-        const int k0 = __ldg(rp + row), k1 = __ldg(rp + row + 1);
-        int p0 = 0, p1 = 0;
-        if (CROSS) { p0 = __ldg(prp + row); p1 = __ldg(prp + row + 1); }
+        const RowView r = row_view<KIND>(g, false, hdr, ent, i - lo, i);
         GatherBatch<BA, false> ga;
         GatherBatch<BP, true> gb;
-        ga.load_entries(col, val, nullptr, k0, k1);
-        if (CROSS) gb.load_entries(pcol, ppm, ppd, p0, p1);
-        const float4 xs_raw = ldcg4(Xs + (size_t)row * 4);
+        ga.load_entries(r.c1, r.v1, nullptr, 0, r.n1);
+        if (CROSS) gb.load_entries(r.c2, r.m2, r.d2, 0, r.n2);
+        const float4 xs_raw = ldcg4(Xs + (size_t)r.row * 4);
         ga.load_rows(Xs);
         if (CROSS) gb.load_rows(Xc);
         float4 x1[NB];
         const float4 xs = f4_affine(xs_raw, sc_s, sh_s);
         x1[0] = xs;
-        x1[1] = make_float4(d * xs.x, d * xs.y, d * xs.z, d * xs.w);
+        x1[1] = make_float4(r.d * xs.x, r.d * xs.y, r.d * xs.z, r.d * xs.w);
         float4 acc0 = f4_zero(), am = f4_zero(), ad = f4_zero(), u4 = f4_zero();
         float ws0 = 0.f, wm = 0.f, wd = 0.f, u = 0.f;
         ga.accumulate(acc0, ws0, u4, u);
         if (CROSS) gb.accumulate(am, wm, ad, wd);
-        for (int k = k0 + BA; k < k1; k += BA) {          // long rows: the remaining entries, batch by batch
+        for (int k = BA; k < r.n1; k += BA) {          // long rows: the remaining entries, batch by batch
             GatherBatch<BA, false> t;
-            t.load_entries(col, val, nullptr, k, k1);
+            t.load_entries(r.c1, r.v1, nullptr, k, r.n1);
             t.load_rows(Xs);
             t.accumulate(acc0, ws0, u4, u);
         }
         if (CROSS)
-            for (int k = p0 + BP; k < p1; k += BP) {
+            for (int k = BP; k < r.n2; k += BP) {
                 GatherBatch<BP, true> t;
-                t.load_entries(pcol, ppm, ppd, k, p1);
+                t.load_entries(r.c2, r.m2, r.d2, k, r.n2);
                 t.load_rows(Xc);
                 t.accumulate(am, wm, ad, wd);
             }
@@ -251,10 +387,10 @@ __device__ __forceinline__ void fwd_side(const Params& P, const Side& sd, const 
             for (int b = 0; b < NB; ++b) acc += f4_dot(x1[b], lds4(W + (o * NB + b) * 4));
             if (o >= sd.relu_from) acc = fmaxf(acc, 0.f);
             out[o] = acc;
-            s1[o] = fmaf(w, acc, s1[o]);
-            s2[o] = fmaf(w * acc, acc, s2[o]);
+            s1[o] = fmaf(r.w, acc, s1[o]);
+            s2[o] = fmaf(r.w * acc, acc, s2[o]);
         }
-        *reinterpret_cast<float4*>(Z + (size_t)row * 4) = make_float4(out[0], out[1], out[2], out[3]);
+        *reinterpret_cast<float4*>(Z + (size_t)r.row * 4) = make_float4(out[0], out[1], out[2], out[3]);
     }
 }
 
@@ -269,10 +405,24 @@ __device__ __forceinline__ void expand_rows(const Graph& g, float* buf) {
 
 #define MK_WSTRIDE 84      // per side: W[4][Cin <= 20] + bias[4]
 
+// dynamic shared memory: [node row headers | line-graph row headers | entries]
+extern __shared__ __align__(16) int mk_dyn[];
+
+__device__ __forceinline__ void stage_all(const Params& P, bool bwd, int*& hdrN, int*& hdrE, int*& ent, int* scratch) {
+    hdrN = mk_dyn;
+    hdrE = hdrN + (size_t)P.max_n * HDR_N;
+    ent = hdrE + (size_t)P.max_e * HDR_E;
+    int used = 0;
+    stage_rows<0>(P.g, bwd, hdrN, ent, P.cap_words, used, scratch);
+    if (P.g.n_act > 0) stage_rows<1>(P.g, bwd, hdrE, ent, P.cap_words, used, scratch);
+    __syncthreads();
+}
+
 __global__ void __launch_bounds__(THREADS, 1) mega_fwd_kernel(const __grid_constant__ Params P) {
     __shared__ __align__(16) float Wsm[MAX_SIDES * MK_WSTRIDE];
     __shared__ __align__(16) float bnv[32];              // [self | cross] x (scale, shift, mean, 1/std)
     __shared__ double red[(THREADS / 32) * 8];
+    __shared__ int scratch[THREADS / 32];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     for (int i = tid; i < P.n_sides * MK_WSTRIDE; i += THREADS) {
         const int s = i / MK_WSTRIDE, j = i - s * MK_WSTRIDE;
@@ -287,24 +437,27 @@ __global__ void __launch_bounds__(THREADS, 1) mega_fwd_kernel(const __grid_const
         }
         Wsm[i] = v;
     }
-    unsigned gen = 0;
-    if (tid == 0) gen = ld_acquire(P.bar + 32);
-    __syncthreads();
+    int *hdrN, *hdrE, *ent;
+    stage_all(P, false, hdrN, hdrE, ent, scratch);
+    unsigned target = 0;
     for (int s = 0; s < P.n_sides; ++s) {
         const Side& sd = P.s[s];
-        if (s > 0) grid_sync(P.bar, gen);
+        trace_mark(P, s, 0);
+        if (s > 0) grid_sync(P.bar, target);
+        trace_mark(P, s, 1);
         const bool cross = sd.src_cross >= 0;
         if (warp == 0) bn_vectors(P.t[sd.src_self], bnv);
         else if (warp == 1 && cross) bn_vectors(P.t[sd.src_cross], bnv + 16);
         __syncthreads();
+        trace_mark(P, s, 2);
         float s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
         const float* W = Wsm + s * MK_WSTRIDE;
         if (sd.kind == 0) {
-            if (cross) fwd_side<0, true, 4, 8>(P, sd, W, W + 80, bnv, s1, s2);
-            else fwd_side<0, false, 8, 1>(P, sd, W, W + 80, bnv, s1, s2);
+            if (cross) fwd_side<0, true, 4, 8>(P, sd, W, W + 80, bnv, hdrN, ent, s1, s2);
+            else fwd_side<0, false, 8, 1>(P, sd, W, W + 80, bnv, hdrN, ent, s1, s2);
         } else {
-            if (cross) fwd_side<1, true, 4, 4>(P, sd, W, W + 80, bnv, s1, s2);
-            else fwd_side<1, false, 4, 1>(P, sd, W, W + 80, bnv, s1, s2);
+            if (cross) fwd_side<1, true, 4, 4>(P, sd, W, W + 80, bnv, hdrE, ent, s1, s2);
+            else fwd_side<1, false, 4, 1>(P, sd, W, W + 80, bnv, hdrE, ent, s1, s2);
         }
         // (sum w z, sum w z^2) of this CTA -> 8 fp64 atomics into the producer bins of the output tensor
         double st[8];
@@ -318,11 +471,13 @@ __global__ void __launch_bounds__(THREADS, 1) mega_fwd_kernel(const __grid_const
             for (int w = 0; w < THREADS / 32; ++w) v += red[w * 8 + tid];
             atomicAdd(const_cast<double*>(P.t[sd.out].acc_f) + (size_t)(blockIdx.x & 3) * 8 + tid, v);
         }
+        trace_mark(P, s, 3);
     }
     if (P.expand >= 0) {
-        grid_sync(P.bar, gen);
+        grid_sync(P.bar, target);
         expand_rows(P.g, P.t[P.expand].data);
     }
+    grid_exit(P.bar);
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -350,17 +505,17 @@ struct Gpre {
 
 // sum_k val[k] * gpre(col[k]) (and the second value array on the same pattern); batches of GB entries
 template <int GB, bool TWO>
-__device__ __forceinline__ void gpre_gather(const Gpre& gp, const int* __restrict__ col, const float* __restrict__ val,
-                                            const float* __restrict__ val2, int k0, int k1, float4& a1, float4& a2) {
+__device__ __forceinline__ void gpre_gather(const Gpre& gp, const int* col, const float* val, const float* val2,
+                                            int k0, int k1, float4& a1, float4& a2) {
     for (int k = k0; k < k1; k += GB) {
         int c[GB];
         float v[GB], v2[TWO ? GB : 1];
 #pragma unroll
         for (int j = 0; j < GB; ++j) {
             const bool on = k + j < k1;
-            c[j] = on ? __ldg(col + k + j) : -1;
-            v[j] = on ? __ldg(val + k + j) : 0.f;
-            if (TWO) v2[j] = on ? __ldg(val2 + k + j) : 0.f;
+            c[j] = on ? col[k + j] : -1;
+            v[j] = on ? val[k + j] : 0.f;
+            if (TWO) v2[j] = on ? val2[k + j] : 0.f;
         }
         float4 g[GB];
 #pragma unroll
@@ -412,10 +567,10 @@ __device__ __forceinline__ void flush_part(float (&dw)[NT * 16], const float (&d
     }
 }
 
-// Self part of side `sd`: rows of its self input; transposed operators [I, D, CSR^T].
+// Self part of side `sd`: rows of its self input; transposed operators [I, D, CSR^T] = entry set 1 of the row.
 template <int KIND, int GB>
 __device__ __forceinline__ void bwd_self(const Params& P, const Side& sd, const Gpre& gp, const float* Ws,
-                                         const float* bi, float* red) {
+                                         const float* bi, const int* hdr, const int* ent, float* red) {
     const Graph& g = P.g;
     const Tensor& tx = P.t[sd.src_self];
     const float* X = tx.data;
@@ -423,20 +578,15 @@ __device__ __forceinline__ void bwd_self(const Params& P, const Side& sd, const 
     double* accb = gX ? tx.acc_b : nullptr;
     const int n = KIND == 0 ? g.Rn : g.n_act;
     const int lo = slice_lo(n, blockIdx.x, gridDim.x), hi = slice_lo(n, blockIdx.x + 1, gridDim.x);
-    const float* diag = KIND == 0 ? g.deg : g.dl;
-    const int* rp = KIND == 0 ? g.at_rp : g.btc_rp;
-    const int* col = KIND == 0 ? g.at_col : g.btc_col;
-    const float* val = KIND == 0 ? g.at_val : g.btc_val;
     const float4 sc = lds4(bi), sh = lds4(bi + 4), mu = lds4(bi + 8), rs = lds4(bi + 12);
     float dw[48];
 #pragma unroll
     for (int i = 0; i < 48; ++i) dw[i] = 0.f;
     float db[4] = {0.f, 0.f, 0.f, 0.f}, sg[4] = {0.f, 0.f, 0.f, 0.f}, sgx[4] = {0.f, 0.f, 0.f, 0.f};
     for (int i = lo + (int)threadIdx.x; i < hi; i += THREADS) {
-        const int row = KIND == 0 ? i : __ldg(g.erow + i);
-        const float w = KIND == 0 ? 1.f : __ldg(g.ew + row);
-        const float d = __ldg(diag + row);
-        const int k0 = __ldg(rp + row), k1 = __ldg(rp + row + 1);
+        const RowView r = row_view<KIND>(g, true, hdr, ent, i - lo, i);
+        const int row = r.row;
+        const float w = r.w;
         float4 T[3];
         T[0] = gp(row);
         const float4 xr = ldcg4(X + (size_t)row * 4);
@@ -444,8 +594,8 @@ __device__ __forceinline__ void bwd_self(const Params& P, const Side& sd, const 
         if (gX && sd.acc_self) old = ldcg4(gX + (size_t)row * 4);
         T[2] = f4_zero();
         float4 unused = f4_zero();
-        gpre_gather<GB, false>(gp, col, val, nullptr, k0, k1, T[2], unused);
-        T[1] = make_float4(d * T[0].x, d * T[0].y, d * T[0].z, d * T[0].w);
+        gpre_gather<GB, false>(gp, r.c1, r.v1, nullptr, 0, r.n1, T[2], unused);
+        T[1] = make_float4(r.d * T[0].x, r.d * T[0].y, r.d * T[0].z, r.d * T[0].w);
         const float4 xn = f4_affine(xr, sc, sh);
         const float xw[4] = {w * xn.x, w * xn.y, w * xn.z, w * xn.w};
         float gv[4] = {0.f, 0.f, 0.f, 0.f};
@@ -476,10 +626,10 @@ __device__ __forceinline__ void bwd_self(const Params& P, const Side& sd, const 
     flush_part<3>(dw, db, sg, sgx, red, sd, 0, true, accb);
 }
 
-// Cross part of side `sd`: rows of its cross input (the OTHER row space), incidence pattern of those rows.
+// Cross part of side `sd`: rows of its cross input (the OTHER row space), incidence entries (set 2) of those rows.
 template <int KIND, int CB>
 __device__ __forceinline__ void bwd_cross(const Params& P, const Side& sd, const Gpre& gp, const float* Wc,
-                                          const float* bi, float* red) {
+                                          const float* bi, const int* hdr, const int* ent, float* red) {
     const Graph& g = P.g;
     const Tensor& tx = P.t[sd.src_cross];
     const float* X = tx.data;
@@ -487,27 +637,23 @@ __device__ __forceinline__ void bwd_cross(const Params& P, const Side& sd, const
     double* accb = gX ? tx.acc_b : nullptr;
     // node side: cross tensor lives on the line graph (rows = active line-graph rows, pattern Pm^T / Pd^T);
     // edge side: cross tensor lives on the nodes (rows = nodes, pattern Pm / Pd)
-    constexpr bool EDGE_ROWS = KIND == 0;
-    const int n = EDGE_ROWS ? g.n_act : g.Rn;
+    constexpr int RK = KIND == 0 ? 1 : 0;
+    const int n = RK == 1 ? g.n_act : g.Rn;
     const int lo = slice_lo(n, blockIdx.x, gridDim.x), hi = slice_lo(n, blockIdx.x + 1, gridDim.x);
-    const int* rp = EDGE_ROWS ? g.pt_rp : g.p_rp;
-    const int* col = EDGE_ROWS ? g.pt_col : g.p_col;
-    const float* vm = EDGE_ROWS ? g.pt_pm : g.p_pm;
-    const float* vd = EDGE_ROWS ? g.pt_pd : g.p_pd;
     const float4 sc = lds4(bi), sh = lds4(bi + 4), mu = lds4(bi + 8), rs = lds4(bi + 12);
     float dw[32];
 #pragma unroll
     for (int i = 0; i < 32; ++i) dw[i] = 0.f;
     float db[4] = {0.f, 0.f, 0.f, 0.f}, sg[4] = {0.f, 0.f, 0.f, 0.f}, sgx[4] = {0.f, 0.f, 0.f, 0.f};
     for (int i = lo + (int)threadIdx.x; i < hi; i += THREADS) {
-        const int row = EDGE_ROWS ? __ldg(g.erow + i) : i;
-        const float w = EDGE_ROWS ? __ldg(g.ew + row) : 1.f;
-        const int k0 = __ldg(rp + row), k1 = __ldg(rp + row + 1);
+        const RowView r = row_view<RK>(g, true, hdr, ent, i - lo, i);
+        const int row = r.row;
+        const float w = r.w;
         const float4 xr = ldcg4(X + (size_t)row * 4);
         float4 old = f4_zero();
         if (gX && sd.acc_cross) old = ldcg4(gX + (size_t)row * 4);
         float4 T[2] = {f4_zero(), f4_zero()};
-        gpre_gather<CB, true>(gp, col, vm, vd, k0, k1, T[0], T[1]);
+        gpre_gather<CB, true>(gp, r.c2, r.m2, r.d2, 0, r.n2, T[0], T[1]);
         const float4 xn = f4_affine(xr, sc, sh);
         const float xw[4] = {w * xn.x, w * xn.y, w * xn.z, w * xn.w};
         float gv[4] = {0.f, 0.f, 0.f, 0.f};
@@ -540,6 +686,7 @@ __global__ void __launch_bounds__(THREADS, 1) mega_bwd_kernel(const __grid_const
     __shared__ __align__(16) float Wsm[MAX_SIDES * 80];   // per side [t][o][f] = W[o][t*4 + f], t < Cin / 4
     __shared__ __align__(16) float vec[48];               // gPre coefficients (12) | pad | self input (16) | cross input (16)
     __shared__ float red[(THREADS / 32) * 80];
+    __shared__ int scratch[THREADS / 32];
     const int tid = threadIdx.x, warp = tid >> 5;
     for (int i = tid; i < P.n_sides * 80; i += THREADS) {
         const int s = i / 80, j = i - s * 80;
@@ -549,18 +696,21 @@ __global__ void __launch_bounds__(THREADS, 1) mega_bwd_kernel(const __grid_const
         if (c < sd.Cin) v = o < sd.Ha ? sd.Wa[(size_t)o * sd.Cin + c] : sd.Wb[(size_t)(o - sd.Ha) * sd.Cin + c];
         Wsm[i] = v;
     }
-    unsigned gen = 0;
-    if (tid == 0) gen = ld_acquire(P.bar + 32);
-    __syncthreads();
+    int *hdrN, *hdrE, *ent;
+    stage_all(P, true, hdrN, hdrE, ent, scratch);
+    unsigned target = 0;
     for (int s = P.n_sides - 1; s >= 0; --s) {
         const Side& sd = P.s[s];
-        if (s < P.n_sides - 1) grid_sync(P.bar, gen);
+        trace_mark(P, MAX_SIDES + s, 0);
+        if (s < P.n_sides - 1) grid_sync(P.bar, target);
+        trace_mark(P, MAX_SIDES + s, 1);
         const bool cross = sd.src_cross >= 0;
         const Tensor& to = P.t[sd.out];
         if (warp == 0) gpre_vectors(to, vec);
         else if (warp == 1) bn_vectors(P.t[sd.src_self], vec + 16);
         else if (warp == 2 && cross) bn_vectors(P.t[sd.src_cross], vec + 32);
         __syncthreads();
+        trace_mark(P, MAX_SIDES + s, 2);
         Gpre gp;
         gp.c0 = lds4(vec); gp.c1 = lds4(vec + 4); gp.c2 = lds4(vec + 8);
         gp.relu_from = sd.relu_from;
@@ -570,17 +720,19 @@ __global__ void __launch_bounds__(THREADS, 1) mega_bwd_kernel(const __grid_const
         gp.Z = to.data;
         const float* Ws = Wsm + s * 80;
         if (sd.kind == 0) {
-            bwd_self<0, 8>(P, sd, gp, Ws, vec + 16, red);
-            if (cross) bwd_cross<0, 4>(P, sd, gp, Ws + 48, vec + 32, red);
+            bwd_self<0, 8>(P, sd, gp, Ws, vec + 16, hdrN, ent, red);
+            if (cross) bwd_cross<0, 4>(P, sd, gp, Ws + 48, vec + 32, hdrE, ent, red);
         } else {
-            bwd_self<1, 4>(P, sd, gp, Ws, vec + 16, red);
-            if (cross) bwd_cross<1, 8>(P, sd, gp, Ws + 48, vec + 32, red);
+            bwd_self<1, 4>(P, sd, gp, Ws, vec + 16, hdrE, ent, red);
+            if (cross) bwd_cross<1, 8>(P, sd, gp, Ws + 48, vec + 32, hdrN, ent, red);
         }
+        trace_mark(P, MAX_SIDES + s, 3);
     }
     if (P.expand >= 0) {
-        grid_sync(P.bar, gen);
+        grid_sync(P.bar, target);
         expand_rows(P.g, P.t[P.expand].grad);
     }
+    grid_exit(P.bar);
 }
 
 }  // namespace mk
@@ -588,6 +740,17 @@ __global__ void __launch_bounds__(THREADS, 1) mega_bwd_kernel(const __grid_const
 // ---------------------------------------------------------------------------------------------------------
 // launch wrappers
 // ---------------------------------------------------------------------------------------------------------
+// profiling aid: device buffer of 2 * MAX_SIDES * grid * 4 time stamps (NULL = off); see profiles/mega_trace.py
+static unsigned long long* g_trace = nullptr;
+extern "C" int hgnn_mega_set_trace(void* dev_ptr) { g_trace = static_cast<unsigned long long*>(dev_ptr); return HGNN_OK; }
+extern "C" int hgnn_mega_grid_for(int Rn, int n_act) {
+    mk::Params p;
+    p.g.Rn = Rn; p.g.n_act = n_act;
+    extern int hgnn_mega_grid_of(const mk::Params&);
+    return hgnn_mega_grid_of(p);
+}
+unsigned long long* hgnn_mega_trace_ptr(void) { return g_trace; }
+
 static int mega_grid(const mk::Params& p) {
     static int sms = 0;
     if (sms == 0) {
@@ -601,13 +764,36 @@ static int mega_grid(const mk::Params& p) {
     return (int)(want < sms ? want : sms);
 }
 
+int hgnn_mega_grid_of(const mk::Params& p) { return mega_grid(p); }
+
+// shared-memory budget of the structure cache: headers of the CTA's rows + as many entry words as fit
+#define MEGA_DYN_SMEM_MAX (200 * 1024)
+void hgnn_mega_plan(mk::Params* p) {
+    p->grid = mega_grid(*p);
+    p->max_n = (p->g.Rn + p->grid - 1) / p->grid + 1;
+    p->max_e = p->g.n_act > 0 ? (p->g.n_act + p->grid - 1) / p->grid + 1 : 0;
+    const long long hdr = (long long)p->max_n * mk::HDR_N + (long long)p->max_e * mk::HDR_E;
+    long long cap = MEGA_DYN_SMEM_MAX / 4 - hdr;
+    if (cap < 0) cap = 0;
+    // no more than the structure can need: all entries of both row spaces spread over the grid, with slack
+    const long long need = (2 * p->nnz1_n + 3 * p->nnz2 + 2 * p->nnz1_e + 3 * p->nnz2) / p->grid * 3 / 2 + 4096;
+    if (p->nnz1_n >= 0 && need < cap) cap = need;
+    p->cap_words = (int)cap;
+}
+
 static int mega_launch(const void* kernel, const mk::Params& p, cudaStream_t stream, const char* what) {
     if (!p.bar) {
         hgnn_set_error("%s: no barrier scratch (hgnn_batch_t.mega_scratch)", what);
         return HGNN_ERR_ARG;
     }
+    static const void* attr_done[2] = {nullptr, nullptr};
+    const size_t smem = ((size_t)p.max_n * mk::HDR_N + (size_t)p.max_e * mk::HDR_E + (size_t)p.cap_words) * sizeof(int);
+    if (attr_done[0] != kernel && attr_done[1] != kernel) {
+        cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MEGA_DYN_SMEM_MAX);
+        attr_done[attr_done[0] ? 1 : 0] = kernel;
+    }
     void* args[] = {const_cast<mk::Params*>(&p)};
-    cudaError_t e = cudaLaunchCooperativeKernel(kernel, dim3(mega_grid(p)), dim3(mk::THREADS), args, 0, stream);
+    cudaError_t e = cudaLaunchCooperativeKernel(kernel, dim3(p.grid), dim3(mk::THREADS), args, smem, stream);
     if (e != cudaSuccess) {
         hgnn_set_error("%s: cudaLaunchCooperativeKernel: %s", what, cudaGetErrorString(e));
         return HGNN_ERR_CUDA;

@@ -24,6 +24,7 @@ struct Tensor {
     const float* bn_b;
     int n_rows;             // rows behind the statistics (ALL rows, phantom copies included)
     int pad;
+    double inv_n;           // 1 / n_rows
 };
 
 struct Side {
@@ -55,7 +56,10 @@ struct Params {
     int expand;             // tensor whose skipped line-graph rows get the representative's value at the end
                             // (forward: data, backward: grad) because a per-side kernel reads it next; -1: none
     int pad;
-    unsigned int* bar;      // grid barrier state: [0] arrival counter, [32] generation (zero-initialised once)
+    int grid, max_n, max_e, cap_words;   // launch plan (hgnn_mega_plan): CTAs, header slots per CTA, entry words of the cache
+    long long nnz1_n, nnz1_e, nnz2;      // entries of the node / line-graph CSR operator and of the incidence pattern (hints; -1 unknown)
+    unsigned int* bar;      // grid barrier state: [0] arrival counter, [32] exit counter (zero-initialised once, left zero)
+    unsigned long long* trace;  // profiling aid (hgnn_mega_set_trace): 4 x %globaltimer per (phase, CTA); NULL = off
     Tensor t[MAX_TENSORS];
     Side s[MAX_SIDES];
 };
@@ -63,5 +67,7 @@ struct Params {
 }  // namespace mk
 
 // launch wrappers (mega.cu); return HGNN_OK or an error code with hgnn_last_error set
+unsigned long long* hgnn_mega_trace_ptr(void);
+void hgnn_mega_plan(mk::Params* p);     // fills grid / max_n / max_e / cap_words from g and the nnz hints
 int hgnn_mega_launch_fwd(const mk::Params& p, cudaStream_t stream);
 int hgnn_mega_launch_bwd(const mk::Params& p, cudaStream_t stream);

@@ -97,9 +97,13 @@ bool check_program(const hgnn_program_t* prog, const hgnn_batch_t* b) {
 
 
 // ---- persistent ("mega") kernels: which sides they take, and their parameter block (mega.cuh) ----------
+// Opt-in (HGNN_B200_MEGA=1): measured on the C2 workload the persistent kernels are SLOWER than the per-side
+// launches (1.39 vs 0.89 ms per step, profiles/README.md "persistent kernels"): a grid barrier plus the reload of
+// the batch-norm sums costs ~4 us per side against ~1 us for a programmatic dependent launch, and 16 warps per SM
+// running thread-per-row code are bound by instruction latency, not by the launch boundary.
 bool mega_disabled() {
     static int v = -1;
-    if (v < 0) { const char* e = getenv("HGNN_B200_NO_MEGA"); v = (e && e[0] == '1') ? 1 : 0; }
+    if (v < 0) { const char* e = getenv("HGNN_B200_MEGA"); v = (e && e[0] == '1') ? 0 : 1; }
     return v == 1;
 }
 
@@ -167,6 +171,12 @@ void mega_params(const hgnn_program_t* prog, const hgnn_batch_t* b, const WorkLa
     P->expand = -1;
     P->pad = 0;
     P->bar = static_cast<unsigned int*>(b->mega_scratch);
+    P->trace = hgnn_mega_trace_ptr();
+    P->nnz1_n = b->node_ops[2].nnz > 0 ? b->node_ops[2].nnz : -1;
+    P->nnz1_e = prog->dual && b->edge_ops[2].nnz > 0 ? b->edge_ops[2].nnz : 0;
+    P->nnz2 = prog->dual ? b->p_nnz : 0;
+    if (prog->dual && (b->edge_ops[2].nnz <= 0 || b->p_nnz <= 0)) P->nnz1_n = -1;
+    hgnn_mega_plan(P);
     for (int t = 0; t < prog->n_tensors; ++t) {
         const hgnn_prog_tensor_t& T = prog->tensors[t];
         mk::Tensor& o = P->t[t];
@@ -179,6 +189,7 @@ void mega_params(const hgnn_program_t* prog, const hgnn_batch_t* b, const WorkLa
         o.bn_b = bn ? param(addr, T.bn_bias) : nullptr;
         o.n_rows = T.rows ? b->Rm : b->Rn;
         o.pad = 0;
+        o.inv_n = o.n_rows > 0 ? 1.0 / (double)o.n_rows : 0.0;
     }
     for (int i = s0; i < s1; ++i) {
         const hgnn_prog_side_t& sd = prog->sides[i];
@@ -225,6 +236,36 @@ int mega_expand_bwd(const hgnn_program_t* prog, int s0, int s1) {
     return found;
 }
 
+
+// ---- collapsed line graph on the per-side kernels --------------------------------------------------------
+// With hgnn_batch_t.collapse_ok the line-graph sides skip the copies of a phantom block (row weight <= 0) and
+// weight the representative by its multiplicity; the transposed operator is then the plain CSR btc instead of
+// the run-length split.  Only the thread-per-row kernels know row weights, so every side must have one of the
+// width combinations they are instantiated for (the feature maps of h = 2: models/gnns/model_mnb.py:48-50,98-100).
+bool collapse_disabled() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("HGNN_B200_NO_COLLAPSE"); v = (e && e[0] == '1') ? 1 : 0; }
+    return v == 1;
+}
+
+bool use_collapse(const hgnn_program_t* prog, const hgnn_batch_t* b) {
+    if (collapse_disabled() || !prog->dual || !b->collapse_ok || !b->ew || !b->btc_rowptr || !b->btc_col || !b->btc_val) return false;
+    if (b->n_ops != 3 || !plain_ops(b->node_ops, 3) || !plain_ops(b->edge_ops, 3) || !plain_ops(b->node_ops_T, 3)) return false;
+    const char* e = getenv("HGNN_B200_NO_ROW4");
+    if (e && e[0] == '1') return false;
+    for (int i = 0; i < prog->n_sides; ++i) {
+        const hgnn_prog_side_t& sd = prog->sides[i];
+        const int Fs = prog->tensors[sd.src_self].F, Fc = sd.src_cross >= 0 ? prog->tensors[sd.src_cross].F : 0;
+        const int Fo = sd.Ha + sd.Hb;
+        const bool row4 = Fs == 4 && Fo == 4 && (Fc == 0 || Fc == 4) && sd.out >= 0;
+        const bool rowg = (Fs == 5 && Fc == 1 && Fo == 4) || (Fs == 1 && Fc == 4 && Fo == 4) ||
+                          (Fs == 4 && Fc == 4 && (Fo == 2 || Fo == 1)) || (Fs == 5 && Fc == 0 && Fo == 4) ||
+                          (Fs == 4 && Fc == 0 && (Fo == 2 || Fo == 1));
+        if (!row4 && !rowg) return false;
+        if (sd.out < 0 && Fo == 4) return false;
+    }
+    return true;
+}
 
 // The one decision both passes share (a forward on the persistent kernels leaves the skipped line-graph rows of
 // its activations unwritten, so the backward must take the same path): range, the tensors to expand, and every
@@ -278,6 +319,8 @@ extern "C" int hgnn_program_fwd(const hgnn_program_t* prog, const hgnn_batch_t* 
     }
     int m0 = 0, m1 = 0, fwd_expand = -1, bwd_expand_unused = -1;
     mega_decide(prog, b, &m0, &m1, &fwd_expand, &bwd_expand_unused);
+    const bool collapse = use_collapse(prog, b);      // per-side kernels on the collapsed line graph
+    if (collapse) fwd_expand = -1;                    // nobody reads the skipped rows then
     for (int i = 0; i < prog->n_sides; ++i) {
         if (m1 > m0 && i == m0) {      // sides [m0, m1): one persistent kernel (mega.cu)
             mk::Params P;
@@ -312,6 +355,7 @@ extern "C" int hgnn_program_fwd(const hgnn_program_t* prog, const hgnn_batch_t* 
             st.Fc = 0;
             st.p_nnz = 0;
         }
+        st.roww = (!node && collapse) ? b->ew : nullptr;
         const bool readout = sd.out < 0;
         float* Z = work + (readout ? w.readout_off : w.off[sd.out]);
         double* acc_out = readout ? nullptr : arena + prog->tensors[sd.out].acc_f;
@@ -386,6 +430,17 @@ extern "C" int hgnn_program_bwd(const hgnn_program_t* prog, const hgnn_batch_t* 
     }
     int m0 = 0, m1 = 0, fwd_expand_unused = -1, bwd_expand = -1;
     mega_decide(prog, b, &m0, &m1, &fwd_expand_unused, &bwd_expand);     // the same decision as the forward
+    const bool collapse = use_collapse(prog, b);
+    if (collapse) bwd_expand = -1;
+    hgnn_op_t edge_T_collapsed[3];
+    if (collapse) {      // [I, D, btc]: plain CSR, the multiplicity of a representative folded into its entries
+        for (int k = 0; k < 3; ++k) edge_T_collapsed[k] = b->edge_ops_T[k];
+        hgnn_op_t& o = edge_T_collapsed[2];
+        o.rowptr = b->btc_rowptr; o.col = b->btc_col; o.val = b->btc_val;
+        o.rng_rowptr = nullptr; o.rng_id = nullptr; o.rng_val = nullptr; o.rng_lo = nullptr; o.rng_hi = nullptr;
+        o.rng_n = 0;
+        o.nnz = b->btc_nnz;
+    }
     for (int i = prog->n_sides - 1; i >= 0; --i) {
         if (m1 > m0 && i == m1 - 1) {     // sides [m0, m1) in reverse: one persistent kernel (mega.cu)
             mk::Params P;
@@ -442,7 +497,11 @@ extern "C" int hgnn_program_bwd(const hgnn_program_t* prog, const hgnn_batch_t* 
         d.db_bins = arena + sd.db_off;
         // self part
         d.R_self = node ? b->Rn : b->Rm;
-        d.ops_T = node ? b->node_ops_T : b->edge_ops_T;
+        d.ops_T = node ? b->node_ops_T : (collapse ? edge_T_collapsed : b->edge_ops_T);
+        d.roww_self = (!node && collapse) ? b->ew : nullptr;
+        d.roww_cross = nullptr;
+        d.active_self = d.roww_self ? b->n_act : 0;
+        d.active_cross = 0;
         d.n_ops = b->n_ops;
         d.Xs = tensor_ptr(prog, w, sd.src_self, X, XL, work);
         d.Fs = Fs;
@@ -475,10 +534,12 @@ extern "C" int hgnn_program_bwd(const hgnn_program_t* prog, const hgnn_batch_t* 
             d.accumulate_cross = fl[i].acc_cross;
             d.acc_b_cross =
                 prog->tensors[sd.src_cross].bn_weight >= 0 ? arena + prog->tensors[sd.src_cross].acc_b : nullptr;
+            d.roww_cross = (node && collapse) ? b->ew : nullptr;      // the cross rows of a node side are line-graph rows
+            d.active_cross = d.roww_cross ? b->n_act : 0;
         }
         d.skip_dw = 0;
         d.rng_scratch = nullptr;
-        if (rng_scratch && !node) {
+        if (rng_scratch && !node && !collapse) {
             d.rng_scratch = static_cast<char*>(rng_scratch) + rng_used;
             rng_used += rng_per_side;
         }

@@ -348,6 +348,7 @@ def _pack_cache(pack):
             c["btc"] = (iptr(pack.btc.rowptr), iptr(pack.btc.col), fptr(pack.btc.val), iptr(pack.erow), fptr(pack.ew))
             b.btc_rowptr, b.btc_col, b.btc_val, b.erow, b.ew = c["btc"]
             b.n_act = int(pack.erow.numel())
+            b.btc_nnz = int(pack.btc.nnz)
         c["batch"] = b
         pack.__dict__["_engine_cache"] = c
     return c

@@ -164,6 +164,10 @@ typedef struct hgnn_side_t {
     const float* Xc;        /* (Rc, Fc) */
     int Fc;
     long long p_nnz;        /* entries of the incidence pattern, 0 = unknown (scheduling hint) */
+    /* optional (hgnn_lg_side_fwd on the thread-per-row kernels only): weight of every output row in sums over rows
+     * (the batch-norm statistics); rows with weight <= 0 are not computed at all.  Used for the collapsed line graph
+     * (hgnn_batch_t.ew): one representative per block of identical phantom rows.  NULL = every row, weight 1. */
+    const float* roww;
 } hgnn_side_t;
 
 int hgnn_side_fwd(const hgnn_side_t* side, const float* Wa, const float* ba, int Ha,
@@ -251,6 +255,10 @@ typedef struct hgnn_side_bwd_t {
      * flag here) and the rows that own range entries just read them - instead of every CTA with such a row summing
      * the range itself after its row loop, a 7 us tail on 31 of 342 CTAs (profiles/logs/cta_times_phases.log). */
     void* rng_scratch;
+    /* optional row weights of the self / cross rows (see hgnn_side_t.roww): rows with weight <= 0 are skipped, the
+     * others enter dW, dbias and the batch-norm sums weight times.  Thread-per-row kernels only; NULL = weight 1. */
+    const float* roww_self; const float* roww_cross;
+    int active_self, active_cross;   /* rows with weight > 0 (0 = all): scheduling hint for the split of the CTAs */
 } hgnn_side_bwd_t;
 long long hgnn_lg_rng_scratch_bytes(int rng_n);
 int hgnn_lg_side_bwd(const hgnn_side_bwd_t* desc, hgnn_stream_t stream);
@@ -368,6 +376,7 @@ typedef struct hgnn_batch_t {
      * the multiplicity folded in. */
     const int* btc_rowptr; const int* btc_col; const float* btc_val;
     const int* erow; const float* ew; int n_act;
+    long long btc_nnz;    /* entries of btc (scheduling hint) */
     int collapse_ok;      /* 1: the edge feature XL of this call is the line-graph degree built by prepare_batch
                            * (functions/batching.py:171), i.e. identical on the copies of a phantom block */
     void* mega_scratch;   /* >= 256 bytes, zeroed once, private to the stream: grid-barrier state */
@@ -387,6 +396,13 @@ int hgnn_program_bwd(const hgnn_program_t* prog, const hgnn_batch_t* batch, cons
                      const long long* param_addr, const float* work, float* gwork, double* arena,
                      const float* g_out, float* gX, float* gflat, void* rng_scratch, long long rng_scratch_bytes,
                      hgnn_stream_t stream);
+/* Profiling aids of the persistent kernels (csrc/mega.cu; no reference counterpart).  hgnn_mega_set_trace: device
+ * buffer of 2 * 48 * grid * 4 uint64 that receives %globaltimer stamps per (phase, CTA) - phase = side index for
+ * the forward, 48 + side index for the backward; stamps: phase entered, barrier passed, batch-norm vectors ready,
+ * rows + flush done; NULL switches it off.  hgnn_mega_grid_for: CTAs a launch over Rn node rows and n_act active
+ * line-graph rows uses. */
+int hgnn_mega_set_trace(void* dev_ptr);
+int hgnn_mega_grid_for(int Rn, int n_act);
 /* bytes of rng_scratch for hgnn_program_bwd (0: none needed); the call zeroes it itself; NULL / too small: without */
 long long hgnn_program_rng_scratch_bytes(const hgnn_program_t* prog, const hgnn_batch_t* batch);
 /* kernels launched by hgnn_program_* calls so far (the host layer adds it to its own launch count) */
