@@ -34,7 +34,7 @@ class OpT(ctypes.Structure):
 class SideT(ctypes.Structure):
     _fields_ = [("R", c_int), ("ops", ctypes.POINTER(OpT)), ("n_ops", c_int), ("Xs", c_void),
                 ("Fs", c_int), ("p_rowptr", c_void), ("p_col", c_void), ("p_pm", c_void),
-                ("p_pd", c_void), ("Xc", c_void), ("Fc", c_int), ("p_nnz", c_ll), ("roww", c_void)]
+                ("p_pd", c_void), ("Xc", c_void), ("Fc", c_int), ("p_nnz", c_ll), ("roww", c_void), ("rowmap", c_void)]
 
 
 class BnRefT(ctypes.Structure):
@@ -53,7 +53,7 @@ class SideBwdT(ctypes.Structure):
                 ("pt_pd", c_void), ("Xc", c_void), ("Fc", c_int), ("bn_cross", BnRefT), ("gXc", c_void),
                 ("accumulate_cross", c_int), ("acc_b_cross", c_void), ("skip_dw", c_int), ("pt_nnz", c_ll),
                 ("rng_scratch", c_void), ("roww_self", c_void), ("roww_cross", c_void),
-                ("active_self", c_int), ("active_cross", c_int)]
+                ("rowmap_self", c_void), ("rowmap_cross", c_void)]
 
 
 class ProgTensorT(ctypes.Structure):
@@ -101,6 +101,7 @@ _SIGS = {
     "hgnn_lg_row4_eligible": [ctypes.POINTER(OpT), c_int, c_int, c_int, c_int],
     "hgnn_lg_wide_eligible": [c_int, c_int, c_int, c_int, c_int],
     "hgnn_lg_side_fits": [c_int, c_int, c_int, c_int],
+    "hgnn_program_uses_collapse": [ctypes.POINTER(ProgramT), ctypes.POINTER(BatchT)],
     "hgnn_mega_set_trace": [_P],
     "hgnn_mega_grid_for": [c_int, c_int],
     "hgnn_lg_side_dw": [_P, _P, c_int, c_int, _P, _P, _P, _P, c_int, _P, _P, _P],

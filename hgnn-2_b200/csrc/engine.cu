@@ -1094,7 +1094,7 @@ static bool eng_try_fwd_row4(const eng::FwdArgs& g, const hgnn_side_t* side, hgn
     a.p_rowptr = g.p_rowptr; a.p_col = g.p_col; a.p_pm = g.p_pm; a.p_pd = g.p_pd; a.Xc = g.Xc; a.bn_c = g.bn_c;
     a.Wa = g.Wa; a.ba = g.ba; a.Ha = g.Ha; a.Wb = g.Wb; a.bb = g.bb; a.Hb = g.Hb;
     a.relu_from = g.relu_from; a.Cin = g.Cin; a.Z = g.Z; a.acc_out = g.acc_out; a.X1 = g.X1;
-    a.roww = side->roww;
+    a.roww = side->roww; a.rowmap = side->rowmap;
     static int ablate = -1;
     if (ablate < 0) { const char* e = getenv("HGNN_B200_ABLATE"); ablate = e ? atoi(e) : 0; }
     a.ablate = ablate;
@@ -1112,7 +1112,9 @@ static bool eng_try_fwd_row4(const eng::FwdArgs& g, const hgnn_side_t* side, hgn
     if (force >= 0) { big_a = force & 1; big_p = (force & 2) != 0; }
 #define R4_FWD(NCSR, CROSS, BA, BP)                                                                      \
     {                                                                                                    \
-        int grid = full_grid ? want : min(want, eng_resident_impl((const void*)eng::fwd_row4_kernel<NCSR, CROSS, BA, BP>, 0, R4_THREADS)); \
+        const int cap_ = eng_resident_impl((const void*)eng::fwd_row4_kernel<NCSR, CROSS, BA, BP>, 0, R4_THREADS);   \
+        /* one row per thread when that needs at most ~12 % more CTAs than are resident (a short second wave) */    \
+        int grid = (full_grid || want <= cap_ + cap_ / 8) ? want : cap_;                                            \
         eng_launch(eng::fwd_row4_kernel<NCSR, CROSS, BA, BP>, grid, R4_THREADS, 0, s, a);                \
     }
 #define R4_FWD_B(NCSR)                                                                                   \
@@ -1148,7 +1150,7 @@ static bool eng_try_fwd_rowg(const eng::FwdArgs& g, const hgnn_side_t* side, hgn
     a.p_rowptr = g.p_rowptr; a.p_col = g.p_col; a.p_pm = g.p_pm; a.p_pd = g.p_pd; a.Xc = g.Xc; a.bn_c = g.bn_c;
     a.Wa = g.Wa; a.ba = g.ba; a.Ha = g.Ha; a.Wb = g.Wb; a.bb = g.bb; a.Hb = g.Hb;
     a.relu_from = g.relu_from; a.Cin = g.Cin; a.Z = g.Z; a.acc_out = g.acc_out; a.X1 = nullptr; a.ablate = 0;
-    a.roww = side->roww;
+    a.roww = side->roww; a.rowmap = side->rowmap;
     cudaStream_t s = to_stream(stream);
     const int want = ceil_div(a.R, R4_THREADS);
     const double avg_a = a.R > 0 ? (double)side->ops[2].nnz / a.R : 0.0;
@@ -1329,7 +1331,7 @@ extern "C" int hgnn_lg_side_fwd(const hgnn_side_t* side, const hgnn_bn_ref_t* bn
     if (eng_try_fwd_row4(a, side, stream)) return hgnn_check_launch("hgnn_lg_side_fwd(row4)");
     if (eng_try_fwd_rowg(a, side, stream)) return hgnn_check_launch("hgnn_lg_side_fwd(rowg)");
     HGNN_REQUIRE(!X1, "x1 rows can only be saved by the width-4 fast path (check hgnn_lg_row4_eligible)");
-    HGNN_REQUIRE(!side->roww, "row weights need the thread-per-row kernels (widths of the h = 2 feature maps)");
+    HGNN_REQUIRE(!side->roww && !side->rowmap, "row weights need the thread-per-row kernels (widths of the h = 2 feature maps)");
     if (eng_try_fwd_tc5(a, stream)) return hgnn_check_launch("hgnn_lg_side_fwd(tc5)");
     if (eng_try_fwd_wide(a, stream)) return hgnn_check_launch("hgnn_lg_side_fwd(wide)");
     const bool vec4 = (a.Fs % 4 == 0) && (a.Fc % 4 == 0) && eng_aligned16(a.Xs) && (a.Fc == 0 || eng_aligned16(a.Xc));
@@ -1488,7 +1490,7 @@ static bool eng_try_bwd_row4(const hgnn_side_bwd_t* d, hgnn_stream_t stream) {
     a.pt_rowptr = d->pt_rowptr; a.pt_col = d->pt_col; a.pt_pm = d->pt_pm; a.pt_pd = d->pt_pd;
     a.Xc = d->Xc; a.bn_c = to_bnref(&d->bn_cross); a.gXc = d->gXc; a.acc_cross = d->accumulate_cross;
     a.acc_b_cross = d->acc_b_cross; a.col0_cross = d->n_ops * 4;
-    a.roww_s = d->roww_self; a.roww_c = d->roww_cross;
+    a.roww_s = d->roww_self; a.roww_c = d->roww_cross; a.rowmap_s = d->rowmap_self; a.rowmap_c = d->rowmap_cross;
     // dedicated range-sum CTAs when the caller provided the (zeroed) scratch: [flags: rng_n ints | sums: 4 floats each]
     a.rng_n = 0; a.range_ctas = 0; a.rng_sum_g = nullptr; a.rng_flag_g = nullptr;
     if (d->rng_scratch && o2.rng_rowptr && o2.rng_n > 0 && !eng_no_range_ctas()) {
@@ -1515,9 +1517,7 @@ static bool eng_try_bwd_row4(const hgnn_side_bwd_t* d, hgnn_stream_t stream) {
         const char* e = getenv("HGNN_B200_BWD_ENTRY_COST");      // "w_self,w_cross" (tuning aid)
         if (e) { w_self = atof(e); const char* c = strchr(e, ','); w_cross = c ? atof(c + 1) : w_self; }
     }
-    // rows that are skipped (row weight <= 0, collapsed line graph) cost next to nothing
-    const double act_s = d->active_self > 0 ? (double)d->active_self : (double)d->R_self;
-    const double act_c = d->active_cross > 0 ? (double)d->active_cross : (double)d->R_cross;
+    const double act_s = (double)d->R_self, act_c = (double)d->R_cross;
     const double cost_s = act_s * 1.0 + w_self * (double)d->ops_T[2].nnz;
     const double cost_c = d->R_cross > 0 ? act_c * 1.0 + w_cross * (double)d->pt_nnz : 0.0;
     static int debug_split = -1;
@@ -1580,7 +1580,7 @@ static bool eng_try_bwd_rowg(const hgnn_side_bwd_t* d, hgnn_stream_t stream) {
     a.pt_rowptr = d->pt_rowptr; a.pt_col = d->pt_col; a.pt_pm = d->pt_pm; a.pt_pd = d->pt_pd;
     a.Xc = d->Xc; a.bn_c = to_bnref(&d->bn_cross); a.gXc = d->gXc; a.acc_cross = d->accumulate_cross;
     a.acc_b_cross = d->acc_b_cross; a.col0_cross = d->n_ops * Fs; a.ablate = 0;
-    a.roww_s = d->roww_self; a.roww_c = d->roww_cross;
+    a.roww_s = d->roww_self; a.roww_c = d->roww_cross; a.rowmap_s = d->rowmap_self; a.rowmap_c = d->rowmap_cross;
     a.rng_n = 0; a.range_ctas = 0; a.rng_sum_g = nullptr; a.rng_flag_g = nullptr;
     cudaStream_t s = to_stream(stream);
     const long long rows = (long long)d->R_self + a.R_cross;
@@ -1656,7 +1656,7 @@ extern "C" int hgnn_lg_side_bwd(const hgnn_side_bwd_t* d, hgnn_stream_t stream) 
     if (eng_try_bwd_row4(d, stream)) return hgnn_check_launch("hgnn_lg_side_bwd(row4)");
     if (eng_try_bwd_rowg(d, stream)) return hgnn_check_launch("hgnn_lg_side_bwd(rowg)");
     HGNN_REQUIRE(!d->skip_dw, "skip_dw needs the width-4 fast path (check hgnn_lg_row4_eligible)");
-    HGNN_REQUIRE(!d->roww_self && !d->roww_cross, "row weights need the thread-per-row kernels (widths of the h = 2 feature maps)");
+    HGNN_REQUIRE(!d->roww_self && !d->roww_cross && !d->rowmap_self && !d->rowmap_cross, "row weights need the thread-per-row kernels (widths of the h = 2 feature maps)");
     eng::BwdArgs a;
     a.gY = d->gY; a.Z = d->Z; a.Fg = d->Fg; a.relu_from = d->relu_from; a.Rg = d->Rg;
     a.acc_f = d->acc_f; a.acc_b = d->acc_b; a.bn_w = d->bn_weight;

@@ -125,6 +125,7 @@ struct Fwd4Args {
     float* X1;                       // optional: the concatenated x1 rows (R, Cin) for the dW pass
     const float* roww;               // optional per-row weight (collapsed line graph): rows with weight <= 0 are skipped,
                                      // the others enter the batch-norm sums weight times
+    const int* rowmap;               // optional list of the R rows to compute (the active rows); NULL: rows 0..R-1
     int ablate;                      // timing experiments only (HGNN_B200_ABLATE): 1 no gathers, 2 no BN, 4 no epilogue
 };
 
@@ -282,10 +283,13 @@ fwd_row4_kernel(const Fwd4Args a) {
     const int stride = gridDim.x * R4_THREADS;
     int row = blockIdx.x * R4_THREADS + tid;
     float d = 0.f, rw = 1.f;
+    int rr = 0;                                        // the row behind list entry `row`
     int k0[NCSR > 0 ? NCSR : 1], k1[NCSR > 0 ? NCSR : 1], p0 = 0, p1 = 0;
     GatherBatch<BA, false> ga;
     GatherBatch<BP, true> gb;
-    auto load_structure = [&](int r) {
+    auto load_structure = [&](int idx) {
+        const int r = a.rowmap ? __ldg(a.rowmap + idx) : idx;
+        rr = r;
         d = __ldg(a.diag + r);
 #pragma unroll
         for (int t = 0; t < NCSR; ++t) {
@@ -308,7 +312,7 @@ fwd_row4_kernel(const Fwd4Args a) {
     if (CROSS) lc.issue_acc(a.bn_c);
     float4 xs_raw = f4_zero();
     if (row < a.R) {
-        xs_raw = ld4(a.Xs + (size_t)row * 4);
+        xs_raw = ld4(a.Xs + (size_t)rr * 4);
         if (NCSR > 0) ga.load_rows(a.Xs);
         if (CROSS) gb.load_rows(a.Xc);
     }
@@ -327,7 +331,7 @@ fwd_row4_kernel(const Fwd4Args a) {
     for (bool first = true; row < a.R; row += stride, first = false) {
         if (!first) {
             load_structure(row);
-            xs_raw = ld4(a.Xs + (size_t)row * 4);
+            xs_raw = ld4(a.Xs + (size_t)rr * 4);
             if (NCSR > 0) ga.load_rows(a.Xs);
             if (CROSS) gb.load_rows(a.Xc);
         }
@@ -374,7 +378,7 @@ fwd_row4_kernel(const Fwd4Args a) {
         }
         if (a.X1) {
 #pragma unroll
-            for (int b = 0; b < NB; ++b) *reinterpret_cast<float4*>(a.X1 + ((size_t)row * NB + b) * 4) = x1[b];
+            for (int b = 0; b < NB; ++b) *reinterpret_cast<float4*>(a.X1 + ((size_t)rr * NB + b) * 4) = x1[b];
         }
         // mat-vec: 4 outputs x (NB*4) inputs, weights broadcast from shared memory
         float out[4];
@@ -389,7 +393,7 @@ fwd_row4_kernel(const Fwd4Args a) {
             s1[o] = fmaf(rw, acc, s1[o]);
             s2[o] = fmaf(rw * acc, acc, s2[o]);
         }
-        *reinterpret_cast<float4*>(a.Z + (size_t)row * 4) = make_float4(out[0], out[1], out[2], out[3]);
+        *reinterpret_cast<float4*>(a.Z + (size_t)rr * 4) = make_float4(out[0], out[1], out[2], out[3]);
     }
     if (a.acc_out && !(a.ablate & 4)) {   // warp shuffle tree -> one row per warp in shared memory -> 8 fp64 atomics per CTA
         const int lane = tid & 31, warp = tid >> 5;
@@ -428,6 +432,7 @@ struct Bwd4Args {
     const float* Xc; BnRef bn_c; float* gXc; int acc_cross; double* acc_b_cross;
     int col0_cross;
     const float* roww_s; const float* roww_c;   // optional row weights of the self / cross rows (see Fwd4Args::roww)
+    const int* rowmap_s; const int* rowmap_c;   // optional row lists (R_self / R_cross entries) of the two parts
     int ctas_self;        // CTAs [0, ctas_self) work on the self rows
     // dedicated range-sum CTAs (optional): the last `range_ctas` CTAs of the grid publish the sums of the rng_n ranges
     // into rng_sum_g (4 floats each) and set rng_flag_g[r]; both zero on entry
@@ -632,7 +637,8 @@ bwd_row4_kernel(const Bwd4Args a) {
                 }
             }
         };
-        for (int row = blockIdx.x * R4_THREADS + tid; row < a.R_self; row += a.ctas_self * R4_THREADS) {
+        for (int ridx = blockIdx.x * R4_THREADS + tid; ridx < a.R_self; ridx += a.ctas_self * R4_THREADS) {
+            const int row = a.rowmap_s ? __ldg(a.rowmap_s + ridx) : ridx;
             const float rw = a.roww_s ? __ldg(a.roww_s + row) : 1.f;
             if (rw <= 0.f) continue;                    // a skipped copy of a phantom line-graph row
             float4 T[NT];
@@ -794,7 +800,8 @@ bwd_row4_kernel(const Bwd4Args a) {
         float* const gX = a.gXc;
         const bool stats = a.acc_b_cross != nullptr && gX != nullptr;
         const int ncta = row_ctas - a.ctas_self;
-        for (int row = (blockIdx.x - a.ctas_self) * R4_THREADS + tid; row < a.R_cross; row += ncta * R4_THREADS) {
+        for (int ridx = (blockIdx.x - a.ctas_self) * R4_THREADS + tid; ridx < a.R_cross; ridx += ncta * R4_THREADS) {
+            const int row = a.rowmap_c ? __ldg(a.rowmap_c + ridx) : ridx;
             const float rw = a.roww_c ? __ldg(a.roww_c + row) : 1.f;
             if (rw <= 0.f) continue;
             float4 Tm = f4_zero(), Td = f4_zero();

@@ -116,10 +116,13 @@ fwd_rowg_kernel(const Fwd4Args a) {
     const int stride = gridDim.x * R4_THREADS;
     int row = blockIdx.x * R4_THREADS + tid;
     float d = 0.f, rw = 1.f;
+    int rr = 0;                                                // the row behind list entry `row`
     int k0[NCSR], k1[NCSR], p0 = 0, p1 = 0;
     GatherBatchG<BA, false, FS> ga;
     GatherBatchG<BP, true, FCC> gb;
-    auto load_structure = [&](int r) {
+    auto load_structure = [&](int idx) {
+        const int r = a.rowmap ? __ldg(a.rowmap + idx) : idx;
+        rr = r;
         d = __ldg(a.diag + r);
 #pragma unroll
         for (int t = 0; t < NCSR; ++t) {
@@ -144,7 +147,7 @@ fwd_rowg_kernel(const Fwd4Args a) {
 #pragma unroll
     for (int f = 0; f < FS; ++f) xs_raw.v[f] = 0.f;
     if (row < a.R) {
-        xs_raw = ldrow<FS>(a.Xs, row);
+        xs_raw = ldrow<FS>(a.Xs, rr);
         ga.load_rows(a.Xs);
         if (CROSS) gb.load_rows(a.Xc);
     }
@@ -160,7 +163,7 @@ fwd_rowg_kernel(const Fwd4Args a) {
     for (bool first = true; row < a.R; row += stride, first = false) {
         if (!first) {
             load_structure(row);
-            xs_raw = ldrow<FS>(a.Xs, row);
+            xs_raw = ldrow<FS>(a.Xs, rr);
             ga.load_rows(a.Xs);
             if (CROSS) gb.load_rows(a.Xc);
         }
@@ -230,10 +233,10 @@ fwd_rowg_kernel(const Fwd4Args a) {
             s2[o] = fmaf(rw * acc, acc, s2[o]);
         }
         if constexpr (FO == 4) {
-            *reinterpret_cast<float4*>(a.Z + (size_t)row * 4) = make_float4(out[0], out[1], out[2], out[3]);
+            *reinterpret_cast<float4*>(a.Z + (size_t)rr * 4) = make_float4(out[0], out[1], out[2], out[3]);
         } else {
 #pragma unroll
-            for (int o = 0; o < FO; ++o) a.Z[(size_t)row * FO + o] = out[o];
+            for (int o = 0; o < FO; ++o) a.Z[(size_t)rr * FO + o] = out[o];
         }
     }
     if (FO == 4 && a.acc_out) {
@@ -396,7 +399,8 @@ bwd_rowg_kernel(const Bwd4Args a) {
                 }
             }
         };
-        for (int row = blockIdx.x * R4_THREADS + tid; row < a.R_self; row += a.ctas_self * R4_THREADS) {
+        for (int ridx = blockIdx.x * R4_THREADS + tid; ridx < a.R_self; ridx += a.ctas_self * R4_THREADS) {
+            const int row = a.rowmap_s ? __ldg(a.rowmap_s + ridx) : ridx;
             if (a.roww_s && __ldg(a.roww_s + row) <= 0.f) continue;        // a skipped copy of a phantom line-graph row
             float T[NT][FG];
             const RowV<FG> t0 = gp(row);
@@ -521,7 +525,8 @@ bwd_rowg_kernel(const Bwd4Args a) {
         float* const gX = a.gXc;
         const bool stats = FC == 4 && a.acc_b_cross != nullptr && gX != nullptr;
         const int ncta = gridDim.x - a.ctas_self;
-        for (int row = (blockIdx.x - a.ctas_self) * R4_THREADS + tid; row < a.R_cross; row += ncta * R4_THREADS) {
+        for (int ridx = (blockIdx.x - a.ctas_self) * R4_THREADS + tid; ridx < a.R_cross; ridx += ncta * R4_THREADS) {
+            const int row = a.rowmap_c ? __ldg(a.rowmap_c + ridx) : ridx;
             const float rw = a.roww_c ? __ldg(a.roww_c + row) : 1.f;
             if (rw <= 0.f) continue;
             float T[2][FG];

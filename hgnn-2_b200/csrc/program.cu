@@ -249,7 +249,7 @@ bool collapse_disabled() {
 }
 
 bool use_collapse(const hgnn_program_t* prog, const hgnn_batch_t* b) {
-    if (collapse_disabled() || !prog->dual || !b->collapse_ok || !b->ew || !b->btc_rowptr || !b->btc_col || !b->btc_val) return false;
+    if (collapse_disabled() || !prog->dual || !b->collapse_ok || !b->ew || !b->erow || !b->btc_rowptr || !b->btc_col || !b->btc_val) return false;
     if (b->n_ops != 3 || !plain_ops(b->node_ops, 3) || !plain_ops(b->edge_ops, 3) || !plain_ops(b->node_ops_T, 3)) return false;
     const char* e = getenv("HGNN_B200_NO_ROW4");
     if (e && e[0] == '1') return false;
@@ -287,6 +287,10 @@ void mega_decide(const hgnn_program_t* prog, const hgnn_batch_t* b, int* m0, int
 }
 
 }  // namespace
+
+extern "C" int hgnn_program_uses_collapse(const hgnn_program_t* prog, const hgnn_batch_t* b) {
+    return (prog && b && prog->sides && prog->tensors && use_collapse(prog, b)) ? 1 : 0;
+}
 
 extern "C" long long hgnn_program_work_floats(const hgnn_program_t* prog, int Rn, int Rm) {
     WorkLayout w;
@@ -356,6 +360,8 @@ extern "C" int hgnn_program_fwd(const hgnn_program_t* prog, const hgnn_batch_t* 
             st.p_nnz = 0;
         }
         st.roww = (!node && collapse) ? b->ew : nullptr;
+        st.rowmap = (!node && collapse) ? b->erow : nullptr;
+        if (st.rowmap) st.R = b->n_act;                      // only the active line-graph rows
         const bool readout = sd.out < 0;
         float* Z = work + (readout ? w.readout_off : w.off[sd.out]);
         double* acc_out = readout ? nullptr : arena + prog->tensors[sd.out].acc_f;
@@ -500,8 +506,9 @@ extern "C" int hgnn_program_bwd(const hgnn_program_t* prog, const hgnn_batch_t* 
         d.ops_T = node ? b->node_ops_T : (collapse ? edge_T_collapsed : b->edge_ops_T);
         d.roww_self = (!node && collapse) ? b->ew : nullptr;
         d.roww_cross = nullptr;
-        d.active_self = d.roww_self ? b->n_act : 0;
-        d.active_cross = 0;
+        d.rowmap_self = d.roww_self ? b->erow : nullptr;
+        d.rowmap_cross = nullptr;
+        if (d.rowmap_self) d.R_self = b->n_act;
         d.n_ops = b->n_ops;
         d.Xs = tensor_ptr(prog, w, sd.src_self, X, XL, work);
         d.Fs = Fs;
@@ -535,7 +542,8 @@ extern "C" int hgnn_program_bwd(const hgnn_program_t* prog, const hgnn_batch_t* 
             d.acc_b_cross =
                 prog->tensors[sd.src_cross].bn_weight >= 0 ? arena + prog->tensors[sd.src_cross].acc_b : nullptr;
             d.roww_cross = (node && collapse) ? b->ew : nullptr;      // the cross rows of a node side are line-graph rows
-            d.active_cross = d.roww_cross ? b->n_act : 0;
+            d.rowmap_cross = d.roww_cross ? b->erow : nullptr;
+            if (d.rowmap_cross) d.R_cross = b->n_act;
         }
         d.skip_dw = 0;
         d.rng_scratch = nullptr;

@@ -346,6 +346,7 @@ def _pack_cache(pack):
         b.mega_scratch = _mega_scratch(pack.device).data_ptr()
         if pack.dual and not pack.generic and getattr(pack, "btc", None) is not None:
             c["btc"] = (iptr(pack.btc.rowptr), iptr(pack.btc.col), fptr(pack.btc.val), iptr(pack.erow), fptr(pack.ew))
+            c["edgeTc"] = make_ops([("ident",), ("diag", pack.dl), pack.btc.desc()])     # [I, D, btc]
             b.btc_rowptr, b.btc_col, b.btc_val, b.erow, b.ew = c["btc"]
             b.n_act = int(pack.erow.numel())
             b.btc_nnz = int(pack.btc.nnz)
@@ -354,12 +355,24 @@ def _pack_cache(pack):
     return c
 
 
-def _side_struct(pack, side, Xs, Xc):
+def _uses_collapse(plan, pack, dev, xl_is_degree):
+    """Whether the step executor runs this (model, batch) on the collapsed line graph (asked of the library, which
+    decides: ``hgnn_program_uses_collapse``); the per-side Python loop below then does the same."""
+    if not (xl_is_degree and plan.lg and "btc" in _pack_cache(pack)):
+        return False
+    batch = _pack_cache(pack)["batch"]
+    batch.collapse_ok = 1
+    return _lib.lib.hgnn_program_uses_collapse(ctypes.byref(plan.program(dev)), ctypes.byref(batch)) == 1
+
+
+def _side_struct(pack, side, Xs, Xc, collapse=False):
     node = side.kind == "node"
     pc = _pack_cache(pack)
     ops, n = pc["node" if node else "edge"]
     s = SideT()
     s.R, s.ops, s.n_ops = (pack.Rn if node else pack.Rm), ops, n
+    if collapse and not node:      # only the active line-graph rows, the representative weighted by its multiplicity
+        s.rowmap, s.roww, s.R = pc["btc"][3], pc["btc"][4], int(pack.erow.numel())
     s.Xs, s.Fs = Xs.data_ptr(), Xs.shape[1]
     if Xc is not None:
         s.p_rowptr, s.p_col, s.p_pm, s.p_pd = pc["p" if node else "pt"]
@@ -398,7 +411,7 @@ def _rows_of(pack, plan, tname):
     return pack.Rn if plan.tensors[tname]["rows"] == "n" else pack.Rm
 
 
-def _forward(plan, pack, Xp, XLp, training, arena, save_x1=False):
+def _forward(plan, pack, Xp, XLp, training, arena, save_x1=False, collapse=False):
     """Runs every side; returns (dict of raw tensors, model output)."""
     dev = Xp.device
     vals = {"X": Xp, "XL": XLp}
@@ -420,12 +433,12 @@ def _forward(plan, pack, Xp, XLp, training, arena, save_x1=False):
     for s in plan.sides:
         Xs = vals[s.src_self]
         Xc = vals[s.src_cross] if s.src_cross else None
-        st, keep = _side_struct(pack, s, Xs, Xc)
+        st, keep = _side_struct(pack, s, Xs, Xc, collapse)
         bs_ = _bn_ref(plan, s.src_self, arena, _rows_of(pack, plan, s.src_self), affine, pp)
         bc_ = _bn_ref(plan, s.src_cross, arena, _rows_of(pack, plan, s.src_cross), affine, pp) if s.src_cross else None
         Ha = s.conv_a.weight.shape[0]
         Hb = s.conv_b.weight.shape[0] if s.conv_b is not None else 0
-        Z = torch.empty(st.R, s.Fout, device=dev)
+        Z = torch.empty(pack.Rn if s.kind == "node" else pack.Rm, s.Fout, device=dev)   # all rows (st.R may be the active rows only)
         _lib.tag = s.name
         acc_out = None
         if s.out is not None and training:
@@ -435,7 +448,7 @@ def _forward(plan, pack, Xp, XLp, training, arena, save_x1=False):
         # accumulators inside the latency-bound backward gather
         X1 = None
         if save_x1 and s.out is not None and _lib.lib.hgnn_lg_row4_eligible(keep, st.n_ops, s.Fs, s.Fc, s.Fout):
-            X1 = torch.empty(st.R, s.Cin, device=dev)
+            X1 = torch.empty(pack.Rn if s.kind == "node" else pack.Rm, s.Cin, device=dev)
             vals["x1:" + s.name] = X1
         call("hgnn_lg_side_fwd", ctypes.byref(st), ctypes.byref(bs_), ctypes.byref(bc_) if bc_ is not None else None,
              pp[id(s.conv_a.weight)], pp[id(s.conv_a.bias)], Ha,
@@ -478,7 +491,9 @@ class _ModelFunction(torch.autograd.Function):
             ctx.need_x = Xp.requires_grad
             return out
         arena = torch.zeros(max(plan.arena_size, 1), dtype=torch.float64, device=dev)
-        vals, out = _forward(plan, pack, Xp, XLp, True, arena, save_x1=SPLIT_DW and any(ctx.needs_input_grad))
+        ctx.collapse = _uses_collapse(plan, pack, dev, xl_is_degree) and not SPLIT_DW
+        vals, out = _forward(plan, pack, Xp, XLp, True, arena, save_x1=SPLIT_DW and any(ctx.needs_input_grad),
+                             collapse=ctx.collapse)
         run = plan.running_flat(dev)
         if run[0] is not None:
             flat, (acc_off, Fs, run_off) = run
@@ -532,7 +547,8 @@ class _ModelFunction(torch.autograd.Function):
 
         # zeroed scratch for the dedicated range-sum CTAs of the width-4 edge-side backward (one region per side)
         rng_bytes, rng_scratch = 0, None
-        if pack.dual and not pack.generic and getattr(pack, "bts", None) is not None:
+        collapse = getattr(ctx, "collapse", False)
+        if pack.dual and not pack.generic and getattr(pack, "bts", None) is not None and not collapse:
             rng_bytes = int(_lib.lib.hgnn_lg_rng_scratch_bytes(int(pack.bts_ranges[3].numel())))
             if rng_bytes:
                 rng_scratch = torch.zeros(rng_bytes * len(plan.sides), dtype=torch.uint8, device=dev)
@@ -564,8 +580,10 @@ class _ModelFunction(torch.autograd.Function):
             d.Cin = s.Cin
             d.dW_bins, d.db_bins = base + 8 * s.dW_off, base + 8 * s.db_off
             # self part
-            opsT, n = pc["nodeT" if node else "edgeT"]
+            opsT, n = pc["nodeT" if node else ("edgeTc" if collapse else "edgeT")]
             d.R_self, d.ops_T, d.n_ops = (pack.Rn if node else pack.Rm), opsT, n
+            if collapse and not node:
+                d.rowmap_self, d.roww_self, d.R_self = pc["btc"][3], pc["btc"][4], int(pack.erow.numel())
             d.Xs, d.Fs = vals[s.src_self].data_ptr(), s.Fs
             d.bn_self = _bn_ref(plan, s.src_self, arena, _rows_of(pack, plan, s.src_self), None, pp)
             ts = plan.tensors[s.src_self]
@@ -583,6 +601,8 @@ class _ModelFunction(torch.autograd.Function):
                 d.Xc, d.Fc = vals[s.src_cross].data_ptr(), s.Fc
                 d.pt_nnz = pc["p_nnz"]
                 d.bn_cross = _bn_ref(plan, s.src_cross, arena, d.R_cross, None, pp)
+                if collapse and node:       # the cross rows of a node side are line-graph rows
+                    d.rowmap_cross, d.roww_cross, d.R_cross = pc["btc"][3], pc["btc"][4], int(pack.erow.numel())
                 need_cross = tc["bn"] is not None or (s.src_cross == "X" and ctx.need_x)
                 d.gXc = grad_buf(s.src_cross).data_ptr() if need_cross else None
                 d.accumulate_cross = 1 if s.src_cross in started else 0

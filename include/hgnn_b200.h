@@ -168,6 +168,7 @@ typedef struct hgnn_side_t {
      * (the batch-norm statistics); rows with weight <= 0 are not computed at all.  Used for the collapsed line graph
      * (hgnn_batch_t.ew): one representative per block of identical phantom rows.  NULL = every row, weight 1. */
     const float* roww;
+    const int* rowmap;      /* optional, with roww: the R rows to compute (hgnn_batch_t.erow); NULL: rows 0..R-1 */
 } hgnn_side_t;
 
 int hgnn_side_fwd(const hgnn_side_t* side, const float* Wa, const float* ba, int Ha,
@@ -258,7 +259,7 @@ typedef struct hgnn_side_bwd_t {
     /* optional row weights of the self / cross rows (see hgnn_side_t.roww): rows with weight <= 0 are skipped, the
      * others enter dW, dbias and the batch-norm sums weight times.  Thread-per-row kernels only; NULL = weight 1. */
     const float* roww_self; const float* roww_cross;
-    int active_self, active_cross;   /* rows with weight > 0 (0 = all): scheduling hint for the split of the CTAs */
+    const int* rowmap_self; const int* rowmap_cross;   /* optional row lists; R_self / R_cross then count their entries */
 } hgnn_side_bwd_t;
 long long hgnn_lg_rng_scratch_bytes(int rng_n);
 int hgnn_lg_side_bwd(const hgnn_side_bwd_t* desc, hgnn_stream_t stream);
@@ -396,6 +397,10 @@ int hgnn_program_bwd(const hgnn_program_t* prog, const hgnn_batch_t* batch, cons
                      const long long* param_addr, const float* work, float* gwork, double* arena,
                      const float* g_out, float* gX, float* gflat, void* rng_scratch, long long rng_scratch_bytes,
                      hgnn_stream_t stream);
+/* 1 when hgnn_program_fwd / _bwd run this (program, batch) on the collapsed line graph (batch->collapse_ok set,
+ * every side on the thread-per-row kernels): the line-graph sides then compute only the active rows batch->erow,
+ * weighted by batch->ew, and the backward gathers through batch->btc_*. */
+int hgnn_program_uses_collapse(const hgnn_program_t* prog, const hgnn_batch_t* batch);
 /* Profiling aids of the persistent kernels (csrc/mega.cu; no reference counterpart).  hgnn_mega_set_trace: device
  * buffer of 2 * 48 * grid * 4 uint64 that receives %globaltimer stamps per (phase, CTA) - phase = side index for
  * the forward, 48 + side index for the backward; stamps: phase entered, barrier passed, batch-norm vectors ready,
