@@ -1540,6 +1540,29 @@ static bool eng_try_bwd_row4(const hgnn_side_bwd_t* d, hgnn_stream_t stream) {
                     cap, grid, row_grid, a.range_ctas, d->R_self, d->R_cross, avg_s, avg_c, a.ctas_self); \
         eng_launch(eng::bwd_row4_kernel<NCSR, DW, GB, CB>, row_grid + a.range_ctas, R4_THREADS, 0, s, a); \
     }
+    // low-register variant: one CSR operator without a run-length part (A^T, or AL^T of the collapsed line graph)
+    // Opt-in (HGNN_B200_BWD_V2=1): measured on C2 it is 0.4 us faster on the node side (11.9 vs 12.3 us) and 5 us SLOWER
+    // on the edge side (18.7 vs 13.7 us) - the per-row tile traffic (24 STS + 32 LDS.128 + 64 FMA) outweighs the higher
+    // occupancy on the light line-graph rows: 0.824 vs 0.754 ms per step (profiles/logs/bench_r2i_*.log).
+    static int v2 = -1;
+    if (v2 < 0) { const char* e = getenv("HGNN_B200_BWD_V2"); v2 = (e && e[0] == '1') ? 1 : 0; }
+    if (v2 && a.n_csr == 1 && !a.rng_rowptr && !d->skip_dw) {
+        const bool big_cross = avg_c > 5.0;
+#define R4C_BWD(GB, CB)                                                                                   \
+        {                                                                                                 \
+            const int cap = eng_resident_impl((const void*)eng::bwd_row4c_kernel<GB, CB>, 0, R4_THREADS); \
+            int grid = (int)min((long long)cap, (rows + R4_THREADS - 1) / R4_THREADS);                    \
+            if (d->R_cross > 0 && grid < 2) grid = 2;                                                     \
+            a.ctas_self = eng_split_ctas(grid, (long long)act_s, d->R_cross > 0 ? (long long)act_c : 0, cost_s, cost_c); \
+            if (debug_split)                                                                              \
+                fprintf(stderr, "bwd_row4c split: cap %d grid %d R_self %d R_cross %d avg_s %.3f avg_c %.3f -> ctas_self %d\n", \
+                        cap, grid, d->R_self, d->R_cross, avg_s, avg_c, a.ctas_self);                     \
+            eng_launch(eng::bwd_row4c_kernel<GB, CB>, grid, R4_THREADS, 0, s, a);                         \
+        }
+        if (big_cross) R4C_BWD(4, 8) else R4C_BWD(4, 4)
+#undef R4C_BWD
+        return true;
+    }
 #define R4_BWD_B(NCSR, DW)                                                                                \
     if (big_s) R4_BWD(NCSR, DW, 8, 4) else if (big_c) R4_BWD(NCSR, DW, 2, 8) else if (mid_s) R4_BWD(NCSR, DW, 4, 4) else R4_BWD(NCSR, DW, 2, 4)
     if (d->skip_dw) { if (a.n_csr == 1) { R4_BWD_B(1, false) } else { R4_BWD_B(2, false) } }

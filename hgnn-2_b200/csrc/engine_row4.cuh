@@ -906,6 +906,240 @@ bwd_row4_kernel(const Bwd4Args a) {
 }
 
 // ---------------------------------------------------------------------------------------------
+// backward, low-register variant (one CSR operator, no run-length part: A^T, or the collapsed AL^T)
+// ---------------------------------------------------------------------------------------------
+// bwd_row4_kernel keeps 48 + 12 per-thread accumulators (dW, dbias, batch-norm sums) alive across its rows:
+// 125 registers, 4 CTAs of 128 threads per SM, and with ~112 k rows per launch at the C2 workload half of the
+// threads walk two rows one after the other (ncu: warps active 20 %, long-scoreboard bound).  Here a thread keeps
+// NOTHING across rows: it writes the 24 per-row values the sums are made of - T (12), g (4), w*xn (4), w*xhat (4) -
+// into a warp-private shared-memory tile, and after a __syncwarp every lane accumulates two of the 52 products
+//   dW[t][o][f] = sum_rows T[t][o] * (w xn[f])            (48)
+//   sum g xhat[f] = sum_rows g[f] * (w xhat[f])           (4)
+// over the 32 rows of the tile (float4 shared loads, 2 registers of state).  dbias and sum g stay in 8 registers.
+// ~80 registers -> 6 CTAs per SM: every row of a launch is in flight at once.
+#define R4C_STRIDE 36                 // floats per tile column block (32 rows + pad, 16-byte aligned)
+#define R4C_VALS 24
+template <int GB, int CB>
+__global__ void __launch_bounds__(R4_THREADS, 6)
+bwd_row4c_kernel(const Bwd4Args a) {
+    __shared__ __align__(16) float Ws[3 * 16];               // [t][o][f] = W[o][t*4+f]
+    __shared__ __align__(16) float Wc[2 * 16];               // [t][o][f] = W[o][col0 + t*4 + f]
+    __shared__ __align__(16) float vec[32];                  // gPre c0,c1,c2 (12) | pad (4) | input sc,sh,mu,rs (16)
+    __shared__ __align__(16) float tile[(R4_THREADS / 32) * R4C_VALS * R4C_STRIDE];
+    __shared__ float red[(R4_THREADS / 32) * 64];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const bool is_self = (int)blockIdx.x < a.ctas_self;
+    pdl_launch_dependents();
+    // ---- parameters only (overlaps the producer's tail under PDL)
+    for (int i = tid; i < 48; i += R4_THREADS) {
+        const int t = i >> 4, o = (i >> 2) & 3, f = i & 3;
+        const float* wrow = (o < a.Ha) ? a.Wa + (size_t)o * a.Cin : a.Wb + (size_t)(o - a.Ha) * a.Cin;
+        Ws[i] = wrow[t * 4 + f];
+    }
+    if (a.R_cross > 0)
+        for (int i = tid; i < 32; i += R4_THREADS) {
+            const int t = i >> 4, o = (i >> 2) & 3, f = i & 3;
+            const float* wrow = (o < a.Ha) ? a.Wa + (size_t)o * a.Cin : a.Wb + (size_t)(o - a.Ha) * a.Cin;
+            Wc[i] = wrow[a.col0_cross + t * 4 + f];
+        }
+    pdl_wait();
+    // ---- coefficient vectors into shared memory: warp 0 the BN + ReLU backward of this side, warp 1 the input's BN
+    if (warp == 0) {
+        float c0 = 1.f, c1 = 0.f, c2 = 0.f;
+        if (a.has_bn) {
+            double tf[8], tb[8];
+            warp_totals8(a.acc_f, tf);
+            warp_totals8(a.acc_b, tb);
+            const int f = lane & 3;
+            const float w = a.bn_w[0];
+            const double inv_n = 1.0 / (double)a.Rg;
+            const double m = tf[f] * inv_n;
+            const double var = fma(-m, m, tf[4 + f] * inv_n);
+            const float r_ = 1.0f / sqrtf(fmaxf((float)var, 0.f) + (float)ENG_BN_EPS);
+            const float k0 = w * r_;
+            const float k2 = -k0 * (float)(tb[4 + f] * inv_n) * r_;
+            c0 = k0; c2 = k2;
+            c1 = -k0 * (float)(tb[f] * inv_n) - k2 * (float)m;
+        }
+        if (lane < 4) { vec[lane] = c0; vec[4 + lane] = c1; vec[8 + lane] = c2; }
+    } else if (warp == 1) {
+        const Bn4 bx = bn4_from_ref(is_self ? a.bn_s : a.bn_c);
+        if (lane == 0) {
+            *reinterpret_cast<float4*>(vec + 16) = bx.sc; *reinterpret_cast<float4*>(vec + 20) = bx.sh;
+            *reinterpret_cast<float4*>(vec + 24) = bx.mu; *reinterpret_cast<float4*>(vec + 28) = bx.rs;
+        }
+    }
+    __syncthreads();
+    Gpre4 gp;
+    gp.relu_from = a.relu_from; gp.bn = a.has_bn != 0; gp.need_z = a.has_bn != 0 || a.relu_from < 4;
+    gp.G = a.gY; gp.Z = a.Z;
+    gp.c0 = *reinterpret_cast<const float4*>(vec); gp.c1 = *reinterpret_cast<const float4*>(vec + 4);
+    gp.c2 = *reinterpret_cast<const float4*>(vec + 8);
+
+    float* const my = tile + warp * (R4C_VALS * R4C_STRIDE);
+    // the two products of this lane: k < 48: T value (k >> 2) x (w xn)[k & 3];  48..51: g[k - 48] x (w xhat)[k - 48]
+    const int k2nd = lane + 32;
+    const int a1 = lane >> 2, b1 = 16 + (lane & 3);
+    const int a2 = k2nd < 48 ? (k2nd >> 2) : 12 + (k2nd - 48), b2 = k2nd < 48 ? 16 + (k2nd & 3) : 20 + (k2nd - 48);
+    const bool two = k2nd < 52;
+    float acc1 = 0.f, acc2 = 0.f;
+    float db[4] = {0.f, 0.f, 0.f, 0.f}, sg[4] = {0.f, 0.f, 0.f, 0.f};
+
+    const int R = is_self ? a.R_self : a.R_cross;
+    const int first = (is_self ? blockIdx.x : blockIdx.x - a.ctas_self) * R4_THREADS;
+    const int step = (is_self ? a.ctas_self : (int)gridDim.x - a.ctas_self) * R4_THREADS;
+    const int* const rowmap = is_self ? a.rowmap_s : a.rowmap_c;
+    const float* const roww = is_self ? a.roww_s : a.roww_c;
+    const float* const X = is_self ? a.Xs : a.Xc;
+    float* const gX = is_self ? a.gXs : a.gXc;
+    const bool accumulate = (is_self ? a.acc_self : a.acc_cross) != 0;
+    const bool stats = (is_self ? a.acc_b_self : a.acc_b_cross) != nullptr && gX != nullptr;
+    // whole warps iterate together (the tile is filled by all 32 lanes, inactive ones with zeros)
+    for (int base = first + warp * 32; base < R; base += step) {
+        const int ridx = base + lane;
+        float4 T[3] = {f4_zero(), f4_zero(), f4_zero()};
+        float4 gq = f4_zero(), xw = f4_zero(), xhw = f4_zero();
+        int row = -1;
+        float rw = 0.f;
+        if (ridx < R) {
+            row = rowmap ? __ldg(rowmap + ridx) : ridx;
+            rw = roww ? __ldg(roww + row) : 1.f;
+            if (rw <= 0.f) row = -1;
+        }
+        if (row >= 0) {
+            const float4 xr = ld4(X + (size_t)row * 4);
+            float4 old = f4_zero();
+            if (gX && accumulate) old = __ldcg(reinterpret_cast<const float4*>(gX + (size_t)row * 4));
+            float g[4] = {0.f, 0.f, 0.f, 0.f};
+            if (is_self) {
+                T[0] = gp(row);
+                const float d = __ldg(a.diag + row);
+                const int k0 = __ldg(a.rowptr[0] + row), k1 = __ldg(a.rowptr[0] + row + 1);
+                T[2] = gpre_gather<GB>(gp, a.col[0], a.val[0], k0, k1);
+                T[1] = make_float4(d * T[0].x, d * T[0].y, d * T[0].z, d * T[0].w);
+#pragma unroll
+                for (int t = 0; t < 3; ++t) {
+                    const float Tv[4] = {T[t].x, T[t].y, T[t].z, T[t].w};
+#pragma unroll
+                    for (int o = 0; o < 4; ++o) {
+                        const float4 w = *reinterpret_cast<const float4*>(Ws + (t * 4 + o) * 4);
+                        g[0] = fmaf(Tv[o], w.x, g[0]); g[1] = fmaf(Tv[o], w.y, g[1]);
+                        g[2] = fmaf(Tv[o], w.z, g[2]); g[3] = fmaf(Tv[o], w.w, g[3]);
+                    }
+                }
+                db[0] = fmaf(rw, T[0].x, db[0]); db[1] = fmaf(rw, T[0].y, db[1]);
+                db[2] = fmaf(rw, T[0].z, db[2]); db[3] = fmaf(rw, T[0].w, db[3]);
+            } else {
+                const int k0 = __ldg(a.pt_rowptr + row), k1 = __ldg(a.pt_rowptr + row + 1);
+                for (int k = k0; k < k1; k += CB) {         // CB entries (2 CB row loads) in flight
+                    int c[CB];
+                    float vm[CB], vd[CB];
+#pragma unroll
+                    for (int j = 0; j < CB; ++j) {
+                        const bool on = k + j < k1;
+                        c[j] = on ? __ldg(a.pt_col + k + j) : -1;
+                        vm[j] = on ? __ldg(a.pt_pm + k + j) : 0.f;
+                        vd[j] = on ? __ldg(a.pt_pd + k + j) : 0.f;
+                    }
+                    float4 gv[CB];
+#pragma unroll
+                    for (int j = 0; j < CB; ++j) gv[j] = c[j] >= 0 ? gp(c[j]) : f4_zero();
+#pragma unroll
+                    for (int j = 0; j < CB; ++j) {
+                        T[0] = f4_fma(vm[j], gv[j], T[0]);
+                        T[1] = f4_fma(vd[j], gv[j], T[1]);
+                    }
+                }
+#pragma unroll
+                for (int t = 0; t < 2; ++t) {
+                    const float Tv[4] = {T[t].x, T[t].y, T[t].z, T[t].w};
+#pragma unroll
+                    for (int o = 0; o < 4; ++o) {
+                        const float4 w = *reinterpret_cast<const float4*>(Wc + (t * 4 + o) * 4);
+                        g[0] = fmaf(Tv[o], w.x, g[0]); g[1] = fmaf(Tv[o], w.y, g[1]);
+                        g[2] = fmaf(Tv[o], w.z, g[2]); g[3] = fmaf(Tv[o], w.w, g[3]);
+                    }
+                }
+            }
+            const float4 sc = *reinterpret_cast<const float4*>(vec + 16), sh = *reinterpret_cast<const float4*>(vec + 20);
+            const float4 xn = f4_affine(xr, sc, sh);
+            xw = make_float4(rw * xn.x, rw * xn.y, rw * xn.z, rw * xn.w);
+            if (gX) {
+                *reinterpret_cast<float4*>(gX + (size_t)row * 4) =
+                    make_float4(g[0] + old.x, g[1] + old.y, g[2] + old.z, g[3] + old.w);
+                if (stats) {
+                    const float4 mu = *reinterpret_cast<const float4*>(vec + 24), rs = *reinterpret_cast<const float4*>(vec + 28);
+                    gq = make_float4(g[0], g[1], g[2], g[3]);
+                    xhw = make_float4(rw * (xr.x - mu.x) * rs.x, rw * (xr.y - mu.y) * rs.y,
+                                      rw * (xr.z - mu.z) * rs.z, rw * (xr.w - mu.w) * rs.w);
+                    sg[0] = fmaf(rw, g[0], sg[0]); sg[1] = fmaf(rw, g[1], sg[1]);
+                    sg[2] = fmaf(rw, g[2], sg[2]); sg[3] = fmaf(rw, g[3], sg[3]);
+                }
+            }
+        }
+        // ---- per-row values -> warp tile (value j of lane l at my[j * STRIDE + l]), then two products per lane
+        __syncwarp();
+        {
+            const float v[R4C_VALS] = {T[0].x, T[0].y, T[0].z, T[0].w, T[1].x, T[1].y, T[1].z, T[1].w,
+                                       T[2].x, T[2].y, T[2].z, T[2].w, gq.x, gq.y, gq.z, gq.w,
+                                       xw.x, xw.y, xw.z, xw.w, xhw.x, xhw.y, xhw.z, xhw.w};
+#pragma unroll
+            for (int j = 0; j < R4C_VALS; ++j) my[j * R4C_STRIDE + lane] = v[j];
+        }
+        __syncwarp();
+        {
+            const float4* pa = reinterpret_cast<const float4*>(my + a1 * R4C_STRIDE);
+            const float4* pb = reinterpret_cast<const float4*>(my + b1 * R4C_STRIDE);
+            float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                const float4 x = pa[q], y = pb[q];
+                s0 = fmaf(x.x, y.x, s0); s1 = fmaf(x.y, y.y, s1); s0 = fmaf(x.z, y.z, s0); s1 = fmaf(x.w, y.w, s1);
+            }
+            acc1 += s0 + s1;
+            if (two) {
+                const float4* qa = reinterpret_cast<const float4*>(my + a2 * R4C_STRIDE);
+                const float4* qb = reinterpret_cast<const float4*>(my + b2 * R4C_STRIDE);
+                float u0 = 0.f, u1 = 0.f;
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    const float4 x = qa[q], y = qb[q];
+                    u0 = fmaf(x.x, y.x, u0); u1 = fmaf(x.y, y.y, u1); u0 = fmaf(x.z, y.z, u0); u1 = fmaf(x.w, y.w, u1);
+                }
+                acc2 += u0 + u1;
+            }
+        }
+    }
+    // ---- flush: products are already warp totals (lane l: k = l and l + 32); dbias / sum g by shuffles
+    float extra[8];
+#pragma unroll
+    for (int f = 0; f < 4; ++f) { extra[f] = db[f]; extra[4 + f] = sg[f]; }
+    warp_reduce_scatter<float, 8>(extra);                // lane l: total of value l >> 2
+    red[warp * 64 + lane] = acc1;
+    if (two) red[warp * 64 + 32 + lane] = acc2;
+    if ((lane & 3) == 0) red[warp * 64 + 52 + (lane >> 2)] = extra[0];
+    __syncthreads();
+    const int nbw = hgnn_ws_bins(4 * a.Cin);
+    const int col_base = is_self ? 0 : a.col0_cross;
+    if (tid < 60) {
+        double v = 0.0;
+        for (int w = 0; w < R4_THREADS / 32; ++w) v += (double)red[w * 64 + tid];
+        if (tid < 48) {
+            const int t = tid >> 4, o = (tid >> 2) & 3, f = tid & 3;
+            if ((is_self || t < 2) && a.dW_bins) accum_add(a.dW_bins, 4 * a.Cin, nbw, o * a.Cin + col_base + t * 4 + f, v);
+        } else if (tid < 52) {              // sum g xhat
+            double* accb = is_self ? a.acc_b_self : a.acc_b_cross;
+            if (stats && accb) accum_add(accb, 8, hgnn_ws_bins(8), 4 + (tid - 48), v);
+        } else if (tid < 56) {              // dbias (self part only)
+            if (is_self && a.db_bins) accum_add(a.db_bins, 4, hgnn_ws_bins(4), tid - 52, v);
+        } else {                            // sum g
+            double* accb = is_self ? a.acc_b_self : a.acc_b_cross;
+            if (stats && accb) accum_add(accb, 8, hgnn_ws_bins(8), tid - 56, v);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // weight gradients as a streaming pass:  dW[o][c] = sum_rows gPre[row][o] * x1[row][c],
 // dbias[o] = sum_rows gPre[row][o], with x1 saved by the forward.  No gathers, no dependent loads;
 // runs on a parallel graph branch, off the critical path of the backward chain.
