@@ -134,3 +134,18 @@ def test_ccn_contraction_and_models():
             assert rel_err(X.grad, g[q + "gX"]) < TOL
             for k, v in p.items():
                 assert rel_err(v.grad, g[q + "grad/" + k]) < TOL, (order, gi, k)
+
+
+def test_workloads_match_synth():
+    """oracle/workloads.py (used by the CPU baseline / reference arm of bench.py without loading the CUDA
+    library) generates exactly the graphs of hgnn_b200.synth."""
+    from hgnn_b200 import synth
+    from oracle import workloads
+    for gid, N, a, b in ((0, 40, 7.0, 3.0), (3, 61, 8.0, 2.0)):
+        s = synth.sbm_instance(gid, N=N, a=a, b=b, J=1, sparse=True)
+        o = workloads.sbm_dense(gid, N=N, a=a, b=b)
+        assert torch.equal(s[0], o[0]) and torch.equal(s[1].to_dense(), o[1]) and torch.equal(s[2], o[2])
+    for gid in (0, 5, 11):
+        s = synth.qm9_shaped_instance(gid, sparse=True)
+        o = workloads.qm9_shaped_dense(gid)
+        assert torch.equal(s[0], o[0]) and torch.equal(s[1], o[1]) and torch.equal(s[2], o[2])
