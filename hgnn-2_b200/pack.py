@@ -137,13 +137,26 @@ def device_pack(graphs, dual=True, skip_bt=False, device="cuda"):
     _lib.call("hgnn_pack_device_upload", bs, blobs, du, sk, buf.data_ptr(), stage.data_ptr(), meta_host.data_ptr(),
               meta_dev.data_ptr(), stream())
     _meta_ring.copied(slot)
-    views = {}
-    base_i, base_f = buf.view(torch.int32), buf.view(torch.float32)      # one slicing op per array below
+    # all array views with ONE split per dtype view (a Python slicing op per array costs ~2 us x 49 arrays)
+    sizes, names, pos = [], [], 0
     for k, name in enumerate(_HOST_KEYS):
         n = lay[2 * k + 1]
-        if n >= 0:
-            o = lay[2 * k] >> 2
-            views[name] = (base_f if name in _FLOAT_KEYS else base_i)[o:o + n]
+        if n < 0:
+            continue
+        o = lay[2 * k] >> 2
+        if o > pos:
+            sizes.append(o - pos)
+            names.append(None)
+        sizes.append(n)
+        names.append(name)
+        pos = o + n
+    tail = (total >> 2) - pos
+    if tail > 0:
+        sizes.append(tail)
+        names.append(None)
+    parts_i = buf.view(torch.int32).split_with_sizes(sizes)
+    parts_f = buf.view(torch.float32).split_with_sizes(sizes)
+    views = {name: (parts_f[i] if name in _FLOAT_KEYS else parts_i[i]) for i, name in enumerate(names) if name is not None}
     return views, buf, stage_b.value + meta_b.value
 
 
