@@ -64,3 +64,14 @@ def test_wide_contractions_run_on_tensor_cores(which):
     assert len(best) / n <= 8.0, (len(best), n, ops.most_common(8))
     # the cvt.rna.tf32 emulation (FSETP against +INF, SEL) must not be back in the loop
     assert ops["FSETP"] == 0 and ops["SEL"] == 0, ops.most_common(8)
+
+
+def test_tcgen05_forward_kernel_is_blackwell_native():
+    """csrc/engine_tc5.cuh (opt-in, HGNN_B200_WIDE_TC5=1; parity-tested on the GPU): the contraction is issued as
+    tcgen05.mma (UTCHMMA) with the accumulator in tensor memory (LDTM = tcgen05.ld) and completion through an
+    mbarrier (UTCBAR = tcgen05.commit) - not as warp-level mma.sync."""
+    ins = _sass("_ZN3eng14fwd_tc5_kernelENS_7FwdArgsE")
+    assert ins, "fwd_tc5_kernel not in the library"
+    ops = collections.Counter(t.split()[0].split(".")[0] for _, t in ins)
+    assert ops["UTCHMMA"] >= 3 and ops["LDTM"] >= 1 and ops["UTCBAR"] >= 1, ops.most_common(12)
+    assert ops["HMMA"] == 0
