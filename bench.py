@@ -629,10 +629,10 @@ def run_ours(a):
         loss = loss_of(a, out, target)
         loss.backward()
         if collective:
-            fp.all_reduce_grad()        # the only collective of the step
+            fp.all_reduce_grad()        # the only collective of the step (NCCL, or fused into opt.step over peer memory)
         else:
             fp.gather_grad()
-        opt.step(grad_scale=1.0 / world)
+        opt.step(grad_scale=1.0 / world, collective=collective)
         return loss
 
     resident, h2d_bytes = work.to_device(work.prepare(0))
@@ -876,6 +876,10 @@ def run_ours(a):
     if ranks_agree is not None:
         line["ranks_agree"] = ranks_agree
         line["allreduce_exposed_us"] = exposed_us
+        line["allreduce"] = ("fused into the Adamax launch over NVLink peer memory (csrc/p2p.cu)" if opt.peers is not None
+                             else "NCCL all-reduce of the flat gradient")
+        if opt.peers is not None:
+            line["peer_fault"] = int(opt.fault.item())
     failed = False
     if not a.skip_cpu:
         parity, cb = parity_check(a, work_cls, dev)

@@ -142,11 +142,19 @@ _SIGS = {
     "hgnn_ccn1_update_fwd": [c_int, c_int, _P, _P, _P, c_int, _P, _P, c_int, _P, _P],
     "hgnn_ccn1_update_bwd": [c_int, c_int, _P, _P, _P, c_int, _P, c_int, _P, _P, _P, _P, _P, _P, c_ll, _P],
     "hgnn_adamax_step": [_P, _P, _P, _P, c_ll, c_float, c_float, c_float, c_float, c_float, _P, _P],
+    "hgnn_p2p_alloc": [c_ll, _P, _P],
+    "hgnn_p2p_open": [_P, _P],
+    "hgnn_p2p_close": [_P],
+    "hgnn_p2p_free": [_P],
+    "hgnn_p2p_max_floats": [],
+    "hgnn_p2p_allreduce_adamax": [_P, _P, _P, _P, c_int, c_float, c_float, c_float, c_float, c_float, _P, _P, c_int,
+                                  c_int, c_ll, _P, _P],
 }
 EXPORTS = sorted(list(_SIGS) + ["hgnn_last_error", "hgnn_version", "hgnn_workspace_bytes", "hgnn_bins_for",
                                 "hgnn_program_work_floats", "hgnn_program_launches", "hgnn_host_pack_n_keys",
                                 "hgnn_host_pack_key", "hgnn_host_pack_layout", "hgnn_host_pack_last_ns",
-                                "hgnn_pack_device_plan", "hgnn_lg_rng_scratch_bytes", "hgnn_program_rng_scratch_bytes"])
+                                "hgnn_pack_device_plan", "hgnn_lg_rng_scratch_bytes", "hgnn_program_rng_scratch_bytes",
+                                "hgnn_p2p_buffer_bytes"])
 
 for _name, _args in _SIGS.items():
     _fn = getattr(lib, _name)
@@ -175,6 +183,8 @@ lib.hgnn_host_pack_n_keys.restype = c_int
 lib.hgnn_host_pack_n_keys.argtypes = []
 lib.hgnn_host_pack_key.restype = ctypes.c_char_p
 lib.hgnn_host_pack_key.argtypes = [c_int]
+lib.hgnn_p2p_buffer_bytes.restype = c_ll
+lib.hgnn_p2p_buffer_bytes.argtypes = [c_ll]
 lib.hgnn_host_pack_layout.restype = c_ll
 lib.hgnn_host_pack_layout.argtypes = [c_int, _P, c_int, c_int, _P]
 

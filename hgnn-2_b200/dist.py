@@ -126,26 +126,81 @@ class FlatParams(object):
             dist.broadcast(self.flat, src)
 
     def all_reduce_grad(self):
-        """Sum of the shard gradients; the 1/world factor is folded into the optimizer launch."""
+        """Sum of the shard gradients; the 1/world factor is folded into the optimizer launch.  With a
+        ``FusedAdamax(..., peer_allreduce=True)`` attached the sum happens INSIDE the optimizer launch (peer
+        memory over NVLink, csrc/p2p.cu) and this only gathers the gradient."""
         self.gather_grad()
+        if self.fused_allreduce:
+            return
         if dist.is_initialized() and dist.get_world_size() > 1:
             dist.all_reduce(self.grad, op=dist.ReduceOp.SUM)
+
+    fused_allreduce = False
 
 
 class FusedAdamax(object):
     """torch.optim.Adamax(lr) semantics (scripts/main_gnn.py:160-167) as one launch over the flat
     buffer (csrc/optim.cu).  The step counter lives on the device so a captured CUDA graph replays
-    correctly."""
+    correctly.
 
-    def __init__(self, flat_params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8):
+    ``peer_allreduce`` (default: on when torch.distributed runs with more than one rank and the gradient fits the
+    peer buffer; env HGNN_B200_NO_P2P=1 turns it off): the data-parallel gradient sum is fused into the optimizer
+    launch - every rank publishes its flat gradient in a CUDA-IPC buffer, the kernel reads the peers' gradients
+    over NVLink, sums them in rank order and updates (csrc/p2p.cu).  ``fp.all_reduce_grad()`` then does not call
+    NCCL.  All ranks must construct the optimizer collectively (handle exchange) and step the same number of times."""
+
+    def __init__(self, flat_params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, peer_allreduce=None):
+        import os
         self.fp, self.lr, self.betas, self.eps = flat_params, lr, betas, eps
         dev = flat_params.flat.device
         self.exp_avg = torch.zeros_like(flat_params.flat)
         self.exp_inf = torch.zeros_like(flat_params.flat)
         self.step_count = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.peers = None
+        world = dist.get_world_size() if dist.is_initialized() else 1
+        if peer_allreduce is None:
+            peer_allreduce = world > 1 and os.environ.get("HGNN_B200_NO_P2P", "0") != "1"
+        if peer_allreduce and world > 1:
+            self._open_peers(dev, world)
 
-    def step(self, grad_scale=1.0):
+    def _open_peers(self, dev, world):
+        import ctypes
+        from . import _lib
+        n = self.fp.n
+        ok = n <= int(_lib.lib.hgnn_p2p_max_floats()) and world <= 16
+        flags = [None] * world
+        dist.all_gather_object(flags, bool(ok))
+        if not all(flags):
+            return                      # every rank falls back to NCCL together
+        torch.cuda.set_device(dev)
+        cap = int(n)
+        ptr, handle = ctypes.c_void_p(), ctypes.create_string_buffer(64)
+        call("hgnn_p2p_alloc", cap, ctypes.byref(ptr), handle)
+        handles = [None] * world
+        dist.all_gather_object(handles, handle.raw)
+        rank = dist.get_rank()
+        bufs = (ctypes.c_void_p * world)()
+        for r in range(world):
+            if r == rank:
+                bufs[r] = ptr.value
+            else:
+                q = ctypes.c_void_p()
+                call("hgnn_p2p_open", ctypes.create_string_buffer(handles[r], 64), ctypes.byref(q))
+                bufs[r] = q.value
+        dist.barrier()                  # every buffer exists and is zeroed before anybody's first step
+        self.peers = (bufs, rank, world, cap, ptr.value)
+        self.fault = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.fp.fused_allreduce = True
+
+    def step(self, grad_scale=1.0, collective=True):
+        """One update.  ``collective=False`` (profiling only): the plain local update even when the peer path is on."""
         fp = self.fp
+        if self.peers is not None and collective:
+            bufs, rank, world, cap, _ = self.peers
+            call("hgnn_p2p_allreduce_adamax", fptr(fp.flat), fptr(fp.grad), fptr(self.exp_avg), fptr(self.exp_inf),
+                 fp.n, float(self.lr), float(self.betas[0]), float(self.betas[1]), float(self.eps),
+                 float(grad_scale), self.step_count.data_ptr(), bufs, rank, world, cap, self.fault.data_ptr(), stream())
+            return
         call("hgnn_adamax_step", fptr(fp.flat), fptr(fp.grad), fptr(self.exp_avg), fptr(self.exp_inf),
              fp.n, float(self.lr), float(self.betas[0]), float(self.betas[1]), float(self.eps),
              float(grad_scale), self.step_count.data_ptr(), stream())

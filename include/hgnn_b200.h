@@ -327,6 +327,25 @@ int hgnn_adamax_step(float* param, const float* grad, float* exp_avg, float* exp
                      float lr, float beta1, float beta2, float eps, float grad_scale,
                      int* step /* device counter, incremented by the call */, hgnn_stream_t stream);
 
+/* ---- gradient all-reduce fused with the Adamax update over NVLink peer memory (csrc/p2p.cu) ----------------
+ * The reference is single-process; data-parallel training over the GPUs of one box is this repo's addition
+ *  and its one exchange is the sum of the flat gradient.  Every rank allocates one peer buffer
+ * (hgnn_p2p_alloc: device pointer + a 64-byte CUDA IPC handle), opens the handles of the other ranks
+ * (hgnn_p2p_open) and then replaces "all-reduce, then hgnn_adamax_step" by ONE launch per step:
+ * publish the local gradient, wait for the peers' flags, read their gradients over NVLink, sum in rank order,
+ * apply the update.  peer_bufs: host array of `world` device pointers indexed by rank (own buffer at [rank]).
+ * n <= cap_floats <= hgnn_p2p_max_floats().  *fault (device int, zeroed) is set if a peer never arrives. */
+long long hgnn_p2p_buffer_bytes(long long cap_floats);
+int hgnn_p2p_max_floats(void);
+int hgnn_p2p_alloc(long long cap_floats, void** dev_ptr, void* handle64);
+int hgnn_p2p_open(const void* handle64, void** dev_ptr);
+int hgnn_p2p_close(void* dev_ptr);
+int hgnn_p2p_free(void* dev_ptr);
+int hgnn_p2p_allreduce_adamax(float* param, const float* grad, float* exp_avg, float* exp_inf, int n, float lr,
+                              float beta1, float beta2, float eps, float grad_scale, int* step,
+                              void* const* peer_bufs, int rank, int world, long long cap_floats, int* fault,
+                              hgnn_stream_t stream);
+
 /* ---- whole-model training step in two calls (csrc/program.cu) ---------------------------------
  * The layer stack of GNN_simple / GNN_lg (models/gnns/model_mnb.py:58-66, 124-129) as a static
  * "program": a table of tensors (0 = X, 1 = XL for the line-graph model, then one per layer side
