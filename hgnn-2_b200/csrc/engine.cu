@@ -1113,8 +1113,7 @@ static bool eng_try_fwd_row4(const eng::FwdArgs& g, const hgnn_side_t* side, hgn
 #define R4_FWD(NCSR, CROSS, BA, BP)                                                                      \
     {                                                                                                    \
         const int cap_ = eng_resident_impl((const void*)eng::fwd_row4_kernel<NCSR, CROSS, BA, BP>, 0, R4_THREADS);   \
-        /* one row per thread when that needs at most ~12 % more CTAs than are resident (a short second wave) */    \
-        int grid = (full_grid || want <= cap_ + cap_ / 8) ? want : cap_;                                            \
+        int grid = full_grid ? want : min(want, cap_);                                                              \
         eng_launch(eng::fwd_row4_kernel<NCSR, CROSS, BA, BP>, grid, R4_THREADS, 0, s, a);                \
     }
 #define R4_FWD_B(NCSR)                                                                                   \

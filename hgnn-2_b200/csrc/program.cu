@@ -325,6 +325,14 @@ extern "C" int hgnn_program_fwd(const hgnn_program_t* prog, const hgnn_batch_t* 
     mega_decide(prog, b, &m0, &m1, &fwd_expand, &bwd_expand_unused);
     const bool collapse = use_collapse(prog, b);      // per-side kernels on the collapsed line graph
     if (collapse) fwd_expand = -1;                    // nobody reads the skipped rows then
+    hgnn_op_t edge_F_collapsed[3];
+    if (collapse) {
+        // Same operators.  The entry-count hint (it picks the gather batch size) deliberately stays the one of the full
+        // operator: with the hint of the active rows (1.5 entries per row) the forward takes the <4, 4> variant, which
+        // needs 131 registers (3 CTAs per SM) or spills at 128, and measured 9.7 us against 7.2 us for <8, 4> on 444 CTAs
+        // (profiles/logs/bench_r2r_edge_fwd_small_batch.log).
+        for (int k = 0; k < 3; ++k) edge_F_collapsed[k] = b->edge_ops[k];
+    }
     for (int i = 0; i < prog->n_sides; ++i) {
         if (m1 > m0 && i == m0) {      // sides [m0, m1): one persistent kernel (mega.cu)
             mk::Params P;
@@ -338,7 +346,7 @@ extern "C" int hgnn_program_fwd(const hgnn_program_t* prog, const hgnn_batch_t* 
         const bool node = sd.kind == 0;
         hgnn_side_t st;
         st.R = node ? b->Rn : b->Rm;
-        st.ops = node ? b->node_ops : b->edge_ops;
+        st.ops = node ? b->node_ops : (collapse ? edge_F_collapsed : b->edge_ops);
         st.n_ops = b->n_ops;
         st.Xs = tensor_ptr(prog, w, sd.src_self, X, XL, work);
         st.Fs = prog->tensors[sd.src_self].F;

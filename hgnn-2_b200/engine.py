@@ -353,6 +353,7 @@ def _pack_cache(pack):
         if pack.dual and not pack.generic and getattr(pack, "btc", None) is not None:
             c["btc"] = (iptr(pack.btc.rowptr), iptr(pack.btc.col), fptr(pack.btc.val), iptr(pack.erow), fptr(pack.ew))
             c["edgeTc"] = make_ops([("ident",), ("diag", pack.dl), pack.btc.desc()])     # [I, D, btc]
+            c["edgeFc"] = make_ops(pack.edge_ops())       # forward operators (same hints as the executor: csrc/program.cu)
             b.btc_rowptr, b.btc_col, b.btc_val, b.erow, b.ew = c["btc"]
             b.n_act = int(pack.erow.numel())
             b.btc_nnz = int(pack.btc.nnz)
@@ -379,6 +380,8 @@ def _side_struct(pack, side, Xs, Xc, collapse=False):
     s.R, s.ops, s.n_ops = (pack.Rn if node else pack.Rm), ops, n
     if collapse and not node:      # only the active line-graph rows, the representative weighted by its multiplicity
         s.rowmap, s.roww, s.R = pc["btc"][3], pc["btc"][4], int(pack.erow.numel())
+        ops, n = pc["edgeFc"]
+        s.ops = ops
     s.Xs, s.Fs = Xs.data_ptr(), Xs.shape[1]
     if Xc is not None:
         s.p_rowptr, s.p_col, s.p_pm, s.p_pd = pc["p" if node else "pt"]
