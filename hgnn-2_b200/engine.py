@@ -246,6 +246,19 @@ class _Plan(object):
         self._programs[key] = (pr, tabs, keep)
         return pr
 
+    def sync_bn_scale(self, device, world):
+        """Flat vector: 1 / world at the positions of batch-norm weights and biases, 1 elsewhere (sync_bn)."""
+        key = (str(device), world)
+        hit = getattr(self, "_sync_scale", None)
+        if hit is None or hit[0] != key:
+            v = torch.ones(self.n_flat)
+            bn_ids = {id(t["bn"].weight) for t in self.bn_list} | {id(t["bn"].bias) for t in self.bn_list}
+            for p_, (pos, n, _shape) in zip(self.params, self.param_slices):
+                if id(p_) in bn_ids:
+                    v[pos:pos + n] = 1.0 / world
+            hit = self._sync_scale = (key, v.to(device))
+        return hit[1]
+
     def param_addresses(self):
         """Device addresses of all parameters (numpy int64, model.parameters() order).  Layout and
         dtype are validated on the first and last parameter per call, on all of them when the plan
@@ -416,12 +429,38 @@ def _bn_ref(plan, tname, arena, rows, affine=None, pp=None):
     return r
 
 
-def _rows_of(pack, plan, tname):
-    return pack.Rn if plan.tensors[tname]["rows"] == "n" else pack.Rm
+def _rows_of(pack, plan, tname, glob=None):
+    """Rows behind a tensor's batch-norm statistics: the local rows, or with ``sync_bn`` the rows of all ranks."""
+    node = plan.tensors[tname]["rows"] == "n"
+    if glob is not None:
+        return glob[0] if node else glob[1]
+    return pack.Rn if node else pack.Rm
 
 
-def _forward(plan, pack, Xp, XLp, training, arena, save_x1=False, collapse=False):
-    """Runs every side; returns (dict of raw tensors, model output)."""
+def _sync_world():
+    import torch.distributed as dist
+    return dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+
+
+def _global_rows(pack, dev):
+    """(sum of Rn, sum of Rm) over all ranks - the divisors of synchronised batch-norm (one tiny all-reduce per batch)."""
+    import torch.distributed as dist
+    t = torch.tensor([pack.Rn, pack.Rm], dtype=torch.int64, device=dev)
+    dist.all_reduce(t)
+    n, m = t.tolist()
+    return int(n), int(m)
+
+
+def _allreduce_bins(arena, off_doubles, width):
+    """Sum one binned accumulator block of the step arena over all ranks, in place (sync_bn)."""
+    import torch.distributed as dist
+    n = _bins(width) * width
+    dist.all_reduce(arena[off_doubles:off_doubles + n])
+
+
+def _forward(plan, pack, Xp, XLp, training, arena, save_x1=False, collapse=False, glob=None):
+    """Runs every side; returns (dict of raw tensors, model output).  ``glob`` = (global Rn, global Rm): synchronised
+    batch-norm - the (sum z, sum z^2) bins of every side are summed over the ranks before its consumers run."""
     dev = Xp.device
     vals = {"X": Xp, "XL": XLp}
     pp = _param_ptrs(plan)
@@ -443,8 +482,8 @@ def _forward(plan, pack, Xp, XLp, training, arena, save_x1=False, collapse=False
         Xs = vals[s.src_self]
         Xc = vals[s.src_cross] if s.src_cross else None
         st, keep = _side_struct(pack, s, Xs, Xc, collapse)
-        bs_ = _bn_ref(plan, s.src_self, arena, _rows_of(pack, plan, s.src_self), affine, pp)
-        bc_ = _bn_ref(plan, s.src_cross, arena, _rows_of(pack, plan, s.src_cross), affine, pp) if s.src_cross else None
+        bs_ = _bn_ref(plan, s.src_self, arena, _rows_of(pack, plan, s.src_self, glob), affine, pp)
+        bc_ = _bn_ref(plan, s.src_cross, arena, _rows_of(pack, plan, s.src_cross, glob), affine, pp) if s.src_cross else None
         Ha = s.conv_a.weight.shape[0]
         Hb = s.conv_b.weight.shape[0] if s.conv_b is not None else 0
         Z = torch.empty(pack.Rn if s.kind == "node" else pack.Rm, s.Fout, device=dev)   # all rows (st.R may be the active rows only)
@@ -465,6 +504,8 @@ def _forward(plan, pack, Xp, XLp, training, arena, save_x1=False, collapse=False
              s.relu_from, Z.data_ptr(), acc_out, X1.data_ptr() if X1 is not None else None, cur)
         if s.out is not None:
             vals[s.out] = Z
+            if glob is not None and training:
+                _allreduce_bins(arena, plan.tensors[s.out]["acc_f"], 2 * s.Fout)
         else:     # readout: sum over all Nmax slots, padded slots add fc.bias (layers_mnb.py:92,:386)
             out = torch.empty(pack.bs, s.Fout, device=dev)
             call("hgnn_segment_sum", Z.data_ptr(), pack.bs, s.Fout, pc["node_off"], pc["pad_n"],
@@ -480,7 +521,11 @@ class _ModelFunction(torch.autograd.Function):
         dev = Xp.device
         ctx.flat_mode = flat_mode
         ctx.xl_is_degree = 1 if xl_is_degree else 0
-        ctx.program = USE_PROGRAM and not SPLIT_DW
+        # synchronised batch-norm (model.sync_bn = True under torch.distributed): statistics over the batches of ALL
+        # ranks, as one process on the global batch would compute them (batch_normalization.py:80-93).
+        # It needs a collective between consecutive sides, so the per-side Python loop runs instead of the executor.
+        ctx.glob = _global_rows(pack, dev) if (getattr(model, "sync_bn", False) and _sync_world() > 1) else None
+        ctx.program = USE_PROGRAM and not SPLIT_DW and ctx.glob is None
         if ctx.program:
             prog = plan.program(dev)
             batch = _pack_cache(pack)["batch"]
@@ -502,13 +547,18 @@ class _ModelFunction(torch.autograd.Function):
         arena = torch.zeros(max(plan.arena_size, 1), dtype=torch.float64, device=dev)
         ctx.collapse = _uses_collapse(plan, pack, dev, xl_is_degree) and not SPLIT_DW
         vals, out = _forward(plan, pack, Xp, XLp, True, arena, save_x1=SPLIT_DW and any(ctx.needs_input_grad),
-                             collapse=ctx.collapse)
+                             collapse=ctx.collapse, glob=ctx.glob)
         run = plan.running_flat(dev)
         if run[0] is not None:
             flat, (acc_off, Fs, run_off) = run
             mom = float(plan.bn_list[0]["bn"].momentum)
+            if ctx.glob is not None:
+                rows_t = torch.tensor([ctx.glob[0] if t["rows"] == "n" else ctx.glob[1] for t in plan.bn_list],
+                                      dtype=torch.int32, device=dev)
+            else:
+                rows_t = _rows_table(pack, plan, dev)
             call("hgnn_bn_running_update", arena.data_ptr(), acc_off.data_ptr(), iptr(Fs),
-                 iptr(_rows_table(pack, plan, dev)), run_off.data_ptr(), len(plan.bn_list), mom, fptr(flat), stream())
+                 iptr(rows_t), run_off.data_ptr(), len(plan.bn_list), mom, fptr(flat), stream())
         ctx.plan, ctx.pack, ctx.vals, ctx.arena = plan, pack, vals, arena
         ctx.need_x = Xp.requires_grad
         return out
@@ -542,6 +592,7 @@ class _ModelFunction(torch.autograd.Function):
                          gflat.data_ptr(), scratch.data_ptr() if scratch is not None else None, n_scr, stream())
             return _ModelFunction._grads_out(ctx, plan, gX, gflat)
         vals = ctx.vals
+        glob = getattr(ctx, "glob", None)
         grads, started = {}, set()
         base = arena.data_ptr()
         main, side_stream, forked = torch.cuda.current_stream(), None, False
@@ -582,7 +633,9 @@ class _ModelFunction(torch.autograd.Function):
                 d.gY, d.Z = grads[s.out].data_ptr(), vals[s.out].data_ptr()
                 d.acc_f, d.acc_b = base + 8 * t["acc_f"], base + 8 * t["acc_b"]
                 d.bn_weight = pp[id(t["bn"].weight)]
-                d.Rg = _rows_of(pack, plan, s.out)
+                d.Rg = _rows_of(pack, plan, s.out, glob)
+                if glob is not None:      # every contribution to (sum g, sum g xhat) of this tensor is in: make it global
+                    _allreduce_bins(arena, t["acc_b"], 2 * t["F"])
             d.Fg, d.relu_from = s.Fout, s.relu_from
             d.Wa, d.Ha = pp[id(s.conv_a.weight)], Ha
             d.Wb, d.Hb = (pp[id(s.conv_b.weight)] if Hb else None), Hb
@@ -594,7 +647,7 @@ class _ModelFunction(torch.autograd.Function):
             if collapse and not node:
                 d.rowmap_self, d.roww_self, d.R_self = pc["btc"][3], pc["btc"][4], int(pack.erow.numel())
             d.Xs, d.Fs = vals[s.src_self].data_ptr(), s.Fs
-            d.bn_self = _bn_ref(plan, s.src_self, arena, _rows_of(pack, plan, s.src_self), None, pp)
+            d.bn_self = _bn_ref(plan, s.src_self, arena, _rows_of(pack, plan, s.src_self, glob), None, pp)
             ts = plan.tensors[s.src_self]
             need_self = ts["bn"] is not None or (s.src_self == "X" and ctx.need_x)
             d.gXs = grad_buf(s.src_self).data_ptr() if need_self else None
@@ -609,7 +662,7 @@ class _ModelFunction(torch.autograd.Function):
                 d.pt_rowptr, d.pt_col, d.pt_pm, d.pt_pd = pc["pt" if node else "p"]   # rows = the cross tensor's rows
                 d.Xc, d.Fc = vals[s.src_cross].data_ptr(), s.Fc
                 d.pt_nnz = pc["p_nnz"]
-                d.bn_cross = _bn_ref(plan, s.src_cross, arena, d.R_cross, None, pp)
+                d.bn_cross = _bn_ref(plan, s.src_cross, arena, _rows_of(pack, plan, s.src_cross, glob), None, pp)
                 if collapse and node:       # the cross rows of a node side are line-graph rows
                     d.rowmap_cross, d.roww_cross, d.R_cross = pc["btc"][3], pc["btc"][4], int(pack.erow.numel())
                 need_cross = tc["bn"] is not None or (s.src_cross == "X" and ctx.need_x)
@@ -642,6 +695,11 @@ class _ModelFunction(torch.autograd.Function):
         gflat = torch.empty(plan.n_flat, device=dev)
         call("hgnn_bins_reduce", arena.data_ptr(), offs.data_ptr(), iptr(nbs), iptr(strides), iptr(cnts),
              plan.n_flat, fptr(gflat), stream())
+        if glob is not None:
+            # The batch-norm weight / bias gradients were formed from GLOBAL sums: every rank already holds the sum
+            # over ranks.  Pre-divide them by the world size so that the flat-gradient sum over ranks (followed by the
+            # 1 / world of the optimizer) treats them like the rank-local conv gradients.
+            gflat.mul_(plan.sync_bn_scale(dev, _sync_world()))
         gX = grads.get("X") if ctx.need_x else None
         return _ModelFunction._grads_out(ctx, plan, gX, gflat)
 
