@@ -249,7 +249,15 @@ def iptr(t):
     return ptr(t, torch.int32)
 
 
+_raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", None)
+_raw_device = getattr(torch._C, "_cuda_getDevice", None)
+
+
 def stream():
+    """Raw handle of torch's current CUDA stream (the fast C accessors when this torch has them: the Python
+    ``torch.cuda.current_stream()`` object costs ~14 us per call, and a step asks ~10 times)."""
+    if _raw_stream is not None and _raw_device is not None:
+        return _raw_stream(_raw_device())
     return torch.cuda.current_stream().cuda_stream
 
 

@@ -55,11 +55,23 @@ def _side_stream(device):
 _MEGA_SCRATCH = {}
 
 
+_MEGA_ON = os.environ.get("HGNN_B200_MEGA", "0") == "1"
+
+
+class _NoScratch(object):
+    @staticmethod
+    def data_ptr():
+        return None
+
+
 def _mega_scratch(device):
-    """256 zeroed bytes per (device, stream): the grid-barrier state of the persistent kernels (csrc/mega.cu)."""
+    """256 zeroed bytes per (device, stream): the grid-barrier state of the persistent kernels (csrc/mega.cu).
+    Only allocated when those kernels are switched on (HGNN_B200_MEGA=1)."""
+    if not _MEGA_ON:
+        return _NoScratch
     device = torch.device(device)
     idx = device.index if device.index is not None else torch.cuda.current_device()
-    key = (idx, torch.cuda.current_stream(idx).cuda_stream)
+    key = (idx, stream())
     buf = _MEGA_SCRATCH.get(key)
     if buf is None:
         buf = _MEGA_SCRATCH[key] = torch.zeros(64, dtype=torch.int32, device=torch.device("cuda", idx))

@@ -85,7 +85,11 @@ def prepare_batch(batch, task, J=1, sparse=None, device="cuda"):
     pin = torch.cuda.is_available()
     X = torch.zeros(bs, n_feat, Nmax, pin_memory=pin)
     XL = torch.zeros(bs, 1, Emax, pin_memory=pin)
-    T = torch.tensor([float(inst[2][task]) for inst in batch], dtype=torch.float32).view(bs, 1)
+    ts = [inst[2] for inst in batch]
+    if all(torch.is_tensor(t) and t.dim() == 1 and t.shape == ts[0].shape and t.dtype == ts[0].dtype for t in ts):
+        T = torch.stack(ts, 0)[:, task].to(torch.float32).reshape(bs, 1)      # one gather instead of bs item() calls
+    else:
+        T = torch.tensor([float(inst[2][task]) for inst in batch], dtype=torch.float32).view(bs, 1)
     Xn, XLn = X.numpy(), XL.numpy()
     for i, inst in enumerate(batch):
         g = graphs[i]

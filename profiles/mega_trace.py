@@ -4,7 +4,7 @@ Every CTA stamps %globaltimer at four points of every phase (phase entered, barr
 ready, rows + flush done).  Printed per phase: how long the slowest CTA waited in the barrier, the row work
 (median / max over CTAs) and the phase span from the first CTA entering to the last CTA finishing.
 
-    python profiles/mega_trace.py [--bs 32] [--nodes 1000] [--layers 20]
+    HGNN_B200_MEGA=1 python profiles/mega_trace.py [--bs 32] [--nodes 1000] [--layers 20]
 """
 import argparse
 import ctypes

@@ -205,3 +205,18 @@ def test_batch_loader_with_power_operators_is_race_free():
         assert len(got) == len(want)
         for a, b in zip(got, want):
             assert torch.equal(a, b)
+
+
+@pytest.mark.parametrize("env", [{"HGNN_B200_MEGA": "1"}, {"HGNN_B200_BWD_V2": "1"}, {"HGNN_B200_NO_COLLAPSE": "1"}])
+def test_opt_in_kernel_variants_keep_parity(env):
+    """The code paths that are not the default - persistent cooperative kernels (csrc/mega.cu), the low-register
+    backward, the uncollapsed line graph - are switched by environment variables read once per process, so the
+    L = 20 oracle comparison and the golden-vector models run again in a child process with each of them."""
+    import subprocess
+    import sys
+    here = os.path.dirname(os.path.abspath(__file__))
+    out = subprocess.run([sys.executable, "-m", "pytest", "-x", "-q", "-m", "gpu",
+                          os.path.join(here, "test_gpu_round2.py") + "::test_headline_depth_and_width_vs_oracle",
+                          os.path.join(here, "test_gpu_gnn.py") + "::test_models_vs_reference_golden"],
+                         env=dict(os.environ, **env), capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-2000:]
