@@ -535,6 +535,29 @@ bwd_row4_kernel(const Bwd4Args a) {
             const float* wrow = (o < a.Ha) ? a.Wa + (size_t)o * a.Cin : a.Wb + (size_t)(o - a.Ha) * a.Cin;
             Wc[i] = wrow[a.col0_cross + t * 4 + f];
         }
+    // Graph structure of the thread's FIRST row (row list, weight, diagonal, row pointers): nothing the producer writes,
+    // so these three dependent rounds run before the wait, under the producer's tail.
+    int pre_row = -1, pre_k0 = 0, pre_k1 = 0;
+    float pre_rw = 1.f, pre_d = 0.f;
+    if (!is_range) {
+        if (is_self) {
+            const int ridx = blockIdx.x * R4_THREADS + tid;
+            if (ridx < a.R_self) {
+                pre_row = a.rowmap_s ? __ldg(a.rowmap_s + ridx) : ridx;
+                pre_rw = a.roww_s ? __ldg(a.roww_s + pre_row) : 1.f;
+                pre_d = __ldg(a.diag + pre_row);
+                if (NCSR > 0) { pre_k0 = __ldg(a.rowptr[0] + pre_row); pre_k1 = __ldg(a.rowptr[0] + pre_row + 1); }
+            }
+        } else {
+            const int ridx = (blockIdx.x - a.ctas_self) * R4_THREADS + tid;
+            if (ridx < a.R_cross) {
+                pre_row = a.rowmap_c ? __ldg(a.rowmap_c + ridx) : ridx;
+                pre_rw = a.roww_c ? __ldg(a.roww_c + pre_row) : 1.f;
+                pre_k0 = __ldg(a.pt_rowptr + pre_row);
+                pre_k1 = __ldg(a.pt_rowptr + pre_row + 1);
+            }
+        }
+    }
     pdl_wait();
     // ---- coefficients of this side's BN + ReLU backward, and the input's BN vectors: warp-level
     Gpre4 gp;
@@ -637,17 +660,22 @@ bwd_row4_kernel(const Bwd4Args a) {
                 }
             }
         };
-        for (int ridx = blockIdx.x * R4_THREADS + tid; ridx < a.R_self; ridx += a.ctas_self * R4_THREADS) {
-            const int row = a.rowmap_s ? __ldg(a.rowmap_s + ridx) : ridx;
-            const float rw = a.roww_s ? __ldg(a.roww_s + row) : 1.f;
+        const int ridx0 = blockIdx.x * R4_THREADS + tid;
+        for (int ridx = ridx0; ridx < a.R_self; ridx += a.ctas_self * R4_THREADS) {
+            const bool pre = ridx == ridx0;             // structure of the first row was loaded before the wait
+            const int row = pre ? pre_row : (a.rowmap_s ? __ldg(a.rowmap_s + ridx) : ridx);
+            const float rw = pre ? pre_rw : (a.roww_s ? __ldg(a.roww_s + row) : 1.f);
             if (rw <= 0.f) continue;                    // a skipped copy of a phantom line-graph row
             float4 T[NT];
             T[0] = gp(row);
-            const float d = __ldg(a.diag + row);
+            const float d = pre ? pre_d : __ldg(a.diag + row);
             T[1] = make_float4(d * T[0].x, d * T[0].y, d * T[0].z, d * T[0].w);
 #pragma unroll
             for (int t = 0; t < NCSR; ++t) {
-                const int k0 = __ldg(a.rowptr[t] + row), k1 = (a.ablate & 1) ? k0 : __ldg(a.rowptr[t] + row + 1);
+                int k0, k1;
+                if (t == 0 && pre) { k0 = pre_k0; k1 = pre_k1; }
+                else { k0 = __ldg(a.rowptr[t] + row); k1 = __ldg(a.rowptr[t] + row + 1); }
+                if (a.ablate & 1) k1 = k0;
                 T[2 + t] = t == 0 ? gpre_gather<GB>(gp, a.col[t], a.val[t], k0, k1)
                                   : gpre_gather<2>(gp, a.col[t], a.val[t], k0, k1);
             }
@@ -800,12 +828,15 @@ bwd_row4_kernel(const Bwd4Args a) {
         float* const gX = a.gXc;
         const bool stats = a.acc_b_cross != nullptr && gX != nullptr;
         const int ncta = row_ctas - a.ctas_self;
-        for (int ridx = (blockIdx.x - a.ctas_self) * R4_THREADS + tid; ridx < a.R_cross; ridx += ncta * R4_THREADS) {
-            const int row = a.rowmap_c ? __ldg(a.rowmap_c + ridx) : ridx;
-            const float rw = a.roww_c ? __ldg(a.roww_c + row) : 1.f;
+        const int ridx0 = (blockIdx.x - a.ctas_self) * R4_THREADS + tid;
+        for (int ridx = ridx0; ridx < a.R_cross; ridx += ncta * R4_THREADS) {
+            const bool pre = ridx == ridx0;
+            const int row = pre ? pre_row : (a.rowmap_c ? __ldg(a.rowmap_c + ridx) : ridx);
+            const float rw = pre ? pre_rw : (a.roww_c ? __ldg(a.roww_c + row) : 1.f);
             if (rw <= 0.f) continue;
             float4 Tm = f4_zero(), Td = f4_zero();
-            const int k0 = __ldg(a.pt_rowptr + row), k1 = (a.ablate & 1) ? k0 : __ldg(a.pt_rowptr + row + 1);
+            int k0 = pre ? pre_k0 : __ldg(a.pt_rowptr + row), k1 = pre ? pre_k1 : __ldg(a.pt_rowptr + row + 1);
+            if (a.ablate & 1) k1 = k0;
             for (int k = k0; k < k1; k += CB) {         // CB entries (2 CB row loads) in flight
                 int c[CB];
                 float vm[CB], vd[CB];
