@@ -13,6 +13,19 @@ from ...pack import PackTensor, resolve_pack
 from ..layers import layers_mnb
 
 
+def _needs_layer_autograd(model, X, XL):
+    """The model-level engine differentiates w.r.t. the parameters and X in train mode only.  The two cases it does
+    not cover take the per-layer autograd path, like the reference's plain autograd would: a gradient asked for the
+    edge features XL, and eval mode with gradients enabled (input-gradient analysis of a trained model)."""
+    import torch
+    if XL is not None and torch.is_tensor(XL) and XL.requires_grad and torch.is_grad_enabled():
+        return True
+    if not model.training and torch.is_grad_enabled():
+        if (torch.is_tensor(X) and X.requires_grad) or (XL is not None and torch.is_tensor(XL) and XL.requires_grad):
+            return True
+    return False
+
+
 class GNN_simple(nn.Module):
     """Power GNN.  ``task`` and ``gru`` are accepted and unused, as in the reference (:42)."""
 
@@ -36,8 +49,8 @@ class GNN_simple(nn.Module):
         require_cuda()
         X, W = state
         pack = resolve_pack(W, N_batch=N_batch)
-        if engine.supported(self):       # whole stack on the model-level engine (csrc/engine.cu)
-            return engine.run_model(self, pack, layers_mnb._pack_nodes(pack, X), None)
+        if engine.supported(self) and not _needs_layer_autograd(self, X, None):
+            return engine.run_model(self, pack, layers_mnb._pack_nodes(pack, X), None)   # model-level engine (csrc/engine.cu)
         cur, _ = self.layer0.forward_packed(layers_mnb._pack_nodes(pack, X), pack)
         for i in range(self.n_layers - 2):
             cur, _ = self._modules['layer{}'.format(i + 1)].forward_packed(cur, pack)
@@ -74,8 +87,8 @@ class GNN_lg(nn.Module):
         # device copy the pack already holds, and let the engine collapse the identical phantom rows
         degree = PackTensor.pack_of(XL) is pack and not pack.generic and not XL.requires_grad
         XLp = pack.dl.view(-1, 1) if degree else layers_mnb._pack_edges(pack, XL)
-        if engine.supported(self):       # whole stack on the model-level engine (csrc/engine.cu)
-            return engine.run_model(self, pack, Xp, XLp, xl_is_degree=degree)
+        if engine.supported(self) and not _needs_layer_autograd(self, X, XL):
+            return engine.run_model(self, pack, Xp, XLp, xl_is_degree=degree)   # model-level engine (csrc/engine.cu)
         Xp, XLp, _, _ = self.layer0.forward_packed(Xp, XLp, pack)
         for i in range(self.n_layers - 2):
             Xp, XLp, _, _ = self._modules['layer{}'.format(i + 1)].forward_packed(Xp, XLp, pack)

@@ -220,3 +220,28 @@ def test_opt_in_kernel_variants_keep_parity(env):
                           os.path.join(here, "test_gpu_gnn.py") + "::test_models_vs_reference_golden"],
                          env=dict(os.environ, **env), capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-2000:]
+
+
+def test_gradients_the_engine_does_not_cover_take_the_layer_path():
+    """d/dXL in train mode and input gradients in eval mode are not silently dropped."""
+    from hgnn_b200 import synth
+    from hgnn_b200.functions.batching import prepare_batch
+    from hgnn_b200.models.gnns.model_mnb import GNN_lg
+    torch.manual_seed(4)
+    X, W, _, XL, WL, Pm, Pd, mask, mask_lg, N_batch, E_batch = prepare_batch(synth.sbm_dataset(3, N=40), 0, 1)
+    model = GNN_lg(0, 2, 4, 5, 2, 1, 1).cuda().train()
+    Xc, XLc = X.cuda().requires_grad_(), XL.cuda().clone().requires_grad_()
+    y = model([Xc, XLc, W, WL, Pm, Pd], N_batch, mask, E_batch, mask_lg)
+    y.sum().backward()
+    assert XLc.grad is not None and torch.isfinite(XLc.grad).all() and float(XLc.grad.abs().max()) > 0
+    # the engine path gives the same X gradient and output
+    Xe = X.cuda().requires_grad_()
+    ye = model([Xe, XL.cuda(), W, WL, Pm, Pd], N_batch, mask, E_batch, mask_lg)
+    ye.sum().backward()
+    assert rel_err(ye.detach().cpu(), y.detach().cpu()) < TOL and rel_err(Xe.grad.cpu(), Xc.grad.cpu()) < TOL
+    model.eval()
+    Xv = X.cuda().requires_grad_()
+    yv = model([Xv, XL.cuda(), W, WL, Pm, Pd], N_batch, mask, E_batch, mask_lg)
+    assert yv.grad_fn is not None
+    yv.sum().backward()
+    assert Xv.grad is not None and torch.isfinite(Xv.grad).all()
