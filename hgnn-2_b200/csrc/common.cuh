@@ -15,6 +15,18 @@ int hgnn_check_launch(const char* what);
 // same chain: such a predecessor writes activations / accumulators only, never parameters or graph
 // structure, which is all a PDL kernel touches before its griddepcontrol.wait).
 void hgnn_eng_set_pdl(bool on);
+// Launch recorder of the thread-per-row engine kernels (engine.cu: eng_launch; program.cu: replay of a pass as one
+// graph launch).  While installed (thread-local), those kernels are not launched but appended here.
+#include <vector>
+struct hgnn_eng_slot_t {
+    const void* func;
+    int grid, block;
+    unsigned smem;
+    int pdl;
+    std::vector<char> args;      // the kernel's single by-value parameter
+};
+struct hgnn_eng_recorder_t { std::vector<hgnn_eng_slot_t> slots; };
+void hgnn_eng_set_recorder(hgnn_eng_recorder_t* r);
 
 #define HGNN_REQUIRE(cond, msg)                      \
     do {                                             \

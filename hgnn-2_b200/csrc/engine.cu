@@ -1036,8 +1036,26 @@ void hgnn_eng_set_pdl(bool on) {
     g_pdl = on && !disabled;
 }
 
+// ---- launch recorder (csrc/program.cu: replay of a pass as ONE graph launch) --------------------------------
+// While a recorder is installed on this thread, eng_launch does not launch: it appends (kernel, grid, block, shared
+// memory, PDL flag, a copy of the by-value argument block) to the recorder.  The step executor then writes these into
+// the kernel nodes of a graph it captured once (cudaGraphExecKernelNodeSetParams: 0.4 us per node against ~2 us for a
+// launch, profiles/graph_update_probe.cu) and launches the graph.  Only kernels that go through eng_launch - the
+// thread-per-row side kernels - can be recorded; hgnn_lg_side_fwd / _bwd refuse the other paths while recording.
+static thread_local hgnn_eng_recorder_t* g_rec = nullptr;
+void hgnn_eng_set_recorder(hgnn_eng_recorder_t* r) { g_rec = r; }
+static inline bool eng_recording() { return g_rec != nullptr; }
+
 template <typename Kernel, typename Args>
 static void eng_launch(Kernel kernel, int grid, int threads, size_t smem, cudaStream_t s, const Args& a) {
+    if (g_rec) {
+        hgnn_eng_slot_t slot;
+        slot.func = reinterpret_cast<const void*>(kernel);
+        slot.grid = grid; slot.block = threads; slot.smem = (unsigned)smem; slot.pdl = g_pdl ? 1 : 0;
+        slot.args.assign(reinterpret_cast<const char*>(&a), reinterpret_cast<const char*>(&a) + sizeof(Args));
+        g_rec->slots.push_back(std::move(slot));
+        return;
+    }
     if (!g_pdl) {
         kernel<<<grid, threads, smem, s>>>(a);
         return;
@@ -1329,6 +1347,7 @@ extern "C" int hgnn_lg_side_fwd(const hgnn_side_t* side, const hgnn_bn_ref_t* bn
     a.Cin = side->n_ops * a.Fs + 2 * a.Fc;
     if (eng_try_fwd_row4(a, side, stream)) return hgnn_check_launch("hgnn_lg_side_fwd(row4)");
     if (eng_try_fwd_rowg(a, side, stream)) return hgnn_check_launch("hgnn_lg_side_fwd(rowg)");
+    HGNN_REQUIRE(!eng_recording(), "recording: this side does not run on the thread-per-row kernels");
     HGNN_REQUIRE(!X1, "x1 rows can only be saved by the width-4 fast path (check hgnn_lg_row4_eligible)");
     HGNN_REQUIRE(!side->roww && !side->rowmap, "row weights need the thread-per-row kernels (widths of the h = 2 feature maps)");
     if (eng_try_fwd_tc5(a, stream)) return hgnn_check_launch("hgnn_lg_side_fwd(tc5)");
@@ -1677,6 +1696,7 @@ extern "C" int hgnn_lg_side_bwd(const hgnn_side_bwd_t* d, hgnn_stream_t stream) 
     HGNN_REQUIRE(d->relu_from >= d->Fg || d->Z, "ReLU backward needs Z");
     if (eng_try_bwd_row4(d, stream)) return hgnn_check_launch("hgnn_lg_side_bwd(row4)");
     if (eng_try_bwd_rowg(d, stream)) return hgnn_check_launch("hgnn_lg_side_bwd(rowg)");
+    HGNN_REQUIRE(!eng_recording(), "recording: this side does not run on the thread-per-row kernels");
     HGNN_REQUIRE(!d->skip_dw, "skip_dw needs the width-4 fast path (check hgnn_lg_row4_eligible)");
     HGNN_REQUIRE(!d->roww_self && !d->roww_cross && !d->rowmap_self && !d->rowmap_cross, "row weights need the thread-per-row kernels (widths of the h = 2 feature maps)");
     eng::BwdArgs a;

@@ -10,6 +10,8 @@
 // Reference semantics: models/gnns/model_mnb.py:58-66,124-129 (layer loop), layers_mnb.py:92,:386
 // (readout sum over the padded slots).  Host code only; no kernels live in this file.
 #include <atomic>
+#include <functional>
+#include <map>
 #include <vector>
 #include <cstdlib>
 #include "common.cuh"
@@ -298,6 +300,173 @@ extern "C" long long hgnn_program_work_floats(const hgnn_program_t* prog, int Rn
     return w.total;
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Replay of a pass as ONE graph launch.
+//
+// A pass issues ~40 dependent side kernels whose sizes and pointers differ from batch to batch, so it cannot be
+// captured once and replayed as it is; issuing them costs the host 0.19 ms per pass, and the synchronous training
+// loop is host-bound (profiles/logs/e2e_phases_r2k.log).  But the SEQUENCE of kernels is the same for every batch of a
+// model.  So the side loop runs with a launch recorder installed (engine.cu: eng_launch appends kernel, launch
+// dimensions and the by-value argument block instead of launching), the recorded slots are written into the kernel
+// nodes of a graph that was captured once from such a recording (cudaGraphExecKernelNodeSetParams: 0.4 us per node),
+// and the graph is launched.  Measured (profiles/graph_update_probe.cu, 40 nodes): 15 us of host time against 75 us
+// for 40 launches.  The few launches around the sides (arena memset, readout sum, running statistics, gradient
+// reduction) stay direct: before the graph, or deferred until after it.
+// ---------------------------------------------------------------------------------------------------------
+struct ReplayCtx {
+    hgnn_eng_recorder_t rec;
+    std::vector<std::function<int()>> post;      // direct launches that must follow the recorded kernels
+    bool restartable = true;                     // false once a non-idempotent direct launch was issued
+};
+
+struct ReplayGraph {
+    cudaGraph_t graph = nullptr;
+    cudaGraphExec_t exec = nullptr;
+    std::vector<cudaGraphNode_t> nodes;
+    std::vector<const void*> funcs;
+    std::vector<int> block, pdl;
+    std::vector<unsigned> smem;
+    int failures = 0;
+};
+
+// Opt-in (HGNN_B200_REPLAY=1).  Measured on C2 (same box, profiles/logs/e2e_replay_ab_r2w.log): issuing a pass drops
+// from 0.35 to 0.27 ms (forward) / 0.41 to 0.36 ms (backward), but the step does not get shorter (1.86 vs 1.86, 2.07 vs
+// 1.77 ms): the GPU cannot start a pass before all of its nodes are parametrised and the graph is launched, whereas
+// direct launches stream - the device works on side 1 while the host issues side 2 - and at ~5 us per launch against
+// 7-13 us per kernel the host stays ahead of the device anyway.  The synchronous loop is a latency chain (prepare ->
+// forward on the device -> loss -> backward on the device -> read-back), not an issue-rate problem.
+bool replay_disabled() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("HGNN_B200_REPLAY"); v = (e && e[0] == '1') ? 0 : 1; }
+    return v == 1;
+}
+
+// every side on the thread-per-row kernels (the only ones the recorder sees): the feature maps of h = 2
+bool rowpath_program(const hgnn_program_t* prog, const hgnn_batch_t* b) {
+    if (b->n_ops != 3 || !plain_ops(b->node_ops, 3) || !b->node_ops_T) return false;
+    if (prog->dual && (!plain_ops(b->edge_ops, 3) || !b->edge_ops_T)) return false;
+    const char* e = getenv("HGNN_B200_NO_ROW4");
+    if (e && e[0] == '1') return false;
+    for (int i = 0; i < prog->n_sides; ++i) {
+        const hgnn_prog_side_t& sd = prog->sides[i];
+        const int Fs = prog->tensors[sd.src_self].F, Fc = sd.src_cross >= 0 ? prog->tensors[sd.src_cross].F : 0;
+        const int Fo = sd.Ha + sd.Hb;
+        const bool row4 = Fs == 4 && Fo == 4 && (Fc == 0 || Fc == 4) && sd.out >= 0;
+        const bool rowg = (Fs == 5 && Fc == 1 && Fo == 4) || (Fs == 1 && Fc == 4 && Fo == 4) ||
+                          (Fs == 4 && Fc == 4 && (Fo == 2 || Fo == 1)) || (Fs == 5 && Fc == 0 && Fo == 4) ||
+                          (Fs == 4 && Fc == 0 && (Fo == 2 || Fo == 1));
+        if (!row4 && !rowg) return false;
+        if (sd.out < 0 && Fo == 4) return false;
+    }
+    return true;
+}
+
+bool replay_wanted(const hgnn_program_t* prog, const hgnn_batch_t* b, cudaStream_t s) {
+    if (replay_disabled() || !rowpath_program(prog, b)) return false;
+    int m0 = 0, m1 = 0, e0 = -1, e1 = -1;
+    mega_decide(prog, b, &m0, &m1, &e0, &e1);
+    if (m1 > m0) return false;                       // the persistent kernels are their own launch
+    cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(s, &st) != cudaSuccess || st != cudaStreamCaptureStatusNone) {
+        cudaGetLastError();
+        return false;                                // inside somebody's capture: issue the launches into it
+    }
+    return true;
+}
+
+void replay_destroy(ReplayGraph& g) {
+    if (g.exec) cudaGraphExecDestroy(g.exec);
+    if (g.graph) cudaGraphDestroy(g.graph);
+    g.exec = nullptr; g.graph = nullptr;
+    g.nodes.clear(); g.funcs.clear(); g.block.clear(); g.pdl.clear(); g.smem.clear();
+}
+
+int replay_launch_slot(const hgnn_eng_slot_t& sl, cudaStream_t s) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(sl.grid);
+    cfg.blockDim = dim3(sl.block);
+    cfg.dynamicSmemBytes = sl.smem;
+    cfg.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = sl.pdl ? 1 : 0;
+    void* kargs[] = {const_cast<char*>(sl.args.data())};
+    return cudaLaunchKernelExC(&cfg, sl.func, kargs) == cudaSuccess ? HGNN_OK : HGNN_ERR_CUDA;
+}
+
+// captures the recorded chain on a private stream and remembers the kernel node of every slot
+bool replay_build(ReplayGraph& g, const hgnn_eng_recorder_t& rec) {
+    replay_destroy(g);
+    static thread_local cudaStream_t cap = nullptr;
+    if (!cap && cudaStreamCreateWithFlags(&cap, cudaStreamNonBlocking) != cudaSuccess) return false;
+    if (cudaStreamBeginCapture(cap, cudaStreamCaptureModeThreadLocal) != cudaSuccess) { cudaGetLastError(); return false; }
+    bool ok = true;
+    for (const hgnn_eng_slot_t& sl : rec.slots) {
+        if (replay_launch_slot(sl, cap) != HGNN_OK) { ok = false; break; }
+        cudaStreamCaptureStatus st;
+        unsigned long long id = 0;
+        cudaGraph_t cg = nullptr;
+        const cudaGraphNode_t* deps = nullptr;
+        size_t nd = 0;
+        if (cudaStreamGetCaptureInfo(cap, &st, &id, &cg, &deps, &nd) != cudaSuccess || nd != 1) { ok = false; break; }
+        g.nodes.push_back(deps[0]);            // the node just added: what the next launch would depend on
+        g.funcs.push_back(sl.func);
+        g.block.push_back(sl.block);
+        g.pdl.push_back(sl.pdl);
+        g.smem.push_back(sl.smem);
+    }
+    cudaGraph_t graph = nullptr;
+    if (cudaStreamEndCapture(cap, &graph) != cudaSuccess || !graph) ok = false;
+    g.graph = graph;
+    if (ok && cudaGraphInstantiate(&g.exec, g.graph, 0) != cudaSuccess) ok = false;
+    if (!ok) { cudaGetLastError(); replay_destroy(g); }
+    return ok;
+}
+
+// writes the recorded slots into the graph (rebuilding it when the kernel sequence changed) and launches it
+int replay_run(ReplayGraph& g, const hgnn_eng_recorder_t& rec, cudaStream_t s) {
+    const size_t n = rec.slots.size();
+    if (n == 0) return HGNN_OK;
+    bool same = g.exec != nullptr && g.nodes.size() == n;
+    for (size_t i = 0; same && i < n; ++i) {
+        const hgnn_eng_slot_t& sl = rec.slots[i];
+        same = g.funcs[i] == sl.func && g.block[i] == sl.block && g.pdl[i] == sl.pdl && g.smem[i] == sl.smem;
+    }
+    if (!same) {
+        if (g.failures > 8 || !replay_build(g, rec)) { ++g.failures; return HGNN_ERR_CUDA; }
+    } else {
+        for (size_t i = 0; i < n; ++i) {
+            const hgnn_eng_slot_t& sl = rec.slots[i];
+            void* kargs[] = {const_cast<char*>(sl.args.data())};
+            cudaKernelNodeParams kp = {};
+            kp.func = const_cast<void*>(sl.func);
+            kp.gridDim = dim3(sl.grid);
+            kp.blockDim = dim3(sl.block);
+            kp.sharedMemBytes = sl.smem;
+            kp.kernelParams = kargs;
+            if (cudaGraphExecKernelNodeSetParams(g.exec, g.nodes[i], &kp) != cudaSuccess) {
+                cudaGetLastError();
+                ++g.failures;
+                replay_destroy(g);
+                return HGNN_ERR_CUDA;
+            }
+        }
+    }
+    if (cudaGraphLaunch(g.exec, s) != cudaSuccess) {
+        hgnn_set_error("hgnn_program: cudaGraphLaunch: %s", cudaGetErrorString(cudaGetLastError()));
+        return HGNN_ERR_CUDA;
+    }
+    return HGNN_OK;
+}
+
+// one graph per (program, direction) and thread
+ReplayGraph& replay_graph_of(const hgnn_program_t* prog, int direction) {
+    static thread_local std::map<std::pair<const void*, int>, ReplayGraph> graphs;
+    return graphs[std::make_pair(static_cast<const void*>(prog), direction)];
+}
+
 #define PROG_CALL(expr)                    \
     do {                                   \
         int rc_ = (expr);                  \
@@ -305,9 +474,11 @@ extern "C" long long hgnn_program_work_floats(const hgnn_program_t* prog, int Rn
         g_program_launches.fetch_add(1);   \
     } while (0)
 
-extern "C" int hgnn_program_fwd(const hgnn_program_t* prog, const hgnn_batch_t* b, const float* X, const float* XL,
-                                const long long* addr, float* work, double* arena, float* running, float* out,
-                                hgnn_stream_t stream) {
+// rc != NULL: a launch recorder is installed - the side kernels are recorded instead of launched, and the direct
+// launches that must follow them are deferred into rc->post
+static int program_fwd_impl(const hgnn_program_t* prog, const hgnn_batch_t* b, const float* X, const float* XL,
+                            const long long* addr, float* work, double* arena, float* running, float* out,
+                            hgnn_stream_t stream, ReplayCtx* rc) {
     WorkLayout w;
     HGNN_REQUIRE(prog && b && X && addr && work && arena && out, "null argument");
     HGNN_REQUIRE(plan_work(prog, b->Rn, b->Rm, &w) && check_program(prog, b), "malformed program or batch");
@@ -379,13 +550,54 @@ extern "C" int hgnn_program_fwd(const hgnn_program_t* prog, const hgnn_batch_t* 
                                             acc_out, nullptr, stream);
         hgnn_eng_set_pdl(false);
         PROG_CALL(rc_fwd);
-        if (readout)   // sum over all Nmax slots; padded slots add fc.bias (layers_mnb.py:92, :386)
-            PROG_CALL(hgnn_segment_sum(Z, b->bs, sd.Ha + sd.Hb, b->node_off, b->pad_n, param(addr, sd.ba), out, stream));
+        if (readout) {  // sum over all Nmax slots; padded slots add fc.bias (layers_mnb.py:92, :386)
+            const int Fo = sd.Ha + sd.Hb;
+            const float* bias = param(addr, sd.ba);
+            auto fn = [=]() { return hgnn_segment_sum(Z, b->bs, Fo, b->node_off, b->pad_n, bias, out, stream); };
+            if (rc) rc->post.push_back(fn);
+            else PROG_CALL(fn());
+        }
     }
-    if (running && prog->n_bn > 0)
-        PROG_CALL(hgnn_bn_running_update_k(arena, prog->bn_acc_off, prog->bn_F, prog->bn_rows_kind, b->Rn, b->Rm,
-                                           prog->bn_run_off, prog->n_bn, prog->momentum, running, stream));
+    if (running && prog->n_bn > 0) {
+        auto fn = [=]() {
+            return hgnn_bn_running_update_k(arena, prog->bn_acc_off, prog->bn_F, prog->bn_rows_kind, b->Rn, b->Rm,
+                                            prog->bn_run_off, prog->n_bn, prog->momentum, running, stream);
+        };
+        if (rc) rc->post.push_back(fn);
+        else PROG_CALL(fn());
+    }
     return HGNN_OK;
+}
+
+// after a recording pass: the recorded kernels as one graph launch (or, should the graph be unavailable, one by one),
+// then the deferred direct launches
+static int replay_finish(const hgnn_program_t* prog, int direction, ReplayCtx& rc, cudaStream_t s) {
+    int r = replay_run(replay_graph_of(prog, direction), rc.rec, s);
+    if (r != HGNN_OK) {
+        cudaGetLastError();
+        for (const hgnn_eng_slot_t& sl : rc.rec.slots)
+            if (replay_launch_slot(sl, s) != HGNN_OK) {
+                hgnn_set_error("hgnn_program: launch of a recorded kernel failed: %s", cudaGetErrorString(cudaGetLastError()));
+                return HGNN_ERR_CUDA;
+            }
+    }
+    for (auto& f : rc.post) PROG_CALL(f());
+    return HGNN_OK;
+}
+
+extern "C" int hgnn_program_fwd(const hgnn_program_t* prog, const hgnn_batch_t* b, const float* X, const float* XL,
+                                const long long* addr, float* work, double* arena, float* running, float* out,
+                                hgnn_stream_t stream) {
+    cudaStream_t s = to_stream(stream);
+    if (prog && b && prog->sides && prog->tensors && replay_wanted(prog, b, s)) {
+        ReplayCtx rc;
+        hgnn_eng_set_recorder(&rc.rec);
+        const int r = program_fwd_impl(prog, b, X, XL, addr, work, arena, running, out, stream, &rc);
+        hgnn_eng_set_recorder(nullptr);
+        if (r == HGNN_OK) return replay_finish(prog, 0, rc, s);
+        // the recording pass launched nothing but the (idempotent) arena memset: issue the pass directly
+    }
+    return program_fwd_impl(prog, b, X, XL, addr, work, arena, running, out, stream, nullptr);
 }
 
 // one scratch region per edge side whose transposed operator has a run-length part
@@ -403,10 +615,10 @@ extern "C" long long hgnn_program_rng_scratch_bytes(const hgnn_program_t* prog, 
     return side_rng_bytes(prog, b) * n;
 }
 
-extern "C" int hgnn_program_bwd(const hgnn_program_t* prog, const hgnn_batch_t* b, const float* X, const float* XL,
-                                const long long* addr, const float* work, float* gwork, double* arena,
-                                const float* g_out, float* gX, float* gflat, void* rng_scratch,
-                                long long rng_scratch_bytes, hgnn_stream_t stream) {
+static int program_bwd_impl(const hgnn_program_t* prog, const hgnn_batch_t* b, const float* X, const float* XL,
+                            const long long* addr, const float* work, float* gwork, double* arena,
+                            const float* g_out, float* gX, float* gflat, void* rng_scratch,
+                            long long rng_scratch_bytes, hgnn_stream_t stream, ReplayCtx* rc) {
     WorkLayout w;
     HGNN_REQUIRE(prog && b && X && addr && work && gwork && arena && g_out && gflat, "null argument");
     HGNN_REQUIRE(plan_work(prog, b->Rn, b->Rm, &w) && check_program(prog, b), "malformed program or batch");
@@ -442,6 +654,12 @@ extern "C" int hgnn_program_bwd(const hgnn_program_t* prog, const hgnn_batch_t* 
             if (f.need_cross) started[sd.src_cross] = 1;
         }
     }
+    if (rc)      // a zero fill between recorded kernels cannot be deferred: such programs are issued directly
+        for (int i = 0; i < prog->n_sides; ++i)
+            if (prog->sides[i].out >= 0 && !fl[i].out_started) {
+                hgnn_set_error("hgnn_program_bwd: recording: side %d has an unused output", i);
+                return HGNN_ERR_ARG;
+            }
     int m0 = 0, m1 = 0, fwd_expand_unused = -1, bwd_expand = -1;
     mega_decide(prog, b, &m0, &m1, &fwd_expand_unused, &bwd_expand);     // the same decision as the forward
     const bool collapse = use_collapse(prog, b);
@@ -455,6 +673,7 @@ extern "C" int hgnn_program_bwd(const hgnn_program_t* prog, const hgnn_batch_t* 
         o.rng_n = 0;
         o.nnz = b->btc_nnz;
     }
+    if (rc) rc->restartable = false;      // from here on direct launches add into the arena
     for (int i = prog->n_sides - 1; i >= 0; --i) {
         if (m1 > m0 && i == m1 - 1) {     // sides [m0, m1) in reverse: one persistent kernel (mega.cu)
             mk::Params P;
@@ -564,7 +783,32 @@ extern "C" int hgnn_program_bwd(const hgnn_program_t* prog, const hgnn_batch_t* 
         hgnn_eng_set_pdl(false);
         PROG_CALL(rc_bwd);
     }
-    PROG_CALL(hgnn_bins_reduce(arena, prog->red_off, prog->red_nb, prog->red_stride, prog->red_cnt, prog->n_flat,
-                               gflat, stream));
+    {
+        auto fn = [=]() {
+            return hgnn_bins_reduce(arena, prog->red_off, prog->red_nb, prog->red_stride, prog->red_cnt, prog->n_flat,
+                                    gflat, stream);
+        };
+        if (rc) rc->post.push_back(fn);
+        else PROG_CALL(fn());
+    }
     return HGNN_OK;
+}
+
+extern "C" int hgnn_program_bwd(const hgnn_program_t* prog, const hgnn_batch_t* b, const float* X, const float* XL,
+                                const long long* addr, const float* work, float* gwork, double* arena,
+                                const float* g_out, float* gX, float* gflat, void* rng_scratch,
+                                long long rng_scratch_bytes, hgnn_stream_t stream) {
+    cudaStream_t s = to_stream(stream);
+    // the pre-pass of the implementation refuses (before launching anything) programs it cannot record
+    if (prog && b && prog->sides && prog->tensors && replay_wanted(prog, b, s)) {
+        ReplayCtx rc;
+        hgnn_eng_set_recorder(&rc.rec);
+        const int r = program_bwd_impl(prog, b, X, XL, addr, work, gwork, arena, g_out, gX, gflat, rng_scratch,
+                                       rng_scratch_bytes, stream, &rc);
+        hgnn_eng_set_recorder(nullptr);
+        if (r == HGNN_OK) return replay_finish(prog, 1, rc, s);
+        if (!rc.restartable) return r;     // failed after a non-idempotent direct launch
+    }
+    return program_bwd_impl(prog, b, X, XL, addr, work, gwork, arena, g_out, gX, gflat, rng_scratch, rng_scratch_bytes,
+                            stream, nullptr);
 }
