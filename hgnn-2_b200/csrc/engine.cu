@@ -964,6 +964,7 @@ bwd_kernel(const BwdArgs a) {
 
 #include "engine_row4.cuh"
 #include "engine_rowg.cuh"
+#include "engine_quad.cuh"
 #include "engine_wide.cuh"
 #include "engine_tc5.cuh"
 
@@ -1117,6 +1118,32 @@ static bool eng_try_fwd_row4(const eng::FwdArgs& g, const hgnn_side_t* side, hgn
     if (ablate < 0) { const char* e = getenv("HGNN_B200_ABLATE"); ablate = e ? atoi(e) : 0; }
     a.ablate = ablate;
     cudaStream_t s = to_stream(stream);
+    // several lanes per row (engine_quad.cuh): one CSR operator, no saved x1 rows.  Opt-in (HGNN_B200_QUAD=1;
+    // HGNN_B200_QUAD_LPR=<heavy>,<light> picks the lanes per row): measured SLOWER on C2 - node side 11.4 vs 7.6 us,
+    // edge side 16.0 vs 7.2 us with 4 lanes, 10.6 / 10.6 us with 2 (profiles/logs/bench_r2x_quad*.log).  ncu
+    // (profiles/prof_quad_r2y_raw.csv): 2.7x the warp instructions of the thread-per-row kernel (4.2 M vs 1.6 M: every
+    // lane repeats the structure loads, address arithmetic and the batch-norm prologue) at 1.8x its issue rate.
+    static int quad = -1, lpr_heavy = 4, lpr_light = 2;
+    if (quad < 0) {
+        const char* e = getenv("HGNN_B200_QUAD");
+        quad = (e && e[0] == '1') ? 1 : 0;
+        const char* l = getenv("HGNN_B200_QUAD_LPR");
+        if (l) { lpr_heavy = atoi(l); const char* c = strchr(l, ','); lpr_light = c ? atoi(c + 1) : lpr_heavy; }
+    }
+    if (quad && a.n_csr == 1 && !a.X1 && !a.ablate) {
+        const double per_row = a.R > 0 ? ((double)side->ops[2].nnz + (cross ? (double)side->p_nnz : 0.0)) / a.R : 0.0;
+        const int lpr = per_row > 8.0 ? lpr_heavy : lpr_light;
+#define QD_FWD(CROSS, LPR, JA, JP)                                                                                   \
+        {                                                                                                            \
+            const int rpc = QD_THREADS / LPR;                                                                        \
+            const int cap = eng_resident_impl((const void*)eng::fwd_quad_kernel<CROSS, LPR, JA, JP>, 0, QD_THREADS); \
+            const int grid = min(ceil_div(a.R, rpc), cap);                                                           \
+            eng_launch(eng::fwd_quad_kernel<CROSS, LPR, JA, JP>, grid, QD_THREADS, 0, s, a);                         \
+        }
+        if (lpr == 4) { if (cross) QD_FWD(true, 4, 2, 4) else QD_FWD(false, 4, 2, 1) return true; }
+        if (lpr == 2) { if (cross) QD_FWD(true, 2, 2, 2) else QD_FWD(false, 2, 4, 1) return true; }
+#undef QD_FWD
+    }
     const int want = ceil_div(a.R, R4_THREADS);
     // entries per gather batch from the average row length (nnz hints; unknown -> 4): a typical row
     // should fit ONE batch so that its loads form three dependent rounds in total

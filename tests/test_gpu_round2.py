@@ -208,7 +208,7 @@ def test_batch_loader_with_power_operators_is_race_free():
 
 
 @pytest.mark.parametrize("env", [{"HGNN_B200_MEGA": "1"}, {"HGNN_B200_BWD_V2": "1"}, {"HGNN_B200_NO_COLLAPSE": "1"},
-                                 {"HGNN_B200_REPLAY": "1"}])
+                                 {"HGNN_B200_REPLAY": "1"}, {"HGNN_B200_QUAD": "1"}])
 def test_opt_in_kernel_variants_keep_parity(env):
     """The code paths that are not the default - persistent cooperative kernels (csrc/mega.cu), the low-register
     backward, the uncollapsed line graph - are switched by environment variables read once per process, so the
