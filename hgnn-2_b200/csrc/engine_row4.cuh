@@ -269,6 +269,7 @@ fwd_row4_kernel(const Fwd4Args a) {
     __shared__ __align__(16) float W[4 * NB * 4];       // [o][Cin]
     __shared__ __align__(16) float bias[4];
     __shared__ double red[(R4_THREADS / 32) * 8];
+    __shared__ __align__(16) float bnv[16];            // self: scale, shift | cross: scale, shift (one warp each computes them)
     const int tid = threadIdx.x;
     pdl_launch_dependents();
     // ---- phase 0
@@ -308,24 +309,32 @@ fwd_row4_kernel(const Fwd4Args a) {
     if (row < a.R) load_structure(row);
     // ---- phase 1: everything the producer wrote
     pdl_wait();
-    ls.issue_acc(a.bn_s);
-    if (CROSS) lc.issue_acc(a.bn_c);
+    // batch-norm vectors of the inputs: warp 0 (self) and warp 1 (cross) derive them - fp64 sums, divide, rsqrt: ~100
+    // instructions - and publish them in shared memory; every thread of every warp used to repeat that
+    const int warp_id = tid >> 5;
+    if (warp_id == 0) ls.issue_acc(a.bn_s);
+    if (CROSS && warp_id == 1) lc.issue_acc(a.bn_c);
     float4 xs_raw = f4_zero();
     if (row < a.R) {
         xs_raw = ld4(a.Xs + (size_t)rr * 4);
         if (NCSR > 0) ga.load_rows(a.Xs);
         if (CROSS) gb.load_rows(a.Xc);
     }
-    Bn4 bs4, bc4;
-    if (a.ablate & 2) {
-        bs4.sc = bs4.rs = make_float4(1.f, 1.f, 1.f, 1.f); bs4.sh = bs4.mu = f4_zero(); bc4 = bs4;
-    } else {
-        bs4 = ls.resolve(a.bn_s);
-        bc4 = bs4;
-        if (CROSS) bc4 = lc.resolve(a.bn_c);
+    if (warp_id == 0) {
+        Bn4 v;
+        if (a.ablate & 2) { v.sc = make_float4(1.f, 1.f, 1.f, 1.f); v.sh = f4_zero(); }
+        else v = ls.resolve(a.bn_s);
+        if (tid == 0) { *reinterpret_cast<float4*>(bnv) = v.sc; *reinterpret_cast<float4*>(bnv + 4) = v.sh; }
+    } else if (CROSS && warp_id == 1) {
+        Bn4 v;
+        if (a.ablate & 2) { v.sc = make_float4(1.f, 1.f, 1.f, 1.f); v.sh = f4_zero(); }
+        else v = lc.resolve(a.bn_c);
+        if ((tid & 31) == 0) { *reinterpret_cast<float4*>(bnv + 8) = v.sc; *reinterpret_cast<float4*>(bnv + 12) = v.sh; }
     }
-    __syncthreads();                                   // weights in shared memory
-    const float4 sc_s = bs4.sc, sh_s = bs4.sh, sc_c = bc4.sc, sh_c = bc4.sh;
+    __syncthreads();                                   // weights and batch-norm vectors in shared memory
+    const float4 sc_s = *reinterpret_cast<const float4*>(bnv), sh_s = *reinterpret_cast<const float4*>(bnv + 4);
+    const float4 sc_c = CROSS ? *reinterpret_cast<const float4*>(bnv + 8) : sc_s;
+    const float4 sh_c = CROSS ? *reinterpret_cast<const float4*>(bnv + 12) : sh_s;
     float s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
 
     for (bool first = true; row < a.R; row += stride, first = false) {
@@ -559,39 +568,43 @@ bwd_row4_kernel(const Bwd4Args a) {
         }
     }
     pdl_wait();
-    // ---- coefficients of this side's BN + ReLU backward, and the input's BN vectors: warp-level
+    // ---- coefficients of this side's BN + ReLU backward (warp 0) and the input's BN vectors (warp 1), once per CTA,
+    //      published in shared memory (every thread used to derive both: ~300 instructions with the fp64 sums)
+    __shared__ __align__(16) float cv[28];             // c0, c1, c2 | scale, shift, mean, 1/std
     Gpre4 gp;
     gp.relu_from = a.relu_from; gp.bn = a.has_bn != 0; gp.need_z = a.has_bn != 0 || a.relu_from < 4;
     gp.G = a.gY; gp.Z = a.Z;
-    if (a.has_bn) {
-        double tf[8], tb[8];
-        warp_totals8(a.acc_f, tf);
-        warp_totals8(a.acc_b, tb);
-        const float w = a.bn_w[0];
-        const double inv_n = 1.0 / (double)a.Rg;
-        float c0[4], c1[4], c2[4];
-#pragma unroll
-        for (int f = 0; f < 4; ++f) {
+    if (warp == 0) {
+        float c0 = 1.f, c1 = 0.f, c2 = 0.f;
+        if (a.has_bn) {
+            double tf[8], tb[8];
+            warp_totals8(a.acc_f, tf);
+            warp_totals8(a.acc_b, tb);
+            const float w = a.bn_w[0];
+            const double inv_n = 1.0 / (double)a.Rg;
+            const int f = lane & 3;
             const double m = tf[f] * inv_n;
             const double var = fma(-m, m, tf[4 + f] * inv_n);
             const float r_ = 1.0f / sqrtf(fmaxf((float)var, 0.f) + (float)ENG_BN_EPS);
             const float k0 = w * r_;
             const float k2 = -k0 * (float)(tb[4 + f] * inv_n) * r_;
-            c0[f] = k0;
-            c2[f] = k2;
-            c1[f] = -k0 * (float)(tb[f] * inv_n) - k2 * (float)m;
+            c0 = k0;
+            c2 = k2;
+            c1 = -k0 * (float)(tb[f] * inv_n) - k2 * (float)m;
         }
-        gp.c0 = make_float4(c0[0], c0[1], c0[2], c0[3]);
-        gp.c1 = make_float4(c1[0], c1[1], c1[2], c1[3]);
-        gp.c2 = make_float4(c2[0], c2[1], c2[2], c2[3]);
-    } else {
-        gp.c0 = make_float4(1.f, 1.f, 1.f, 1.f);
-        gp.c1 = f4_zero();
-        gp.c2 = f4_zero();
+        if (lane < 4) { cv[lane] = c0; cv[4 + lane] = c1; cv[8 + lane] = c2; }
+    } else if (warp == 1) {
+        const Bn4 bx = bn4_from_ref(is_self ? a.bn_s : a.bn_c);
+        if (lane == 0) {
+            *reinterpret_cast<float4*>(cv + 12) = bx.sc; *reinterpret_cast<float4*>(cv + 16) = bx.sh;
+            *reinterpret_cast<float4*>(cv + 20) = bx.mu; *reinterpret_cast<float4*>(cv + 24) = bx.rs;
+        }
     }
-    const Bn4 bx = bn4_from_ref(is_self ? a.bn_s : a.bn_c);
-    __syncthreads();                                   // weights in shared memory
-    const float4 sc = bx.sc, sh = bx.sh, mu = bx.mu, rs = bx.rs;
+    __syncthreads();                                   // weights and coefficient vectors in shared memory
+    gp.c0 = *reinterpret_cast<const float4*>(cv); gp.c1 = *reinterpret_cast<const float4*>(cv + 4);
+    gp.c2 = *reinterpret_cast<const float4*>(cv + 8);
+    const float4 sc = *reinterpret_cast<const float4*>(cv + 12), sh = *reinterpret_cast<const float4*>(cv + 16);
+    const float4 mu = *reinterpret_cast<const float4*>(cv + 20), rs = *reinterpret_cast<const float4*>(cv + 24);
 
     if (is_range) {
         // ---- a range CTA: sum gPre over each of its ranges (4 rows = 8 loads in flight per thread), publish the
