@@ -963,6 +963,7 @@ bwd_kernel(const BwdArgs a) {
 }
 
 #include "engine_row4.cuh"
+#include "engine_row4p.cuh"
 #include "engine_rowg.cuh"
 #include "engine_quad.cuh"
 #include "engine_wide.cuh"
@@ -1608,6 +1609,30 @@ static bool eng_try_bwd_row4(const hgnn_side_bwd_t* d, hgnn_stream_t stream) {
 #undef R4C_BWD
         return true;
     }
+    // pipelined variant (engine_row4p.cuh): one CSR operator, no run-length part, weight gradients in the same launch.
+    // HGNN_B200_BWD_P=0 switches back to bwd_row4_kernel.
+    static int pvar = -1;
+    if (pvar < 0) { const char* e = getenv("HGNN_B200_BWD_P"); pvar = (e && e[0] == '0') ? 0 : 1; }
+    if (pvar && a.n_csr == 1 && !a.rng_rowptr && a.range_ctas == 0 && !d->skip_dw && !(a.ablate & 7)) {
+#define R4P_BWD(GB, CB)                                                                                   \
+        {                                                                                                 \
+            const int cap = eng_resident_impl((const void*)eng::bwd_row4p_kernel<GB, CB>, 0, R4_THREADS); \
+            int grid = (int)min((long long)cap, (rows + R4_THREADS - 1) / R4_THREADS);                    \
+            if (d->R_cross > 0 && grid < 2) grid = 2;                                                     \
+            a.ctas_self = eng_split_ctas(grid, (long long)act_s, d->R_cross > 0 ? (long long)act_c : 0, cost_s, cost_c); \
+            if (d->R_cross <= 0) a.ctas_self = grid;                                                      \
+            if (debug_split)                                                                              \
+                fprintf(stderr, "bwd_row4p split: cap %d grid %d R_self %d R_cross %d avg_s %.3f avg_c %.3f -> ctas_self %d\n", \
+                        cap, grid, d->R_self, d->R_cross, avg_s, avg_c, a.ctas_self);                     \
+            eng_launch(eng::bwd_row4p_kernel<GB, CB>, grid, R4_THREADS, 0, s, a);                         \
+        }
+        // batch sizes: 2 entries for the transposed CSR operator (more spills under the 128-register bound); the incidence
+        // pattern takes 2 when its rows are line-graph nodes (two end points each), else 4.  HGNN_B200_BWD_BATCH: 3 = (4, 4),
+        // 2 = (2, 8) (both spill; measurement only), 5 = (2, 2), 0 = (2, 4).
+        if (mid_s) R4P_BWD(4, 4) else if (big_c) R4P_BWD(2, 8) else if (bforce == 5 || (bforce < 0 && avg_c <= 2.5)) R4P_BWD(2, 2) else R4P_BWD(2, 4)
+#undef R4P_BWD
+        return true;
+    }
 #define R4_BWD_B(NCSR, DW)                                                                                \
     if (big_s) R4_BWD(NCSR, DW, 8, 4) else if (big_c) R4_BWD(NCSR, DW, 2, 8) else if (mid_s) R4_BWD(NCSR, DW, 4, 4) else R4_BWD(NCSR, DW, 2, 4)
     if (d->skip_dw) { if (a.n_csr == 1) { R4_BWD_B(1, false) } else { R4_BWD_B(2, false) } }
@@ -1682,7 +1707,7 @@ extern "C" int hgnn_debug_cta_times(unsigned long long* out, int n) {
     return HGNN_OK;
 }
 
-// (end of the row loop ns, end of the range phase ns, flagged rows) of the self CTAs of the same launch
+// (end of the row loop ns, end of the range phase ns, coefficient vectors ready ns) of the row CTAs of the same launch
 extern "C" int hgnn_debug_cta_phases(unsigned long long* out, int n) {
     HGNN_REQUIRE(out && n > 0 && n <= 2048, "bad argument");
     cudaError_t e = cudaMemcpyFromSymbol(out, eng::g_cta_phase, (size_t)n * 3 * sizeof(unsigned long long));

@@ -9,6 +9,7 @@
 // no shared-memory tile and no barrier in the row loop.  Loads are issued in three dependent
 // rounds (row pointers -> entries -> feature rows), batches of up to 4 entries in flight.
 #pragma once
+#include "engine_mma.cuh"
 
 #define R4_THREADS 128
 
@@ -499,7 +500,7 @@ __device__ __forceinline__ float4 gpre_gather(const Gpre4& gp, const int* __rest
 // over the x1 rows saved by the forward on a parallel graph branch): ~48 fewer live registers.
 // profiling aid (HGNN_B200_ABLATE bit 8): per-CTA start / end / role of the last backward launch
 __device__ unsigned long long g_cta_times[2048 * 3];
-__device__ unsigned long long g_cta_phase[2048 * 3];   // end of row loop, end of range phase, number of flagged rows
+__device__ unsigned long long g_cta_phase[2048 * 3];   // end of row loop, end of range phase (cross CTAs: = row loop), coefficients ready
 __device__ __forceinline__ unsigned long long global_ns() {
     unsigned long long t;
     asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
@@ -605,6 +606,7 @@ bwd_row4_kernel(const Bwd4Args a) {
     gp.c2 = *reinterpret_cast<const float4*>(cv + 8);
     const float4 sc = *reinterpret_cast<const float4*>(cv + 12), sh = *reinterpret_cast<const float4*>(cv + 16);
     const float4 mu = *reinterpret_cast<const float4*>(cv + 20), rs = *reinterpret_cast<const float4*>(cv + 24);
+    if ((a.ablate & 8) && tid == 0 && blockIdx.x < 2048) g_cta_phase[blockIdx.x * 3 + 2] = global_ns();   // coefficients ready
 
     if (is_range) {
         // ---- a range CTA: sum gPre over each of its ranges (4 rows = 8 loads in flight per thread), publish the
@@ -835,7 +837,6 @@ bwd_row4_kernel(const Bwd4Args a) {
         }
         if ((a.ablate & 8) && tid == 0 && blockIdx.x < 2048) {
             g_cta_phase[blockIdx.x * 3 + 1] = global_ns();
-            g_cta_phase[blockIdx.x * 3 + 2] = (unsigned long long)n_flagged;
         }
     } else {
         float* const gX = a.gXc;
@@ -904,6 +905,7 @@ bwd_row4_kernel(const Bwd4Args a) {
                 }
             }
         }
+        if ((a.ablate & 8) && tid == 0 && blockIdx.x < 2048) g_cta_phase[blockIdx.x * 3] = g_cta_phase[blockIdx.x * 3 + 1] = global_ns();
     }
     // ---- flush: warp shuffle tree -> per-warp rows in shared memory -> one fp64 atomic per value
     const int nvals = is_self ? NT * 16 : 32;
@@ -950,17 +952,21 @@ bwd_row4_kernel(const Bwd4Args a) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// backward, low-register variant (one CSR operator, no run-length part: A^T, or the collapsed AL^T)
+// backward with the weight-gradient reduction on the tensor cores (one CSR operator, no run-length part: A^T, or
+// the collapsed AL^T)
 // ---------------------------------------------------------------------------------------------
-// bwd_row4_kernel keeps 48 + 12 per-thread accumulators (dW, dbias, batch-norm sums) alive across its rows:
-// 125 registers, 4 CTAs of 128 threads per SM, and with ~112 k rows per launch at the C2 workload half of the
-// threads walk two rows one after the other (ncu: warps active 20 %, long-scoreboard bound).  Here a thread keeps
-// NOTHING across rows: it writes the 24 per-row values the sums are made of - T (12), g (4), w*xn (4), w*xhat (4) -
-// into a warp-private shared-memory tile, and after a __syncwarp every lane accumulates two of the 52 products
-//   dW[t][o][f] = sum_rows T[t][o] * (w xn[f])            (48)
-//   sum g xhat[f] = sum_rows g[f] * (w xhat[f])           (4)
-// over the 32 rows of the tile (float4 shared loads, 2 registers of state).  dbias and sum g stay in 8 registers.
-// ~80 registers -> 6 CTAs per SM: every row of a launch is in flight at once.
+// bwd_row4_kernel keeps 48 + 12 per-thread accumulators (dW, dbias, batch-norm sums) alive across its rows and folds
+// them at the end with reduce-scatter butterflies: ncu attributes 22 % of all executed warp instructions of the
+// kernel to that flush (profiles/README.md round 2, item 10) - paid per warp, and a warp walks only 1-2 rows per
+// thread.  The sums are an outer-product reduction over the rows of a warp,
+//   dW[t][o][f]   = sum_rows T[t][o] * (w xn[f])        (12 x 4)
+//   sum g xhat[f] = sum_rows g[f] * (w xhat[f])         (diagonal of 4 x 4)
+// i.e. C (16 x 8) = A^T B with A = [T | g] (32 rows x 16) and B = [w xn | w xhat] (32 rows x 8): exactly one
+// mma.m16n8k8 tile, K = the 32 lanes.  So per iteration every lane writes its 24 values into a warp-private
+// shared-memory tile (conflict-free: value j of lane l at j * 36 + l), the warp loads the A / B fragments back
+// (4 k-steps x 6 LDS), splits them (3xTF32: x = hi + lo, lo*hi + hi*lo + hi*hi - fp32-grade, as in engine_wide.cuh) and
+// issues 12 mma.sync; C lives in 4 registers.  ~120 instructions per iteration against 60 FMA + a 450-instruction
+// flush; no accumulator arrays (80 registers -> 6 CTAs of 128 threads per SM).  dbias and sum g stay in 8 registers.
 #define R4C_STRIDE 36                 // floats per tile column block (32 rows + pad, 16-byte aligned)
 #define R4C_VALS 24
 template <int GB, int CB>
@@ -1021,12 +1027,8 @@ bwd_row4c_kernel(const Bwd4Args a) {
     gp.c2 = *reinterpret_cast<const float4*>(vec + 8);
 
     float* const my = tile + warp * (R4C_VALS * R4C_STRIDE);
-    // the two products of this lane: k < 48: T value (k >> 2) x (w xn)[k & 3];  48..51: g[k - 48] x (w xhat)[k - 48]
-    const int k2nd = lane + 32;
-    const int a1 = lane >> 2, b1 = 16 + (lane & 3);
-    const int a2 = k2nd < 48 ? (k2nd >> 2) : 12 + (k2nd - 48), b2 = k2nd < 48 ? 16 + (k2nd & 3) : 20 + (k2nd - 48);
-    const bool two = k2nd < 52;
-    float acc1 = 0.f, acc2 = 0.f;
+    const int fg = lane >> 2, ft = lane & 3;            // fragment coordinates of mma.m16n8k8
+    float cfr[4] = {0.f, 0.f, 0.f, 0.f};                 // C fragment: (fg, 2ft) (fg, 2ft+1) (fg+8, 2ft) (fg+8, 2ft+1)
     float db[4] = {0.f, 0.f, 0.f, 0.f}, sg[4] = {0.f, 0.f, 0.f, 0.f};
 
     const int R = is_self ? a.R_self : a.R_cross;
@@ -1131,36 +1133,39 @@ bwd_row4c_kernel(const Bwd4Args a) {
             for (int j = 0; j < R4C_VALS; ++j) my[j * R4C_STRIDE + lane] = v[j];
         }
         __syncwarp();
-        {
-            const float4* pa = reinterpret_cast<const float4*>(my + a1 * R4C_STRIDE);
-            const float4* pb = reinterpret_cast<const float4*>(my + b1 * R4C_STRIDE);
-            float s0 = 0.f, s1 = 0.f;
 #pragma unroll
-            for (int q = 0; q < 8; ++q) {
-                const float4 x = pa[q], y = pb[q];
-                s0 = fmaf(x.x, y.x, s0); s1 = fmaf(x.y, y.y, s1); s0 = fmaf(x.z, y.z, s0); s1 = fmaf(x.w, y.w, s1);
-            }
-            acc1 += s0 + s1;
-            if (two) {
-                const float4* qa = reinterpret_cast<const float4*>(my + a2 * R4C_STRIDE);
-                const float4* qb = reinterpret_cast<const float4*>(my + b2 * R4C_STRIDE);
-                float u0 = 0.f, u1 = 0.f;
+        for (int pr = 0; pr < 2; ++pr) {                 // two pairs of k-steps (8 lanes = 8 rows each)
+            uint32_t ah[2][4], al[2][4];
+            SplitB bb[2];
 #pragma unroll
-                for (int q = 0; q < 8; ++q) {
-                    const float4 x = qa[q], y = qb[q];
-                    u0 = fmaf(x.x, y.x, u0); u1 = fmaf(x.y, y.y, u1); u0 = fmaf(x.z, y.z, u0); u1 = fmaf(x.w, y.w, u1);
-                }
-                acc2 += u0 + u1;
+            for (int h = 0; h < 2; ++h) {
+                const int k0 = 8 * (2 * pr + h) + ft;
+#pragma unroll
+                for (int e = 0; e < 4; ++e)
+                    tf32_split(my[(fg + 8 * (e & 1)) * R4C_STRIDE + k0 + 4 * (e >> 1)], ah[h][e], al[h][e]);
+                bb[h] = split_b(my[(16 + fg) * R4C_STRIDE + k0], my[(16 + fg) * R4C_STRIDE + k0 + 4]);
             }
+            mma_3xtf32_fresh_pair(cfr, ah[0], al[0], bb[0], ah[1], al[1], bb[1]);
         }
     }
-    // ---- flush: products are already warp totals (lane l: k = l and l + 32); dbias / sum g by shuffles
+    // ---- flush: the C fragment holds the warp totals; dbias / sum g by shuffles.  red[warp]: [0, 48) dW (m * 4 + f),
+    //      [48, 52) sum g xhat, [52, 56) dbias, [56, 60) sum g
     float extra[8];
 #pragma unroll
     for (int f = 0; f < 4; ++f) { extra[f] = db[f]; extra[4 + f] = sg[f]; }
     warp_reduce_scatter<float, 8>(extra);                // lane l: total of value l >> 2
-    red[warp * 64 + lane] = acc1;
-    if (two) red[warp * 64 + 32 + lane] = acc2;
+    if (ft < 2) {                                        // columns 0..3 = dW
+        red[warp * 64 + fg * 4 + 2 * ft] = cfr[0];
+        red[warp * 64 + fg * 4 + 2 * ft + 1] = cfr[1];
+        if (fg < 4) {
+            red[warp * 64 + (fg + 8) * 4 + 2 * ft] = cfr[2];
+            red[warp * 64 + (fg + 8) * 4 + 2 * ft + 1] = cfr[3];
+        }
+    } else if (fg >= 4) {                                // rows 12..15 x columns 4..7: the diagonal is sum g xhat
+        const int f = fg - 4;                            // row 12 + f = fg + 8, column 4 + f
+        if (2 * ft == 4 + f) red[warp * 64 + 48 + f] = cfr[2];
+        if (2 * ft + 1 == 4 + f) red[warp * 64 + 48 + f] = cfr[3];
+    }
     if ((lane & 3) == 0) red[warp * 64 + 52 + (lane >> 2)] = extra[0];
     __syncthreads();
     const int nbw = hgnn_ws_bins(4 * a.Cin);

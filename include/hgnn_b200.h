@@ -266,7 +266,8 @@ int hgnn_lg_side_bwd(const hgnn_side_bwd_t* desc, hgnn_stream_t stream);
 /* profiling aid (HGNN_B200_ABLATE bit 8): (start ns, end ns, is_self) of the first n <= 2048 CTAs of the last
  * width-4 backward launch, copied to the HOST array out (3 n values); synchronises the device */
 int hgnn_debug_cta_times(unsigned long long* out, int n);
-/* same launch, self CTAs: (end of the row loop ns, end of the range phase ns, number of flagged rows) */
+/* same launch, row CTAs: (end of the row loop ns, end of the range phase ns [cross CTAs: = row loop], batch-norm /
+ * gPre coefficient vectors ready ns) */
 int hgnn_debug_cta_phases(unsigned long long* out, int n);
 
 /* out[i] = sum_{b<nb[i]} sum_{c<cnt[i]} arena[off[i] + b*stride[i] + c]: every binned accumulator of
