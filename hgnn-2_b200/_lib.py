@@ -108,6 +108,7 @@ _SIGS = {
     "hgnn_lg_side_bwd": [ctypes.POINTER(SideBwdT), _P],
     "hgnn_debug_cta_times": [_P, c_int],
     "hgnn_debug_cta_phases": [_P, c_int],
+    "hgnn_debug_ktrace": [_P, c_int, c_int],
     "hgnn_bins_reduce": [_P, _P, _P, _P, _P, c_int, _P, _P],
     "hgnn_bn_running_update": [_P, _P, _P, _P, _P, c_int, c_float, _P, _P],
     "hgnn_readout_bwd_prep": [_P, c_int, c_int, _P, _P, _P, _P, _P],

@@ -107,19 +107,44 @@ static inline int make_oplist(const hgnn_op_t* ops, int n_ops, OpList* out) {
 // runs the finalizer in the same launch.
 #define HGNN_WS_HEADER 256
 
-// number of accumulator bins for a reduction of `width` values (host and device agree on this):
-// 32 / width rounded down to a power of two, at least 1 - i.e. small reductions (the 2F batch-norm
-// sums) spread over a few bins so that nb*width = 32 doubles = one load per lane of a warp, wide
-// ones (dW) use a single bin: same-address fp64 RED throughput (~1 op/clk at the L2 slice) is ample
-// for the <= ~1000 CTAs of a launch.
+// number of accumulator bins for a reduction of `width` values (host and device agree on this).  Every CTA of a launch
+// ends with fire-and-forget fp64 reductions into its bin, and the launch is complete - its dependent released - only when
+// the L2 atomic units have worked through all of them.  A launch of ~600 CTAs used to send 28 k reductions at the five
+// cache lines of a single 80-value dW block: the dependent launch was released 1.8 us after the last CTA had exited instead
+// of 0.7 us (profiles/logs/step_timeline_r3e.log vs _r3g).  So:
+//   width <= 16 (the 2F batch-norm sums, dbias): bins x width = HGNN_WS_SMALL_DOUBLES = 32 doubles (width 8: 4 bins, one
+//                load per lane of a consumer warp, hgnn_bins8_lane).  128 doubles (16 bins, four loads per lane) measured
+//                SLOWER on C2: 0.629 vs 0.610 ms per step (profiles/logs/bench_r3i_*.log);
+//   width <= 256 (the dW of a narrow side): 8 bins;
+//   wider (dW of a wide side: one bin is already hundreds of cache lines): 1 bin.
+#ifndef HGNN_WS_SMALL_DOUBLES
+#define HGNN_WS_SMALL_DOUBLES 32
+#endif
+#define HGNN_WS_WIDE_BINS 8
 __host__ __device__ inline int hgnn_ws_bins(int width) {
+    if (width > 256) return 1;
+    if (width > 16) return HGNN_WS_WIDE_BINS;
     int nb = 1;
-    while (nb * 2 * width <= 32) nb *= 2;
+    while (nb * 2 * width <= HGNN_WS_SMALL_DOUBLES) nb *= 2;
     return nb;
 }
 
 __device__ __forceinline__ void accum_add(double* accum, int width, int nb, int idx, double v) {
     atomicAdd(accum + (size_t)(blockIdx.x & (nb - 1)) * width + idx, v);
+}
+
+// One warp reads a width-8 accumulator block (hgnn_ws_bins(8) bins x 8 doubles): lane l sums the entries l, l + 32, ... -
+// independent loads - so that lanes with equal (l & 7) hold parts of column l & 7; fold them with xor 8 and xor 16.
+__device__ __forceinline__ double hgnn_bins8_lane(const double* __restrict__ acc) {
+    constexpr int N = HGNN_WS_SMALL_DOUBLES / 32;
+    const int lane = threadIdx.x & 31;
+    double part[N];
+#pragma unroll
+    for (int j = 0; j < N; ++j) part[j] = __ldcg(acc + lane + 32 * j);
+    double v = part[0];
+#pragma unroll
+    for (int j = 1; j < N; ++j) v += part[j];
+    return v;
 }
 
 // last CTA only: total of column idx over the bins (fixed order), re-zeroing as it goes

@@ -1075,6 +1075,13 @@ static void eng_launch(Kernel kernel, int grid, int threads, size_t smem, cudaSt
     cudaLaunchKernelEx(&cfg, kernel, a);
 }
 
+// ---- launch timeline (HGNN_B200_ABLATE bit 16): one g_ktrace slot per traced launch, in issue order -------------
+static int g_ktrace_next = 0;
+static int eng_trace_slot(int ablate) {
+    if (!(ablate & 16) || g_ktrace_next >= KTRACE_SLOTS) return -1;
+    return g_ktrace_next++;
+}
+
 // ---- thread-per-row fast path for width-4 states (h = 2) ---------------------------------------
 static bool eng_row4_ops(const hgnn_op_t* ops, int n_ops) {
     if (n_ops < 3 || n_ops > 4) return false;
@@ -1117,7 +1124,8 @@ static bool eng_try_fwd_row4(const eng::FwdArgs& g, const hgnn_side_t* side, hgn
     a.roww = side->roww; a.rowmap = side->rowmap;
     static int ablate = -1;
     if (ablate < 0) { const char* e = getenv("HGNN_B200_ABLATE"); ablate = e ? atoi(e) : 0; }
-    a.ablate = ablate;
+    a.ablate = ablate & ~16;
+    a.trace_slot = eng_trace_slot(ablate);
     cudaStream_t s = to_stream(stream);
     // several lanes per row (engine_quad.cuh): one CSR operator, no saved x1 rows.  Opt-in (HGNN_B200_QUAD=1;
     // HGNN_B200_QUAD_LPR=<heavy>,<light> picks the lanes per row): measured SLOWER on C2 - node side 11.4 vs 7.6 us,
@@ -1194,7 +1202,7 @@ static bool eng_try_fwd_rowg(const eng::FwdArgs& g, const hgnn_side_t* side, hgn
     a.Xs = g.Xs; a.bn_s = g.bn_s;
     a.p_rowptr = g.p_rowptr; a.p_col = g.p_col; a.p_pm = g.p_pm; a.p_pd = g.p_pd; a.Xc = g.Xc; a.bn_c = g.bn_c;
     a.Wa = g.Wa; a.ba = g.ba; a.Ha = g.Ha; a.Wb = g.Wb; a.bb = g.bb; a.Hb = g.Hb;
-    a.relu_from = g.relu_from; a.Cin = g.Cin; a.Z = g.Z; a.acc_out = g.acc_out; a.X1 = nullptr; a.ablate = 0;
+    a.relu_from = g.relu_from; a.Cin = g.Cin; a.Z = g.Z; a.acc_out = g.acc_out; a.X1 = nullptr; a.ablate = 0; a.trace_slot = -1;
     a.roww = side->roww; a.rowmap = side->rowmap;
     cudaStream_t s = to_stream(stream);
     const int want = ceil_div(a.R, R4_THREADS);
@@ -1547,7 +1555,8 @@ static bool eng_try_bwd_row4(const hgnn_side_bwd_t* d, hgnn_stream_t stream) {
     }
     static int ablate = -1;
     if (ablate < 0) { const char* e = getenv("HGNN_B200_ABLATE"); ablate = e ? atoi(e) : 0; }
-    a.ablate = ablate;
+    a.ablate = ablate & ~16;
+    a.trace_slot = -1;
     cudaStream_t s = to_stream(stream);
     const long long rows = (long long)d->R_self + (d->R_cross > 0 ? d->R_cross : 0);
     // The CTAs of one launch are split between the two parts in proportion to their estimated cost, not
@@ -1614,9 +1623,9 @@ static bool eng_try_bwd_row4(const hgnn_side_bwd_t* d, hgnn_stream_t stream) {
     static int pvar = -1;
     if (pvar < 0) { const char* e = getenv("HGNN_B200_BWD_P"); pvar = (e && e[0] == '0') ? 0 : 1; }
     if (pvar && a.n_csr == 1 && !a.rng_rowptr && a.range_ctas == 0 && !d->skip_dw && !(a.ablate & 7)) {
-#define R4P_BWD(GB, CB)                                                                                   \
+#define R4P_BWD_(GB, CB, RMW)                                                                                  \
         {                                                                                                 \
-            const int cap = eng_resident_impl((const void*)eng::bwd_row4p_kernel<GB, CB>, 0, R4_THREADS); \
+            const int cap = eng_resident_impl((const void*)eng::bwd_row4p_kernel<GB, CB, RMW>, 0, R4_THREADS); \
             int grid = (int)min((long long)cap, (rows + R4_THREADS - 1) / R4_THREADS);                    \
             if (d->R_cross > 0 && grid < 2) grid = 2;                                                     \
             a.ctas_self = eng_split_ctas(grid, (long long)act_s, d->R_cross > 0 ? (long long)act_c : 0, cost_s, cost_c); \
@@ -1624,13 +1633,18 @@ static bool eng_try_bwd_row4(const hgnn_side_bwd_t* d, hgnn_stream_t stream) {
             if (debug_split)                                                                              \
                 fprintf(stderr, "bwd_row4p split: cap %d grid %d R_self %d R_cross %d avg_s %.3f avg_c %.3f -> ctas_self %d\n", \
                         cap, grid, d->R_self, d->R_cross, avg_s, avg_c, a.ctas_self);                     \
-            eng_launch(eng::bwd_row4p_kernel<GB, CB>, grid, R4_THREADS, 0, s, a);                         \
+            a.trace_slot = eng_trace_slot(ablate);                                                        \
+            eng_launch(eng::bwd_row4p_kernel<GB, CB, RMW>, grid, R4_THREADS, 0, s, a);                         \
         }
         // batch sizes: 2 entries for the transposed CSR operator (more spills under the 128-register bound); the incidence
         // pattern takes 2 when its rows are line-graph nodes (two end points each), else 4.  HGNN_B200_BWD_BATCH: 3 = (4, 4),
         // 2 = (2, 8) (both spill; measurement only), 5 = (2, 2), 0 = (2, 4).
+        static int rmw = -1;
+        if (rmw < 0) { const char* e = getenv("HGNN_B200_BWD_RMW"); rmw = (e && e[0] == '1') ? 1 : 0; }   // measured equal on C2 (0.634 vs 0.630 ms per step); the reduction form spills less
+#define R4P_BWD(GB, CB) { if (rmw) R4P_BWD_(GB, CB, true) else R4P_BWD_(GB, CB, false) }
         if (mid_s) R4P_BWD(4, 4) else if (big_c) R4P_BWD(2, 8) else if (bforce == 5 || (bforce < 0 && avg_c <= 2.5)) R4P_BWD(2, 2) else R4P_BWD(2, 4)
 #undef R4P_BWD
+#undef R4P_BWD_
         return true;
     }
 #define R4_BWD_B(NCSR, DW)                                                                                \
@@ -1672,7 +1686,7 @@ static bool eng_try_bwd_rowg(const hgnn_side_bwd_t* d, hgnn_stream_t stream) {
     a.R_cross = d->R_cross > 0 ? d->R_cross : 0;
     a.pt_rowptr = d->pt_rowptr; a.pt_col = d->pt_col; a.pt_pm = d->pt_pm; a.pt_pd = d->pt_pd;
     a.Xc = d->Xc; a.bn_c = to_bnref(&d->bn_cross); a.gXc = d->gXc; a.acc_cross = d->accumulate_cross;
-    a.acc_b_cross = d->acc_b_cross; a.col0_cross = d->n_ops * Fs; a.ablate = 0;
+    a.acc_b_cross = d->acc_b_cross; a.col0_cross = d->n_ops * Fs; a.ablate = 0; a.trace_slot = -1;
     a.roww_s = d->roww_self; a.roww_c = d->roww_cross; a.rowmap_s = d->rowmap_self; a.rowmap_c = d->rowmap_cross;
     a.rng_n = 0; a.range_ctas = 0; a.rng_sum_g = nullptr; a.rng_flag_g = nullptr;
     cudaStream_t s = to_stream(stream);
@@ -1712,6 +1726,25 @@ extern "C" int hgnn_debug_cta_phases(unsigned long long* out, int n) {
     HGNN_REQUIRE(out && n > 0 && n <= 2048, "bad argument");
     cudaError_t e = cudaMemcpyFromSymbol(out, eng::g_cta_phase, (size_t)n * 3 * sizeof(unsigned long long));
     if (e != cudaSuccess) { hgnn_set_error("hgnn_debug_cta_phases: %s", cudaGetErrorString(e)); return HGNN_ERR_CUDA; }
+    return HGNN_OK;
+}
+
+// Launch timeline (HGNN_B200_ABLATE bit 16).  out != NULL: copies the first n slots (4 values each: min CTA start, min /
+// max "wait passed", max CTA end; ns) to the HOST array.  reset = 1: slots back to (max, max, 0, 0) and the next traced
+// launch takes slot 0 again; reset = 2: slot values only (before re-running a captured graph whose launches keep their slots).
+extern "C" int hgnn_debug_ktrace(unsigned long long* out, int n, int reset) {
+    HGNN_REQUIRE(n >= 0 && n <= KTRACE_SLOTS, "bad argument");
+    if (out && n > 0) {
+        cudaError_t e = cudaMemcpyFromSymbol(out, eng::g_ktrace, (size_t)n * 4 * sizeof(unsigned long long));
+        if (e != cudaSuccess) { hgnn_set_error("hgnn_debug_ktrace: %s", cudaGetErrorString(e)); return HGNN_ERR_CUDA; }
+    }
+    if (reset) {
+        static unsigned long long init[KTRACE_SLOTS * 4];
+        for (int i = 0; i < KTRACE_SLOTS; ++i) { init[i * 4] = init[i * 4 + 1] = ~0ull; init[i * 4 + 2] = init[i * 4 + 3] = 0ull; }
+        cudaError_t e = cudaMemcpyToSymbol(eng::g_ktrace, init, sizeof(init));
+        if (e != cudaSuccess) { hgnn_set_error("hgnn_debug_ktrace: %s", cudaGetErrorString(e)); return HGNN_ERR_CUDA; }
+        if (reset == 1) g_ktrace_next = 0;
+    }
     return HGNN_OK;
 }
 

@@ -13,6 +13,30 @@
 
 #define R4_THREADS 128
 
+__device__ __forceinline__ unsigned long long global_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+// profiling aid (HGNN_B200_ABLATE bit 16): timeline of the traced launches of a step, one slot per launch in issue
+// order: [min CTA start, min "wait passed", max "wait passed", max CTA end] (ns, %globaltimer); read and reset with
+// hgnn_debug_ktrace.  Works inside a replayed CUDA graph (the slot is a kernel argument).
+#define KTRACE_SLOTS 1024
+__device__ unsigned long long g_ktrace[KTRACE_SLOTS * 4];
+__device__ __forceinline__ void ktrace_start(int slot) {
+    if (slot >= 0 && threadIdx.x == 0) atomicMin(&g_ktrace[slot * 4], global_ns());
+}
+__device__ __forceinline__ void ktrace_waited(int slot) {
+    if (slot >= 0 && threadIdx.x == 0) {
+        const unsigned long long t = global_ns();
+        atomicMin(&g_ktrace[slot * 4 + 1], t);
+        atomicMax(&g_ktrace[slot * 4 + 2], t);
+    }
+}
+__device__ __forceinline__ void ktrace_end(int slot) {
+    if (slot >= 0 && threadIdx.x == 0) atomicMax(&g_ktrace[slot * 4 + 3], global_ns());
+}
+
 __device__ __forceinline__ float4 ld4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
 __device__ __forceinline__ float4 f4_fma(float a, float4 x, float4 acc) {
     acc.x = fmaf(a, x.x, acc.x); acc.y = fmaf(a, x.y, acc.y); acc.z = fmaf(a, x.z, acc.z); acc.w = fmaf(a, x.w, acc.w);
@@ -48,12 +72,11 @@ __device__ __forceinline__ void csr_gather4(const int* __restrict__ col, const f
 }
 
 // ---- warp-level batch-norm prologue for width-4 tensors: the binned (sum, sum^2) accumulators are
-// hgnn_ws_bins(8) x 8 = 32 doubles = one load per lane; two shuffles fold the bins, eight more
+// hgnn_ws_bins(8) x 8 doubles = four independent loads per lane (hgnn_bins8_lane); two shuffles fold the bins, eight more
 // broadcast the totals, and every thread derives the vectors in registers - no shared memory and
 // no block barrier.
 __device__ __forceinline__ void warp_totals8(const double* __restrict__ acc, double tot[8]) {
-    const int lane = threadIdx.x & 31;
-    double v = __ldcg(acc + lane);            // nb * 8 == 32 by construction (hgnn_ws_bins(8) == 4)
+    double v = hgnn_bins8_lane(acc);
     v += __shfl_xor_sync(0xffffffffu, v, 8);
     v += __shfl_xor_sync(0xffffffffu, v, 16);
 #pragma unroll
@@ -128,6 +151,7 @@ struct Fwd4Args {
                                      // the others enter the batch-norm sums weight times
     const int* rowmap;               // optional list of the R rows to compute (the active rows); NULL: rows 0..R-1
     int ablate;                      // timing experiments only (HGNN_B200_ABLATE): 1 no gathers, 2 no BN, 4 no epilogue
+    int trace_slot;                  // >= 0: record this launch in g_ktrace (HGNN_B200_ABLATE bit 16)
 };
 
 // One batch of a CSR gather, split in two so that the index loads of several operators can be in
@@ -215,7 +239,7 @@ struct Bn4Loader {
     }
     __device__ __forceinline__ void issue_acc(const BnRef& r) {
         v = 0.0;
-        if (mode == 2) v = __ldcg(r.acc + (threadIdx.x & 31));
+        if (mode == 2) v = hgnn_bins8_lane(r.acc);
     }
     __device__ __forceinline__ Bn4 resolve(const BnRef& r) const {
         if (mode != 2) return bn4_from_ref(r);
@@ -273,6 +297,7 @@ fwd_row4_kernel(const Fwd4Args a) {
     __shared__ __align__(16) float bnv[16];            // self: scale, shift | cross: scale, shift (one warp each computes them)
     const int tid = threadIdx.x;
     pdl_launch_dependents();
+    ktrace_start(a.trace_slot);
     // ---- phase 0
     for (int i = tid; i < 4 * NB * 4; i += R4_THREADS) {
         const int o = i / (NB * 4), c = i - o * (NB * 4);
@@ -310,6 +335,7 @@ fwd_row4_kernel(const Fwd4Args a) {
     if (row < a.R) load_structure(row);
     // ---- phase 1: everything the producer wrote
     pdl_wait();
+    ktrace_waited(a.trace_slot);
     // batch-norm vectors of the inputs: warp 0 (self) and warp 1 (cross) derive them - fp64 sums, divide, rsqrt: ~100
     // instructions - and publish them in shared memory; every thread of every warp used to repeat that
     const int warp_id = tid >> 5;
@@ -419,6 +445,7 @@ fwd_row4_kernel(const Fwd4Args a) {
             accum_add(a.acc_out, 8, hgnn_ws_bins(8), tid, v);
         }
     }
+    ktrace_end(a.trace_slot);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -448,6 +475,7 @@ struct Bwd4Args {
     // into rng_sum_g (4 floats each) and set rng_flag_g[r]; both zero on entry
     int rng_n, range_ctas; float* rng_sum_g; int* rng_flag_g;
     int ablate;           // timing experiments only (HGNN_B200_ABLATE): 1 no gathers, 2 no range phase, 4 no flush, 8 CTA times
+    int trace_slot;       // >= 0: record this launch in g_ktrace (HGNN_B200_ABLATE bit 16)
 };
 
 struct Gpre4 {
@@ -501,11 +529,6 @@ __device__ __forceinline__ float4 gpre_gather(const Gpre4& gp, const int* __rest
 // profiling aid (HGNN_B200_ABLATE bit 8): per-CTA start / end / role of the last backward launch
 __device__ unsigned long long g_cta_times[2048 * 3];
 __device__ unsigned long long g_cta_phase[2048 * 3];   // end of row loop, end of range phase (cross CTAs: = row loop), coefficients ready
-__device__ __forceinline__ unsigned long long global_ns() {
-    unsigned long long t;
-    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
-    return t;
-}
 
 // GB / CB: entries per gather batch of the self part (first transposed operator) / of the cross part,
 // picked by the host from the average row lengths so that a typical row needs one batch.

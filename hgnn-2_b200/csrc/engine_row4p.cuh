@@ -20,6 +20,7 @@
 // Rows with run-length parts (the uncollapsed line graph) and the gather-only variant stay on bwd_row4_kernel.
 #pragma once
 
+
 template <int B, bool TWO>
 struct Ent4 {
     int c[B];
@@ -66,7 +67,10 @@ __device__ __forceinline__ float4 gpre_fin(const Gpre4& gp, const float* __restr
 
 // One part of the launch (CTA-uniform): SELF = transposed [IDENT, DIAG, CSR] on the rows of the side's own input,
 // !SELF = the Pm^T / Pd^T pattern on the rows of the cross input.  B entries per gather batch.
-template <int B, bool SELF>
+// R4P_RMW_LOAD: accumulate into gX with load + add + store (the load goes out with the row's other loads) instead of
+// red.global.add.v4.f32 (no load, 4 registers fewer - but the reductions of 80 k rows drain for ~1 us after the last CTA,
+// which delays the release of the dependent launch: profiles/logs/step_timeline_r3e.log)
+template <int B, bool SELF, bool R4P_RMW_LOAD>
 __device__ __forceinline__ void bwd4p_part(const Bwd4Args& a, const float* __restrict__ W, float* __restrict__ red,
                                            float* __restrict__ cv) {
     constexpr int NT = SELF ? 3 : 2;
@@ -117,16 +121,18 @@ __device__ __forceinline__ void bwd4p_part(const Bwd4Args& a, const float* __res
     if (PRE2) load_entries(nxt, nxtE);
 
     pdl_wait();
+    ktrace_waited(a.trace_slot);
 
     // ---- every producer-written load of the first row, before the coefficient round
     Gpre4 gp;
     gp.relu_from = a.relu_from; gp.bn = a.has_bn != 0; gp.need_z = a.has_bn != 0 || a.relu_from < 4;
     gp.G = a.gY; gp.Z = a.Z;
-    float4 own_g = f4_zero(), own_z = f4_zero(), xr = f4_zero();
+    float4 own_g = f4_zero(), own_z = f4_zero(), xr = f4_zero(), old = f4_zero();
     float4 dg[B], dz[B];
     auto issue = [&](const Row4S& s, const Ent4<B, TWO>& e) {
         if (SELF) gpre_raw(gp, s.row, own_g, own_z);
         xr = ld4(X + (size_t)s.row * 4);
+        if (R4P_RMW_LOAD && gX && accum) old = __ldcg(reinterpret_cast<const float4*>(gX + (size_t)s.row * 4));
 #pragma unroll
         for (int j = 0; j < B; ++j) {
             if (e.c[j] >= 0) gpre_raw(gp, e.c[j], dg[j], dz[j]);
@@ -224,9 +230,14 @@ __device__ __forceinline__ void bwd4p_part(const Bwd4Args& a, const float* __res
             if (gX) {
                 // every row has exactly one writer per launch: the vector reduction is the same sum as load + add + store,
                 // without the load (red.global.add.v4.f32)
-                const float4 o4 = make_float4(g[0], g[1], g[2], g[3]);
-                if (accum) atomicAdd(reinterpret_cast<float4*>(gX + (size_t)cur.row * 4), o4);
-                else *reinterpret_cast<float4*>(gX + (size_t)cur.row * 4) = o4;
+                float4 o4 = make_float4(g[0], g[1], g[2], g[3]);
+                if (R4P_RMW_LOAD) {
+                    if (accum) { o4.x += old.x; o4.y += old.y; o4.z += old.z; o4.w += old.w; }
+                    *reinterpret_cast<float4*>(gX + (size_t)cur.row * 4) = o4;
+                } else {
+                    if (accum) atomicAdd(reinterpret_cast<float4*>(gX + (size_t)cur.row * 4), o4);
+                    else *reinterpret_cast<float4*>(gX + (size_t)cur.row * 4) = o4;
+                }
                 if (stats) {
                     const float4 mu = *reinterpret_cast<const float4*>(cv + 20), rs = *reinterpret_cast<const float4*>(cv + 24);
                     const float xh[4] = {(xr.x - mu.x) * rs.x, (xr.y - mu.y) * rs.y, (xr.z - mu.z) * rs.z, (xr.w - mu.w) * rs.w};
@@ -287,7 +298,7 @@ __device__ __forceinline__ void bwd4p_part(const Bwd4Args& a, const float* __res
     }
 }
 
-template <int GB, int CB>
+template <int GB, int CB, bool RMW>
 __global__ void __launch_bounds__(R4_THREADS, R4_BWD_MIN_CTAS)
 bwd_row4p_kernel(const Bwd4Args a) {
     __shared__ __align__(16) float Ws[3 * 4 * 4];         // [t][o][f] = W[o][t*4+f]
@@ -297,6 +308,7 @@ bwd_row4p_kernel(const Bwd4Args a) {
     const int tid = threadIdx.x;
     const bool is_self = (int)blockIdx.x < a.ctas_self;
     pdl_launch_dependents();
+    ktrace_start(a.trace_slot);
     if ((a.ablate & 8) && tid == 0 && blockIdx.x < 2048) {
         g_cta_times[blockIdx.x * 3] = global_ns();
         g_cta_times[blockIdx.x * 3 + 2] = is_self ? 1 : 0;
@@ -308,14 +320,15 @@ bwd_row4p_kernel(const Bwd4Args a) {
             const float* wrow = (o < a.Ha) ? a.Wa + (size_t)o * a.Cin : a.Wb + (size_t)(o - a.Ha) * a.Cin;
             Ws[i] = wrow[t * 4 + f];
         }
-        bwd4p_part<GB, true>(a, Ws, red, cv);
+        bwd4p_part<GB, true, RMW>(a, Ws, red, cv);
     } else {
         for (int i = tid; i < 32; i += R4_THREADS) {
             const int t = i >> 4, o = (i >> 2) & 3, f = i & 3;
             const float* wrow = (o < a.Ha) ? a.Wa + (size_t)o * a.Cin : a.Wb + (size_t)(o - a.Ha) * a.Cin;
             Wc[i] = wrow[a.col0_cross + t * 4 + f];
         }
-        bwd4p_part<CB, false>(a, Wc, red, cv);
+        bwd4p_part<CB, false, RMW>(a, Wc, red, cv);
     }
     if ((a.ablate & 8) && tid == 0 && blockIdx.x < 2048) g_cta_times[blockIdx.x * 3 + 1] = global_ns();
+    ktrace_end(a.trace_slot);
 }

@@ -249,7 +249,7 @@ __device__ __forceinline__ void bn_vectors(const Tensor& t, float* out) {
         if (lane < 4) { out[lane] = 1.f; out[4 + lane] = 0.f; out[8 + lane] = 0.f; out[12 + lane] = 1.f; }
         return;
     }
-    double v = __ldcg(t.acc_f + lane);             // hgnn_ws_bins(8) x 8 = 32 doubles
+    double v = hgnn_bins8_lane(t.acc_f);           // hgnn_ws_bins(8) x 8 doubles
     v += __shfl_xor_sync(FULL, v, 8);
     v += __shfl_xor_sync(FULL, v, 16);
     const int f = lane & 3;
@@ -274,7 +274,7 @@ __device__ __forceinline__ void gpre_vectors(const Tensor& t, float* out) {
         if (lane < 4) { out[lane] = 1.f; out[4 + lane] = 0.f; out[8 + lane] = 0.f; }
         return;
     }
-    double vf = __ldcg(t.acc_f + lane), vb = __ldcg(t.acc_b + lane);
+    double vf = hgnn_bins8_lane(t.acc_f), vb = hgnn_bins8_lane(t.acc_b);
     vf += __shfl_xor_sync(FULL, vf, 8); vf += __shfl_xor_sync(FULL, vf, 16);
     vb += __shfl_xor_sync(FULL, vb, 8); vb += __shfl_xor_sync(FULL, vb, 16);
     const int f = lane & 3;

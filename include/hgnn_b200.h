@@ -269,6 +269,11 @@ int hgnn_debug_cta_times(unsigned long long* out, int n);
 /* same launch, row CTAs: (end of the row loop ns, end of the range phase ns [cross CTAs: = row loop], batch-norm /
  * gPre coefficient vectors ready ns) */
 int hgnn_debug_cta_phases(unsigned long long* out, int n);
+/* profiling aid (HGNN_B200_ABLATE bit 16): timeline of the width-4 side launches of a step, one slot per launch in issue
+ * order, 4 values each (min CTA start, min / max "producer wait passed", max CTA end; ns).  out != NULL: the first n <= 1024
+ * slots to the HOST array; reset 1: clear the slots and restart the numbering, 2: clear the slots only (a captured graph
+ * keeps its slots across replays); synchronises the device */
+int hgnn_debug_ktrace(unsigned long long* out, int n, int reset);
 
 /* out[i] = sum_{b<nb[i]} sum_{c<cnt[i]} arena[off[i] + b*stride[i] + c]: every binned accumulator of
  * a step -> the flat fp32 gradient buffer, one launch. */
