@@ -1488,9 +1488,28 @@ extern "C" int hgnn_lg_side_fits(int n_ops, int Fs, int Fc, int Fout) {
 // max(ceil(rows_self / threads_self) * row cost_self, ceil(rows_cross / threads_cross) * row cost_cross); ties go to the
 // split closest to the cost-proportional one.  (A proportional split left e.g. 1.3 rows per thread on the heavy
 // part - a third of its threads did two rows and set the kernel time: profiles/logs/cta_times_*.log.)
+static int eng_split_ctas_search(int grid, long long R_self, long long R_cross, double cost_s, double cost_c);
+// The search walks every split of the grid (~600 candidates, two 64-bit divisions each: ~5 us of host time per
+// backward launch, 0.15 ms per step); the 36 middle sides of a step ask the same two questions, so the last few
+// answers are kept (per thread: no locking).
 static int eng_split_ctas(int grid, long long R_self, long long R_cross, double cost_s, double cost_c) {
     if (R_cross <= 0) return grid;
     if (grid < 2) return 1;
+    struct Memo { int grid; long long rs, rc; double cs, cc; int best; };
+    static thread_local Memo memo[8];
+    static thread_local int n_memo = 0, next = 0;
+    for (int i = 0; i < n_memo; ++i) {
+        const Memo& m = memo[i];
+        if (m.grid == grid && m.rs == R_self && m.rc == R_cross && m.cs == cost_s && m.cc == cost_c) return m.best;
+    }
+    const int best = eng_split_ctas_search(grid, R_self, R_cross, cost_s, cost_c);
+    Memo& m = memo[next];
+    m.grid = grid; m.rs = R_self; m.rc = R_cross; m.cs = cost_s; m.cc = cost_c; m.best = best;
+    next = (next + 1) & 7;
+    if (n_memo < 8) ++n_memo;
+    return best;
+}
+static int eng_split_ctas_search(int grid, long long R_self, long long R_cross, double cost_s, double cost_c) {
     const double row_s = cost_s / (double)R_self, row_c = cost_c / (double)R_cross;
     const double prop = grid * cost_s / (cost_s + cost_c);
     int best = 1;
@@ -1637,12 +1656,13 @@ static bool eng_try_bwd_row4(const hgnn_side_bwd_t* d, hgnn_stream_t stream) {
             eng_launch(eng::bwd_row4p_kernel<GB, CB, RMW>, grid, R4_THREADS, 0, s, a);                         \
         }
         // batch sizes: 2 entries for the transposed CSR operator (more spills under the 128-register bound); the incidence
-        // pattern takes 2 when its rows are line-graph nodes (two end points each), else 4.  HGNN_B200_BWD_BATCH: 3 = (4, 4),
+        // pattern takes 2 when its rows are line-graph nodes (two end points each: a listed cross part, whatever the average
+        // over all rows says), else 4.  HGNN_B200_BWD_BATCH: 3 = (4, 4),
         // 2 = (2, 8) (both spill; measurement only), 5 = (2, 2), 0 = (2, 4).
         static int rmw = -1;
         if (rmw < 0) { const char* e = getenv("HGNN_B200_BWD_RMW"); rmw = (e && e[0] == '1') ? 1 : 0; }   // measured equal on C2 (0.634 vs 0.630 ms per step); the reduction form spills less
 #define R4P_BWD(GB, CB) { if (rmw) R4P_BWD_(GB, CB, true) else R4P_BWD_(GB, CB, false) }
-        if (mid_s) R4P_BWD(4, 4) else if (big_c) R4P_BWD(2, 8) else if (bforce == 5 || (bforce < 0 && avg_c <= 2.5)) R4P_BWD(2, 2) else R4P_BWD(2, 4)
+        if (mid_s) R4P_BWD(4, 4) else if (big_c) R4P_BWD(2, 8) else if (bforce == 5 || (bforce < 0 && (avg_c <= 2.5 || d->rowmap_cross))) R4P_BWD(2, 2) else R4P_BWD(2, 4)
 #undef R4P_BWD
 #undef R4P_BWD_
         return true;

@@ -83,8 +83,10 @@ def prepare_batch(batch, task, J=1, sparse=None, device="cuda"):
     Nmax, Emax = int(N_batch.max()), int(E_batch.max())
     # host tensors in pinned memory (when CUDA is there) so that the caller's .cuda() is one DMA each
     pin = torch.cuda.is_available()
-    X = torch.zeros(bs, n_feat, Nmax, pin_memory=pin)
-    XL = torch.zeros(bs, 1, Emax, pin_memory=pin)
+    # uninitialised + explicit zero tails: a pinned torch.zeros of the two padded tensors (1.3 MB on C2) costs ~0.2 ms of
+    # host memset per batch although almost every slot is overwritten below
+    X = torch.empty(bs, n_feat, Nmax, pin_memory=pin)
+    XL = torch.empty(bs, 1, Emax, pin_memory=pin)
     ts = [inst[2] for inst in batch]
     if all(torch.is_tensor(t) and t.dim() == 1 and t.shape == ts[0].shape and t.dtype == ts[0].dtype for t in ts):
         T = torch.stack(ts, 0)[:, task].to(torch.float32).reshape(bs, 1)      # one gather instead of bs item() calls
@@ -95,6 +97,10 @@ def prepare_batch(batch, task, J=1, sparse=None, device="cuda"):
         g = graphs[i]
         Xn[i, :, :g.N] = inst[0].numpy().T
         XLn[i, 0, :g.M] = g.dl
+        if g.N < Nmax:
+            Xn[i, :, g.N:] = 0.0
+        if g.M < Emax:
+            XLn[i, 0, g.M:] = 0.0
     XL = PackTensor.wrap(XL, pack)      # remembers that it is this pack's line-graph degree (pack.PackTensor)
     W, WL = OperatorHandle(pack, "W"), OperatorHandle(pack, "WL")
     Pm, Pd = OperatorHandle(pack, "Pm"), OperatorHandle(pack, "Pd")
