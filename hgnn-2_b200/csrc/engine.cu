@@ -1662,6 +1662,9 @@ static bool eng_try_bwd_row4(const hgnn_side_bwd_t* d, hgnn_stream_t stream) {
         static int rmw = -1;
         if (rmw < 0) { const char* e = getenv("HGNN_B200_BWD_RMW"); rmw = (e && e[0] == '1') ? 1 : 0; }   // measured equal on C2 (0.634 vs 0.630 ms per step); the reduction form spills less
 #define R4P_BWD(GB, CB) { if (rmw) R4P_BWD_(GB, CB, true) else R4P_BWD_(GB, CB, false) }
+        static int edge44 = -1;
+        if (edge44 < 0) { const char* e = getenv("HGNN_B200_BWD_EDGE44"); edge44 = (e && e[0] == '1') ? 1 : 0; }
+        if (edge44 && d->rowmap_self && bforce < 0) mid_s = true;      // experiment: (4, 4) on the collapsed edge side only
         if (mid_s) R4P_BWD(4, 4) else if (big_c) R4P_BWD(2, 8) else if (bforce == 5 || (bforce < 0 && (avg_c <= 2.5 || d->rowmap_cross))) R4P_BWD(2, 2) else R4P_BWD(2, 4)
 #undef R4P_BWD
 #undef R4P_BWD_
