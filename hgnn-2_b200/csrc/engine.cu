@@ -327,6 +327,8 @@ struct BnRef {
     const float* w;        // scalar BN weight / bias (device)
     const float* b;
     int n;                 // rows behind the statistics
+    double inv_n;          // 1 / n, divided on the host (an fp64 division is a ~40-instruction dependent sequence, and the
+                           // coefficient round sits on the critical path of every launch)
 };
 
 // Fill scale/shift (and mean/rstd when asked) for a tensor of width F.  All threads; ends synced.
@@ -1027,6 +1029,7 @@ static eng::BnRef to_bnref(const hgnn_bn_ref_t* r) {
     o.w = r ? r->weight : nullptr;
     o.b = r ? r->bias : nullptr;
     o.n = r ? r->n_rows : 0;
+    o.inv_n = o.n > 0 ? 1.0 / (double)o.n : 0.0;
     return o;
 }
 
@@ -1545,7 +1548,7 @@ static bool eng_try_bwd_row4(const hgnn_side_bwd_t* d, hgnn_stream_t stream) {
         return false;
     for (int i = 3; i < d->n_ops; ++i) if (d->ops_T[i].rng_rowptr) return false;   // ranges only on the first CSR op
     eng::Bwd4Args a;
-    a.gY = d->gY; a.Z = d->Z; a.relu_from = d->relu_from; a.Rg = d->Rg; a.has_bn = d->acc_b != nullptr;
+    a.gY = d->gY; a.Z = d->Z; a.relu_from = d->relu_from; a.Rg = d->Rg; a.inv_Rg = d->Rg > 0 ? 1.0 / (double)d->Rg : 0.0; a.has_bn = d->acc_b != nullptr;
     a.acc_f = d->acc_f; a.acc_b = d->acc_b; a.bn_w = d->bn_weight;
     a.Wa = d->Wa; a.Ha = d->Ha; a.Wb = d->Wb; a.Hb = d->Hb; a.Cin = d->Cin;
     a.dW_bins = d->dW_bins; a.db_bins = d->db_bins;
@@ -1692,7 +1695,7 @@ static bool eng_try_bwd_rowg(const hgnn_side_bwd_t* d, hgnn_stream_t stream) {
     if (Fg == 4 && (!eng_aligned16(d->gY) || (d->Z && !eng_aligned16(d->Z)))) return false;
     if ((Fs == 4 && !eng_aligned16(d->Xs)) || (Fc == 4 && !eng_aligned16(d->Xc))) return false;
     eng::Bwd4Args a;
-    a.gY = d->gY; a.Z = d->Z; a.relu_from = d->relu_from; a.Rg = d->Rg; a.has_bn = has_bn;
+    a.gY = d->gY; a.Z = d->Z; a.relu_from = d->relu_from; a.Rg = d->Rg; a.inv_Rg = d->Rg > 0 ? 1.0 / (double)d->Rg : 0.0; a.has_bn = has_bn;
     a.acc_f = d->acc_f; a.acc_b = d->acc_b; a.bn_w = d->bn_weight;
     a.Wa = d->Wa; a.Ha = d->Ha; a.Wb = d->Wb; a.Hb = d->Hb; a.Cin = d->Cin;
     a.dW_bins = d->dW_bins; a.db_bins = d->db_bins;

@@ -21,6 +21,11 @@ __device__ __forceinline__ unsigned long long global_ns() {
 // profiling aid (HGNN_B200_ABLATE bit 16): timeline of the traced launches of a step, one slot per launch in issue
 // order: [min CTA start, min "wait passed", max "wait passed", max CTA end] (ns, %globaltimer); read and reset with
 // hgnn_debug_ktrace.  Works inside a replayed CUDA graph (the slot is a kernel argument).
+// per-CTA stamps of the last traced width-4 launch (HGNN_B200_ABLATE bit 8): hgnn_debug_cta_times / _phases.
+// backward: times = (start, end, is_self), phase = (end of row loop, end of range phase, coefficients ready);
+// forward:  times = (start, end, 2),       phase = (end of row loop, producer wait passed, coefficients ready)
+__device__ unsigned long long g_cta_times[2048 * 3];
+__device__ unsigned long long g_cta_phase[2048 * 3];
 #define KTRACE_SLOTS 1024
 __device__ unsigned long long g_ktrace[KTRACE_SLOTS * 4];
 __device__ __forceinline__ void ktrace_start(int slot) {
@@ -88,6 +93,23 @@ struct Bn4 {
     bool on;
 };
 
+// One warp, one feature per lane (f = lane & 3): the folded totals of a width-4 tensor's (sum, sum^2) block -> this
+// lane's scale / shift / mean / 1/std.  `v` is the lane's part of the block (hgnn_bins8_lane).  Lanes 0..3 hold the four
+// features (the other lanes repeat them).  ~25 instructions per lane on the critical path instead of the 4-feature loop
+// behind eight broadcast shuffles that bn4_from_totals runs.
+__device__ __forceinline__ void bn4_lane(double v, float w, float b, double inv_n, float& sc, float& sh, float& mu, float& rs) {
+    const int f = threadIdx.x & 3;
+    v += __shfl_xor_sync(0xffffffffu, v, 8);
+    v += __shfl_xor_sync(0xffffffffu, v, 16);
+    const double sum = __shfl_sync(0xffffffffu, v, f), sq = __shfl_sync(0xffffffffu, v, 4 + f);
+    const double m = sum * inv_n;
+    const double var = fma(-m, m, sq * inv_n);
+    rs = 1.0f / sqrtf(fmaxf((float)var, 0.f) + (float)ENG_BN_EPS);
+    mu = (float)m;
+    sc = w * rs;
+    sh = b - w * mu * rs;
+}
+
 __device__ __forceinline__ Bn4 bn4_from_ref(const BnRef& r) {
     Bn4 o;
     o.on = true;
@@ -111,7 +133,7 @@ __device__ __forceinline__ Bn4 bn4_from_ref(const BnRef& r) {
     // E[x^2] - mean^2 in fp64 (the only cancellation-prone step); everything after in fp32 - fp64
     // divide / sqrt are long software sequences and every thread runs this prologue
     const float w = r.w[0], b = r.b[0];
-    const double inv_n = 1.0 / (double)r.n;
+    const double inv_n = r.inv_n;
     float sc[4], sh[4], mu[4], rs[4];
 #pragma unroll
     for (int f = 0; f < 4; ++f) {
@@ -245,7 +267,7 @@ struct Bn4Loader {
         if (mode != 2) return bn4_from_ref(r);
         double tot[8];
         warp_totals8_from(v, tot);
-        return bn4_from_totals(tot, w, b, 1.0 / (double)r.n);
+        return bn4_from_totals(tot, w, b, r.inv_n);
     }
 };
 
@@ -298,6 +320,8 @@ fwd_row4_kernel(const Fwd4Args a) {
     const int tid = threadIdx.x;
     pdl_launch_dependents();
     ktrace_start(a.trace_slot);
+    const bool stamp = (a.ablate & 8) && tid == 0 && blockIdx.x < 2048;
+    if (stamp) { g_cta_times[blockIdx.x * 3] = global_ns(); g_cta_times[blockIdx.x * 3 + 2] = 2; }
     // ---- phase 0
     for (int i = tid; i < 4 * NB * 4; i += R4_THREADS) {
         const int o = i / (NB * 4), c = i - o * (NB * 4);
@@ -336,6 +360,7 @@ fwd_row4_kernel(const Fwd4Args a) {
     // ---- phase 1: everything the producer wrote
     pdl_wait();
     ktrace_waited(a.trace_slot);
+    if (stamp) g_cta_phase[blockIdx.x * 3 + 1] = global_ns();
     // batch-norm vectors of the inputs: warp 0 (self) and warp 1 (cross) derive them - fp64 sums, divide, rsqrt: ~100
     // instructions - and publish them in shared memory; every thread of every warp used to repeat that
     const int warp_id = tid >> 5;
@@ -348,17 +373,30 @@ fwd_row4_kernel(const Fwd4Args a) {
         if (CROSS) gb.load_rows(a.Xc);
     }
     if (warp_id == 0) {
-        Bn4 v;
-        if (a.ablate & 2) { v.sc = make_float4(1.f, 1.f, 1.f, 1.f); v.sh = f4_zero(); }
-        else v = ls.resolve(a.bn_s);
-        if (tid == 0) { *reinterpret_cast<float4*>(bnv) = v.sc; *reinterpret_cast<float4*>(bnv + 4) = v.sh; }
+        if (ls.mode == 2 && !(a.ablate & 2)) {          // batch statistics: one feature per lane
+            float sc, sh, mu, rs;
+            bn4_lane(ls.v, ls.w, ls.b, a.bn_s.inv_n, sc, sh, mu, rs);
+            if (tid < 4) { bnv[tid] = sc; bnv[4 + tid] = sh; }
+        } else {
+            Bn4 v;
+            if (a.ablate & 2) { v.sc = make_float4(1.f, 1.f, 1.f, 1.f); v.sh = f4_zero(); }
+            else v = ls.resolve(a.bn_s);
+            if (tid == 0) { *reinterpret_cast<float4*>(bnv) = v.sc; *reinterpret_cast<float4*>(bnv + 4) = v.sh; }
+        }
     } else if (CROSS && warp_id == 1) {
-        Bn4 v;
-        if (a.ablate & 2) { v.sc = make_float4(1.f, 1.f, 1.f, 1.f); v.sh = f4_zero(); }
-        else v = lc.resolve(a.bn_c);
-        if ((tid & 31) == 0) { *reinterpret_cast<float4*>(bnv + 8) = v.sc; *reinterpret_cast<float4*>(bnv + 12) = v.sh; }
+        if (lc.mode == 2 && !(a.ablate & 2)) {
+            float sc, sh, mu, rs;
+            bn4_lane(lc.v, lc.w, lc.b, a.bn_c.inv_n, sc, sh, mu, rs);
+            if ((tid & 31) < 4) { bnv[8 + (tid & 31)] = sc; bnv[12 + (tid & 31)] = sh; }
+        } else {
+            Bn4 v;
+            if (a.ablate & 2) { v.sc = make_float4(1.f, 1.f, 1.f, 1.f); v.sh = f4_zero(); }
+            else v = lc.resolve(a.bn_c);
+            if ((tid & 31) == 0) { *reinterpret_cast<float4*>(bnv + 8) = v.sc; *reinterpret_cast<float4*>(bnv + 12) = v.sh; }
+        }
     }
     __syncthreads();                                   // weights and batch-norm vectors in shared memory
+    if (stamp) g_cta_phase[blockIdx.x * 3 + 2] = global_ns();
     const float4 sc_s = *reinterpret_cast<const float4*>(bnv), sh_s = *reinterpret_cast<const float4*>(bnv + 4);
     const float4 sc_c = CROSS ? *reinterpret_cast<const float4*>(bnv + 8) : sc_s;
     const float4 sh_c = CROSS ? *reinterpret_cast<const float4*>(bnv + 12) : sh_s;
@@ -431,6 +469,7 @@ fwd_row4_kernel(const Fwd4Args a) {
         }
         *reinterpret_cast<float4*>(a.Z + (size_t)rr * 4) = make_float4(out[0], out[1], out[2], out[3]);
     }
+    if (stamp) g_cta_phase[blockIdx.x * 3] = global_ns();
     if (a.acc_out && !(a.ablate & 4)) {   // warp shuffle tree -> one row per warp in shared memory -> 8 fp64 atomics per CTA
         const int lane = tid & 31, warp = tid >> 5;
         double st[8];
@@ -445,6 +484,7 @@ fwd_row4_kernel(const Fwd4Args a) {
             accum_add(a.acc_out, 8, hgnn_ws_bins(8), tid, v);
         }
     }
+    if (stamp) g_cta_times[blockIdx.x * 3 + 1] = global_ns();
     ktrace_end(a.trace_slot);
 }
 
@@ -476,6 +516,7 @@ struct Bwd4Args {
     int rng_n, range_ctas; float* rng_sum_g; int* rng_flag_g;
     int ablate;           // timing experiments only (HGNN_B200_ABLATE): 1 no gathers, 2 no range phase, 4 no flush, 8 CTA times
     int trace_slot;       // >= 0: record this launch in g_ktrace (HGNN_B200_ABLATE bit 16)
+    double inv_Rg;        // 1 / Rg (host-divided)
 };
 
 struct Gpre4 {
@@ -527,8 +568,6 @@ __device__ __forceinline__ float4 gpre_gather(const Gpre4& gp, const int* __rest
 // DW = false: the gather-only variant (the weight gradients come from dw_row4_kernel, which streams
 // over the x1 rows saved by the forward on a parallel graph branch): ~48 fewer live registers.
 // profiling aid (HGNN_B200_ABLATE bit 8): per-CTA start / end / role of the last backward launch
-__device__ unsigned long long g_cta_times[2048 * 3];
-__device__ unsigned long long g_cta_phase[2048 * 3];   // end of row loop, end of range phase (cross CTAs: = row loop), coefficients ready
 
 // GB / CB: entries per gather batch of the self part (first transposed operator) / of the cross part,
 // picked by the host from the average row lengths so that a typical row needs one batch.
@@ -605,7 +644,7 @@ bwd_row4_kernel(const Bwd4Args a) {
             warp_totals8(a.acc_f, tf);
             warp_totals8(a.acc_b, tb);
             const float w = a.bn_w[0];
-            const double inv_n = 1.0 / (double)a.Rg;
+            const double inv_n = a.inv_Rg;
             const int f = lane & 3;
             const double m = tf[f] * inv_n;
             const double var = fma(-m, m, tf[4 + f] * inv_n);
@@ -1025,7 +1064,7 @@ bwd_row4c_kernel(const Bwd4Args a) {
             warp_totals8(a.acc_b, tb);
             const int f = lane & 3;
             const float w = a.bn_w[0];
-            const double inv_n = 1.0 / (double)a.Rg;
+            const double inv_n = a.inv_Rg;
             const double m = tf[f] * inv_n;
             const double var = fma(-m, m, tf[4 + f] * inv_n);
             const float r_ = 1.0f / sqrtf(fmaxf((float)var, 0.f) + (float)ENG_BN_EPS);

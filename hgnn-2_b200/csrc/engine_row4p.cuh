@@ -144,28 +144,37 @@ __device__ __forceinline__ void bwd4p_part(const Bwd4Args& a, const float* __res
     // ---- coefficients of this side's BN + ReLU backward (warp 0) and the input's BN vectors (warp 1), once per CTA
     if (warp == 0) {
         float c0 = 1.f, c1 = 0.f, c2 = 0.f;
-        if (a.has_bn) {
-            double tf[8], tb[8];
-            warp_totals8(a.acc_f, tf);
-            warp_totals8(a.acc_b, tb);
+        if (a.has_bn) {     // one feature per lane: (sum z, sum z^2) and (sum g, sum g xhat) of this side's output
+            double vf = hgnn_bins8_lane(a.acc_f), vb = hgnn_bins8_lane(a.acc_b);
             const float w = a.bn_w[0];
-            const double inv_n = 1.0 / (double)a.Rg;
             const int f = lane & 3;
-            const double m = tf[f] * inv_n;
-            const double var = fma(-m, m, tf[4 + f] * inv_n);
+            vf += __shfl_xor_sync(0xffffffffu, vf, 8); vb += __shfl_xor_sync(0xffffffffu, vb, 8);
+            vf += __shfl_xor_sync(0xffffffffu, vf, 16); vb += __shfl_xor_sync(0xffffffffu, vb, 16);
+            const double sum = __shfl_sync(0xffffffffu, vf, f), sq = __shfl_sync(0xffffffffu, vf, 4 + f);
+            const double sgt = __shfl_sync(0xffffffffu, vb, f), sgx = __shfl_sync(0xffffffffu, vb, 4 + f);
+            const double inv_n = a.inv_Rg;
+            const double m = sum * inv_n;
+            const double var = fma(-m, m, sq * inv_n);
             const float r_ = 1.0f / sqrtf(fmaxf((float)var, 0.f) + (float)ENG_BN_EPS);
             const float k0 = w * r_;
-            const float k2 = -k0 * (float)(tb[4 + f] * inv_n) * r_;
+            const float k2 = -k0 * (float)(sgx * inv_n) * r_;
             c0 = k0;
             c2 = k2;
-            c1 = -k0 * (float)(tb[f] * inv_n) - k2 * (float)m;
+            c1 = -k0 * (float)(sgt * inv_n) - k2 * (float)m;
         }
         if (lane < 4) { cv[lane] = c0; cv[4 + lane] = c1; cv[8 + lane] = c2; }
     } else if (warp == 1) {
-        const Bn4 bx = bn4_from_ref(SELF ? a.bn_s : a.bn_c);
-        if (lane == 0) {
-            *reinterpret_cast<float4*>(cv + 12) = bx.sc; *reinterpret_cast<float4*>(cv + 16) = bx.sh;
-            *reinterpret_cast<float4*>(cv + 20) = bx.mu; *reinterpret_cast<float4*>(cv + 24) = bx.rs;
+        const BnRef& r = SELF ? a.bn_s : a.bn_c;
+        if (!r.affine && r.acc) {
+            float sc, sh, mu, rs;
+            bn4_lane(hgnn_bins8_lane(r.acc), r.w[0], r.b[0], r.inv_n, sc, sh, mu, rs);
+            if (lane < 4) { cv[12 + lane] = sc; cv[16 + lane] = sh; cv[20 + lane] = mu; cv[24 + lane] = rs; }
+        } else {
+            const Bn4 bx = bn4_from_ref(r);
+            if (lane == 0) {
+                *reinterpret_cast<float4*>(cv + 12) = bx.sc; *reinterpret_cast<float4*>(cv + 16) = bx.sh;
+                *reinterpret_cast<float4*>(cv + 20) = bx.mu; *reinterpret_cast<float4*>(cv + 24) = bx.rs;
+            }
         }
     }
     __syncthreads();                                   // weights and coefficient vectors in shared memory

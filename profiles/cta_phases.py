@@ -1,4 +1,4 @@
-"""Per-CTA phase breakdown of the width-4 backward kernel (HGNN_B200_ABLATE=8): start -> coefficient vectors in shared
+"""Per-CTA phase breakdown of the width-4 forward and backward kernels (HGNN_B200_ABLATE=8): start -> coefficient vectors in shared
 memory -> end of the row loop -> end (flush done), medians / p90 / max over the self and the cross CTAs.  Per-side Python
 path (eager launches, no PDL overlap)."""
 import os
@@ -28,8 +28,9 @@ NC = 1024
 
 def rec(name, *args):
     rc = orig(name, *args)
-    if name == "hgnn_lg_side_bwd" and (_lib.tag.endswith(".edge") or _lib.tag.endswith(".node")) and not _lib.tag.startswith("L0."):
-        kind = _lib.tag.split(".")[-1]
+    if name in ("hgnn_lg_side_bwd", "hgnn_lg_side_fwd") and (_lib.tag.endswith(".edge") or _lib.tag.endswith(".node")) \
+            and not _lib.tag.startswith("L0.") and not _lib.tag.startswith("layer0"):
+        kind = ("bwd " if name.endswith("bwd") else "fwd ") + _lib.tag.split(".")[-1]
         buf = (ctypes.c_ulonglong * (3 * NC))()
         orig("hgnn_debug_cta_times", buf, NC)
         ph = (ctypes.c_ulonglong * (3 * NC))()
@@ -52,12 +53,18 @@ def q(v):
 
 
 for kind, (t, ph) in seen.items():
-    live = t[:, 0] > 0
+    live = (t[:, 0] > 0) & (t[:, 0] > t[:, 0].max() - 50000)      # slots of this launch only (older launches had more CTAs)
+    live &= (t[:, 2] == 2) if kind.startswith("fwd") else (t[:, 2] != 2)
     t, ph = t[live], ph[live]
     t0 = t[:, 0].min()
     start, end, role = (t[:, 0] - t0) / 1e3, (t[:, 1] - t0) / 1e3, t[:, 2]
     coef, loop = (ph[:, 2] - t0) / 1e3, (ph[:, 0] - t0) / 1e3
-    print("== bwd %s side: %d CTAs, kernel span %.2f us; CTA start spread %.2f us" % (kind, len(t), end.max(), start.max()))
+    print("== %s side: %d CTAs, kernel span %.2f us; CTA start spread %.2f us" % (kind, len(t), end.max(), start.max()))
+    if kind.startswith("fwd"):
+        wait = (ph[:, 1] - t0) / 1e3
+        print("   all   CTAs %3d | start->wait passed %s | ->coef %s | coef->rows done %s | rows done->end %s | end at %s"
+              % (len(t), q(wait - start), q(coef - wait), q(loop - coef), q(end - loop), q(end)))
+        continue
     for r, name in ((1, "self"), (0, "cross")):
         m = (role == r) & (ph[:, 2] > 0)
         if not m.any():
