@@ -95,6 +95,7 @@ _SIGS = {
     "hgnn_program_bwd": [ctypes.POINTER(ProgramT), ctypes.POINTER(BatchT), _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, c_ll, _P],
     "hgnn_bn_running_update_k": [_P, _P, _P, _P, c_int, c_int, _P, c_int, c_float, _P, _P],
     "hgnn_host_pack_fill": [c_int, _P, c_int, c_int, _P, _P, c_int],
+    "hgnn_host_fill_features": [c_int, _P, _P, c_int, c_ll, _P, c_ll, _P],
     "hgnn_pack_device_upload": [c_int, _P, c_int, c_int, _P, _P, _P, _P, _P],
     "hgnn_lg_side_fwd": [ctypes.POINTER(SideT), ctypes.POINTER(BnRefT), ctypes.POINTER(BnRefT), _P, _P, c_int,
                          _P, _P, c_int, c_int, _P, _P, _P, _P],

@@ -577,3 +577,33 @@ extern "C" int hgnn_pack_device_upload(int bs, const void* const* blobs, int dua
         static_cast<const PackTask*>(meta_dev), nt);
     return hgnn_check_launch("hgnn_pack_device_upload");
 }
+
+// ---- padded host feature tensors of prepare_batch -------------------------------------------------------------------
+// X (bs, n_feat, Nmax): X[g, f, j] = x_g[j, f] for j < N_g, zero beyond (functions/batching.py:113-127 of the reference
+// builds the same zero-padded tensor with a Python loop); XL (bs, 1, Emax): the line-graph degree `dl` of every graph
+// (:171), read straight from the graph blobs.  One foreign call instead of ~130 numpy slice operations per batch
+// (0.12 ms of the 0.55 ms prepare_batch took on C2).  Host code only.  XL == NULL: primal batch.
+extern "C" int hgnn_host_fill_features(int bs, const void* const* blobs, const float* const* x_rows, int n_feat,
+                                       long long Nmax, float* X, long long Emax, float* XL) {
+    HGNN_REQUIRE(bs >= 0 && blobs && x_rows && n_feat > 0 && X && Nmax >= 0, "bad argument");
+    std::vector<Blob> B;
+    HGNN_REQUIRE(open_blobs(bs, blobs, XL != nullptr, &B), "malformed graph blob (magic / field count)");
+    for (int g = 0; g < bs; ++g) {
+        const long long n = B[g].N();
+        HGNN_REQUIRE(n <= Nmax && x_rows[g], "graph larger than the padded width");
+        const float* src = x_rows[g];
+        for (int f = 0; f < n_feat; ++f) {
+            float* dst = X + ((size_t)g * n_feat + f) * Nmax;
+            for (long long j = 0; j < n; ++j) dst[j] = src[j * n_feat + f];
+            for (long long j = n; j < Nmax; ++j) dst[j] = 0.f;
+        }
+        if (XL) {
+            const long long m = B[g].M();
+            HGNN_REQUIRE(m <= Emax && B[g].len(F_DL) == m, "line graph larger than the padded width");
+            float* dst = XL + (size_t)g * Emax;
+            memcpy(dst, B[g].ptr(F_DL), (size_t)m * sizeof(float));
+            for (long long j = m; j < Emax; ++j) dst[j] = 0.f;
+        }
+    }
+    return HGNN_OK;
+}

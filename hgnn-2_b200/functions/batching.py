@@ -8,6 +8,7 @@ light handles that accept ``.requires_grad = ...`` and ``.cuda()`` exactly as
 scripts/train_mnb.py:56-66 uses them.  ``sparse=False`` returns the reference's dense tensors
 (built on the GPU from the same pack, bit-exact).
 """
+import ctypes
 import os
 import weakref
 from random import shuffle
@@ -15,6 +16,7 @@ from random import shuffle
 import numpy as np
 import torch
 
+from .. import _lib
 from ..pack import BatchPack, GraphHandle, MaskHandle, OperatorHandle, PackTensor
 from .operators import graph_ops_of
 
@@ -92,15 +94,26 @@ def prepare_batch(batch, task, J=1, sparse=None, device="cuda"):
         T = torch.stack(ts, 0)[:, task].to(torch.float32).reshape(bs, 1)      # one gather instead of bs item() calls
     else:
         T = torch.tensor([float(inst[2][task]) for inst in batch], dtype=torch.float32).view(bs, 1)
-    Xn, XLn = X.numpy(), XL.numpy()
-    for i, inst in enumerate(batch):
-        g = graphs[i]
-        Xn[i, :, :g.N] = inst[0].numpy().T
-        XLn[i, 0, :g.M] = g.dl
-        if g.N < Nmax:
-            Xn[i, :, g.N:] = 0.0
-        if g.M < Emax:
-            XLn[i, 0, g.M:] = 0.0
+    xs = [inst[0] for inst in batch]
+    if all(torch.is_tensor(x) and x.dtype == torch.float32 and x.dim() == 2 and x.shape[1] == n_feat
+           and x.is_contiguous() and not x.is_cuda for x in xs):
+        # one foreign call: transposed copy of every graph's (N, F) features, line-graph degrees straight from the graph
+        # blobs, zero tails (csrc/hostpack.cu: hgnn_host_fill_features)
+        blobs = (ctypes.c_void_p * bs)(*[g.blob_ptr() for g in graphs])
+        rows = (ctypes.c_void_p * bs)(*[x.data_ptr() for x in xs])
+        rc = _lib.lib.hgnn_host_fill_features(bs, blobs, rows, n_feat, Nmax, X.data_ptr(), Emax, XL.data_ptr())
+        if rc != 0:
+            raise RuntimeError("hgnn_host_fill_features failed (%d): %s" % (rc, _lib.lib.hgnn_last_error().decode()))
+    else:
+        Xn, XLn = X.numpy(), XL.numpy()
+        for i, inst in enumerate(batch):
+            g = graphs[i]
+            Xn[i, :, :g.N] = np.asarray(inst[0], dtype=np.float32).T
+            XLn[i, 0, :g.M] = g.dl
+            if g.N < Nmax:
+                Xn[i, :, g.N:] = 0.0
+            if g.M < Emax:
+                XLn[i, 0, g.M:] = 0.0
     XL = PackTensor.wrap(XL, pack)      # remembers that it is this pack's line-graph degree (pack.PackTensor)
     W, WL = OperatorHandle(pack, "W"), OperatorHandle(pack, "WL")
     Pm, Pd = OperatorHandle(pack, "Pm"), OperatorHandle(pack, "Pd")

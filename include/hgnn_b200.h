@@ -461,6 +461,12 @@ const char* hgnn_host_pack_key(int k);
  * (length -1: array absent, e.g. the line-graph arrays when dual == 0 or bt when skip_bt != 0).
  * Returns the total number of bytes (16-byte aligned sub-arrays), < 0 on error. */
 long long hgnn_host_pack_layout(int bs, const void* const* blobs, int dual, int skip_bt, long long* layout);
+/* Padded host feature tensors of prepare_batch (functions/batching.py:113-127,:171 of the reference): X (bs, n_feat, Nmax)
+ * with X[g, f, j] = x_rows[g][j * n_feat + f] for j < N_g and zero beyond; XL (bs, 1, Emax) = the line-graph degree of every
+ * graph, read from its blob (NULL: primal batch).  Host code only. */
+int hgnn_host_fill_features(int bs, const void* const* blobs, const float* const* x_rows, int n_feat, long long Nmax,
+                            float* X, long long Emax, float* XL);
+
 /* Fills `out` (total bytes from hgnn_host_pack_layout) using up to n_threads host threads. */
 int hgnn_host_pack_fill(int bs, const void* const* blobs, int dual, int skip_bt, const long long* layout,
                         void* out, int n_threads);

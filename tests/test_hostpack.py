@@ -82,3 +82,28 @@ def test_host_pack_rejects_a_foreign_blob():
     assert hgnn_b200._lib.lib.hgnn_host_pack_layout(1, blobs, 1, 0, lay) < 0
     assert b"blob" in hgnn_b200._lib.lib.hgnn_last_error()
     assert torch is not None
+
+
+def test_fill_features_matches_the_python_loop():
+    """hgnn_host_fill_features (the padded X / XL host tensors of prepare_batch, reference functions/batching.py:113-127,
+    :171) against the per-graph slice loop, ragged graph sizes, pre-filled destination (the tails must be zeroed)."""
+    import ctypes
+    import numpy as np
+    import torch
+    from hgnn_b200 import _lib, synth
+    ds = synth.sbm_dataset(3, N=50, sparse=True) + synth.sbm_dataset(2, N=37, sparse=True, first_id=7)
+    graphs = [inst[3].graph_ops for inst in ds]
+    bs, F = len(ds), ds[0][0].shape[1]
+    Nmax, Emax = max(g.N for g in graphs), max(g.M for g in graphs)
+    X, XL = torch.full((bs, F, Nmax), 7.0), torch.full((bs, 1, Emax), 7.0)
+    blobs = (ctypes.c_void_p * bs)(*[g.blob_ptr() for g in graphs])
+    rows = (ctypes.c_void_p * bs)(*[inst[0].data_ptr() for inst in ds])
+    assert _lib.lib.hgnn_host_fill_features(bs, blobs, rows, F, Nmax, X.data_ptr(), Emax, XL.data_ptr()) == 0
+    Xr, XLr = torch.zeros(bs, F, Nmax), torch.zeros(bs, 1, Emax)
+    for i, inst in enumerate(ds):
+        g = graphs[i]
+        Xr[i, :, :g.N] = inst[0].T
+        XLr[i, 0, :g.M] = torch.from_numpy(np.asarray(g.dl))
+    assert torch.equal(X, Xr) and torch.equal(XL, XLr)
+    # a graph wider than the padded tensor is refused
+    assert _lib.lib.hgnn_host_fill_features(bs, blobs, rows, F, Nmax - 1, X.data_ptr(), Emax, XL.data_ptr()) != 0
