@@ -436,6 +436,41 @@ inline bool on_device_path(const KeyDesc& k, int dual, int skip_bt) {
     return present(k, dual, skip_bt) && k.type != T_SEG && k.type != T_FIXUP;
 }
 
+// Offsets of the graph blobs inside the device staging buffer.  Consecutive graphs of a dataset sit back to back in the
+// pinned slabs (64-byte aligned), so a batch of neighbours is ONE contiguous host range: blobs that follow their
+// predecessor within HGNN_STAGE_MAX_GAP bytes keep their host spacing (the alignment gap rides along) and the whole run
+// goes up in one DMA - 512 QM9-sized graphs are a handful of copies instead of 512 x ~2 us of cudaMemcpyAsync.  Anything
+// else (shuffled batches, blobs whose transposed-operator tail is skipped) starts a new run.  off has bs + 1 entries:
+// off[bs] = bytes of staging needed; run_start[g] = 1 where a new DMA begins.
+#define HGNN_STAGE_MAX_GAP 512
+long long stage_offsets(const std::vector<Blob>& B, int skip_bt, std::vector<long long>* off, std::vector<char>* run_start) {
+    const int bs = (int)B.size();
+    off->assign(bs + 1, 0);
+    if (run_start) run_start->assign(bs + 1, 0);
+    long long end = 0;      // end of the previous blob in the staging buffer
+    for (int g = 0; g < bs; ++g) {
+        const long long bytes = blob_bytes(B[g], skip_bt);
+        bool joined = false;
+        if (g > 0) {
+            const long long prev_bytes = blob_bytes(B[g - 1], skip_bt);
+            const long long gap = (long long)(B[g].base - B[g - 1].base) - prev_bytes;
+            // both bases are 64-byte aligned in the slabs; a distance that keeps 16-byte alignment keeps the fields aligned
+            if (B[g].base > B[g - 1].base && gap >= 0 && gap <= HGNN_STAGE_MAX_GAP && ((prev_bytes + gap) & 15) == 0) {
+                (*off)[g] = (*off)[g - 1] + prev_bytes + gap;
+                joined = true;
+            }
+        }
+        if (!joined) {
+            (*off)[g] = (end + 15) & ~15ll;
+            if (run_start) (*run_start)[g] = 1;
+        }
+        end = (*off)[g] + bytes;
+    }
+    (*off)[bs] = end;
+    if (run_start) (*run_start)[bs] = 1;
+    return end < 16 ? 16 : end;
+}
+
 struct DevicePlan {
     long long out_bytes = 0, stage_bytes = 0, meta_bytes = 0;
     int n_tasks = 0, n_small = 0;   // n_small: ints of small arrays kept in the meta buffer
@@ -464,8 +499,10 @@ DevicePlan plan_device(const std::vector<Blob>& B, int dual, int skip_bt, long l
         }
     }
     if (p.out_bytes < 16) p.out_bytes = 16;
-    for (const Blob& b : B) p.stage_bytes += blob_bytes(b, skip_bt);
-    if (p.stage_bytes < 16) p.stage_bytes = 16;
+    {
+        std::vector<long long> off;
+        p.stage_bytes = stage_offsets(B, skip_bt, &off, nullptr);
+    }
     p.small_off = ((long long)p.n_tasks * sizeof(PackTask) + 15) & ~15ll;
     p.meta_bytes = p.small_off + 4ll * p.n_small + 16;
     return p;
@@ -499,15 +536,20 @@ extern "C" int hgnn_pack_device_upload(int bs, const void* const* blobs, int dua
     const DevicePlan p = plan_device(B, dual, skip_bt, layout);
     cudaStream_t s = to_stream(stream);
     // ---- graph blobs -> device staging, one DMA each
-    std::vector<long long> blob_off(bs + 1, 0);
-    for (int g = 0; g < bs; ++g) blob_off[g + 1] = blob_off[g] + blob_bytes(B[g], skip_bt);
+    std::vector<long long> blob_off;
+    std::vector<char> run_start;
+    stage_offsets(B, skip_bt, &blob_off, &run_start);
     char* stage = static_cast<char*>(stage_dev);
-    for (int g = 0; g < bs; ++g) {
-        cudaError_t e = cudaMemcpyAsync(stage + blob_off[g], B[g].base, (size_t)blob_bytes(B[g], skip_bt), cudaMemcpyHostToDevice, s);
+    for (int g = 0; g < bs;) {          // one DMA per run of host-adjacent blobs
+        int e_ = g + 1;
+        while (e_ < bs && !run_start[e_]) ++e_;
+        const size_t bytes = (size_t)(blob_off[e_ - 1] + blob_bytes(B[e_ - 1], skip_bt) - blob_off[g]);
+        cudaError_t e = cudaMemcpyAsync(stage + blob_off[g], B[g].base, bytes, cudaMemcpyHostToDevice, s);
         if (e != cudaSuccess) {
-            hgnn_set_error("hgnn_pack_device_upload: cudaMemcpyAsync(blob %d): %s", g, cudaGetErrorString(e));
+            hgnn_set_error("hgnn_pack_device_upload: cudaMemcpyAsync(blobs %d..%d): %s", g, e_ - 1, cudaGetErrorString(e));
             return HGNN_ERR_CUDA;
         }
+        g = e_;
     }
     // ---- task table + small arrays in the meta buffer
     PackTask* tasks = static_cast<PackTask*>(meta_host);

@@ -17,7 +17,7 @@ import numpy as np
 import torch
 
 from .. import _lib
-from ..pack import BatchPack, GraphHandle, MaskHandle, OperatorHandle, PackTensor
+from ..pack import BatchPack, GraphHandle, MaskHandle, OperatorHandle, PackTensor, device_pack
 from .operators import graph_ops_of
 
 
@@ -95,11 +95,16 @@ def prepare_batch(batch, task, J=1, sparse=None, device="cuda"):
     else:
         T = torch.tensor([float(inst[2][task]) for inst in batch], dtype=torch.float32).view(bs, 1)
     xs = [inst[0] for inst in batch]
-    if all(torch.is_tensor(x) and x.dtype == torch.float32 and x.dim() == 2 and x.shape[1] == n_feat
-           and x.is_contiguous() and not x.is_cuda for x in xs):
+    f32, row_major = torch.float32, (n_feat, 1)
+    if all(type(x) is torch.Tensor and x.dtype is f32 and x.stride() == row_major and x.shape[1] == n_feat
+           and not x.is_cuda for x in xs):
         # one foreign call: transposed copy of every graph's (N, F) features, line-graph degrees straight from the graph
         # blobs, zero tails (csrc/hostpack.cu: hgnn_host_fill_features)
-        blobs = (ctypes.c_void_p * bs)(*[g.blob_ptr() for g in graphs])
+        last = getattr(device_pack, "last_blobs", None)
+        if last is not None and last[0] is graphs:
+            blobs = last[1]
+        else:
+            blobs = (ctypes.c_void_p * bs)(*[g.blob_ptr() for g in graphs])
         rows = (ctypes.c_void_p * bs)(*[x.data_ptr() for x in xs])
         rc = _lib.lib.hgnn_host_fill_features(bs, blobs, rows, n_feat, Nmax, X.data_ptr(), Emax, XL.data_ptr())
         if rc != 0:

@@ -124,6 +124,7 @@ def device_pack(graphs, dual=True, skip_bt=False, device="cuda"):
         _HOST_KEYS = [lib.hgnn_host_pack_key(k).decode() for k in range(lib.hgnn_host_pack_n_keys())]
     bs = len(graphs)
     blobs = (ctypes.c_void_p * max(bs, 1))(*[g.blob_ptr() for g in graphs])
+    device_pack.last_blobs = (graphs, blobs)      # prepare_batch reuses the pointer table (a Python call per graph)
     lay = (ctypes.c_longlong * (2 * len(_HOST_KEYS)))()
     stage_b, meta_b = ctypes.c_longlong(), ctypes.c_longlong()
     du, sk = 1 if dual else 0, 1 if skip_bt else 0

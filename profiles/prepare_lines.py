@@ -1,3 +1,4 @@
+"""Line-level wall time of prepare_batch (a copy of its body with timers): C2 batch, or `qm9`: 512 QM9-shaped graphs."""
 import os, sys, time, ctypes
 sys.path.insert(0, "/root/repo" if os.path.isdir("/root/repo/hgnn-2_b200") else os.getcwd())
 import numpy as np, torch
@@ -5,7 +6,10 @@ import hgnn_b200
 from hgnn_b200 import _lib, synth
 from hgnn_b200.functions import batching as B
 from hgnn_b200.pack import BatchPack, GraphHandle, MaskHandle, OperatorHandle, PackTensor
-hosts = [synth.sbm_dataset(32, N=1000, sparse=True, first_id=k * 32) for k in range(2)]
+if len(sys.argv) > 1 and sys.argv[1] == "qm9":
+    hosts = [synth.qm9_shaped_dataset(512, J=1, sparse=True, first_id=k * 512) for k in range(2)]
+else:
+    hosts = [synth.sbm_dataset(32, N=1000, sparse=True, first_id=k * 32) for k in range(2)]
 acc = {}
 def run(batch, task=0, J=1):
     ts=[time.perf_counter()]

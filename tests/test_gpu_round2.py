@@ -208,10 +208,12 @@ def test_batch_loader_with_power_operators_is_race_free():
 
 
 @pytest.mark.parametrize("env", [{"HGNN_B200_MEGA": "1"}, {"HGNN_B200_BWD_V2": "1"}, {"HGNN_B200_NO_COLLAPSE": "1"},
-                                 {"HGNN_B200_REPLAY": "1"}, {"HGNN_B200_QUAD": "1"}])
+                                 {"HGNN_B200_REPLAY": "1"}, {"HGNN_B200_QUAD": "1"}, {"HGNN_B200_BWD_P": "0"},
+                                 {"HGNN_B200_BWD_RMW": "1"}, {"HGNN_B200_BWD_BATCH": "3"}])
 def test_opt_in_kernel_variants_keep_parity(env):
     """The code paths that are not the default - persistent cooperative kernels (csrc/mega.cu), the low-register
-    backward, the uncollapsed line graph - are switched by environment variables read once per process, so the
+    backward, the uncollapsed line graph, the backward before its load rounds were pipelined (HGNN_B200_BWD_P=0), its
+    load + add + store accumulation and its wider gather batches - are switched by environment variables read once per process, so the
     L = 20 oracle comparison and the golden-vector models run again in a child process with each of them."""
     import subprocess
     import sys
