@@ -80,6 +80,30 @@ def test_engine_matches_module_path(kind, order, h, J, N):
     assert rel_err(oe.cpu(), om.cpu()) < 1e-4
 
 
+def test_many_rows_per_thread_match_module_path():
+    """A batch large enough that every thread of the width-4 kernels walks SEVERAL rows (12 graphs of N = 6000:
+    ~190 k active line-graph rows over the 592 x 128 resident threads of a backward launch): the pipelined backward
+    (csrc/engine_row4p.cuh) then runs its peeled first row, the pre-fetched second row AND the in-loop structure
+    fetch of the rows after it.  Checked against the per-module kernels (csrc/side.cu), as above."""
+    import hgnn_b200  # noqa: F401
+    from hgnn_b200 import synth
+    from hgnn_b200.functions.batching import prepare_batch
+    from hgnn_b200.models.gnns.model_mnb import GNN_lg
+    torch.manual_seed(5)
+    inst = synth.sbm_dataset(12, N=6000, J=1, sparse=True)
+    batch = prepare_batch(inst, 0, 1)
+    pack = batch[1].pack
+    assert int(pack.erow.numel()) > 2 * 592 * 128 // 2        # more than two rows per self-part thread
+    model = GNN_lg(0, 2, 4, 5, 2, 1, 1).cuda()
+    ref_model = copy.deepcopy(model)
+    out_e, g_e = _run(model, batch, True)
+    out_m, g_m = _run(ref_model, batch, False)
+    assert rel_err(out_e.cpu(), out_m.cpu()) < 1e-4
+    fl = 0.1 * max(float(v.abs().max()) for v in g_m.values())
+    for k in g_m:
+        assert rel_err(g_e[k].cpu(), g_m[k].cpu(), fl) < 1e-4, k
+
+
 def test_split_dw_variant_matches():
     """engine.SPLIT_DW = True (x1 saved by the forward, streaming dW pass on a side stream) gives the
     same gradients as the fused backward."""
