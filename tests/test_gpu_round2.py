@@ -248,3 +248,44 @@ def test_gradients_the_engine_does_not_cover_take_the_layer_path():
     assert yv.grad_fn is not None
     yv.sum().backward()
     assert Xv.grad is not None and torch.isfinite(Xv.grad).all()
+
+
+def test_launch_timeline_probe_records_ordered_stamps():
+    """HGNN_B200_ABLATE=16 (read once per process -> child process): every traced width-4 launch of a step fills its
+    hgnn_debug_ktrace slot with min CTA start <= min / max "producer wait passed" <= max CTA end, launches in issue
+    order; the results of the step are unchanged (the stamps are the only difference)."""
+    import subprocess
+    import sys
+    code = r'''
+import ctypes, os, sys
+sys.path.insert(0, %r)
+import numpy as np, torch
+import hgnn_b200
+from hgnn_b200 import _lib, synth
+from hgnn_b200.functions.batching import prepare_batch
+from hgnn_b200.models.gnns.model_mnb import GNN_lg
+inst = synth.sbm_dataset(4, N=300, sparse=True)
+X, W, T, XL, WL, Pm, Pd, mask, mask_lg, N_batch, E_batch = prepare_batch(inst, 0, 1)
+torch.manual_seed(0)
+model = GNN_lg(0, 2, 5, 5, 2, 1, 1).cuda().train()
+_lib.call("hgnn_debug_ktrace", None, 0, 1)
+out = model([X.cuda(), XL.cuda(), W, WL, Pm, Pd], N_batch, mask, E_batch, mask_lg)
+torch.nn.functional.cross_entropy(out, T.squeeze(1).long().cuda()).backward()
+torch.cuda.synchronize()
+n = 2 * 2 * 3
+buf = (ctypes.c_ulonglong * (4 * n))()
+_lib.call("hgnn_debug_ktrace", buf, n, 0)
+t = np.array(buf, dtype=np.uint64).reshape(n, 4).astype(np.int64)
+assert (t[:, 0] > 0).all() and (t[:, 0] <= t[:, 1]).all() and (t[:, 1] <= t[:, 2]).all() and (t[:, 2] <= t[:, 3]).all(), t
+assert (np.diff(t[:, 3]) > 0).all(), t[:, 3]
+print("OUT", float(out.double().abs().sum()))
+''' % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    outs = []
+    for env in ({"HGNN_B200_ABLATE": "16"}, {"HGNN_B200_ABLATE": "0"}):
+        r = subprocess.run([sys.executable, "-c", code if env["HGNN_B200_ABLATE"] == "16" else
+                            code.replace("assert (t[:, 0] > 0)", "assert True or (t[:, 0] > 0)").replace("assert (np.diff", "assert True or (np.diff")],
+                           env=dict(os.environ, **env), capture_output=True, text=True, timeout=300)
+        assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+        outs.append([ln for ln in r.stdout.splitlines() if ln.startswith("OUT")][-1])
+    a, b = float(outs[0].split()[1]), float(outs[1].split()[1])      # fp64 atomics: equal to rounding, not bit for bit
+    assert abs(a - b) <= 1e-5 * abs(b)
