@@ -273,32 +273,59 @@ def run_reference(a):
 # clocks sampling during the timed region
 # --------------------------------------------------------------------------------------------
 class ClockSampler(object):
-    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+    """SM clocks and throttle reasons DURING the timed region: ONE `nvidia-smi -lms 200` process (the profiling recipe's
+    clocks line), started by local rank 0 for every GPU of the job well before the timed region (NVML initialisation on
+    an 8-GPU host takes longer than the region itself) and killed after it; only the samples whose time stamps fall
+    inside the region count.  (A sampler per rank that spawned nvidia-smi every 100 ms put eight NVML initialisations
+    on the host at once, inside the timed region.)"""
+    Q = ("timestamp,clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, index):
-        self.index, self.samples, self.stop = index, [], False
-        self.t = threading.Thread(target=self._run, daemon=True)
+    def __init__(self, index, n_gpus=1):
+        self.samples, self.proc, self.t0 = [], None, None
+        self.ids = ",".join(str(i) for i in range(n_gpus)) if index == 0 else None
 
-    def _run(self):
-        while not self.stop:
+    def start(self):
+        if self.ids is not None:
             try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                      "--format=csv,noheader,nounits"], capture_output=True, text=True,
-                                     timeout=5).stdout.strip()
-                if out:
-                    self.samples.append([x.strip() for x in out.split(",")])
+                self.proc = subprocess.Popen(["nvidia-smi", "-i", self.ids, "--query-gpu=" + self.Q,
+                                              "--format=csv,noheader,nounits", "-lms", "200"],
+                                             stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             except Exception:
-                pass
-            time.sleep(0.1)
-
-    def __enter__(self):
-        self.t.start()
+                self.proc = None
         return self
 
-    def __exit__(self, *exc):
-        self.stop = True
-        self.t.join(timeout=6)
+    def __enter__(self):          # the timed region begins
+        import datetime
+        self.t0 = datetime.datetime.now()
+        return self
+
+    def __exit__(self, *exc):     # ... and ends
+        import datetime
+        t1 = datetime.datetime.now()
+        if self.proc is None:
+            return
+        try:
+            self.proc.terminate()
+            out, _ = self.proc.communicate(timeout=6)
+        except Exception:
+            try:
+                self.proc.kill()
+            except Exception:
+                pass
+            out = ""
+        self.proc = None
+        slack = datetime.timedelta(milliseconds=50)
+        for ln in (out or "").splitlines():
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                ts = datetime.datetime.strptime(f[0], "%Y/%m/%d %H:%M:%S.%f")
+            except ValueError:
+                continue
+            if self.t0 - slack <= ts <= t1 + slack:
+                self.samples.append(f[1:])
 
     def summary(self):
         sm = [float(s[0]) for s in self.samples if s and s[0].replace(".", "").isdigit()]
@@ -306,7 +333,7 @@ class ClockSampler(object):
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         reasons = sorted({n for s in self.samples for n, v in zip(names, s[2:6]) if v.lower().startswith("active")})
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(self.samples)}
+                "sm_mhz_min": min(sm) if sm else None, "reasons": reasons, "samples": len(self.samples)}
 
 
 # --------------------------------------------------------------------------------------------
@@ -622,6 +649,7 @@ def run_ours(a):
     fp.broadcast(0)
     _trace("broadcast done")
     opt = FusedAdamax(fp, lr=1e-3)
+    sampler = ClockSampler(local, world).start()      # NVML is up long before the timed region
 
     def train_step(dbatch, collective=True):
         fp.zero_grad()
@@ -678,7 +706,7 @@ def run_ours(a):
         dist.barrier()
     torch.cuda.synchronize()
     events = []
-    with ClockSampler(local) as clocks:
+    with sampler as clocks:
         for _ in range(a.steps):
             flush.zero_()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -693,12 +721,16 @@ def run_ours(a):
         # keep the GPU busy a little longer so that the clock sampler sees it under load.  A FIXED number
         # of extra steps: every replay contains the gradient all-reduce, so all ranks must issue the
         # same count (a time-based loop would leave unmatched collectives behind).
-        for _ in range(300):
+        for _ in range(700):
             step()
         torch.cuda.synchronize()
     elapsed = sum(e0.elapsed_time(e1) for e0, e1 in events) * 1e-3
     t = torch.tensor([elapsed], device=dev, dtype=torch.float64)
+    per_rank_ms = None
     if world > 1:
+        allt = [torch.empty_like(t) for _ in range(world)]
+        dist.all_gather(allt, t)                      # every rank's own device time: shows the skew the MAX hides
+        per_rank_ms = [round(float(x.item()) * 1e3 / a.steps, 4) for x in allt]
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     elapsed = float(t.item())
     _trace("timed region done")
@@ -873,6 +905,8 @@ def run_ours(a):
             "gpu_launches": launches_per_step * a.steps, "launches_per_step": launches_per_step,
             "cuda_graph": graph is not None, "final_loss": final_loss, "roofline": roofline,
             "pack": work.describe(resident)}
+    if per_rank_ms is not None:
+        line["ms_per_step_by_rank"] = per_rank_ms
     if ranks_agree is not None:
         line["ranks_agree"] = ranks_agree
         line["allreduce_exposed_us"] = exposed_us
