@@ -291,9 +291,18 @@ class ClockSampler(object):
                 self.proc = subprocess.Popen(["nvidia-smi", "-i", self.ids, "--query-gpu=" + self.Q,
                                               "--format=csv,noheader,nounits", "-lms", "200"],
                                              stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                import atexit
+                atexit.register(self._kill)      # the loop never ends by itself: no orphan if the run dies early
             except Exception:
                 self.proc = None
         return self
+
+    def _kill(self):
+        if self.proc is not None:
+            try:
+                self.proc.kill()
+            except Exception:
+                pass
 
     def __enter__(self):          # the timed region begins
         import datetime
