@@ -93,7 +93,7 @@ p2p_allreduce_adamax_kernel(float* __restrict__ p, const float* __restrict__ g, 
 __global__ void __launch_bounds__(P2P_THREADS)
 p2p_push_allreduce_adamax_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                                  float* __restrict__ u, int n, float lr, float beta1, float beta2, float eps, float gscale,
-                                 int* __restrict__ step, P2pPeers peers, int rank, int world, long long cap, int* fault) {
+                                 int* __restrict__ step, P2pPeers peers, int rank, int world, long long cap, int* fault, int fence_all) {
     __shared__ int s_step;
     const int tid = threadIdx.x;
     if (tid == 0) s_step = step[0] + 1;
@@ -114,7 +114,10 @@ p2p_push_allreduce_adamax_kernel(float* __restrict__ p, const float* __restrict_
             for (int i = tid; i < n; i += P2P_THREADS) dst[i] = g[i];
         }
     }
-    __threadfence_system();                  // every thread: its stores are performed system-wide before the flags go up
+    // The flags go up with st.release.sys by the threads below: a release is cumulative over everything that happens
+    // before it, and the CTA barrier orders every thread's data stores before it - no system fence per thread (1 024
+    // fences cost ~1.5 us of the exposed time).  HGNN_B200_P2P_FENCE=1 restores the per-thread fence.
+    if (fence_all) __threadfence_system();
     __syncthreads();
     if (tid == 0) step[0] = s;
     // ---- 2. flag[rank] = s in every peer's header; 3. wait for flag[q] >= s in MY header (one thread per peer)
@@ -212,6 +215,8 @@ extern "C" int hgnn_p2p_allreduce_adamax(float* param, const float* grad, float*
     for (int r = 0; r < world; ++r) HGNN_REQUIRE(peers.buf[r], "null peer buffer");
     static int pull = -1;
     if (pull < 0) { const char* e = getenv("HGNN_B200_P2P_PULL"); pull = (e && e[0] == '1') ? 1 : 0; }
+    static int fence_all = -1;
+    if (fence_all < 0) { const char* e = getenv("HGNN_B200_P2P_FENCE"); fence_all = (e && e[0] == '1') ? 1 : 0; }
     if (pull)
         p2p_allreduce_adamax_kernel<<<1, P2P_THREADS, 0, to_stream(stream)>>>(param, grad, exp_avg, exp_inf, n, lr, beta1,
                                                                               beta2, eps, grad_scale, step, peers, rank,
@@ -219,6 +224,7 @@ extern "C" int hgnn_p2p_allreduce_adamax(float* param, const float* grad, float*
     else
         p2p_push_allreduce_adamax_kernel<<<1, P2P_THREADS, 0, to_stream(stream)>>>(param, grad, exp_avg, exp_inf, n, lr,
                                                                                    beta1, beta2, eps, grad_scale, step,
-                                                                                   peers, rank, world, cap_floats, fault);
+                                                                                   peers, rank, world, cap_floats, fault,
+                                                                                   fence_all);
     return hgnn_check_launch("hgnn_p2p_allreduce_adamax");
 }
