@@ -100,3 +100,23 @@ def test_batch_loader_propagates_errors_and_stops_early():
     with pytest.raises(IndexError):
         for _ in BatchLoader(data, [[0, 1], [99]], 0, 1):
             pass
+
+
+def test_upload_coalesces_adjacent_blobs_and_survives_any_order():
+    """Graph blobs built one after the other sit back to back in the pinned slabs and go up in ONE DMA per run
+    (csrc/hostpack.cu: stage_offsets); a batch that takes them in another order, repeats one, or mixes in a blob from
+    elsewhere must give the same arrays as the host concatenation."""
+    graphs = _graphs([20, 9, 33, 14, 27, 6], seed=11, dual=False)
+    for g in graphs:
+        g.blob_ptr()                                  # allocation order = list order: one contiguous run
+    ptrs = [g.blob_ptr() for g in graphs]
+    assert all(0 < b - a < (1 << 20) for a, b in zip(ptrs, ptrs[1:]))
+    _check(graphs, False, False)                      # one run
+    _check(graphs[::-1], False, False)                # descending addresses: every blob its own DMA
+    _check([graphs[2], graphs[3], graphs[0], graphs[1], graphs[5]], False, False)      # two runs and a single
+    _check([graphs[1], graphs[1], graphs[2]], False, False)                            # a repeated graph
+    dual = _graphs([12, 12, 30], seed=3)
+    for g in dual:
+        g.blob_ptr()
+    _check(dual, True, True)                          # skipped transposed-operator tails: gaps too wide to join
+    _check(dual, True, False)
