@@ -475,7 +475,16 @@ struct DevicePlan {
     long long out_bytes = 0, stage_bytes = 0, meta_bytes = 0;
     int n_tasks = 0, n_small = 0;   // n_small: ints of small arrays kept in the meta buffer
     long long small_off = 0;        // byte offset of the small arrays inside the meta buffer
+    // Many small blobs that are NOT neighbours in host memory (a shuffled batch of QM9-sized graphs: 512 x ~1 KB) would be
+    // hundreds of ~2 us DMAs: they are copied into the pinned meta buffer behind the task table instead (a few tens of
+    // microseconds of memcpy) and ride on its ONE host->device copy.  blob_meta_off: where they start in the meta buffer.
+    bool stage_in_meta = false;
+    long long blob_meta_off = 0;
+    std::vector<long long> blob_off;     // per blob: offset inside the staging area (device staging buffer, or meta)
+    std::vector<char> run_start;         // per blob: 1 where a new DMA begins (device staging mode)
 };
+#define HGNN_STAGE_IN_META_MAX_BYTES (4ll << 20)
+#define HGNN_STAGE_IN_META_MIN_RUNS 8
 
 DevicePlan plan_device(const std::vector<Blob>& B, int dual, int skip_bt, long long* layout) {
     DevicePlan p;
@@ -499,12 +508,23 @@ DevicePlan plan_device(const std::vector<Blob>& B, int dual, int skip_bt, long l
         }
     }
     if (p.out_bytes < 16) p.out_bytes = 16;
-    {
-        std::vector<long long> off;
-        p.stage_bytes = stage_offsets(B, skip_bt, &off, nullptr);
-    }
+    p.stage_bytes = stage_offsets(B, skip_bt, &p.blob_off, &p.run_start);
     p.small_off = ((long long)p.n_tasks * sizeof(PackTask) + 15) & ~15ll;
     p.meta_bytes = p.small_off + 4ll * p.n_small + 16;
+    int runs = 0;
+    for (int g = 0; g < bs; ++g) runs += p.run_start[g] ? 1 : 0;
+    if (runs >= HGNN_STAGE_IN_META_MIN_RUNS && p.stage_bytes <= HGNN_STAGE_IN_META_MAX_BYTES) {
+        long long end = 0;                       // tight layout, 16-byte aligned blobs
+        for (int g = 0; g < bs; ++g) {
+            p.blob_off[g] = (end + 15) & ~15ll;
+            end = p.blob_off[g] + blob_bytes(B[g], skip_bt);
+        }
+        p.blob_off[bs] = end;
+        p.stage_in_meta = true;
+        p.blob_meta_off = (p.meta_bytes + 15) & ~15ll;
+        p.meta_bytes = p.blob_meta_off + end + 16;
+        p.stage_bytes = 16;                      // the separate device staging buffer is not used
+    }
     return p;
 }
 
@@ -535,21 +555,25 @@ extern "C" int hgnn_pack_device_upload(int bs, const void* const* blobs, int dua
     long long layout[2 * N_KEYS];
     const DevicePlan p = plan_device(B, dual, skip_bt, layout);
     cudaStream_t s = to_stream(stream);
-    // ---- graph blobs -> device staging, one DMA each
-    std::vector<long long> blob_off;
-    std::vector<char> run_start;
-    stage_offsets(B, skip_bt, &blob_off, &run_start);
-    char* stage = static_cast<char*>(stage_dev);
-    for (int g = 0; g < bs;) {          // one DMA per run of host-adjacent blobs
-        int e_ = g + 1;
-        while (e_ < bs && !run_start[e_]) ++e_;
-        const size_t bytes = (size_t)(blob_off[e_ - 1] + blob_bytes(B[e_ - 1], skip_bt) - blob_off[g]);
-        cudaError_t e = cudaMemcpyAsync(stage + blob_off[g], B[g].base, bytes, cudaMemcpyHostToDevice, s);
-        if (e != cudaSuccess) {
-            hgnn_set_error("hgnn_pack_device_upload: cudaMemcpyAsync(blobs %d..%d): %s", g, e_ - 1, cudaGetErrorString(e));
-            return HGNN_ERR_CUDA;
+    // ---- graph blobs -> device staging: one DMA per run of host-adjacent blobs, or (many small scattered blobs) a host
+    //      copy into the meta buffer, which goes up in one piece below
+    const std::vector<long long>& blob_off = p.blob_off;
+    char* stage = p.stage_in_meta ? static_cast<char*>(meta_dev) + p.blob_meta_off : static_cast<char*>(stage_dev);
+    if (p.stage_in_meta) {
+        char* dst = static_cast<char*>(meta_host) + p.blob_meta_off;
+        for (int g = 0; g < bs; ++g) memcpy(dst + blob_off[g], B[g].base, (size_t)blob_bytes(B[g], skip_bt));
+    } else {
+        for (int g = 0; g < bs;) {
+            int e_ = g + 1;
+            while (e_ < bs && !p.run_start[e_]) ++e_;
+            const size_t bytes = (size_t)(blob_off[e_ - 1] + blob_bytes(B[e_ - 1], skip_bt) - blob_off[g]);
+            cudaError_t e = cudaMemcpyAsync(stage + blob_off[g], B[g].base, bytes, cudaMemcpyHostToDevice, s);
+            if (e != cudaSuccess) {
+                hgnn_set_error("hgnn_pack_device_upload: cudaMemcpyAsync(blobs %d..%d): %s", g, e_ - 1, cudaGetErrorString(e));
+                return HGNN_ERR_CUDA;
+            }
+            g = e_;
         }
-        g = e_;
     }
     // ---- task table + small arrays in the meta buffer
     PackTask* tasks = static_cast<PackTask*>(meta_host);

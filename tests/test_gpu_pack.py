@@ -105,7 +105,8 @@ def test_batch_loader_propagates_errors_and_stops_early():
 def test_upload_coalesces_adjacent_blobs_and_survives_any_order():
     """Graph blobs built one after the other sit back to back in the pinned slabs and go up in ONE DMA per run
     (csrc/hostpack.cu: stage_offsets); a batch that takes them in another order, repeats one, or mixes in a blob from
-    elsewhere must give the same arrays as the host concatenation."""
+    elsewhere must give the same arrays as the host concatenation; eight or more scattered small blobs are copied into
+    the pinned meta buffer and go up with it."""
     graphs = _graphs([20, 9, 33, 14, 27, 6], seed=11, dual=False)
     for g in graphs:
         g.blob_ptr()                                  # allocation order = list order: one contiguous run
@@ -115,6 +116,16 @@ def test_upload_coalesces_adjacent_blobs_and_survives_any_order():
     _check(graphs[::-1], False, False)                # descending addresses: every blob its own DMA
     _check([graphs[2], graphs[3], graphs[0], graphs[1], graphs[5]], False, False)      # two runs and a single
     _check([graphs[1], graphs[1], graphs[2]], False, False)                            # a repeated graph
+    many = _graphs([7, 12, 9, 15, 5, 11, 8, 14, 6, 10, 13, 4], seed=23, dual=False)
+    for g in many:
+        g.blob_ptr()
+    _check(many[::-1], False, False)                  # 12 scattered small blobs: staged inside the meta buffer, one copy
+    _check(many[::2] + many[1::2], False, False)
+    dual_many = _graphs([9, 6, 12, 8, 7, 10, 5, 11, 9], seed=29)
+    for g in dual_many:
+        g.blob_ptr()
+    _check(dual_many, True, True)                     # skipped tails: nine separate prefixes -> meta staging too
+    _check(dual_many[::-1], True, False)
     dual = _graphs([12, 12, 30], seed=3)
     for g in dual:
         g.blob_ptr()
