@@ -75,3 +75,35 @@ def test_tcgen05_forward_kernel_is_blackwell_native():
     ops = collections.Counter(t.split()[0].split(".")[0] for _, t in ins)
     assert ops["UTCHMMA"] >= 3 and ops["LDTM"] >= 1 and ops["UTCBAR"] >= 1, ops.most_common(12)
     assert ops["HMMA"] == 0
+
+
+H2_KERNELS = {
+    # the default width-4 (h = 2) training kernels of the C2 / C4 steps: name -> (max registers, max stack bytes)
+    "_ZN3eng16bwd_row4p_kernelILi2ELi4ELb0EEEvNS_8Bwd4ArgsE": (128, 16),      # 4 CTAs of 128 threads per SM
+    "_ZN3eng16bwd_row4p_kernelILi2ELi2ELb0EEEvNS_8Bwd4ArgsE": (128, 16),
+    "_ZN3eng15fwd_row4_kernelILi1ELb1ELi8ELi4EEEvNS_8Fwd4ArgsE": (170, 16),    # 3 CTAs per SM
+    "_ZN3eng15fwd_row4_kernelILi1ELb1ELi8ELi16EEEvNS_8Fwd4ArgsE": (255, 32),   # 2 CTAs per SM
+}
+
+
+def test_default_h2_kernels_keep_their_register_budget():
+    """The thread-per-row kernels are latency bound: their CTAs-per-SM (registers) and the absence of spills in the row
+    loop are what the measured step time rests on; a change that silently adds 10 registers to the
+    pipelined backward drops it from 4 to 3 CTAs per SM (measured: 0.59 -> 0.68 ms per step)."""
+    out = subprocess.run(["cuobjdump", "-res-usage", _lib_path()], capture_output=True, text=True).stdout
+    for fn, (max_reg, max_stack) in H2_KERNELS.items():
+        m = re.search(re.escape(fn) + r":\s*\n\s*REG:(\d+) STACK:(\d+)", out)
+        assert m, "kernel %s not in the library" % fn
+        reg, stack = map(int, m.groups())
+        assert reg <= max_reg and stack <= max_stack, (fn, reg, stack)
+
+
+def test_default_h2_kernels_use_dependent_launch_and_vector_reductions():
+    """Programmatic dependent launch (griddepcontrol.wait = ACQBULK) in the forward and the pipelined backward; the
+    backward accumulates into gX with red.global.add.v4.f32 (REDG.E.ADD.F32x4) and flushes its sums with fp64 REDs."""
+    for fn in H2_KERNELS:
+        ops = collections.Counter(t.split()[0] for _, t in _sass(fn))
+        assert ops["ACQBULK"] >= 1, (fn, "no griddepcontrol.wait")
+        assert any(k.startswith("REDG.E.ADD.F64") for k in ops), (fn, "no fp64 reductions")
+        if "bwd_row4p" in fn:
+            assert any(k.startswith("REDG.E.ADD.F32x4") for k in ops), (fn, "no vector reduction into gX")
